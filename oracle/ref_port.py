@@ -1,0 +1,70 @@
+"""Timed CPU baseline: the reference's own torch-CPU op sequence for the hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py); used by bench.py's ``cpu_baseline``
+leg and ``--impl reference`` arm.  /root/reference is Python and cannot travel to the
+GPU box, so this is a *port* (kind="port"): the same library calls the reference makes
+on CPU, nothing hand-optimised:
+
+  encoder  model/model.py:151-163,195-198   nn.LSTM(bidirectional, batch_first) + nn.Linear, x2
+  loss     the north_star's nn.CTCLoss call site replacing training/train.py:289,503-505
+           (log_softmax + F.ctc_loss, torch CPU)
+  decode   training/utils.py:122-150         argmax + the per-element Python loop
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class RefBlock(nn.Module):
+    """Parameter names match the reference block so state dicts interchange."""
+
+    def __init__(self, n_in: int, n_hidden: int, n_out: int):
+        super().__init__()
+        self.rnn = nn.LSTM(n_in, n_hidden, bidirectional=True, batch_first=True)
+        self.linear = nn.Linear(2 * n_hidden, n_out)
+
+    def forward(self, x):
+        seq, _ = self.rnn(x)
+        return self.linear(seq)
+
+
+def make_encoder(n_in: int, hidden: int) -> nn.Sequential:
+    return nn.Sequential(RefBlock(n_in, hidden, hidden), RefBlock(hidden, hidden, hidden))
+
+
+def greedy_decode_loop(logits: torch.Tensor, alphabet, blank: int = 0):
+    """The reference's host loop (one .item() per frame)."""
+    if logits.dim() == 3 and logits.shape[0] < logits.shape[1]:
+        logits = logits.permute(1, 0, 2)
+    best = logits.argmax(dim=2)
+    texts, seqs = [], []
+    for row in best:
+        last, seq = blank, []
+        for v in row:
+            k = v.item()
+            if k != blank and k != last:
+                seq.append(k)
+            last = k
+        seqs.append(seq)
+        texts.append("".join(alphabet[k - 1] for k in seq))
+    return texts, seqs
+
+
+def train_step(encoder, head, feats, targets, in_len, tg_len, blank=0):
+    """fwd + CTC + bwd on CPU; returns the loss value."""
+    for p in list(encoder.parameters()) + list(head.parameters()):
+        p.grad = None
+    logits = head(encoder(feats))                       # [B,T,C]
+    lp = F.log_softmax(logits, dim=2).permute(1, 0, 2)  # [T,B,C]
+    loss = F.ctc_loss(lp, targets, in_len, tg_len, blank=blank, reduction="mean",
+                      zero_infinity=True)
+    loss.backward()
+    return float(loss)
+
+
+@torch.no_grad()
+def infer_step(encoder, head, feats, alphabet, blank=0):
+    logits = head(encoder(feats))
+    return greedy_decode_loop(logits, alphabet, blank)

@@ -1,0 +1,158 @@
+"""Generate tests/golden/*.npz from the REFERENCE's own code and torch float64.
+
+Run in the build container only (it reads /root/reference, which does not exist on
+the GPU box):   python tests/make_golden.py
+
+  decode_*.npz   training/utils.py:122-150  ctc_greedy_decoder  (reference code, imported)
+  bilstm_*.npz   model/model.py:151-163     BidirectionalLSTM   (reference code, imported)
+  encrnn_*.npz   model/model.py:195-198     Sequential of two blocks, outputs + all grads
+  ctc_*.npz      torch.nn.functional.ctc_loss, CPU float64 (the reference has no CTC code;
+                 SURVEY.md section 0) -- loss per reduction and the gradient AT THE LOGITS.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+from model.model import BidirectionalLSTM  # noqa: E402
+from training.utils import ctc_greedy_decoder  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def charset():
+    itos = []
+    with open(os.path.join(REF, "configs", "charset.txt"), encoding="utf-8") as fh:
+        for line in fh:
+            tok = line.rstrip("\n")
+            if tok:
+                itos.append(tok)
+    return itos
+
+
+def gen_decode():
+    itos = charset()
+    g = torch.Generator().manual_seed(1234)
+    cases = {}
+    # random, B >= T (no permute), full charset
+    cases["rand_b8_t6"] = (torch.randn(8, 6, len(itos) + 1, generator=g), itos)
+    # B < T in batch-first layout: the reference heuristic permutes (utils.py:132-133)
+    cases["heur_b3_t7"] = (torch.randn(3, 7, len(itos) + 1, generator=g), itos)
+    # time-major input with T < B: heuristic permutes to batch-first
+    cases["tmajor_t5_b9"] = (torch.randn(5, 9, 11, generator=g), list("abcdefghij"))
+    # ties: quantised logits -> many equal maxima (first index must win)
+    cases["ties"] = (torch.randint(0, 3, (16, 12, 7), generator=g).float(), list("abcdef"))
+    # all blank / all same label / alternating
+    x = torch.full((4, 4, 5), -1.0)
+    x[0, :, 0] = 1.0
+    x[1, :, 2] = 1.0
+    x[2, 0::2, 3] = 1.0
+    x[2, 1::2, 0] = 1.0
+    x[3, 0, 1] = 1.0; x[3, 1, 1] = 1.0; x[3, 2, 0] = 1.0; x[3, 3, 1] = 1.0
+    cases["patterns"] = (x, list("wxyz"))
+    # NaN and inf entries
+    y = torch.randn(6, 5, 9, generator=g)
+    y[0, 0, 4] = float("nan"); y[1, 2, 0] = float("nan"); y[1, 2, 7] = float("nan")
+    y[2, 1, 3] = float("inf"); y[3, :, :] = float("-inf"); y[4, 3, 8] = float("inf"); y[4, 3, 2] = float("inf")
+    cases["nan_inf"] = (y, list("abcdefgh"))
+    # cfg-B-like shape, reduced batch
+    cases["cfgb_b16_t16"] = (torch.randn(16, 16, len(itos) + 1, generator=g), itos)
+    for name, (logits, alpha) in cases.items():
+        texts, seqs = ctc_greedy_decoder(logits, alpha, blank=0)
+        np.savez_compressed(os.path.join(OUT, f"decode_{name}.npz"), logits=logits.numpy(),
+                            alphabet=json.dumps(alpha), texts=json.dumps(texts), seqs=json.dumps(seqs))
+    # non-zero blank
+    logits = torch.randn(10, 8, 6, generator=g)
+    texts, seqs = ctc_greedy_decoder(logits, list("abcdef"), blank=3)
+    np.savez_compressed(os.path.join(OUT, "decode_blank3.npz"), logits=logits.numpy(), blank=3,
+                        alphabet=json.dumps(list("abcdef")), texts=json.dumps(texts), seqs=json.dumps(seqs))
+
+
+def gen_bilstm():
+    for name, (B, T, I, H, O) in {"tiny": (3, 5, 8, 4, 6), "odd": (2, 7, 24, 16, 8),
+                                   "h32": (4, 9, 32, 32, 32)}.items():
+        torch.manual_seed(7)
+        m = BidirectionalLSTM(I, H, O).double()
+        x = torch.randn(B, T, I, dtype=torch.float64, requires_grad=True)
+        # non-contiguous batch-first view, as produced by model/model.py:218
+        xin = x.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+        out = m(xin)
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+        d = {f"p.{k}": v.detach().numpy() for k, v in m.state_dict().items()}
+        d.update({f"g.{k}": v.grad.numpy() for k, v in m.named_parameters()})
+        np.savez_compressed(os.path.join(OUT, f"bilstm_{name}.npz"), x=x.detach().numpy(),
+                            out=out.detach().numpy(), w=w.numpy(), gx=x.grad.numpy(), **d)
+    # the stacked encoder (model/model.py:195-198) at a small size
+    torch.manual_seed(11)
+    enc = torch.nn.Sequential(BidirectionalLSTM(48, 32, 32), BidirectionalLSTM(32, 32, 32)).double()
+    x = torch.randn(5, 6, 48, dtype=torch.float64, requires_grad=True)
+    out = enc(x)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    d = {f"p.{k}": v.detach().numpy() for k, v in enc.state_dict().items()}
+    d.update({f"g.{k}": v.grad.numpy() for k, v in enc.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, "encrnn_small.npz"), x=x.detach().numpy(),
+                        out=out.detach().numpy(), w=w.numpy(), gx=x.grad.numpy(), **d)
+
+
+def gen_ctc():
+    g = torch.Generator().manual_seed(4321)
+
+    def case(name, T, N, C, max_l, blank=0, var_in=False, peaky=False, lens=None, zero_len=False, big=False):
+        x = torch.randn(T, N, C, generator=g, dtype=torch.float64) * (6.0 if peaky else 1.0)
+        x.requires_grad_(True)
+        tl = torch.randint(0 if zero_len else 1, max_l + 1, (N,), generator=g) if lens is None else torch.tensor(lens)
+        labels = [c for c in range(C) if c != blank]
+        tg = torch.zeros(N, max(int(tl.max()), 1), dtype=torch.long)
+        for n in range(N):
+            idx = torch.randint(0, len(labels), (int(tl[n]),), generator=g)
+            tg[n, : int(tl[n])] = torch.tensor(labels)[idx] if int(tl[n]) else tg[n, :0]
+        # force some repeated labels
+        for n in range(0, N, 3):
+            if int(tl[n]) >= 2:
+                tg[n, 1] = tg[n, 0]
+        il = torch.full((N,), T, dtype=torch.long)
+        if var_in:
+            il = torch.randint(1, T + 1, (N,), generator=g)
+        out = dict(x=x.detach().numpy(), targets=tg.numpy(), input_lengths=il.numpy(),
+                   target_lengths=tl.numpy(), blank=blank)
+        lp = x.log_softmax(2)
+        for zi in (False, True):
+            nll = F.ctc_loss(lp, tg, il, tl, blank=blank, reduction="none", zero_infinity=zi)
+            out[f"nll_zi{int(zi)}"] = nll.detach().numpy()
+            for red in ("mean", "sum"):
+                if big and not (red == "mean" and zi):
+                    continue
+                loss = F.ctc_loss(lp, tg, il, tl, blank=blank, reduction=red, zero_infinity=zi)
+                gx, = torch.autograd.grad(loss, x, retain_graph=True)
+                out[f"loss_{red}_zi{int(zi)}"] = loss.detach().numpy()
+                out[f"grad_{red}_zi{int(zi)}"] = gx.numpy()
+        # concatenated-target form must give the same numbers
+        cat = torch.cat([tg[n, : int(tl[n])] for n in range(N)])
+        loss_cat = F.ctc_loss(lp, cat, il, tl, blank=blank, reduction="mean", zero_infinity=True)
+        assert torch.allclose(loss_cat, torch.as_tensor(out["loss_mean_zi1"])), name
+        out["targets_concat"] = cat.numpy()
+        np.savez_compressed(os.path.join(OUT, f"ctc_{name}.npz"), **out)
+
+    case("small", 12, 6, 5, 4)
+    case("varlen", 20, 9, 11, 6, var_in=True)            # includes infeasible samples (inf / NaN grads)
+    case("peaky", 24, 5, 8, 8, peaky=True)
+    case("blank2", 10, 4, 6, 3, blank=2)
+    case("emptytgt", 8, 5, 4, 3, zero_len=True, lens=[0, 2, 0, 3, 1])
+    case("tight", 6, 4, 5, 0, lens=[6, 3, 5, 4])          # T == L (+repeats -> infeasible rows)
+    case("cfgb", 64, 3, 195, 32, big=True)                # cfg-B geometry, reduced batch
+
+
+if __name__ == "__main__":
+    gen_decode()
+    gen_bilstm()
+    gen_ctc()
+    tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")
