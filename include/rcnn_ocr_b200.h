@@ -1,0 +1,123 @@
+/*
+ * rcnn_ocr_b200.h -- C ABI of the B200-native RCNN-OCR sequence-recognition hot path.
+ *
+ * The upstream reference (sherstpasha/RCNN-OCR) is pure Python/PyTorch and has no FFI
+ * layer of its own; its boundary for this path is the Python
+ * nn.Module / function surface.  This header is the boundary a binding for that surface
+ * calls: plain pointers and sizes, no torch types.  Each entry point names the reference
+ * interface it replaces (path:line under the reference tree).
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller (workspaces included);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates, never synchronises, never throws;
+ *   - return value 0 = OK; non-zero = RCNN_ERR_* (argument errors) or 1000 + cudaError_t;
+ *     rcnn_last_error() returns a thread-local message for the last failure;
+ *   - kernels are compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef RCNN_OCR_B200_H
+#define RCNN_OCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCNN_OK 0
+#define RCNN_ERR_ARG 1          /* invalid argument / unsupported shape              */
+#define RCNN_ERR_WORKSPACE 2    /* workspace missing or too small                    */
+#define RCNN_ERR_DEVICE 3       /* current device is not compute capability 10.x     */
+#define RCNN_ERR_CUDA_BASE 1000 /* + cudaError_t                                     */
+
+/* element types */
+#define RCNN_F32 0
+#define RCNN_BF16 1
+
+/* CTC reductions (torch.nn.CTCLoss `reduction`) */
+#define RCNN_REDUCE_NONE 0
+#define RCNN_REDUCE_MEAN 1
+#define RCNN_REDUCE_SUM 2
+
+typedef void *rcnn_stream_t; /* cudaStream_t */
+
+int rcnn_version(void);
+const char *rcnn_last_error(void);
+/* 0 when the current CUDA device can run these kernels (sm_100), else RCNN_ERR_DEVICE. */
+int rcnn_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  greedy CTC decode: argmax over classes, collapse repeats, strip blank.
+ * Replaces training/utils.py:122-150 (ctc_greedy_decoder: `logits.argmax(dim=2)` + the
+ * per-frame host loop) and the decode step of inference.py:167-180.
+ *   logits    [B,T,C] addressed as logits[b*stride_b + t*stride_t + c] (element strides;
+ *             class stride is 1), dtype RCNN_F32 or RCNN_BF16
+ *   ids_out   [B,T] int32: the collapsed label ids, left-packed, padded with -1
+ *   len_out   [B]   int32: number of ids per sequence
+ *   conf_out  [B]   float or NULL: mean over non-blank frames of max softmax probability
+ *             (the CTC analogue of inference.py:183-189; 0 when no such frame)
+ * argmax follows torch: first maximal index wins, NaN is maximal.
+ * ------------------------------------------------------------------------------------- */
+int rcnn_ctc_greedy(const void *logits, int dtype, int B, int T, int C,
+                    int64_t stride_b, int64_t stride_t, int blank,
+                    int32_t *ids_out, int32_t *len_out, float *conf_out,
+                    rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  CTC loss forward-backward, fused with log_softmax and its backward.
+ * The reference has no CTC code; this is the nn.CTCLoss(blank,
+ * reduction, zero_infinity) call the north_star places at training/train.py:289 and
+ * :503-505 (and :557-559 for validation).
+ *   x            [T,N,C] float32 addressed as x[t*stride_t + n*stride_n + c]
+ *   from_logits  1: x are raw logits, log_softmax is applied inside and grad_out is the
+ *                   gradient w.r.t. the logits;
+ *                0: x are log-probabilities (nn.CTCLoss input) and grad_out follows ATen's
+ *                   backward convention exp(x) - occupancy
+ *   targets      int64; padded [N, tgt_stride] when tgt_stride > 0, else 1-D concatenated
+ *                (offsets are derived on the device from target_lengths)
+ *   input_lengths, target_lengths   int64 [N]
+ *   max_target_len   host-side upper bound on target_lengths (sizes the label lattice)
+ *   nll_out      [N] float32: per-sample negative log likelihood (inf if no alignment and
+ *                !zero_infinity; 0 if zero_infinity)
+ *   loss_out     [1] float32: the reduced loss (mean: mean_n nll_n / max(tgt_len_n,1);
+ *                sum); untouched for RCNN_REDUCE_NONE
+ *   grad_out     NULL (forward only) or float32 addressed like x through
+ *                (gstride_t, gstride_n): gradient of the REDUCED loss (of sum_n nll_n for
+ *                RCNN_REDUCE_NONE).  Frames t >= input_length get 0.
+ *   workspace    rcnn_ctc_workspace_bytes(T, N, C, max_target_len) bytes
+ * ------------------------------------------------------------------------------------- */
+size_t rcnn_ctc_workspace_bytes(int T, int N, int C, int max_target_len);
+int rcnn_ctc_loss(const float *x, int from_logits, int T, int N, int C,
+                  int64_t stride_t, int64_t stride_n,
+                  const int64_t *targets, int64_t tgt_stride,
+                  const int64_t *input_lengths, const int64_t *target_lengths,
+                  int max_target_len, int blank, int reduction, int zero_infinity,
+                  float *nll_out, float *loss_out,
+                  float *grad_out, int64_t gstride_t, int64_t gstride_n,
+                  void *workspace, size_t workspace_bytes, rcnn_stream_t stream);
+
+/* grad[t,n,:] *= scale[per_sample ? n : 0] (scale read on the device; rows whose factor is
+ * exactly 1.0f are not touched).  Used to apply autograd's upstream gradient. */
+int rcnn_ctc_scale_grad(float *grad, int T, int N, int C, int64_t gstride_t, int64_t gstride_n,
+                        const float *scale, int per_sample, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
+ * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
+ * rcnn_prof_read synchronises the recorded events and returns the summed duration.
+ * ------------------------------------------------------------------------------------- */
+#define RCNN_K_DECODE 0
+#define RCNN_K_CTC 1
+#define RCNN_K_GEMM 2
+#define RCNN_K_LSTM_FWD 3
+#define RCNN_K_LSTM_BWD 4
+#define RCNN_K_COUNT 8
+int rcnn_prof_enable(int on);
+int rcnn_prof_reset(void);
+int rcnn_prof_read(int kernel, double *total_ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCNN_OCR_B200_H */

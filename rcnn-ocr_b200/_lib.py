@@ -1,0 +1,82 @@
+"""ctypes binding of include/rcnn_ocr_b200.h.  Fails loudly when the CUDA library is absent."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librcnn_ocr_b200.so")
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def _declare(L: ctypes.CDLL) -> None:
+    i, i64, vp, sz = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
+    L.rcnn_version.restype = i
+    L.rcnn_last_error.restype = ctypes.c_char_p
+    L.rcnn_device_check.restype = i
+    L.rcnn_ctc_greedy.restype = i
+    L.rcnn_ctc_greedy.argtypes = [vp, i, i, i, i, i64, i64, i, vp, vp, vp, vp]
+    L.rcnn_ctc_workspace_bytes.restype = sz
+    L.rcnn_ctc_workspace_bytes.argtypes = [i, i, i, i]
+    L.rcnn_ctc_loss.restype = i
+    L.rcnn_ctc_loss.argtypes = [vp, i, i, i, i, i64, i64, vp, i64, vp, vp, i, i, i, i,
+                                vp, vp, vp, i64, i64, vp, sz, vp]
+    L.rcnn_prof_enable.restype = i
+    L.rcnn_prof_enable.argtypes = [i]
+    L.rcnn_prof_reset.restype = i
+    L.rcnn_prof_read.restype = i
+    L.rcnn_prof_read.argtypes = [i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+    L.rcnn_ctc_scale_grad.restype = i
+    L.rcnn_ctc_scale_grad.argtypes = [vp, i, i, i, i64, i64, vp, i, vp]
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded shared library.  Raises LibraryMissing if it has not been built --
+    there is deliberately no other execution path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise LibraryMissing(
+                f"{_LIB_PATH} not found: build it with `python rcnn-ocr_b200/build.py` "
+                "(or __graft_entry__.build()); rcnn-ocr_b200 has no CPU or eager fallback")
+        L = ctypes.CDLL(_LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().rcnn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (got {t.device}); rcnn-ocr_b200 has no CPU path")
+
+
+def prof_enable(on: bool) -> None:
+    check(lib().rcnn_prof_enable(int(on)), "rcnn_prof_enable")
+    lib().rcnn_prof_reset()
+
+
+def prof_read(kernel: int):
+    """(total_ms, launches) of a dominant kernel since the last reset (CUDA events on the
+    launching stream; see include/rcnn_ocr_b200.h)."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_int(0)
+    check(lib().rcnn_prof_read(int(kernel), ctypes.byref(ms), ctypes.byref(n)), "rcnn_prof_read")
+    return ms.value, n.value

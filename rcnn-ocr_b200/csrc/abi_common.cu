@@ -1,0 +1,110 @@
+// Error plumbing and device probing behind the C ABI (include/rcnn_ocr_b200.h).
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace rcnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return RCNN_ERR_CUDA_BASE + (int)e;
+}
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        cached = p.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// ---- per-kernel event timing -----------------------------------------------------------
+static const int kProfSlots = 16384;
+static bool g_prof_on = false;
+static cudaEvent_t *g_ev0 = nullptr, *g_ev1 = nullptr;
+static int *g_slot_kernel = nullptr;
+static int g_prof_used = 0;
+
+int prof_begin(int kernel, cudaStream_t s) {
+    if (!g_prof_on || g_prof_used >= kProfSlots) return -1;
+    const int slot = g_prof_used++;
+    g_slot_kernel[slot] = kernel;
+    cudaEventRecord(g_ev0[slot], s);
+    return slot;
+}
+
+void prof_end(int slot, cudaStream_t s) {
+    if (slot >= 0) cudaEventRecord(g_ev1[slot], s);
+}
+
+}  // namespace rcnn
+
+extern "C" {
+
+int rcnn_prof_enable(int on) {
+    using namespace rcnn;
+    if (on && !g_ev0) {
+        g_ev0 = new cudaEvent_t[kProfSlots];
+        g_ev1 = new cudaEvent_t[kProfSlots];
+        g_slot_kernel = new int[kProfSlots];
+        for (int i = 0; i < kProfSlots; ++i) {
+            RCNN_CUDA(cudaEventCreate(&g_ev0[i]));
+            RCNN_CUDA(cudaEventCreate(&g_ev1[i]));
+        }
+    }
+    g_prof_on = on != 0;
+    return RCNN_OK;
+}
+
+int rcnn_prof_reset(void) {
+    rcnn::g_prof_used = 0;
+    return RCNN_OK;
+}
+
+int rcnn_prof_read(int kernel, double *total_ms, int *launches) {
+    using namespace rcnn;
+    double tot = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < g_prof_used; ++i) {
+        if (g_slot_kernel[i] != kernel) continue;
+        RCNN_CUDA(cudaEventSynchronize(g_ev1[i]));
+        float ms = 0.f;
+        RCNN_CUDA(cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]));
+        tot += ms;
+        ++cnt;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = cnt;
+    return RCNN_OK;
+}
+
+int rcnn_version(void) { return 100; }
+
+const char *rcnn_last_error(void) { return rcnn::g_err; }
+
+int rcnn_device_check(void) {
+    int dev = 0;
+    RCNN_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    RCNN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        rcnn::set_error("device %d has compute capability %d.x; these kernels are sm_100a only", dev, major);
+        return RCNN_ERR_DEVICE;
+    }
+    return RCNN_OK;
+}
+
+}  // extern "C"

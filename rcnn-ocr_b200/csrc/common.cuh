@@ -1,0 +1,87 @@
+// Shared helpers for the sm_100a kernels (error plumbing, warp primitives, loads).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/rcnn_ocr_b200.h"
+
+namespace rcnn {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define RCNN_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::rcnn::set_error(__VA_ARGS__);       \
+            return RCNN_ERR_ARG;                  \
+        }                                         \
+    } while (0)
+
+#define RCNN_CUDA(call)                                             \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return ::rcnn::cuda_fail(e__, #call); \
+    } while (0)
+
+#define RCNN_LAUNCH_CHECK(name)                                      \
+    do {                                                             \
+        cudaError_t e__ = cudaGetLastError();                        \
+        if (e__ != cudaSuccess) return ::rcnn::cuda_fail(e__, name); \
+    } while (0)
+
+int num_sms();
+
+// Optional per-kernel event timing (see rcnn_prof_* in the header).
+int prof_begin(int kernel, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+struct ProfScope {
+    int slot;
+    cudaStream_t s;
+    ProfScope(int kernel, cudaStream_t st) : slot(prof_begin(kernel, st)), s(st) {}
+    ~ProfScope() { prof_end(slot, s); }
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_min_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// streaming 128-bit load that does not pollute L1
+__device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_nc_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+}  // namespace rcnn

@@ -1,0 +1,72 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol that
+include/rcnn_ocr_b200.h declares, validates arguments before touching CUDA, and the host-side
+mirror of the reference interface behaves like the reference (errors included)."""
+import os
+import re
+
+import pytest
+import torch
+
+import rcnn_ocr_b200 as R
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rcnn_ocr_b200.h"), encoding="utf-8").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = R.lib()
+    names = _declared_symbols()
+    assert len(names) >= 6
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rcnn_ocr_b200.h but not exported"
+    assert L.rcnn_version() >= 100
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    L = R.lib()
+    assert L.rcnn_ctc_greedy(None, 0, 4, 4, 0, 0, 0, 0, None, None, None, None) == 1
+    assert b"bad shape" in L.rcnn_last_error()
+    assert L.rcnn_ctc_greedy(None, 7, 4, 4, 5, 20, 5, 0, None, None, None, None) == 1
+    assert b"dtype" in L.rcnn_last_error()
+    # blank outside the class range
+    assert L.rcnn_ctc_loss(None, 1, 4, 2, 5, 10, 5, None, 0, None, None, 3, 9, 1, 0,
+                           None, None, None, 0, 0, None, 0, None) == 1
+    # target length beyond the supported lattice
+    assert L.rcnn_ctc_loss(None, 1, 4, 2, 5, 10, 5, None, 0, None, None, 300, 0, 1, 0,
+                           None, None, None, 0, 0, None, 0, None) == 1
+
+
+def test_workspace_sizes():
+    L = R.lib()
+    small = L.rcnn_ctc_workspace_bytes(64, 256, 195, 32)
+    assert small >= 8 * 257 and small < 16384          # offsets only: tables fit shared memory
+    big = L.rcnn_ctc_workspace_bytes(512, 4, 195, 200)  # lattice spills to the workspace
+    assert big >= 3 * 512 * 401 * 4 * 4
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(4, 2, 5).log_softmax(2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        R.ctc_loss(x, torch.tensor([[1], [2]]), [4, 4], [1, 1])
+    with pytest.raises(ValueError):
+        R.ctc_loss(x, torch.tensor([[1], [2]]), [4, 4], [1, 1], reduction="avg")
+    with pytest.raises(ValueError, match="Unsupported decode method"):
+        R.decode(torch.zeros(2, 2, 3), "ab", method="beam")
+
+
+def test_charset_matches_reference_semantics(tmp_path):
+    p = tmp_path / "charset.txt"
+    p.write_text("<PAD>\n<SOS>\n<EOS>\n \na\nb\n\nc", encoding="utf-8")
+    itos, stoi = R.load_charset(str(p))
+    assert itos == ["<PAD>", "<SOS>", "<EOS>", " ", "a", "b", "c"]
+    assert stoi["<PAD>"] == 0 and stoi[" "] == 3 and stoi["c"] == 6
+    alphabet, C, blank = R.ctc_alphabet(itos)
+    assert C == 8 and blank == 0 and alphabet[stoi["a"]] == "a"
+    assert R.decode_tokens([4, 0, 5, 2, 6], itos, 0, 2) == "ab"
+    from rcnn_ocr_b200.charset import encode_ctc_targets
+    flat, lens = encode_ctc_targets(["ab", "", "c a"], stoi)
+    assert flat == [5, 6, 7, 4, 5] and lens == [2, 0, 3]
