@@ -103,6 +103,20 @@ int rcnn_ctc_scale_grad(float *grad, int T, int N, int C, int64_t gstride_t, int
                         const float *scale, int per_sample, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K1  dense bf16 GEMM on tcgen05/TMEM fed by TMA:  D[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).
+ * Replaces the library GEMMs behind the reference's encoder block: the input projection
+ * W_ih x_t for all timesteps inside nn.LSTM (model/model.py:154-156,161) and
+ * nn.Linear(2H -> out) (model/model.py:157,162); also used for the CTC head and, in the
+ * backward pass, for dX and dW.
+ *   A [M,K], B [N,K]  bf16 row-major, leading dimensions lda/ldb in elements (multiples of 8,
+ *                     16-byte aligned bases)
+ *   D [M,N]           row-major, ldd in elements, out_dtype RCNN_F32 or RCNN_BF16
+ *   bias [N]          float32 or NULL
+ * ------------------------------------------------------------------------------------- */
+int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd,
+                   int out_dtype, const float *bias, int M, int N, int K, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

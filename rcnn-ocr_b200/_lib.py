@@ -29,6 +29,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_ctc_loss.restype = i
     L.rcnn_ctc_loss.argtypes = [vp, i, i, i, i, i64, i64, vp, i64, vp, vp, i, i, i, i,
                                 vp, vp, vp, i64, i64, vp, sz, vp]
+    L.rcnn_gemm_bf16.restype = i
+    L.rcnn_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i, vp, i, i, i, vp]
     L.rcnn_prof_enable.restype = i
     L.rcnn_prof_enable.argtypes = [i]
     L.rcnn_prof_reset.restype = i

@@ -198,7 +198,7 @@ extern "C" int rcnn_ctc_greedy(const void *logits, int dtype, int B, int T, int 
     RCNN_CHECK_ARG(B >= 0 && T >= 0 && C > 0, "ctc_greedy: bad shape B=%d T=%d C=%d", B, T, C);
     RCNN_CHECK_ARG(dtype == RCNN_F32 || dtype == RCNN_BF16, "ctc_greedy: unsupported dtype %d", dtype);
     if (B == 0) return RCNN_OK;
-    RCNN_CHECK_ARG(logits && len_out && (ids_out || T == 0), "ctc_greedy: null pointer");
+    RCNN_CHECK_ARG(len_out && ((logits && ids_out) || T == 0), "ctc_greedy: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     if (T == 0) {
         RCNN_CUDA(cudaMemsetAsync(len_out, 0, sizeof(int32_t) * (size_t)B, s));

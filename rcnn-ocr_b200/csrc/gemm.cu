@@ -1,0 +1,244 @@
+// K1: dense bf16 GEMM on the 5th-gen tensor cores: tcgen05.mma with the accumulator in TMEM,
+// operands staged in shared memory by TMA (128-byte swizzle), mbarrier pipeline.
+//
+//     D[M,N] = A[M,K] * B[N,K]^T (+ bias[N])        A, B bf16 row-major; D fp32 or bf16
+//
+// This is the LSTM input projection for all timesteps at once (the `W_ih x_t + b` half of
+// nn.LSTM at model/model.py:154-156,161, M = T*B rows), the block's nn.Linear(2H -> H)
+// (model/model.py:157,162) and the CTC head; the backward pass reuses it for dX and dW.
+//
+// Tile 128 x 128 x 64 per CTA, warp-specialised: warp 0 = TMA producer (one elected lane),
+// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (one warp per
+// TMEM lane quadrant: tcgen05.ld -> +bias -> convert -> global).  Three smem stages of 32 KB
+// so that two CTAs share an SM and one CTA's epilogue overlaps the other's main loop.
+// M / N / K tails: TMA zero-fills out-of-bounds rows and columns; stores are masked.
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace rcnn {
+
+// ---- tensor maps (host) -----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode(CUtensorMap *out, const void *base, int elem_bytes, int rank, const cuuint64_t *gdim,
+                  const cuuint64_t *gstride, const cuuint32_t *box, int swizzle128) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return RCNN_ERR_DEVICE;
+    }
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=(%llu,%llu) pitch=%llu box=(%u,%u)", (int)r,
+                  base, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
+                  (unsigned long long)gstride[0], box[0], box[1]);
+        return RCNN_ERR_ARG;
+    }
+    return RCNN_OK;
+}
+
+int make_tmap_2d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle128) {
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {row_pitch_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    return encode(out, base, elem_bytes, 2, gdim, gstride, box, swizzle128);
+}
+
+int make_tmap_3d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t d2, uint64_t rows, uint64_t cols,
+                 uint64_t pitch2_bytes, uint64_t row_pitch_bytes, uint32_t box2, uint32_t box_rows,
+                 uint32_t box_cols, int swizzle128) {
+    const cuuint64_t gdim[3] = {cols, rows, d2};
+    const cuuint64_t gstride[2] = {row_pitch_bytes, pitch2_bytes};
+    const cuuint32_t box[3] = {box_cols, box_rows, box2};
+    return encode(out, base, elem_bytes, 3, gdim, gstride, box, swizzle128);
+}
+
+namespace {
+
+using namespace sm100;
+
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + BN * sizeof(float);
+
+__device__ __forceinline__ void store_row_chunk(float *dst, const float (&v)[32], int ncols, bool vec_ok) {
+    if (vec_ok && ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = v[j];
+    }
+}
+__device__ __forceinline__ void store_row_chunk(__nv_bfloat16 *dst, const float (&v)[32], int ncols, bool vec_ok) {
+    if (vec_ok && ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            q.x = *reinterpret_cast<uint32_t *>(&h0); q.y = *reinterpret_cast<uint32_t *>(&h1);
+            q.z = *reinterpret_cast<uint32_t *>(&h2); q.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(dst + j) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tiles = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    float *bias_s = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<BN>(tmem_slot);
+    }
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < BN; j += kThreads - 64) {
+            const int col = tile_n * BN + j;
+            bias_s[j] = (bias != nullptr && col < N) ? bias[col] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                tma_load_2d(tiles + s * kStageBytes, &tmA, &full[s], kb * BK, tile_m * BM);
+                tma_load_2d(tiles + s * kStageBytes + kABytes, &tmB, &full[s], kb * BK, tile_n * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes), 16, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes + kABytes), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)  // +32 bytes along K inside the 128-byte swizzle row
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = tile_m * BM + q * 32 + lane;
+        const bool vec_ok = (ldd % (16 / (long long)sizeof(OutT)) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int col0 = tile_n * BN + c0;
+            if (row < M && col0 < N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
+                store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+template <typename OutT>
+int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
+                int N, int K, cudaStream_t s) {
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    ProfScope prof(RCNN_K_GEMM, s);
+    gemm_tn_kernel<OutT><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
+    RCNN_LAUNCH_CHECK("gemm_tn_kernel");
+    return RCNN_OK;
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd,
+                              int out_dtype, const float *bias, int M, int N, int K, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    RCNN_CHECK_ARG(out_dtype == RCNN_F32 || out_dtype == RCNN_BF16, "gemm: bad out dtype %d", out_dtype);
+    if (M == 0 || N == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(A && B && D, "gemm: null pointer");
+    RCNN_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension smaller than the row");
+    RCNN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0,
+                   "gemm: A/B rows must be 16-byte aligned (lda=%lld ldb=%lld)", (long long)lda, (long long)ldb);
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, BM, BK, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, BN, BK, 1);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out_dtype == RCNN_F32) return launch_gemm<float>(ta, tb, D, ldd, bias, M, N, K, s);
+    return launch_gemm<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
+}

@@ -1,0 +1,52 @@
+"""GPU parity: tcgen05 GEMM (K1) vs a plain torch fp32 matmul of the same bf16-rounded operands.
+Tolerance: fp32 accumulation of exact bf16 products -> differences are summation-order only
+(rtol 1e-4 of the row scale); bf16 outputs add one rounding (2^-8 relative)."""
+import pytest
+import torch
+
+from rcnn_ocr_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias):
+    r = a.float() @ b.float().t()
+    return r + bias if bias is not None else r
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 128), (16384, 4096, 512),
+                                   (16384, 512, 1024), (16384, 195, 512), (100, 72, 40), (1, 8, 8),
+                                   (257, 129, 72), (2048, 1024, 256), (300, 200, 1000)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_matches_fp32_matmul(M, N, K, out_dtype):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    got = ops.gemm_bf16(a, b, bias, out_dtype)
+    want = _ref(a, b, bias)
+    scale = float(want.abs().max())
+    tol = 1e-4 if out_dtype == torch.float32 else 2 ** -7
+    torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol * scale)
+    got_nb = ops.gemm_bf16(a, b, None, out_dtype)
+    torch.testing.assert_close(got_nb.float(), _ref(a, b, None), rtol=tol, atol=tol * scale)
+
+
+def test_gemm_strided_operands_and_output():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    big_a = torch.randn(200, 256, device="cuda", generator=g).bfloat16()
+    big_b = torch.randn(96, 256, device="cuda", generator=g).bfloat16()
+    a, b = big_a[:, 64:192], big_b[:, 64:192]                    # row pitch 256, K = 128
+    out = torch.zeros(200, 128, device="cuda")
+    ops.gemm_bf16(a, b, None, out=out[:, 16:112])
+    torch.testing.assert_close(out[:, 16:112], _ref(a, b, None), rtol=1e-4, atol=1e-3)
+    assert float(out[:, :16].abs().max()) == 0 and float(out[:, 112:].abs().max()) == 0
+
+
+def test_gemm_exact_small_integers():
+    """Small-integer operands make every product and partial sum exact: bit-exact result."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randint(-4, 5, (384, 320), device="cuda", generator=g).bfloat16()
+    b = torch.randint(-4, 5, (256, 320), device="cuda", generator=g).bfloat16()
+    got = ops.gemm_bf16(a, b)
+    assert torch.equal(got, _ref(a, b, None))
