@@ -117,6 +117,41 @@ int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void 
                    int out_dtype, const float *bias, int M, int N, int K, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K2  BidirectionalLSTM recurrence (model/model.py:151-163: nn.LSTM(bidirectional=True,
+ * batch_first=True), gate order i,f,g,o, h0 = c0 = 0, final state discarded).
+ *
+ * rcnn_lstm_pack_weights: one launch converts the eight nn.LSTM parameter tensors of a block
+ *   (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0 and their _reverse twins, float32,
+ *   torch layout) into the bf16 views the kernels read.  `packed` holds, in this order
+ *   (P = packed gate-row order p(c,j,g) = c*128 + j*4 + g  <->  torch row g*H + 32c + j):
+ *     wih_p  bf16 [2*4H, I]   rows in P order, direction-major   (B operand of the xp GEMM)
+ *     bias_p f32  [2*4H]      b_ih + b_hh in P order
+ *     whh_p  bf16 [2*4H, H]   rows in P order                    (resident operand, forward)
+ *     whh_pt bf16 [2, H, 4H]  per-direction transpose of whh_p   (resident operand, backward)
+ *     wih_pt bf16 [I, 2*4H]   transpose of wih_p                 (B operand of the dX GEMM)
+ * rcnn_lstm_forward: the T dependent steps of both directions in one persistent kernel.
+ *   xp        f32  [B*T, 2*4H]  x W_ih^T + b for every (b,t) (row b*T+t), columns in P order
+ *   whh_p     the whh_p view of `packed`
+ *   hcat      bf16 [B, T, 2H]   output: h_t of the forward (cols [0,H)) and reverse ([H,2H))
+ *                               direction; also the buffer h_{t-1} is re-read from
+ *   gates_save f16 [2, T, B, 4H] activated gates in P order, c_save f32 [2, T, B, H]: both NULL
+ *                               for inference, both set when a backward pass will follow
+ *   H must be 64, 128, 256 or 512 (cluster of H/32 CTAs per direction and 128 sequences).
+ * ------------------------------------------------------------------------------------- */
+size_t rcnn_lstm_packed_bytes(int I, int H);
+int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
+                           const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
+                           int I, int H, void *packed, rcnn_stream_t stream);
+int rcnn_lstm_forward(const float *xp, const void *whh_p, int B, int T, int H, void *hcat,
+                      void *gates_save, float *c_save, rcnn_stream_t stream);
+
+/* Layout helpers used by the host side of the block (fp32 strided -> bf16 contiguous; 2-D
+ * bf16 transpose). */
+int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64_t sc, void *dst, int B, int T, int C,
+                      rcnn_stream_t stream);
+int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int R, int C, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

@@ -31,6 +31,16 @@ def _declare(L: ctypes.CDLL) -> None:
                                 vp, vp, vp, i64, i64, vp, sz, vp]
     L.rcnn_gemm_bf16.restype = i
     L.rcnn_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i, vp, i, i, i, vp]
+    L.rcnn_lstm_packed_bytes.restype = sz
+    L.rcnn_lstm_packed_bytes.argtypes = [i, i]
+    L.rcnn_lstm_pack_weights.restype = i
+    L.rcnn_lstm_pack_weights.argtypes = [vp] * 8 + [i, i, vp, vp]
+    L.rcnn_lstm_forward.restype = i
+    L.rcnn_lstm_forward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.rcnn_cast_bf16_3d.restype = i
+    L.rcnn_cast_bf16_3d.argtypes = [vp, i64, i64, i64, vp, i, i, i, vp]
+    L.rcnn_transpose_bf16.restype = i
+    L.rcnn_transpose_bf16.argtypes = [vp, i64, vp, i, i, vp]
     L.rcnn_prof_enable.restype = i
     L.rcnn_prof_enable.argtypes = [i]
     L.rcnn_prof_reset.restype = i

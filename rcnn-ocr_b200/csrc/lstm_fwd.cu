@@ -1,0 +1,313 @@
+// K2 (forward): persistent recurrent LSTM kernel, both directions of a BidirectionalLSTM block.
+//
+// Replaces the T dependent timesteps inside nn.LSTM(bidirectional=True, batch_first=True) at
+// model/model.py:154-156,161 (cuDNN RNN in the reference): gates = xp_t + h_{t-1} W_hh^T,
+// c = f*c + i*g, h = o*tanh(c), h_0 = c_0 = 0, gate order i,f,g,o.  The input projection
+// xp = x W_ih^T + b_ih + b_hh for all timesteps comes from the tcgen05 GEMM (gemm.cu).
+//
+// Decomposition.  One thread-block CLUSTER owns (direction, tile of 128 sequences).  CTA c of
+// the cluster owns hidden units [32c, 32c+32) with all four gates, so cluster size = H/32
+// (16 CTAs for H=512 -- a non-portable cluster -- 8 for H=256).  Its 128 x H slice of W_hh
+// (bf16, 128 KB for H=512) is loaded ONCE by TMA and stays resident in shared memory for all T
+// steps.  Per timestep:
+//   warp 0  (TMA)      streams h_{t-1}[128 seq, H] (bf16, straight out of the block's output
+//                      tensor, 64-column chunks, 3-slot ring) and prefetches the next xp tiles;
+//   warp 1  (MMA)      tcgen05.mma  D[128 seq, 128 gate cols] += h_chunk * W_chunk^T, fp32 in TMEM;
+//   warps 2-5 (cell)   tcgen05.ld the accumulator row of "their" sequence, add xp, sigmoid/tanh,
+//                      update c (fp32, in registers for the whole sequence), write h_t (bf16) and,
+//                      for training, the activated gates (fp16) and c_t (fp32);
+//   all               barrier.cluster (release/acquire): h_t of every unit slice is visible to
+//                      the other CTAs' TMA loads of the next step.
+// Only h crosses CTAs, through L2; nothing is exchanged between clusters.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace rcnn {
+namespace {
+
+using namespace sm100;
+
+constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
+constexpr int LN = 128;   // gate columns per CTA: 32 units x 4 gates (UMMA N)
+constexpr int LK = 64;    // K chunk (one 128-byte swizzle row of bf16)
+constexpr int kARing = 3, kXRing = 3;
+constexpr uint32_t kTile = 16384;  // every staged tile is 16 KB: 128x64 bf16 or 128x32 fp32
+constexpr int kThreads = 192;
+
+struct FwdParams {
+    int B, T, H;
+    __nv_bfloat16 *hcat;  // [B, T, 2H]
+    __half *gates;        // [2, T, B, 4H] packed column order, activated (training only)
+    float *csave;         // [2, T, B, H]  (training only)
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
+template <bool SAVE>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int nkc = H / LK;
+    unsigned char *w_s = smem;                          // nkc tiles [128 n x 64 k] bf16, SW128
+    unsigned char *a_s = w_s + (size_t)nkc * kTile;     // kARing tiles [128 b x 64 k] bf16, SW128
+    unsigned char *x_s = a_s + kARing * kTile;          // kXRing tiles [128 b x 32 col] fp32, SW128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + kXRing * kTile);
+    uint64_t *w_full = bars;
+    uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
+    uint64_t *x_full = a_empty + kARing, *x_empty = x_full + kXRing;
+    uint64_t *tmem_full = x_empty + kXRing;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = (int)cluster_ctarank();        // unit slice
+    const int cid = (int)cluster_id_x();
+    const int dir = cid & 1, tile = cid >> 1;
+    const int b0 = tile * LB;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(w_full, 1);
+            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < kXRing; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<LN>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer ======================================================================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
+            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kTile);
+            for (int kc = 0; kc < nkc; ++kc)
+                tma_load_2d(w_s + (size_t)kc * kTile, &tmW, w_full, kc * LK, dir * 4 * H + c * LN);
+        }
+        int an = 0, xn = 0;
+        const int xtotal = 4 * T;
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0) {
+                const int t = dir ? T - 1 - s : s;
+                if (s > 0) {
+                    const int tprev = dir ? t + 1 : t - 1;
+                    fence_proxy_async_all();  // h_{t-1} was written through the generic proxy
+                    for (int kc = 0; kc < nkc; ++kc, ++an) {
+                        const int slot = an % kARing;
+                        mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&a_full[slot], kTile);
+                        tma_load_3d(a_s + slot * kTile, &tmH, &a_full[slot], dir * H + kc * LK, tprev, b0);
+                    }
+                }
+                // keep the xp ring full: chunks of this step first, then the next step's
+                while (xn < xtotal && xn < 4 * (s + 1) + kXRing) {
+                    const int slot = xn % kXRing;
+                    const int xs = xn >> 2, q = xn & 3;
+                    const int xt = dir ? T - 1 - xs : xs;
+                    mbar_wait(&x_empty[slot], ((xn / kXRing) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&x_full[slot], kTile);
+                    tma_load_3d(x_s + slot * kTile, &tmX, &x_full[slot], dir * 4 * H + c * LN + q * 32, xt, b0);
+                    ++xn;
+                }
+            }
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ========================================================================
+        constexpr uint32_t idesc = make_idesc_bf16(LB, LN);
+        int am = 0;
+        if (lane == 0) mbar_wait(w_full, 0);
+        __syncwarp();
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0 && s > 0) {
+                for (int kc = 0; kc < nkc; ++kc, ++am) {
+                    const int slot = am % kARing;
+                    mbar_wait(&a_full[slot], (am / kARing) & 1);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kTile), 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kTile), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < LK / 16; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                    umma_commit(&a_empty[slot]);
+                }
+                umma_commit(tmem_full);
+            }
+            __syncwarp();
+            cluster_sync_all();
+        }
+    } else {
+        // ===== cell update (one thread per sequence of the tile) ================================
+        const int qd = warp & 3;            // TMEM lane quadrant of this warp
+        const int row = qd * 32 + lane;     // sequence within the tile == accumulator row
+        const int b = b0 + row;
+        const bool valid = b < B;
+        float cst[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cst[i] = 0.f;
+        int xm = 0;
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? T - 1 - s : s;
+            if (s > 0) {
+                mbar_wait(tmem_full, (s - 1) & 1);
+                tc_fence_after();
+            }
+            __nv_bfloat16 *hrow = p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c;
+            __half *grow = SAVE ? p.gates + (((size_t)dir * T + t) * B + b) * 4 * H + (size_t)c * LN : nullptr;
+            float *crow = SAVE ? p.csave + (((size_t)dir * T + t) * B + b) * H + 32 * c : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q, ++xm) {
+                const int slot = xm % kXRing;
+                uint32_t acc[32];
+                if (s > 0) {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(q * 32), acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0u;
+                }
+                mbar_wait(&x_full[slot], (xm / kXRing) & 1);
+                const unsigned char *xrow = x_s + slot * kTile + row * 128;
+                float pre[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = *reinterpret_cast<const float4 *>(xrow + ((j ^ (row & 7)) << 4));
+                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_empty[slot]);
+                if (s > 0) tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);
+                float hv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float ig = sigmoid_fast(pre[4 * j]);
+                    const float fg = sigmoid_fast(pre[4 * j + 1]);
+                    const float gg = tanh_fast(pre[4 * j + 2]);
+                    const float og = sigmoid_fast(pre[4 * j + 3]);
+                    const float cn = fmaf(fg, cst[q * 8 + j], ig * gg);
+                    cst[q * 8 + j] = cn;
+                    hv[j] = og * tanh_fast(cn);
+                    pre[4 * j] = ig; pre[4 * j + 1] = fg; pre[4 * j + 2] = gg; pre[4 * j + 3] = og;
+                }
+                if (valid) {
+                    uint4 hq;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(hv[0], hv[1]), h1 = __floats2bfloat162_rn(hv[2], hv[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(hv[4], hv[5]), h3 = __floats2bfloat162_rn(hv[6], hv[7]);
+                    hq.x = *reinterpret_cast<uint32_t *>(&h0); hq.y = *reinterpret_cast<uint32_t *>(&h1);
+                    hq.z = *reinterpret_cast<uint32_t *>(&h2); hq.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(hrow + q * 8) = hq;
+                    if (SAVE) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 gq;
+                            __half2 g0 = __floats2half2_rn(pre[8 * j], pre[8 * j + 1]);
+                            __half2 g1 = __floats2half2_rn(pre[8 * j + 2], pre[8 * j + 3]);
+                            __half2 g2 = __floats2half2_rn(pre[8 * j + 4], pre[8 * j + 5]);
+                            __half2 g3 = __floats2half2_rn(pre[8 * j + 6], pre[8 * j + 7]);
+                            gq.x = *reinterpret_cast<uint32_t *>(&g0); gq.y = *reinterpret_cast<uint32_t *>(&g1);
+                            gq.z = *reinterpret_cast<uint32_t *>(&g2); gq.w = *reinterpret_cast<uint32_t *>(&g3);
+                            *reinterpret_cast<uint4 *>(grow + q * 32 + j * 8) = gq;
+                        }
+                        *reinterpret_cast<float4 *>(crow + q * 8) =
+                            make_float4(cst[q * 8], cst[q * 8 + 1], cst[q * 8 + 2], cst[q * 8 + 3]);
+                        *reinterpret_cast<float4 *>(crow + q * 8 + 4) =
+                            make_float4(cst[q * 8 + 4], cst[q * 8 + 5], cst[q * 8 + 6], cst[q * 8 + 7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_all();  // order the h_t stores before the other CTAs' TMA reads
+            cluster_sync_all();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<LN>(tmem_base);
+    }
+}
+
+size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK + kARing + kXRing) * kTile + 256; }
+
+template <bool SAVE>
+int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &tx, const FwdParams &p,
+               cudaStream_t s) {
+    const int csize = p.H / 32;
+    const int ntiles = (p.B + LB - 1) / LB;
+    const size_t smem = fwd_smem_bytes(p.H);
+    RCNN_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8)
+        RCNN_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<SAVE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * ntiles * 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(RCNN_K_LSTM_FWD, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, p));
+    return RCNN_OK;
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" int rcnn_lstm_forward(const float *xp, const void *whh_packed, int B, int T, int H, void *hcat,
+                                 void *gates_save, float *c_save, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_forward: bad shape B=%d T=%d", B, T);
+    RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
+                   "lstm_forward: hidden size %d unsupported (64, 128, 256 or 512)", H);
+    if (B == 0 || T == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(xp && whh_packed && hcat, "lstm_forward: null pointer");
+    RCNN_CHECK_ARG((gates_save == nullptr) == (c_save == nullptr), "lstm_forward: gates_save and c_save go together");
+    CUtensorMap tw, th, tx;
+    int rc = make_tmap_2d(&tw, whh_packed, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, LN, LK, 1);
+    if (rc) return rc;
+    rc = make_tmap_3d(&th, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, LB, 1, LK, 1);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tx, xp, 4, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 4, 8ull * H * 4, LB, 1, 32, 1);
+    if (rc) return rc;
+    FwdParams p;
+    p.B = B; p.T = T; p.H = H;
+    p.hcat = (__nv_bfloat16 *)hcat;
+    p.gates = (__half *)gates_save;
+    p.csave = c_save;
+    cudaStream_t s = (cudaStream_t)stream;
+    return gates_save ? launch_fwd<true>(tw, th, tx, p, s) : launch_fwd<false>(tw, th, tx, p, s);
+}

@@ -1,0 +1,175 @@
+// Layout preparation around the recurrent kernels: weight packing, casts, transposes.
+//
+// The recurrent kernels partition one LSTM direction by HIDDEN UNIT: CTA c of a cluster owns
+// units [32c, 32c+32) and all four gates of those units, so the cell update is CTA-local.
+// Its 128 gate rows are ordered n = j*4 + g (unit j of the slice, gate g in torch's i,f,g,o
+// order), which puts the four gates of a unit in adjacent TMEM columns of one accumulator row.
+// "Packed" order of the 4H gate rows of one direction is therefore
+//     p(c, j, g) = c*128 + j*4 + g   <->   torch row  g*H + 32c + j.
+// The pack kernel writes every weight view the forward and backward kernels need in one launch.
+#include "common.cuh"
+
+namespace rcnn {
+namespace {
+
+struct PackArgs {
+    const float *w_ih[2], *w_hh[2], *b_ih[2], *b_hh[2];
+    int I, H;
+    __nv_bfloat16 *wih_p;   // [2*4H, I]      packed rows (dir-major)
+    float *bias_p;          // [2*4H]         b_ih + b_hh, packed
+    __nv_bfloat16 *whh_p;   // [2*4H, H]      packed rows
+    __nv_bfloat16 *whh_pt;  // [2, H, 4H]     transpose of whh_p per direction (k = packed column)
+    __nv_bfloat16 *wih_pt;  // [I, 2*4H]      transpose of wih_p
+};
+
+__device__ __forceinline__ int torch_row(int p, int H) {
+    const int c = p >> 7, j = (p >> 2) & 31, g = p & 3;
+    return g * H + 32 * c + j;
+}
+
+// one block per packed row (dir, p)
+__global__ void lstm_pack_kernel(const PackArgs a) {
+    const int H = a.H, I = a.I;
+    const int dir = blockIdx.x / (4 * H), p = blockIdx.x % (4 * H);
+    const int r = torch_row(p, H);
+    const float *wi = a.w_ih[dir] + (size_t)r * I;
+    const float *wh = a.w_hh[dir] + (size_t)r * H;
+    const size_t prow = (size_t)dir * 4 * H + p;
+    for (int k = threadIdx.x; k < I; k += blockDim.x) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(wi[k]);
+        a.wih_p[prow * I + k] = v;
+        a.wih_pt[(size_t)k * 8 * H + prow] = v;
+    }
+    for (int k = threadIdx.x; k < H; k += blockDim.x) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(wh[k]);
+        a.whh_p[prow * H + k] = v;
+        a.whh_pt[((size_t)dir * H + k) * 4 * H + p] = v;
+    }
+    if (threadIdx.x == 0) a.bias_p[prow] = a.b_ih[dir][r] + a.b_hh[dir][r];
+}
+
+// strided fp32 [R, C] (row stride ld) -> contiguous bf16 [R, C]
+__global__ void cast_bf16_kernel(const float *__restrict__ src, long long ld, __nv_bfloat16 *__restrict__ dst,
+                                 long long rows, int cols) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        dst[i] = __float2bfloat16_rn(src[r * ld + c]);
+    }
+}
+
+// 3-D strided fp32 [B, T, C] (strides sb, st, sc) -> contiguous bf16 [B, T, C]
+// (the encoder input is a permuted view of [B, C, T], model/model.py:218)
+__global__ void cast3_bf16_kernel(const float *__restrict__ src, long long sb, long long st, long long sc,
+                                  __nv_bfloat16 *__restrict__ dst, int B, int T, int C) {
+    __shared__ float tile[32][33];
+    // tile over (t, c) for one b; handles both c-contiguous and t-contiguous sources coalesced
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float *s = src + (long long)b * sb;
+    const bool c_fast = (sc == 1) || (st != 1);
+    if (c_fast) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int t = t0 + i, c = c0 + threadIdx.x;
+            if (t < T && c < C) tile[i][threadIdx.x] = s[t * st + c * sc];
+        }
+    } else {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int c = c0 + i, t = t0 + threadIdx.x;
+            if (t < T && c < C) tile[threadIdx.x][i] = s[t * st + c * sc];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < T && c < C) dst[((long long)b * T + t) * C + c] = __float2bfloat16_rn(tile[i][threadIdx.x]);
+    }
+}
+
+// bf16 [R, C] (row stride ld) -> bf16 [C, R] contiguous
+__global__ void transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld,
+                                      __nv_bfloat16 *__restrict__ dst, int R, int C) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const int r = r0 + i;
+        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+            const int c = c0 + j;
+            if (r < R && c < C) tile[i][j] = src[(long long)r * ld + c];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const int c = c0 + i;
+        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+            const int r = r0 + j;
+            if (r < R && c < C) dst[(long long)c * R + r] = tile[j][i];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" size_t rcnn_lstm_packed_bytes(int I, int H) {
+    if (I <= 0 || H <= 0) return 0;
+    const size_t H8 = 8 * (size_t)H;
+    size_t b = 0;
+    b += H8 * I * 2;          // wih_p
+    b += H8 * 4;              // bias_p
+    b += H8 * H * 2;          // whh_p
+    b += H8 * H * 2;          // whh_pt
+    b += H8 * I * 2;          // wih_pt
+    return (b + 255) & ~(size_t)255;
+}
+
+extern "C" int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
+                                      const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
+                                      int I, int H, void *packed, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(I > 0 && H > 0 && H % 32 == 0, "lstm_pack: bad sizes I=%d H=%d", I, H);
+    RCNN_CHECK_ARG(w_ih_f && w_hh_f && b_ih_f && b_hh_f && w_ih_r && w_hh_r && b_ih_r && b_hh_r && packed,
+                   "lstm_pack: null pointer");
+    PackArgs a;
+    a.w_ih[0] = w_ih_f; a.w_hh[0] = w_hh_f; a.b_ih[0] = b_ih_f; a.b_hh[0] = b_hh_f;
+    a.w_ih[1] = w_ih_r; a.w_hh[1] = w_hh_r; a.b_ih[1] = b_ih_r; a.b_hh[1] = b_hh_r;
+    a.I = I; a.H = H;
+    const size_t H8 = 8 * (size_t)H;
+    char *p = (char *)packed;
+    a.wih_p = (__nv_bfloat16 *)p;  p += H8 * I * 2;
+    a.bias_p = (float *)p;         p += H8 * 4;
+    a.whh_p = (__nv_bfloat16 *)p;  p += H8 * H * 2;
+    a.whh_pt = (__nv_bfloat16 *)p; p += H8 * H * 2;
+    a.wih_pt = (__nv_bfloat16 *)p;
+    lstm_pack_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
+    RCNN_LAUNCH_CHECK("lstm_pack_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64_t sc, void *dst, int B, int T, int C,
+                                 rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 0 && C >= 0, "cast_bf16_3d: bad shape");
+    if (B == 0 || T == 0 || C == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(src && dst, "cast_bf16_3d: null pointer");
+    RCNN_CHECK_ARG(B <= 65535, "cast_bf16_3d: batch %d exceeds the grid limit", B);
+    dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
+    cast3_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, sb, st, sc, (__nv_bfloat16 *)dst, B, T, C);
+    RCNN_LAUNCH_CHECK("cast3_bf16_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int R, int C, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(R >= 0 && C >= 0, "transpose_bf16: bad shape");
+    if (R == 0 || C == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(src && dst, "transpose_bf16: null pointer");
+    dim3 grid((C + 63) / 64, (R + 63) / 64), block(32, 8);
+    RCNN_CHECK_ARG(grid.y <= 65535, "transpose_bf16: too many rows");
+    transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, ld,
+                                                                   (__nv_bfloat16 *)dst, R, C);
+    RCNN_LAUNCH_CHECK("transpose_bf16_kernel");
+    return RCNN_OK;
+}

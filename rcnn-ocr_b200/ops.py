@@ -35,3 +35,86 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None
                                        M, N, K, _lib.stream_ptr())
         _lib.check(rc, "rcnn_gemm_bf16")
     return out
+
+
+class PackedLSTMWeights:
+    """bf16 views of one block's nn.LSTM parameters in the kernels' layouts (see
+    rcnn_lstm_pack_weights in include/rcnn_ocr_b200.h)."""
+
+    def __init__(self, blob: torch.Tensor, I: int, H: int):
+        self.blob, self.I, self.H = blob, I, H
+        H8 = 8 * H
+        off = 0
+
+        def take(nbytes, dtype, shape):
+            nonlocal off
+            v = blob[off: off + nbytes].view(dtype).view(shape)
+            off += nbytes
+            return v
+
+        self.wih_p = take(H8 * I * 2, torch.bfloat16, (H8, I))
+        self.bias_p = take(H8 * 4, torch.float32, (H8,))
+        self.whh_p = take(H8 * H * 2, torch.bfloat16, (H8, H))
+        self.whh_pt = take(H8 * H * 2, torch.bfloat16, (2, H, 4 * H))
+        self.wih_pt = take(H8 * I * 2, torch.bfloat16, (I, H8))
+
+
+def lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r) -> PackedLSTMWeights:
+    ts = [w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r]
+    for t in ts:
+        _lib.require_cuda(t, "LSTM parameter")
+    ts = [t.detach().float().contiguous() for t in ts]
+    H = ts[1].shape[1]
+    I = ts[0].shape[1]
+    L = _lib.lib()
+    nbytes = L.rcnn_lstm_packed_bytes(I, H)
+    with torch.cuda.device(ts[0].device):
+        blob = torch.empty((nbytes,), dtype=torch.uint8, device=ts[0].device)
+        rc = L.rcnn_lstm_pack_weights(*[t.data_ptr() for t in ts], I, H, blob.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_pack_weights")
+    return PackedLSTMWeights(blob, I, H)
+
+
+def cast_bf16_3d(x: torch.Tensor) -> torch.Tensor:
+    """[B,T,C] float32 in any strides -> contiguous bf16 (bf16 contiguous inputs pass through)."""
+    _lib.require_cuda(x, "x")
+    if x.dtype == torch.bfloat16:
+        return x if x.is_contiguous() else x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, T, C = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, T, C), dtype=torch.bfloat16, device=x.device)
+        rc = _lib.lib().rcnn_cast_bf16_3d(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), out.data_ptr(),
+                                          B, T, C, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_cast_bf16_3d")
+    return out
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[R,C] bf16 (row stride arbitrary) -> contiguous [C,R]."""
+    _lib.require_cuda(x, "x")
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((C, R), dtype=torch.bfloat16, device=x.device)
+        rc = _lib.lib().rcnn_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), R, C, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_transpose_bf16")
+    return out
+
+
+def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool):
+    """Recurrence of both directions (kernel K2).  xp: float32 [B*T, 8H] in packed column order.
+    Returns (hcat bf16 [B,T,2H], gates f16 [2,T,B,4H] | None, c f32 [2,T,B,H] | None)."""
+    H = packed.H
+    assert xp.dtype == torch.float32 and xp.shape == (B * T, 8 * H) and xp.is_contiguous()
+    dev = xp.device
+    with torch.cuda.device(dev):
+        hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
+        gates = torch.empty((2, T, B, 4 * H), dtype=torch.float16, device=dev) if save else None
+        csave = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
+        rc = _lib.lib().rcnn_lstm_forward(xp.data_ptr(), packed.whh_p.data_ptr(), B, T, H, hcat.data_ptr(),
+                                          gates.data_ptr() if save else None, csave.data_ptr() if save else None,
+                                          _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_forward")
+    return hcat, gates, csave
