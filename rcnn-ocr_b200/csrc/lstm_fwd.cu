@@ -201,8 +201,13 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const float4 v = *reinterpret_cast<const float4 *>(xrow + ((j ^ (row & 7)) << 4));
                     pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&x_empty[slot]);
+                // Free the slot only once every lane's loads have RETURNED: fold one word of each
+                // 16-byte load into a value the arrive depends on, and vote it across the warp.
+                uint32_t dep = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dep |= __float_as_uint(pre[4 * j]);
+                dep = __any_sync(FULL, dep != 0u) ? 1u : 0u;
+                if (lane == 0) mbar_arrive_after(&x_empty[slot], dep);
                 if (s > 0) tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);

@@ -34,6 +34,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive that is data-dependent on `dep`: used to release a TMA-filled buffer only after the
+// shared-memory LOADS that produced `dep` have returned (an arrive is not ordered behind loads
+// still queued in the LSU, e.g. behind a burst of global stores).
+__device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t dep) {
+    asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n"
+                 ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

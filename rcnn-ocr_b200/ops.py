@@ -103,14 +103,15 @@ def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool):
+def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool, hcat=None):
     """Recurrence of both directions (kernel K2).  xp: float32 [B*T, 8H] in packed column order.
     Returns (hcat bf16 [B,T,2H], gates f16 [2,T,B,4H] | None, c f32 [2,T,B,H] | None)."""
     H = packed.H
     assert xp.dtype == torch.float32 and xp.shape == (B * T, 8 * H) and xp.is_contiguous()
     dev = xp.device
     with torch.cuda.device(dev):
-        hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
+        if hcat is None:
+            hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float16, device=dev) if save else None
         csave = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
         rc = _lib.lib().rcnn_lstm_forward(xp.data_ptr(), packed.whh_p.data_ptr(), B, T, H, hcat.data_ptr(),
