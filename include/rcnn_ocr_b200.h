@@ -145,11 +145,33 @@ int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float
 int rcnn_lstm_forward(const float *xp, const void *whh_p, int B, int T, int H, void *hcat,
                       void *gates_save, float *c_save, rcnn_stream_t stream);
 
+/* rcnn_lstm_backward: BPTT through the recurrence of both directions (autograd of nn.LSTM in the
+ * reference, model/model.py:161).
+ *   whh_pt      the whh_pt view of `packed`
+ *   gates_save, c_save   as written by rcnn_lstm_forward
+ *   dhcat       f32 [B, T, 2H]  gradient w.r.t. hcat
+ *   dG          bf16 [B, T, 2*4H] out: gradient w.r.t. the gate pre-activations (= w.r.t. xp),
+ *               columns in P order.  dX = dG wih_p, dW_ih_p = dG^T X, dW_hh_p = dG^T H_prev,
+ *               db_p = column sums of dG are then GEMMs / reductions (rcnn_gemm_bf16,
+ *               rcnn_colsum_bf16, rcnn_lstm_hprev_t) and rcnn_lstm_unpack_grads scatters the
+ *               P-ordered results back to torch's parameter layout. */
+int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
+                       int B, int T, int H, void *dG, rcnn_stream_t stream);
+/* out[col] = sum over rows of src[row, col]  (bf16 [rows, cols] contiguous -> f32 [cols]) */
+int rcnn_colsum_bf16(const void *src, int64_t rows, int cols, float *out, rcnn_stream_t stream);
+/* out bf16 [2, H, ldo >= B*T]: out[dir][u][b*T+t] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at
+ * the direction's first step: the h that multiplied W_hh when gates_t were formed, transposed. */
+int rcnn_lstm_hprev_t(const void *hcat, void *out, int64_t ldo, int B, int T, int H, rcnn_stream_t stream);
+int rcnn_lstm_unpack_grads(const float *dwih_p, const float *dwhh_p, const float *db_p, int I, int H,
+                           float *dw_ih_f, float *dw_hh_f, float *db_ih_f, float *db_hh_f,
+                           float *dw_ih_r, float *dw_hh_r, float *db_ih_r, float *db_hh_r,
+                           rcnn_stream_t stream);
+
 /* Layout helpers used by the host side of the block (fp32 strided -> bf16 contiguous; 2-D
- * bf16 transpose). */
+ * bf16 transpose with output row stride ldo >= R, so that odd R still gives 16-byte rows). */
 int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64_t sc, void *dst, int B, int T, int C,
                       rcnn_stream_t stream);
-int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int R, int C, rcnn_stream_t stream);
+int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int R, int C, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch

@@ -37,10 +37,18 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_lstm_pack_weights.argtypes = [vp] * 8 + [i, i, vp, vp]
     L.rcnn_lstm_forward.restype = i
     L.rcnn_lstm_forward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
+    L.rcnn_lstm_backward.restype = i
+    L.rcnn_lstm_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
+    L.rcnn_colsum_bf16.restype = i
+    L.rcnn_colsum_bf16.argtypes = [vp, i64, i, vp, vp]
+    L.rcnn_lstm_hprev_t.restype = i
+    L.rcnn_lstm_hprev_t.argtypes = [vp, vp, i64, i, i, i, vp]
+    L.rcnn_lstm_unpack_grads.restype = i
+    L.rcnn_lstm_unpack_grads.argtypes = [vp, vp, vp, i, i] + [vp] * 8 + [vp]
     L.rcnn_cast_bf16_3d.restype = i
     L.rcnn_cast_bf16_3d.argtypes = [vp, i64, i64, i64, vp, i, i, i, vp]
     L.rcnn_transpose_bf16.restype = i
-    L.rcnn_transpose_bf16.argtypes = [vp, i64, vp, i, i, vp]
+    L.rcnn_transpose_bf16.argtypes = [vp, i64, vp, i64, i, i, vp]
     L.rcnn_prof_enable.restype = i
     L.rcnn_prof_enable.argtypes = [i]
     L.rcnn_prof_reset.restype = i

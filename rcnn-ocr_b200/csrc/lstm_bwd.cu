@@ -1,0 +1,428 @@
+// K2 (backward): persistent BPTT kernel for both directions of a BidirectionalLSTM block.
+//
+// Backward of the recurrence in lstm_fwd.cu (the reference gets it from autograd through
+// nn.LSTM / cuDNN RNN backward, model/model.py:161):
+//     dh_t   = dhcat[:, t] + dG_{t'} W_hh            (t' = the step processed just before)
+//     do     = dh_t * tanh(c_t)            dc += dh_t * o * (1 - tanh(c_t)^2)
+//     di = dc*g   dg = dc*i   df = dc*c_prev   dc <- dc*f
+//     dG_t   = [di*i(1-i), df*f(1-f), dg*(1-g^2), do*o(1-o)]   (pre-activation gradients)
+// dW_ih, dW_hh, db and dX are GEMMs / reductions over dG after the loop (host side).
+//
+// Same cluster decomposition as the forward kernel: CTA c owns hidden units [32c, 32c+32).
+// Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for H=512) and
+// the streamed operand is the full dG_{t'} tile [128 seq, 4H] (64-column chunks through a
+// 3-slot TMA ring), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
+// threads (one per sequence) keep dc in registers for the whole sequence, read the saved gates
+// / cell states / upstream dh directly from global memory (prefetched one 8-unit chunk ahead)
+// and write dG_t in the packed column order, which is at once the next step's MMA operand and
+// the operand of the dX / dW GEMMs.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace rcnn {
+namespace {
+
+using namespace sm100;
+
+constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
+constexpr int LU = 32;    // hidden units per CTA (UMMA N)
+constexpr int LK = 64;
+constexpr int kARing = 3;
+constexpr uint32_t kATile = LB * LK * 2;   // 16 KB
+constexpr uint32_t kWTile = LU * LK * 2;   // 4 KB
+constexpr int kThreads = 192;
+
+struct BwdParams {
+    int B, T, H;
+    const __half *gates;       // [2, T, B, 4H] activated gates, packed order
+    const float *csave;        // [2, T, B, H]
+    const float *dhcat;        // [B, T, 2H] upstream gradient of the block's LSTM output
+    __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank_b() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x_b() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_b() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_fast_b(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct ChunkIn {     // saved state of 8 units of one sequence at one step
+    uint4 g[4];      // 32 halves: (i,f,g,o) x 8 units
+    float4 c[2], cp[2], dh[2];
+};
+
+__device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, const float *crow, const float *cprow,
+                                           const float *dhrow, int q, bool valid) {
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ci.g[j] = ld_nc_v4(grow + q * 32 + j * 8);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint4 a = ld_nc_v4(crow + q * 8 + j * 4);
+            ci.c[j] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+            const uint4 d = ld_nc_v4(dhrow + q * 8 + j * 4);
+            ci.dh[j] = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z), __uint_as_float(d.w));
+            if (cprow) {
+                const uint4 b = ld_nc_v4(cprow + q * 8 + j * 4);
+                ci.cp[j] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+            } else {
+                ci.cp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ci.g[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            ci.c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ci.cp[j] = ci.c[j];
+            ci.dh[j] = ci.c[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, B = p.B;
+    const int nkc = 4 * H / LK;
+    unsigned char *w_s = smem;                          // nkc tiles [32 n x 64 k] bf16, SW128
+    unsigned char *a_s = w_s + (size_t)nkc * kWTile;    // kARing tiles [128 b x 64 k] bf16, SW128
+    uint64_t *bars = reinterpret_cast<uint64_t *>(a_s + kARing * kATile);
+    uint64_t *w_full = bars;
+    uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
+    uint64_t *tmem_full = a_empty + kARing;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = (int)cluster_ctarank_b();
+    const int cid = (int)cluster_id_x_b();
+    const int dir = cid & 1, tile = cid >> 1;
+    const int b0 = tile * LB;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(w_full, 1);
+            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<LU>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
+    // reverse direction from t = 0 up to T-1.
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmG);
+            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
+            for (int kc = 0; kc < nkc; ++kc)
+                tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
+        }
+        int an = 0;
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0 && s > 0) {
+                const int t = dir ? s : T - 1 - s;
+                const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
+                fence_proxy_async_all();
+                for (int kc = 0; kc < nkc; ++kc, ++an) {
+                    const int slot = an % kARing;
+                    mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&a_full[slot], kATile);
+                    tma_load_3d(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0);
+                }
+            }
+            __syncwarp();
+            cluster_sync_b();
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(LB, LU);
+        int am = 0;
+        if (lane == 0) mbar_wait(w_full, 0);
+        __syncwarp();
+        for (int s = 0; s < T; ++s) {
+            if (lane == 0 && s > 0) {
+                for (int kc = 0; kc < nkc; ++kc, ++am) {
+                    const int slot = am % kARing;
+                    mbar_wait(&a_full[slot], (am / kARing) & 1);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kATile), 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < LK / 16; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                    umma_commit(&a_empty[slot]);
+                }
+                umma_commit(tmem_full);
+            }
+            __syncwarp();
+            cluster_sync_b();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const int b = b0 + row;
+        const bool valid = b < B;
+        float dc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dc[i] = 0.f;
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? s : T - 1 - s;
+            const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
+            const size_t rtb = ((size_t)dir * T + t) * B + b;
+            const __half *grow = p.gates + rtb * 4 * H + (size_t)c * 128;
+            const float *crow = p.csave + rtb * H + 32 * c;
+            const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c : nullptr;
+            const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c;
+            __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128;
+
+            ChunkIn cur, nxt;
+            load_chunk(cur, grow, crow, cprow, dhrow, 0, valid);
+            uint32_t acc[32];
+            if (s > 0) {
+                mbar_wait(tmem_full, (s - 1) & 1);
+                tc_fence_after();
+                tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16), acc);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < 3) load_chunk(nxt, grow, crow, cprow, dhrow, q + 1, valid);
+                const __half2 *gh = reinterpret_cast<const __half2 *>(cur.g);
+                const float cc[8] = {cur.c[0].x, cur.c[0].y, cur.c[0].z, cur.c[0].w, cur.c[1].x, cur.c[1].y, cur.c[1].z, cur.c[1].w};
+                const float cp[8] = {cur.cp[0].x, cur.cp[0].y, cur.cp[0].z, cur.cp[0].w, cur.cp[1].x, cur.cp[1].y, cur.cp[1].z, cur.cp[1].w};
+                const float dhu[8] = {cur.dh[0].x, cur.dh[0].y, cur.dh[0].z, cur.dh[0].w, cur.dh[1].x, cur.dh[1].y, cur.dh[1].z, cur.dh[1].w};
+                float o32[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 if_ = __half22float2(gh[2 * j]);       // (i, f)
+                    const float2 go_ = __half22float2(gh[2 * j + 1]);   // (g, o)
+                    const float ig = if_.x, fg = if_.y, gg = go_.x, og = go_.y;
+                    const float dh = dhu[j] + __uint_as_float(acc[q * 8 + j]);
+                    const float tc = tanh_fast_b(cc[j]);
+                    const float d_o = dh * tc;
+                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[q * 8 + j]);
+                    dc[q * 8 + j] = dct * fg;
+                    o32[4 * j] = dct * gg * ig * (1.f - ig);
+                    o32[4 * j + 1] = dct * cp[j] * fg * (1.f - fg);
+                    o32[4 * j + 2] = dct * ig * (1.f - gg * gg);
+                    o32[4 * j + 3] = d_o * og * (1.f - og);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 v;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(o32[8 * j], o32[8 * j + 1]);
+                        __nv_bfloat162 h1 = __floats2bfloat162_rn(o32[8 * j + 2], o32[8 * j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o32[8 * j + 4], o32[8 * j + 5]);
+                        __nv_bfloat162 h3 = __floats2bfloat162_rn(o32[8 * j + 6], o32[8 * j + 7]);
+                        v.x = *reinterpret_cast<uint32_t *>(&h0); v.y = *reinterpret_cast<uint32_t *>(&h1);
+                        v.z = *reinterpret_cast<uint32_t *>(&h2); v.w = *reinterpret_cast<uint32_t *>(&h3);
+                        *reinterpret_cast<uint4 *>(dgrow + q * 32 + j * 8) = v;
+                    }
+                }
+                if (q < 3) cur = nxt;
+            }
+            tc_fence_before();
+            fence_proxy_async_all();   // dG_t stores before the other CTAs' TMA reads
+            cluster_sync_b();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<LU>(tmem_base);
+    }
+}
+
+size_t bwd_smem_bytes(int H) { return 1024 + (size_t)(4 * H / LK) * kWTile + kARing * kATile + 256; }
+
+// column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
+__global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long rows, int cols, float *__restrict__ out) {
+    // block = 32 x 8 threads: 32 consecutive columns, 8 row phases; grid.y splits the rows
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (col < cols) {
+        for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8)
+            s += __bfloat162float(src[r * cols + col]);
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < cols) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x];
+        atomicAdd(&out[col], tot);
+    }
+}
+
+// hprev^T for the dW_hh GEMM: out[dir][u][b*T + t] = hcat[b, t -/+ 1, dir*H + u] (0 at the first
+// step of that direction), i.e. the h that multiplied W_hh when gates_t were formed.
+__global__ void hprev_transpose_kernel(const __nv_bfloat16 *__restrict__ hcat, __nv_bfloat16 *__restrict__ out,
+                                       long long ldo, int B, int T, int H) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int dir = blockIdx.z;
+    const long long BT = (long long)B * T;
+    const long long r0 = (long long)blockIdx.y * 64;   // rows of (b,t)
+    const int u0 = blockIdx.x * 64;
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const long long r = r0 + i;
+        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+            const int u = u0 + j;
+            __nv_bfloat16 v = __float2bfloat16(0.f);
+            if (r < BT && u < H) {
+                const long long b = r / T;
+                const int t = (int)(r - b * T);
+                const int tp = dir ? t + 1 : t - 1;
+                if (tp >= 0 && tp < T) v = hcat[(b * T + tp) * 2 * H + (long long)dir * H + u];
+            }
+            tile[i][j] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+        const int u = u0 + i;
+        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+            const long long r = r0 + j;
+            if (r < BT && u < H) out[((long long)dir * H + u) * ldo + r] = tile[j][i];
+        }
+    }
+}
+
+// Scatter the packed-order weight gradients back to torch's layout (fp32):
+//   dW_ih[dir][g*H+32c+j, :] = dWih_p[dir*4H + p, :], same for dW_hh; db_ih = db_hh = db_p.
+struct UnpackArgs {
+    const float *dwih_p, *dwhh_p, *db_p;   // [8H, I], [8H, H], [8H]
+    float *dw_ih[2], *dw_hh[2], *db_ih[2], *db_hh[2];
+    int I, H;
+};
+__global__ void lstm_unpack_grads_kernel(const UnpackArgs a) {
+    const int H = a.H, I = a.I;
+    const int dir = blockIdx.x / (4 * H), pidx = blockIdx.x % (4 * H);
+    const int cc = pidx >> 7, j = (pidx >> 2) & 31, g = pidx & 3;
+    const int r = g * H + 32 * cc + j;
+    const size_t prow = (size_t)dir * 4 * H + pidx;
+    for (int k = threadIdx.x; k < I; k += blockDim.x) a.dw_ih[dir][(size_t)r * I + k] = a.dwih_p[prow * I + k];
+    for (int k = threadIdx.x; k < H; k += blockDim.x) a.dw_hh[dir][(size_t)r * H + k] = a.dwhh_p[prow * H + k];
+    if (threadIdx.x == 0) {
+        const float v = a.db_p[prow];
+        a.db_ih[dir][r] = v;
+        a.db_hh[dir][r] = v;
+    }
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
+                                  int B, int T, int H, void *dG, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_backward: bad shape B=%d T=%d", B, T);
+    RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
+                   "lstm_backward: hidden size %d unsupported (64, 128, 256 or 512)", H);
+    if (B == 0 || T == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(whh_pt && gates_save && c_save && dhcat && dG, "lstm_backward: null pointer");
+    CUtensorMap tw, tg;
+    int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, LU, LK, 1);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tg, dG, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, LB, 1, LK, 1);
+    if (rc) return rc;
+    BwdParams p;
+    p.B = B; p.T = T; p.H = H;
+    p.gates = (const __half *)gates_save;
+    p.csave = c_save;
+    p.dhcat = dhcat;
+    p.dG = (__nv_bfloat16 *)dG;
+    const int csize = H / 32;
+    const int ntiles = (B + LB - 1) / LB;
+    const size_t smem = bwd_smem_bytes(H);
+    cudaStream_t s = (cudaStream_t)stream;
+    RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * ntiles * 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(RCNN_K_LSTM_BWD, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, tg, p));
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_colsum_bf16(const void *src, int64_t rows, int cols, float *out, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(rows >= 0 && cols >= 0, "colsum: bad shape");
+    if (cols == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(out, "colsum: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    RCNN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, s));
+    if (rows == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(src, "colsum: null pointer");
+    dim3 block(32, 8), grid((cols + 31) / 32, (unsigned)(((rows + 7) / 8) < 64 ? ((rows + 7) / 8) : 64));
+    colsum_bf16_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16 *)src, rows, cols, out);
+    RCNN_LAUNCH_CHECK("colsum_bf16_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_lstm_hprev_t(const void *hcat, void *out, int64_t ldo, int B, int T, int H, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 0 && H > 0, "hprev_t: bad shape");
+    if (B == 0 || T == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(hcat && out && ldo >= (int64_t)B * T, "hprev_t: null pointer or ldo < B*T");
+    const long long BT = (long long)B * T;
+    dim3 block(32, 8), grid((H + 63) / 64, (unsigned)((BT + 63) / 64), 2);
+    RCNN_CHECK_ARG(grid.y <= 65535, "hprev_t: B*T too large");
+    hprev_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)hcat, (__nv_bfloat16 *)out, ldo, B, T, H);
+    RCNN_LAUNCH_CHECK("hprev_transpose_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_lstm_unpack_grads(const float *dwih_p, const float *dwhh_p, const float *db_p, int I, int H,
+                                      float *dw_ih_f, float *dw_hh_f, float *db_ih_f, float *db_hh_f,
+                                      float *dw_ih_r, float *dw_hh_r, float *db_ih_r, float *db_hh_r,
+                                      rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(I > 0 && H > 0 && H % 32 == 0, "unpack_grads: bad sizes");
+    RCNN_CHECK_ARG(dwih_p && dwhh_p && db_p && dw_ih_f && dw_hh_f && db_ih_f && db_hh_f && dw_ih_r && dw_hh_r &&
+                       db_ih_r && db_hh_r, "unpack_grads: null pointer");
+    UnpackArgs a;
+    a.dwih_p = dwih_p; a.dwhh_p = dwhh_p; a.db_p = db_p;
+    a.dw_ih[0] = dw_ih_f; a.dw_hh[0] = dw_hh_f; a.db_ih[0] = db_ih_f; a.db_hh[0] = db_hh_f;
+    a.dw_ih[1] = dw_ih_r; a.dw_hh[1] = dw_hh_r; a.db_ih[1] = db_ih_r; a.db_hh[1] = db_hh_r;
+    a.I = I; a.H = H;
+    lstm_unpack_grads_kernel<<<8 * H, 128, 0, (cudaStream_t)stream>>>(a);
+    RCNN_LAUNCH_CHECK("lstm_unpack_grads_kernel");
+    return RCNN_OK;
+}

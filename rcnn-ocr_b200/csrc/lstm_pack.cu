@@ -88,9 +88,9 @@ __global__ void cast3_bf16_kernel(const float *__restrict__ src, long long sb, l
     }
 }
 
-// bf16 [R, C] (row stride ld) -> bf16 [C, R] contiguous
+// bf16 [R, C] (row stride ld) -> bf16 [C, R] with output row stride ldo >= R
 __global__ void transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld,
-                                      __nv_bfloat16 *__restrict__ dst, int R, int C) {
+                                      __nv_bfloat16 *__restrict__ dst, long long ldo, int R, int C) {
     __shared__ __nv_bfloat16 tile[64][66];
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     for (int i = threadIdx.y; i < 64; i += blockDim.y) {
@@ -105,7 +105,7 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ src, lon
         const int c = c0 + i;
         for (int j = threadIdx.x; j < 64; j += blockDim.x) {
             const int r = r0 + j;
-            if (r < R && c < C) dst[(long long)c * R + r] = tile[j][i];
+            if (r < R && c < C) dst[(long long)c * ldo + r] = tile[j][i];
         }
     }
 }
@@ -161,15 +161,16 @@ extern "C" int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64
     return RCNN_OK;
 }
 
-extern "C" int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int R, int C, rcnn_stream_t stream) {
+extern "C" int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int R, int C,
+                                   rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(R >= 0 && C >= 0, "transpose_bf16: bad shape");
     if (R == 0 || C == 0) return RCNN_OK;
-    RCNN_CHECK_ARG(src && dst, "transpose_bf16: null pointer");
+    RCNN_CHECK_ARG(src && dst && ldo >= R, "transpose_bf16: null pointer or ldo < R");
     dim3 grid((C + 63) / 64, (R + 63) / 64), block(32, 8);
     RCNN_CHECK_ARG(grid.y <= 65535, "transpose_bf16: too many rows");
     transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, ld,
-                                                                   (__nv_bfloat16 *)dst, R, C);
+                                                                   (__nv_bfloat16 *)dst, ldo, R, C);
     RCNN_LAUNCH_CHECK("transpose_bf16_kernel");
     return RCNN_OK;
 }

@@ -8,6 +8,15 @@ from . import _lib
 _OUT = {torch.float32: 0, torch.bfloat16: 1}
 
 
+def _repitch(m: torch.Tensor) -> torch.Tensor:
+    """Copy a bf16 matrix into rows whose pitch is a multiple of 8 elements (host-side layout fix
+    for oddly shaped operands; the hot path never takes this branch)."""
+    R, C = m.shape
+    buf = torch.zeros((R, (C + 7) // 8 * 8), dtype=m.dtype, device=m.device)
+    buf[:, :C] = m
+    return buf[:, :C]
+
+
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None,
               out_dtype: torch.dtype = torch.float32, out: torch.Tensor | None = None) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[N,K]^T (+ bias[N]) on tcgen05 (kernel K1).  a, b: bf16, rows
@@ -17,13 +26,11 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16, "gemm_bf16 takes bf16 operands"
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1], (a.shape, b.shape)
     if a.stride(1) != 1 or a.stride(0) % 8 or a.data_ptr() % 16:
-        a = a.contiguous()
+        a = _repitch(a)
     if b.stride(1) != 1 or b.stride(0) % 8 or b.data_ptr() % 16:
-        b = b.contiguous()
+        b = _repitch(b)
     M, K = a.shape
     N = b.shape[0]
-    if K % 8:
-        raise ValueError(f"K={K} must be a multiple of 8 (16-byte rows)")
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in _OUT
@@ -91,16 +98,22 @@ def cast_bf16_3d(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
 def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
-    """[R,C] bf16 (row stride arbitrary) -> contiguous [C,R]."""
+    """[R,C] bf16 (row stride arbitrary) -> [C,R] whose row pitch is padded to a multiple of 8
+    elements (16-byte rows for TMA); the pad columns are never read."""
     _lib.require_cuda(x, "x")
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
     R, C = x.shape
+    ldo = _pad8(R)
     with torch.cuda.device(x.device):
-        out = torch.empty((C, R), dtype=torch.bfloat16, device=x.device)
-        rc = _lib.lib().rcnn_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), R, C, _lib.stream_ptr())
+        out = torch.empty((C, ldo), dtype=torch.bfloat16, device=x.device)
+        rc = _lib.lib().rcnn_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), ldo, R, C, _lib.stream_ptr())
         _lib.check(rc, "rcnn_transpose_bf16")
-    return out
+    return out[:, :R]
 
 
 def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool, hcat=None):
@@ -119,3 +132,54 @@ def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, sa
                                           _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_forward")
     return hcat, gates, csave
+
+
+def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int):
+    """BPTT of both directions (kernel K2 backward).  dhcat: float32 [B,T,2H] contiguous.
+    Returns dG bf16 [B,T,8H] (gradient w.r.t. the gate pre-activations, packed column order)."""
+    H = packed.H
+    assert dhcat.dtype == torch.float32 and dhcat.is_contiguous() and dhcat.shape == (B, T, 2 * H)
+    with torch.cuda.device(dhcat.device):
+        dG = torch.empty((B, T, 8 * H), dtype=torch.bfloat16, device=dhcat.device)
+        rc = _lib.lib().rcnn_lstm_backward(packed.whh_pt.data_ptr(), gates.data_ptr(), csave.data_ptr(),
+                                           dhcat.data_ptr(), B, T, H, dG.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_backward")
+    return dG
+
+
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    """float32 column sums of a contiguous bf16 [rows, cols] matrix."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+        rc = _lib.lib().rcnn_colsum_bf16(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "rcnn_colsum_bf16")
+    return out
+
+
+def lstm_hprev_t(hcat: torch.Tensor) -> torch.Tensor:
+    """[B,T,2H] bf16 -> [2, H, B*T]: previous-step h of each direction, transposed."""
+    B, T, H2 = hcat.shape
+    ldo = _pad8(B * T)
+    with torch.cuda.device(hcat.device):
+        out = torch.empty((2, H2 // 2, ldo), dtype=torch.bfloat16, device=hcat.device)
+        rc = _lib.lib().rcnn_lstm_hprev_t(hcat.data_ptr(), out.data_ptr(), ldo, B, T, H2 // 2, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_hprev_t")
+    return out[:, :, :B * T]
+
+
+def lstm_unpack_grads(dwih_p, dwhh_p, db_p, I: int, H: int):
+    """Packed-order weight gradients -> eight float32 tensors in torch's nn.LSTM layout
+    (w_ih, w_hh, b_ih, b_hh for the forward direction, then the reverse one)."""
+    dev = dwih_p.device
+    with torch.cuda.device(dev):
+        outs = []
+        for _ in range(2):
+            outs += [torch.empty((4 * H, I), dtype=torch.float32, device=dev),
+                     torch.empty((4 * H, H), dtype=torch.float32, device=dev),
+                     torch.empty((4 * H,), dtype=torch.float32, device=dev),
+                     torch.empty((4 * H,), dtype=torch.float32, device=dev)]
+        rc = _lib.lib().rcnn_lstm_unpack_grads(dwih_p.data_ptr(), dwhh_p.data_ptr(), db_p.data_ptr(), I, H,
+                                               *[o.data_ptr() for o in outs], _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_unpack_grads")
+    return outs
