@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Benchmark of the RCNN-OCR sequence-recognition hot path on B200 (BASELINE.json metric:
+text-lines/sec for the train step and greedy inference; % of roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (port)
+
+Workload ("cfgB", BASELINE.json configs[1]+[2]): per GPU 256 synthetic text lines,
+T=64 feature columns of 512 channels -> 2 x BidirectionalLSTM(hidden 512) -> CTC head (195
+classes = configs/charset.txt + blank) -> fused log_softmax + CTC loss (labels U{1..32}) ->
+backward -> NCCL gradient all-reduce (N > 1) -> Adam step.  A "step" is one such pass over one
+batch; weak scaling (per-GPU batch fixed).  The SE-ResNet31 backbone is outside the hot path
+ and is not part of the timed region: the inputs are its feature columns.
+
+One JSON line on rank 0; see DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(T=64, IN=512, H=512, C=195, LMAX=32, B=256)
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def make_batch(B, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, CFG["T"], CFG["IN"], generator=g)
+    tl = torch.randint(1, CFG["LMAX"] + 1, (B,), generator=g)
+    tg = torch.randint(1, CFG["C"], (B, CFG["LMAX"]), generator=g)
+    il = torch.full((B,), CFG["T"], dtype=torch.long)
+    out = [feats, tg, il, tl]
+    if pin:
+        out = [t.pin_memory() for t in out]
+    if device != "cpu":
+        out = [t.to(device) for t in out]
+    return out
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (port)
+def cpu_reference(steps, warmup, sample_B, workload="train"):
+    """The reference's own torch-CPU op sequence for the path (oracle/ref_port.py), all host
+    threads, on a bounded sample of the workload.  Returns (lines/s, ms/step, cores)."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    enc = ref_port.make_encoder(CFG["IN"], CFG["H"])
+    head = torch.nn.Linear(CFG["H"], CFG["C"])
+    feats, tg, il, tl = make_batch(sample_B, 1234)
+    alphabet = [chr(0x4E00 + i) for i in range(CFG["C"] - 1)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if workload == "train":
+            ref_port.train_step(enc, head, feats, tg, il, tl)
+        else:
+            ref_port.infer_step(enc, head, feats, alphabet)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return sample_B / (ms / 1e3), ms, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample_B = args.ref_batch
+    val, ms, cores = cpu_reference(args.steps, max(args.warmup, 1), sample_B)
+    line = {
+        "impl": "reference", "metric": "text-lines/sec", "value": round(val, 2), "unit": "lines/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_B, 1),
+        "cpu_baseline": {"value": round(val, 2), "unit": "lines/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_B} lines/step x {args.steps} steps of the same T/H/C workload "
+                                   "(oracle/ref_port.py: the reference's torch-CPU op sequence)"},
+        "e2e": {"value": round(val, 2), "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B, world):
+    return {"workload": "cfgB train step: 2xBiLSTM(512)+CTC head+fused CTC loss fwd/bwd+Adam "
+                        "(BASELINE configs[1]+[2]); infer: same encoder + greedy CTC decode",
+            "per_gpu_batch": B, "global_batch": B * world, "T": CFG["T"], "in": CFG["IN"], "hidden": CFG["H"],
+            "classes": CFG["C"], "label_len": "U{1..32}", "parallelism": f"dp{world}",
+            "l2_policy": "inputs rotate over a ring larger than L2 (8 sets x 33.5 MB features + 8 gradient/"
+                         "activation sets)"}
+
+
+# ----------------------------------------------------------------------------- ours
+class TrainStep:
+    def __init__(self, device, world, rank):
+        import rcnn_ocr_b200 as R
+        from rcnn_ocr_b200.dist import GradAllReducer
+        self.R = R
+        torch.manual_seed(0)
+        self.enc = R.make_enc_rnn(CFG["IN"], CFG["H"]).to(device)
+        self.head = R.CTCHead(CFG["H"], CFG["C"]).to(device)
+        self.params = list(self.enc.parameters()) + list(self.head.parameters())
+        self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True)
+        self.reducer = GradAllReducer(self.params) if world > 1 else None
+        self.world = world
+
+    def __call__(self, feats, tg, il, tl):
+        self.opt.zero_grad(set_to_none=True)
+        logits = self.head(self.enc(feats))                                  # [B,T,C] fp32
+        loss = self.R.ctc_loss_from_logits(logits.permute(1, 0, 2), tg, il, tl, 0, "mean", True,
+                                           max_target_length=CFG["LMAX"])
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        return loss
+
+
+class InferStep:
+    def __init__(self, train: TrainStep):
+        self.t = train
+        self.alphabet = [chr(0x4E00 + i) for i in range(CFG["C"] - 1)]
+
+    @torch.no_grad()
+    def device(self, feats):
+        logits = self.t.head(self.t.enc(feats))
+        return self.t.R.ctc_greedy_ids(logits)
+
+    @torch.no_grad()
+    def e2e(self, feats):
+        logits = self.t.head(self.t.enc(feats))
+        return self.t.R.ctc_greedy_decoder(logits, self.alphabet, batch_first=True)
+
+
+def timed(fn, steps, warmup, sync, barrier):
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    sync()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from rcnn_ocr_b200 import _lib, ops
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.check(_lib.lib().rcnn_device_check(), "rcnn_device_check")
+    peaks = load_peaks()
+    B = args.batch
+    RING = 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def sync():
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    host = [make_batch(B, 1234 + 17 * rank + i, pin=True) for i in range(RING)]
+    dev = [[t.to(device) for t in b] for b in host]
+    step = TrainStep(device, world, rank)
+    infer = InferStep(step)
+
+    # ---- device-resident train step (headline `value`) -----------------------------------------
+    clocks = ClockSampler(local_rank)
+    l0 = ops.launch_count()
+    clocks.start()
+    ms_train = timed(lambda i: step(*dev[i % RING]), args.steps, args.warmup, sync, barrier)
+    clk = clocks.stop()
+    launches = (ops.launch_count() - l0) / (args.steps + args.warmup)
+    ms_train = max_over_ranks(ms_train)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------
+    copy_stream = torch.cuda.Stream()
+    slots = [[torch.empty_like(t, device=device) for t in host[0]] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for d, h in zip(slots[s], host[i % RING]):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    losses = []
+
+    def e2e_train(i):
+        s = i % 2
+        if e2e_train.primed is False:
+            stage(i)
+            e2e_train.primed = True
+        stage(i + 1)                                    # overlap the next step's H2D with this step
+        torch.cuda.current_stream().wait_event(ready[s])
+        loss = step(*slots[s])
+        freed[s].record()
+        losses.append(loss.item())                      # D2H read of the result, every step
+
+    e2e_train.primed = False
+    for f in freed:
+        f.record()
+    ms_e2e = max_over_ranks(timed(e2e_train, args.steps, args.warmup, sync, barrier))
+    sync()
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- greedy inference (same encoder, decode on device) --------------------------------------
+    ms_inf = max_over_ranks(timed(lambda i: infer.device(dev[i % RING][0]), args.steps, args.warmup, sync, barrier))
+
+    def e2e_infer(i):
+        texts, _ = infer.e2e(host[i % RING][0])          # pinned host features in, python strings out
+        return texts
+
+    ms_inf_e2e = max_over_ranks(timed(e2e_infer, args.steps, args.warmup, sync, barrier))
+
+    # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
+    _lib.prof_enable(True)
+    for i in range(args.steps):
+        step(*dev[i % RING])
+    sync()
+    names = {0: "decode", 1: "ctc", 2: "gemm", 3: "lstm_fwd", 4: "lstm_bwd"}
+    kern = {}
+    for kid, name in names.items():
+        ms, n = _lib.prof_read(kid)
+        if n:
+            kern[name] = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
+    _lib.lib().rcnn_prof_reset()
+    for i in range(args.steps):
+        infer.device(dev[i % RING][0])
+    sync()
+    ms_dec, n_dec = _lib.prof_read(0)
+    _lib.prof_enable(False)
+
+    T, H, C, IN = CFG["T"], CFG["H"], CFG["C"], CFG["IN"]
+    rec_flops = 2.0 * B * T * H * 4 * H * 2                 # recurrent matmuls of one block, both directions
+    roof = None
+    if kern:
+        dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+        k = kern[dom]
+        per_launch_ms = k["ms_per_step"] / k["launches_per_step"]
+        if dom in ("lstm_fwd", "lstm_bwd"):
+            ach = rec_flops / (per_launch_ms * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sus"],
+                    "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": None,
+                    "algorithmic": f"2*B*T*H*4H*2dirs = {rec_flops / 1e9:.1f} GFLOP per launch (one block)",
+                    "us_per_timestep": round(per_launch_ms * 1e3 / T, 3), "peak_source": peaks["src"]}
+        elif dom == "gemm":
+            # all GEMMs of the step: projections, linears, head and their backward GEMMs
+            g_flops = 2.0 * B * T * (IN * 8 * H + 2 * H * H + H * 8 * H + 2 * H * H + H * C) * 3
+            ach = g_flops / (k["ms_per_step"] * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sus"],
+                    "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": None,
+                    "algorithmic": f"{g_flops / 1e9:.1f} GFLOP over all GEMM launches of a step",
+                    "peak_source": peaks["src"]}
+        else:
+            nbytes = 2.0 * T * C * 4 * B
+            ach = nbytes / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm"], 4), "traffic": None, "peak_source": peaks["src"]}
+    kernels = {n: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"]}
+               for n, v in kern.items()}
+    if "ctc" in kern:
+        per = kern["ctc"]["ms_per_step"] / kern["ctc"]["launches_per_step"]
+        kernels["ctc"]["hbm_frac"] = round(2.0 * T * C * 4 * B / (per * 1e-3) / 1e9 / peaks["hbm"], 4)
+    if n_dec:
+        per = ms_dec / n_dec
+        kernels["decode"] = {"ms_per_launch": round(per, 4),
+                             "hbm_frac": round((T * C * 4 + T * 4 + 4) * B / (per * 1e-3) / 1e9 / peaks["hbm"], 4)}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference(2, 1, B)
+            cpu = {"value": round(v, 2), "unit": "lines/s", "cores": cores, "kind": "port",
+                   "sample": f"{B} lines/step x 2 steps (after 1 warm-up) of the same train-step workload on the "
+                             "host CPU: oracle/ref_port.py = the reference's torch-CPU op sequence "
+                             "(nn.LSTM+nn.Linear x2, log_softmax+F.ctc_loss, backward)",
+                   "ms_per_step": round(ms, 1)}
+        total_B = B * world
+        line = {
+            "metric": "text-lines/sec", "value": round(total_B / (ms_train * 1e-3), 1), "unit": "lines/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_train, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args, B, world),
+            "e2e": {"value": round(total_B / (ms_e2e * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "note": "pinned host features/targets -> H2D (double-buffered on a copy stream) -> train step "
+                            "-> loss.item() every step"},
+            "infer": {"value": round(total_B / (ms_inf * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_inf, 4),
+                      "e2e": {"value": round(total_B / (ms_inf_e2e * 1e-3), 1), "ms_per_step": round(ms_inf_e2e, 4),
+                              "h2d_bytes_per_step": host[0][0].numel() * 4, "d2h_bytes_per_step": B * (T + 1) * 4,
+                              "note": "pinned host features in, decoded python strings out"}},
+            "gpu_launches": round(launches * args.steps),
+            "gpu_launches_per_step": round(launches, 1),
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
+            "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)] if losses else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["B"], help="lines per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=64, help="lines per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"}))
+        sys.exit(2)
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

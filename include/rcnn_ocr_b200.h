@@ -157,8 +157,8 @@ int rcnn_lstm_forward(const float *xp, const void *whh_p, int B, int T, int H, v
  *               P-ordered results back to torch's parameter layout. */
 int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
                        int B, int T, int H, void *dG, rcnn_stream_t stream);
-/* out[col] = sum over rows of src[row, col]  (bf16 [rows, cols] contiguous -> f32 [cols]) */
-int rcnn_colsum_bf16(const void *src, int64_t rows, int cols, float *out, rcnn_stream_t stream);
+/* out[col] = sum over rows of src[row*ld + col]  (bf16 [rows, cols] -> f32 [cols]) */
+int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float *out, rcnn_stream_t stream);
 /* out bf16 [2, H, ldo >= B*T]: out[dir][u][b*T+t] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at
  * the direction's first step: the h that multiplied W_hh when gates_t were formed, transposed. */
 int rcnn_lstm_hprev_t(const void *hcat, void *out, int64_t ldo, int B, int T, int H, rcnn_stream_t stream);
@@ -170,6 +170,9 @@ int rcnn_lstm_unpack_grads(const float *dwih_p, const float *dwhh_p, const float
 /* Layout helpers used by the host side of the block (fp32 strided -> bf16 contiguous; 2-D
  * bf16 transpose with output row stride ldo >= R, so that odd R still gives 16-byte rows). */
 int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64_t sc, void *dst, int B, int T, int C,
+                      rcnn_stream_t stream);
+/* fp32 [rows, cols] (row stride ld_src) -> bf16 (row stride ld_dst >= cols; pad columns zeroed) */
+int rcnn_cast_bf16_2d(const float *src, int64_t ld_src, void *dst, int64_t ld_dst, int64_t rows, int cols,
                       rcnn_stream_t stream);
 int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int R, int C, rcnn_stream_t stream);
 
@@ -184,6 +187,8 @@ int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int
 #define RCNN_K_LSTM_FWD 3
 #define RCNN_K_LSTM_BWD 4
 #define RCNN_K_COUNT 8
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long rcnn_launch_count(void);
 int rcnn_prof_enable(int on);
 int rcnn_prof_reset(void);
 int rcnn_prof_read(int kernel, double *total_ms, int *launches);

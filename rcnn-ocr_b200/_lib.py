@@ -40,7 +40,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_lstm_backward.restype = i
     L.rcnn_lstm_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
     L.rcnn_colsum_bf16.restype = i
-    L.rcnn_colsum_bf16.argtypes = [vp, i64, i, vp, vp]
+    L.rcnn_colsum_bf16.argtypes = [vp, i64, i64, i, vp, vp]
+    L.rcnn_cast_bf16_2d.restype = i
+    L.rcnn_cast_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i, vp]
+    L.rcnn_launch_count.restype = ctypes.c_ulonglong
     L.rcnn_lstm_hprev_t.restype = i
     L.rcnn_lstm_hprev_t.argtypes = [vp, vp, i64, i, i, i, vp]
     L.rcnn_lstm_unpack_grads.restype = i

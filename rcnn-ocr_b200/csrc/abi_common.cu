@@ -31,6 +31,9 @@ int num_sms() {
     return cached;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 // ---- per-kernel event timing -----------------------------------------------------------
 static const int kProfSlots = 16384;
 static bool g_prof_on = false;
@@ -53,6 +56,8 @@ void prof_end(int slot, cudaStream_t s) {
 }  // namespace rcnn
 
 extern "C" {
+
+unsigned long long rcnn_launch_count(void) { return rcnn::g_launches; }
 
 int rcnn_prof_enable(int on) {
     using namespace rcnn;

@@ -29,9 +29,11 @@ int cuda_fail(cudaError_t e, const char *what);
     do {                                                             \
         cudaError_t e__ = cudaGetLastError();                        \
         if (e__ != cudaSuccess) return ::rcnn::cuda_fail(e__, name); \
+        ::rcnn::count_launch();                                      \
     } while (0)
 
 int num_sms();
+void count_launch();
 
 // Optional per-kernel event timing (see rcnn_prof_* in the header).
 int prof_begin(int kernel, cudaStream_t s);

@@ -262,14 +262,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 size_t bwd_smem_bytes(int H) { return 1024 + (size_t)(4 * H / LK) * kWTile + kARing * kATile + 256; }
 
 // column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
-__global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long rows, int cols, float *__restrict__ out) {
+__global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, long long rows, int cols,
+                                   float *__restrict__ out) {
     // block = 32 x 8 threads: 32 consecutive columns, 8 row phases; grid.y splits the rows
     __shared__ float part[8][33];
     const int col = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (col < cols) {
         for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8)
-            s += __bfloat162float(src[r * cols + col]);
+            s += __bfloat162float(src[r * ld + col]);
     }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
@@ -378,10 +379,11 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_BWD, s);
     RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, tg, p));
+    count_launch();
     return RCNN_OK;
 }
 
-extern "C" int rcnn_colsum_bf16(const void *src, int64_t rows, int cols, float *out, rcnn_stream_t stream) {
+extern "C" int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float *out, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(rows >= 0 && cols >= 0, "colsum: bad shape");
     if (cols == 0) return RCNN_OK;
@@ -391,7 +393,7 @@ extern "C" int rcnn_colsum_bf16(const void *src, int64_t rows, int cols, float *
     if (rows == 0) return RCNN_OK;
     RCNN_CHECK_ARG(src, "colsum: null pointer");
     dim3 block(32, 8), grid((cols + 31) / 32, (unsigned)(((rows + 7) / 8) < 64 ? ((rows + 7) / 8) : 64));
-    colsum_bf16_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16 *)src, rows, cols, out);
+    colsum_bf16_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16 *)src, ld, rows, cols, out);
     RCNN_LAUNCH_CHECK("colsum_bf16_kernel");
     return RCNN_OK;
 }

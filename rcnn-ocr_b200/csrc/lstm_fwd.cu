@@ -286,6 +286,7 @@ int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_FWD, s);
     RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, p));
+    count_launch();
     return RCNN_OK;
 }
 

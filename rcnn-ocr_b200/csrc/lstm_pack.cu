@@ -48,15 +48,15 @@ __global__ void lstm_pack_kernel(const PackArgs a) {
     if (threadIdx.x == 0) a.bias_p[prow] = a.b_ih[dir][r] + a.b_hh[dir][r];
 }
 
-// strided fp32 [R, C] (row stride ld) -> contiguous bf16 [R, C]
+// fp32 [R, C] (row stride ld) -> bf16 [R, ldd] (columns [C, ldd) zero-filled)
 __global__ void cast_bf16_kernel(const float *__restrict__ src, long long ld, __nv_bfloat16 *__restrict__ dst,
-                                 long long rows, int cols) {
-    const long long total = rows * cols;
+                                 long long ldd, long long rows, int cols) {
+    const long long total = rows * ldd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / cols;
-        const int c = (int)(i - r * cols);
-        dst[i] = __float2bfloat16_rn(src[r * ld + c]);
+        const long long r = i / ldd;
+        const int c = (int)(i - r * ldd);
+        dst[i] = __float2bfloat16_rn(c < cols ? src[r * ld + c] : 0.f);
     }
 }
 
@@ -158,6 +158,19 @@ extern "C" int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64
     dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
     cast3_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, sb, st, sc, (__nv_bfloat16 *)dst, B, T, C);
     RCNN_LAUNCH_CHECK("cast3_bf16_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_cast_bf16_2d(const float *src, int64_t ld_src, void *dst, int64_t ld_dst, int64_t rows, int cols,
+                                 rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(rows >= 0 && cols >= 0 && ld_dst >= cols, "cast_bf16_2d: bad shape");
+    if (rows == 0 || ld_dst == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(src && dst, "cast_bf16_2d: null pointer");
+    const long long total = rows * ld_dst;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__nv_bfloat16 *)dst, ld_dst, rows, cols);
+    RCNN_LAUNCH_CHECK("cast_bf16_kernel");
     return RCNN_OK;
 }
 

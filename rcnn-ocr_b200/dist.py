@@ -1,0 +1,104 @@
+"""Data-parallel plumbing for the training step.
+
+The reference is single-process / single-device; the north_star shards the batch over 1/2/4/8
+B200 of one box, one process per GPU.  Every hot-path kernel is per-sequence independent, so the
+only exchange is the weight-gradient all-reduce: parameters are grouped into flat buckets in
+reverse registration order (the order backward produces them); a post-accumulate-grad hook copies
+each finished gradient into its bucket and, when a bucket is complete, launches an asynchronous
+all-reduce on the communication stream so it overlaps the rest of backward.  ``finish()`` waits
+for the outstanding collectives and averages.  Inference is batch-sharded with no collective.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced slice of ``n_items`` for ``rank`` (first ranks take the remainder)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradAllReducer:
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []          # (flat tensor, [(param, offset, numel)])
+        self._bucket_of = {}
+        self._pending = {}
+        self._works = []
+        self._handles = []
+        if self.world == 1 or not self.params:
+            return
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self._close(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close(cur)
+        self._avg = dist.get_backend(group) == "nccl"
+        self._stream = torch.cuda.Stream() if self.params[0].is_cuda else None
+        for p in self.params:
+            self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _close(self, plist):
+        total = sum(p.numel() for p in plist)
+        flat = torch.zeros(total, dtype=torch.float32, device=plist[0].device)
+        layout, off = [], 0
+        for p in plist:
+            layout.append((p, off, p.numel()))
+            self._bucket_of[p] = len(self.buckets)
+            off += p.numel()
+        self.buckets.append((flat, layout))
+
+    def _on_grad(self, p):
+        bi = self._bucket_of[p]
+        flat, layout = self.buckets[bi]
+        for q, off, n in layout:
+            if q is p:
+                view = flat[off:off + n].view_as(p)
+                view.copy_(p.grad)
+                p.grad = view          # the optimizer reads the reduced values in place
+                break
+        left = self._pending.get(bi, len(layout)) - 1
+        self._pending[bi] = left
+        if left == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        flat, _ = self.buckets[bi]
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
+        else:
+            self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
+
+    def finish(self):
+        """Call after backward(): waits for every bucket and leaves averaged gradients in p.grad."""
+        if self.world == 1:
+            return
+        for bi, (flat, layout) in enumerate(self.buckets):   # buckets whose params got no grad this step
+            if self._pending.get(bi, len(layout)) != 0 and any(p.grad is not None for p, _, _ in layout):
+                self._launch(bi)
+        for work, flat in self._works:
+            work.wait()
+            if not self._avg:
+                flat.div_(self.world)
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        self._works.clear()
+        self._pending.clear()
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles.clear()

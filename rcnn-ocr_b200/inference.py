@@ -1,0 +1,69 @@
+"""Inference surface mirroring inference.py:12-194 of the reference (``OCRInference.predict``)
+for the CTC path: batch loop -> model -> greedy CTC decode on the device -> strings.
+
+Image file / PIL preprocessing (cv2 + albumentations, inference.py:93-124) is host-side I/O
+outside the hot path; ``predict`` takes preprocessed tensors
+[3, img_h, img_w] in [-1, 1] (or an already batched [B, 3, H, W] tensor)."""
+from __future__ import annotations
+
+from typing import List, Union
+
+import torch
+
+from .charset import ctc_alphabet, load_charset
+from .decode import _to_host, ctc_greedy_ids
+from .model import RCNN
+
+
+class OCRInference:
+    def __init__(self, model_path=None, charset_path=None, device: str = "auto", img_h: int = 64,
+                 img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256):
+        if device == "auto":
+            device = "cuda"
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("rcnn-ocr_b200 has no CPU path; pass a CUDA device")
+        self.img_h, self.img_w = img_h, img_w
+        self.itos, self.stoi = load_charset(charset_path)
+        self.alphabet, self.num_ctc_classes, self.blank = ctc_alphabet(self.itos)
+        if model is None:
+            model = RCNN(num_classes=len(self.itos), hidden_size=hidden_size,
+                         sos_id=self.stoi.get("<SOS>", 1), eos_id=self.stoi.get("<EOS>", 2),
+                         pad_id=self.stoi.get("<PAD>", 0), blank_id=self.stoi.get("<BLANK>"))
+            if model_path is not None:
+                state = torch.load(model_path, map_location="cpu")
+                if isinstance(state, dict) and "model_state" in state:
+                    state = state["model_state"]
+                elif isinstance(state, dict) and "model_state_dict" in state:
+                    state = state["model_state_dict"]
+                if any(k.startswith("ctc_head.") for k in state):
+                    model.load_state_dict(state, strict=True)
+                else:
+                    model.load_reference_state_dict(state)
+        self.model = model.to(self.device).eval()
+
+    @torch.no_grad()
+    def predict(self, images: Union[torch.Tensor, List[torch.Tensor]], max_length: int = 25,
+                batch_size: int = 32, return_confidence: bool = False):
+        is_single = isinstance(images, torch.Tensor) and images.dim() == 3
+        if isinstance(images, torch.Tensor):
+            items = [images] if images.dim() == 3 else list(images)
+        else:
+            items = list(images)
+        for it in items:
+            if not isinstance(it, torch.Tensor):
+                raise TypeError("predict() takes preprocessed tensors; file/PIL preprocessing is outside "
+                                "the hot path (see module docstring)")
+        results = []
+        for i in range(0, len(items), batch_size):
+            chunk = torch.stack([t.float() for t in items[i:i + batch_size]])
+            if not chunk.is_cuda:
+                chunk = chunk.pin_memory().to(self.device, non_blocking=True)
+            logits = self.model(chunk, is_train=False, batch_max_length=max_length)
+            out = ctc_greedy_ids(logits, blank=self.blank, return_confidence=return_confidence)
+            ids_h, lens_h = _to_host(out[0], out[1])
+            conf_h = out[2].cpu().tolist() if return_confidence else None
+            for j in range(ids_h.shape[0]):
+                text = "".join(self.alphabet[k - 1] for k in ids_h[j, : lens_h[j]])
+                results.append((text, conf_h[j]) if return_confidence else text)
+        return results[0] if is_single else results

@@ -140,3 +140,164 @@ def make_enc_rnn(enc_dim: int, hidden_size: int) -> nn.Sequential:
     """RCNN.enc_rnn (model/model.py:195-198): two stacked blocks, state-dict keys '0.*', '1.*'."""
     return nn.Sequential(BidirectionalLSTM(enc_dim, hidden_size, hidden_size),
                          BidirectionalLSTM(hidden_size, hidden_size, hidden_size))
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), any N."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, save):
+        _lib.require_cuda(x, "x")
+        lead = x.shape[:-1]
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        xb = x2 if x2.dtype == torch.bfloat16 and x2.is_contiguous() else ops.cast_bf16_2d(x2)
+        wb = ops.cast_bf16_2d(weight.detach())
+        out = ops.gemm_bf16(xb, wb, bias.detach().float().contiguous() if bias is not None else None, torch.float32)
+        if save:
+            ctx.save_for_backward(xb, wb)
+            ctx.x_dtype = x.dtype
+            ctx.has_bias = bias is not None
+        return out.view(*lead, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, wb = ctx.saved_tensors
+        N, K = wb.shape
+        M = xb.shape[0]
+        dob = ops.cast_bf16_2d(dout.reshape(M, N))            # row pitch padded to 8 for odd N (C = 195)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt = ops.transpose_bf16(wb)                        # [K, N]
+            dx = ops.gemm_bf16(dob, wt, None, torch.float32).view(*dout.shape[:-1], K).to(ctx.x_dtype)
+        dw = ops.gemm_bf16(ops.transpose_bf16(dob), ops.transpose_bf16(xb), None, torch.float32)
+        db = ops.colsum_bf16(dob) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+class CTCHead(nn.Module):
+    """Linear(hidden -> num_ctc_classes) over enc[B,T,H] -> logits[B,T,C] (fp32).  Not present in
+    the reference (its live head is the attention decoder); the north_star adds it behind the
+    unchanged RCNN.forward signature."""
+
+    def __init__(self, hidden_size: int, num_ctc_classes: int):
+        super().__init__()
+        lin = nn.Linear(hidden_size, num_ctc_classes)
+        self.weight, self.bias = lin.weight, lin.bias
+
+    def forward(self, enc: torch.Tensor) -> torch.Tensor:
+        save = torch.is_grad_enabled() and (enc.requires_grad or self.weight.requires_grad)
+        return _LinearFn.apply(enc, self.weight, self.bias, save)
+
+
+# ---------------------------------------------------------------------------------------------
+# Backbone adapter.  The SE-ResNet31 conv stack is outside the hot path (SURVEY.md section 2 #5:
+# it stays on cuDNN through PyTorch); it is restated here only so that RCNN keeps the reference's
+# constructor, forward signature and state-dict keys (model/seresnet31.py:70-187).
+# ---------------------------------------------------------------------------------------------
+
+class _SEGate(nn.Module):
+    def __init__(self, ch: int, reduction: int):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(ch, ch // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(ch // reduction, ch, bias=False), nn.Sigmoid())
+
+    def forward(self, x):
+        return x * self.fc(x.mean(dim=(2, 3)))[:, :, None, None]
+
+
+class _SEResidual(nn.Module):
+    def __init__(self, cin, cout, stride, reduction, dropblock_p, dropblock_block_size):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.se = _SEGate(cout, reduction)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+        if dropblock_p > 0:
+            from torchvision.ops import DropBlock2d
+            self.dropblock = DropBlock2d(p=dropblock_p, block_size=dropblock_block_size)
+        else:
+            self.dropblock = nn.Identity()
+
+    def forward(self, x):
+        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        y = self.dropblock(self.se(y))
+        skip = x if self.downsample is None else self.downsample(x)
+        return self.relu(y + skip)
+
+
+class SEResNet31(nn.Module):
+    _STAGES = ((128, 256, 1, 2), (256, 256, 2, 1), (256, 512, 5, 2), (512, 512, 3, 1))  # cin, cout, blocks, stride
+
+    def __init__(self, in_channels=3, out_channels=512, reduction=16, dropblock_p=0.0, dropblock_block_size=5):
+        super().__init__()
+
+        def cbr(ci, co, k, s, p):
+            return [nn.Conv2d(ci, co, k, s, p, bias=False), nn.BatchNorm2d(co), nn.ReLU(True)]
+
+        self.conv0 = nn.Sequential(*cbr(in_channels, 64, 3, 1, 1), *cbr(64, 128, 3, 1, 1), nn.MaxPool2d(2, 2))
+        for idx, (ci, co, n, s) in enumerate(self._STAGES, 1):
+            blocks = [_SEResidual(ci if i == 0 else co, co, s if i == 0 else 1, reduction, dropblock_p,
+                                  dropblock_block_size) for i in range(n)]
+            setattr(self, f"layer{idx}", nn.Sequential(*blocks))
+        self.conv_out = nn.Sequential(*cbr(512, out_channels, 2, (2, 1), (0, 1)), *cbr(out_channels, out_channels, 2, 1, 0))
+        self.out_channels = out_channels
+
+    def forward(self, x):
+        x = self.conv0(x)
+        for idx in range(1, 5):
+            x = getattr(self, f"layer{idx}")(x)
+        return self.conv_out(x)
+
+
+class RCNN(nn.Module):
+    """Drop-in for model.model.RCNN (model/model.py:166-227) with a CTC head.
+
+    Same constructor and ``forward(x, text=None, is_train=True, batch_max_length=25)`` signature;
+    ``encode`` is the reference's (CNN -> mean over height -> [B,W',512] -> enc_rnn -> dropout,
+    model/model.py:215-221) with ``enc_rnn`` running on the sm_100a kernels.  ``forward`` returns
+    CTC logits [B, T, num_classes + 1] (class 0 = blank, class k = itos[k-1]); ``text`` and
+    ``batch_max_length`` belong to the reference's attention decoder and are accepted but unused.
+    """
+
+    def __init__(self, num_classes, hidden_size=256, sos_id: int = 1, eos_id: int = 2, pad_id: int = 0,
+                 blank_id=3, enc_dropout_p: float = 0.1, dropblock_p: float = 0.0, dropblock_block_size: int = 5):
+        super().__init__()
+        self.num_classes = num_classes
+        self.hidden_size = hidden_size
+        self.sos_id, self.eos_id, self.pad_id, self.blank_id = sos_id, eos_id, pad_id, blank_id
+        self.ctc_blank = 0
+        self.num_ctc_classes = num_classes + 1
+        self.cnn = SEResNet31(3, 512, dropblock_p=dropblock_p, dropblock_block_size=dropblock_block_size)
+        self.enc_rnn = make_enc_rnn(self.cnn.out_channels, hidden_size)
+        self.enc_dropout = nn.Dropout(enc_dropout_p)
+        self.ctc_head = CTCHead(hidden_size, self.num_ctc_classes)
+
+    def encode_features(self, feats: torch.Tensor) -> torch.Tensor:
+        """[B, T, 512] feature columns -> [B, T, H] (the hot path without the backbone)."""
+        return self.enc_dropout(self.enc_rnn(feats))
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        f = self.cnn(x).mean(dim=2)          # AdaptiveAvgPool2d((1, None)) + squeeze(2): [B, C, W']
+        return self.encode_features(f.permute(0, 2, 1))
+
+    def forward(self, x, text=None, is_train=True, batch_max_length=25):
+        return self.ctc_head(self.encode(x))
+
+    def load_reference_state_dict(self, state_dict, strict_encoder: bool = True):
+        """Load ``cnn.*`` and ``enc_rnn.*`` from a reference checkpoint; its attention decoder
+        (``attn.*``) has no counterpart here and the CTC head keeps its own weights."""
+        own = self.state_dict()
+        picked = {k: v for k, v in state_dict.items() if k.startswith(("cnn.", "enc_rnn."))}
+        if strict_encoder:
+            missing = [k for k in own if k.startswith(("cnn.", "enc_rnn.")) and k not in picked]
+            if missing:
+                raise KeyError(f"reference state dict lacks encoder keys: {missing[:5]}...")
+        own.update(picked)
+        self.load_state_dict(own, strict=True)
+        return [k for k in state_dict if k not in picked]

@@ -147,12 +147,30 @@ def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int
     return dG
 
 
+def cast_bf16_2d(x: torch.Tensor) -> torch.Tensor:
+    """float32 [R,C] (rows contiguous) -> bf16 [R,C] view whose row pitch is padded to a multiple of
+    8 elements (pad columns zero), ready to be a GEMM operand for any C."""
+    _lib.require_cuda(x, "x")
+    assert x.dim() == 2
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.shape[1] > 1 and x.stride(1) != 1:
+        x = x.contiguous()
+    R, C = x.shape
+    ldd = _pad8(C)
+    with torch.cuda.device(x.device):
+        out = torch.empty((R, ldd), dtype=torch.bfloat16, device=x.device)
+        rc = _lib.lib().rcnn_cast_bf16_2d(x.data_ptr(), x.stride(0), out.data_ptr(), ldd, R, C, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_cast_bf16_2d")
+    return out[:, :C]
+
+
 def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
-    """float32 column sums of a contiguous bf16 [rows, cols] matrix."""
-    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+    """float32 column sums of a bf16 [rows, cols] matrix (rows contiguous, any row pitch)."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and (x.stride(1) == 1 or x.shape[1] <= 1)
     with torch.cuda.device(x.device):
         out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
-        rc = _lib.lib().rcnn_colsum_bf16(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _lib.stream_ptr())
+        rc = _lib.lib().rcnn_colsum_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rcnn_colsum_bf16")
     return out
 
@@ -183,3 +201,8 @@ def lstm_unpack_grads(dwih_p, dwhh_p, db_p, I: int, H: int):
                                                *[o.data_ptr() for o in outs], _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_unpack_grads")
     return outs
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far in this process."""
+    return int(_lib.lib().rcnn_launch_count())
