@@ -200,6 +200,7 @@ class InferStep:
 
     @torch.no_grad()
     def e2e(self, feats):
+        feats = feats.to(self.t.params[0].device, non_blocking=True)   # pinned host -> device
         logits = self.t.head(self.t.enc(feats))
         return self.t.R.ctc_greedy_decoder(logits, self.alphabet, batch_first=True)
 

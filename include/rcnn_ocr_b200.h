@@ -116,6 +116,13 @@ int rcnn_ctc_scale_grad(float *grad, int T, int N, int C, int64_t gstride_t, int
 int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd,
                    int out_dtype, const float *bias, int M, int N, int K, rcnn_stream_t stream);
 
+/* Weight-gradient shape of K1:  D[M,N] (+)= A[K,M]^T * B[K,N], fp32 output.  A and B are row-major
+ * bf16 with the CONTRACTION index as the row (MN-major UMMA operands, no transposed copies);
+ * split-K with fp32 red.add.  accumulate == 0 zeroes D first.  Used for dW = dY^T X (autograd of
+ * nn.Linear / nn.LSTM weights in the reference, model/model.py:154-157). */
+int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
+                       int M, int N, int K, int accumulate, rcnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K2  BidirectionalLSTM recurrence (model/model.py:151-163: nn.LSTM(bidirectional=True,
  * batch_first=True), gate order i,f,g,o, h0 = c0 = 0, final state discarded).
@@ -153,15 +160,16 @@ int rcnn_lstm_forward(const float *xp, const void *whh_p, int B, int T, int H, v
  *   dG          bf16 [B, T, 2*4H] out: gradient w.r.t. the gate pre-activations (= w.r.t. xp),
  *               columns in P order.  dX = dG wih_p, dW_ih_p = dG^T X, dW_hh_p = dG^T H_prev,
  *               db_p = column sums of dG are then GEMMs / reductions (rcnn_gemm_bf16,
- *               rcnn_colsum_bf16, rcnn_lstm_hprev_t) and rcnn_lstm_unpack_grads scatters the
+ *               rcnn_gemm_bf16_atb, rcnn_colsum_bf16, rcnn_lstm_hprev) and rcnn_lstm_unpack_grads scatters the
  *               P-ordered results back to torch's parameter layout. */
 int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
                        int B, int T, int H, void *dG, rcnn_stream_t stream);
 /* out[col] = sum over rows of src[row*ld + col]  (bf16 [rows, cols] -> f32 [cols]) */
 int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float *out, rcnn_stream_t stream);
-/* out bf16 [2, H, ldo >= B*T]: out[dir][u][b*T+t] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at
- * the direction's first step: the h that multiplied W_hh when gates_t were formed, transposed. */
-int rcnn_lstm_hprev_t(const void *hcat, void *out, int64_t ldo, int B, int T, int H, rcnn_stream_t stream);
+/* out bf16 [B, T, 2H]: out[b, t, dir*H+u] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at the
+ * direction's first step: the h that multiplied W_hh when gates_t were formed (B operand of the
+ * dW_hh GEMM). */
+int rcnn_lstm_hprev(const void *hcat, void *out, int B, int T, int H, rcnn_stream_t stream);
 int rcnn_lstm_unpack_grads(const float *dwih_p, const float *dwhh_p, const float *db_p, int I, int H,
                            float *dw_ih_f, float *dw_hh_f, float *db_ih_f, float *db_hh_f,
                            float *dw_ih_r, float *dw_hh_r, float *db_ih_r, float *db_hh_r,
@@ -187,6 +195,9 @@ int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int
 #define RCNN_K_LSTM_FWD 3
 #define RCNN_K_LSTM_BWD 4
 #define RCNN_K_COUNT 8
+/* Debug aid: when buf != NULL the recurrent kernels record clock64() marks of cluster 0 / CTA 0 per
+ * timestep into buf[step*8 + k] (int64); NULL switches it off. */
+int rcnn_debug_timeline(void *buf);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long rcnn_launch_count(void);
 int rcnn_prof_enable(int on);

@@ -44,14 +44,18 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_cast_bf16_2d.restype = i
     L.rcnn_cast_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i, vp]
     L.rcnn_launch_count.restype = ctypes.c_ulonglong
-    L.rcnn_lstm_hprev_t.restype = i
-    L.rcnn_lstm_hprev_t.argtypes = [vp, vp, i64, i, i, i, vp]
+    L.rcnn_debug_timeline.restype = i
+    L.rcnn_debug_timeline.argtypes = [vp]
+    L.rcnn_lstm_hprev.restype = i
+    L.rcnn_lstm_hprev.argtypes = [vp, vp, i, i, i, vp]
     L.rcnn_lstm_unpack_grads.restype = i
     L.rcnn_lstm_unpack_grads.argtypes = [vp, vp, vp, i, i] + [vp] * 8 + [vp]
     L.rcnn_cast_bf16_3d.restype = i
     L.rcnn_cast_bf16_3d.argtypes = [vp, i64, i64, i64, vp, i, i, i, vp]
     L.rcnn_transpose_bf16.restype = i
     L.rcnn_transpose_bf16.argtypes = [vp, i64, vp, i64, i, i, vp]
+    L.rcnn_gemm_bf16_atb.restype = i
+    L.rcnn_gemm_bf16_atb.argtypes = [vp, i64, vp, i64, vp, i64, i, i, i, i, vp]
     L.rcnn_prof_enable.restype = i
     L.rcnn_prof_enable.argtypes = [i]
     L.rcnn_prof_reset.restype = i

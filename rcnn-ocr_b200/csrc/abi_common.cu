@@ -31,6 +31,8 @@ int num_sms() {
     return cached;
 }
 
+static long long *g_timeline = nullptr;
+long long *debug_timeline() { return g_timeline; }
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
@@ -56,6 +58,8 @@ void prof_end(int slot, cudaStream_t s) {
 }  // namespace rcnn
 
 extern "C" {
+
+int rcnn_debug_timeline(void *buf) { rcnn::g_timeline = (long long *)buf; return RCNN_OK; }
 
 unsigned long long rcnn_launch_count(void) { return rcnn::g_launches; }
 

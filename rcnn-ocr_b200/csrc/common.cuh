@@ -33,6 +33,8 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int num_sms();
+// optional per-step clock64 timeline of cluster 0 / CTA 0 of the recurrent kernels (debug aid)
+long long *debug_timeline();
 void count_launch();
 
 // Optional per-kernel event timing (see rcnn_prof_* in the header).
@@ -69,6 +71,16 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
+}
+// read-only 128-bit load that may allocate in L1 (neighbouring 16-byte pieces of a sector are re-used)
+__device__ __forceinline__ uint4 ld_ro_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ float ld_nc_f32(const float *p) {
     float r;

@@ -209,6 +209,122 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// ---- D[M,N] += A[K,M]^T * B[K,N]  (weight-gradient shape) -------------------------------------
+// Both operands are "MN-major": the contraction index k is the ROW of the row-major global
+// arrays, so no transposed copies are needed for dW = dY^T X.  A k-block of 64 rows is staged as
+// two TMA boxes per operand (64 k-rows x 64 contiguous M/N elements = 128-byte swizzled rows);
+// the UMMA descriptors use the MN-major canonical layout (LBO = distance between the two
+// 64-element halves, SBO = 8 k-rows) and idesc.a_major = idesc.b_major = 1.  Split-K over
+// blockIdx.z (K = T*B is 16384 while M*N gives only 32-128 tiles): fp32 partial tiles are
+// added with red.global.add.v4.f32 into a zero-initialised D.
+constexpr uint32_t kHalf = 64 * BK * 2;   // one 64-wide box: 64 k-rows x 128 B = 8 KB
+
+__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                float *__restrict__ D, long long ldd, int M, int N, int K, int kb_per_split) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tiles = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const int total_kb = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int num_kb = min(kb_per_split, total_kb - kb0);
+    if (num_kb <= 0) return;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<BN>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                unsigned char *st = tiles + s * kStageBytes;
+                const int k0 = (kb0 + kb) * BK;
+                tma_load_2d(st, &tmA, &full[s], tile_m * BM, k0);
+                tma_load_2d(st + kHalf, &tmA, &full[s], tile_m * BM + 64, k0);
+                tma_load_2d(st + kABytes, &tmB, &full[s], tile_n * BN, k0);
+                tma_load_2d(st + kABytes + kHalf, &tmB, &full[s], tile_n * BN + 64, k0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes), kHalf, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes + kABytes), kHalf, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)   // 16 k-rows = 2048 bytes further down each half
+                    umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = tile_m * BM + q * 32 + lane;
+        const bool vec_ok = (ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int col0 = tile_n * BN + c0;
+            if (row < M && col0 < N) {
+                float *dst = D + (long long)row * ldd + col0;
+                const int ncols = min(32, N - col0);
+                if (vec_ok && ncols == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) atomicAdd(dst + j, __uint_as_float(r[j]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
 template <typename OutT>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
                 int N, int K, cudaStream_t s) {
@@ -241,4 +357,36 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     cudaStream_t s = (cudaStream_t)stream;
     if (out_dtype == RCNN_F32) return launch_gemm<float>(ta, tb, D, ldd, bias, M, N, K, s);
     return launch_gemm<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
+}
+
+extern "C" int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
+                                  int M, int N, int K, int accumulate, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_atb: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(D && ldd >= N, "gemm_atb: bad output");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!accumulate) RCNN_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, s));
+    if (K == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(A && B, "gemm_atb: null pointer");
+    RCNN_CHECK_ARG(lda >= M && ldb >= N, "gemm_atb: leading dimension smaller than the row");
+    RCNN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0,
+                   "gemm_atb: A/B rows must be 16-byte aligned (lda=%lld ldb=%lld)", (long long)lda, (long long)ldb);
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, 64, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, 64, 1);
+    if (rc) return rc;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int total_kb = (K + BK - 1) / BK;
+    int splits = (2 * num_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
+    splits = splits < 1 ? 1 : (splits > total_kb ? total_kb : splits);
+    const int kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + kb_per_split - 1) / kb_per_split;
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    ProfScope prof(RCNN_K_GEMM, s);
+    gemm_atb_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split);
+    RCNN_LAUNCH_CHECK("gemm_atb_kernel");
+    return RCNN_OK;
 }

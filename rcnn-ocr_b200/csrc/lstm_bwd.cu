@@ -11,12 +11,13 @@
 // Same cluster decomposition as the forward kernel: CTA c owns hidden units [32c, 32c+32).
 // Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for H=512) and
 // the streamed operand is the full dG_{t'} tile [128 seq, 4H] (64-column chunks through a
-// 3-slot TMA ring), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
+// 6-slot TMA ring), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
 // threads (one per sequence) keep dc in registers for the whole sequence, read the saved gates
 // / cell states / upstream dh directly from global memory (prefetched one 8-unit chunk ahead)
 // and write dG_t in the packed column order, which is at once the next step's MMA operand and
 // the operand of the dX / dW GEMMs.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -28,7 +29,7 @@ using namespace sm100;
 constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
 constexpr int LU = 32;    // hidden units per CTA (UMMA N)
 constexpr int LK = 64;
-constexpr int kARing = 3;
+constexpr int kMaxRing = 6;
 constexpr uint32_t kATile = LB * LK * 2;   // 16 KB
 constexpr uint32_t kWTile = LU * LK * 2;   // 4 KB
 constexpr int kThreads = 192;
@@ -39,7 +40,9 @@ struct BwdParams {
     const float *csave;        // [2, T, B, H]
     const float *dhcat;        // [B, T, 2H] upstream gradient of the block's LSTM output
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
+    long long *tl;             // debug timeline or nullptr
 };
+#define TL_MARK(k) do { if (tl) tl[s * 8 + (k)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank_b() {
     uint32_t r;
@@ -70,15 +73,15 @@ __device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, cons
                                            const float *dhrow, int q, bool valid) {
     if (valid) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ci.g[j] = ld_nc_v4(grow + q * 32 + j * 8);
+        for (int j = 0; j < 4; ++j) ci.g[j] = ld_ro_v4(grow + q * 32 + j * 8);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const uint4 a = ld_nc_v4(crow + q * 8 + j * 4);
+            const uint4 a = ld_ro_v4(crow + q * 8 + j * 4);
             ci.c[j] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-            const uint4 d = ld_nc_v4(dhrow + q * 8 + j * 4);
+            const uint4 d = ld_ro_v4(dhrow + q * 8 + j * 4);
             ci.dh[j] = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z), __uint_as_float(d.w));
             if (cprow) {
-                const uint4 b = ld_nc_v4(cprow + q * 8 + j * 4);
+                const uint4 b = ld_ro_v4(cprow + q * 8 + j * 4);
                 ci.cp[j] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
             } else {
                 ci.cp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -96,6 +99,7 @@ __device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, cons
     }
 }
 
+template <int kARing, bool MCAST>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -115,11 +119,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int cid = (int)cluster_id_x_b();
     const int dir = cid & 1, tile = cid >> 1;
     const int b0 = tile * LB;
+    long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
+    const int csize = H / 32;
+    const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], MCAST ? csize : 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
@@ -130,6 +137,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (MCAST) cluster_sync_b();   // every CTA's barriers exist before any remote arrive / multicast lands
 
     // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
     // reverse direction from t = 0 up to T-1.
@@ -145,13 +153,23 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (lane == 0 && s > 0) {
                 const int t = dir ? s : T - 1 - s;
                 const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
-                fence_proxy_async_all();
-                for (int kc = 0; kc < nkc; ++kc, ++an) {
+                TL_MARK(0);
+                fence_proxy_async_global();
+                for (int i = 0; i < nkc; ++i, ++an) {
+                    const int kc = i;
                     const int slot = an % kARing;
+                    // MCAST: a_empty counts the commits of ALL CTAs of the cluster, so a completed
+                    // phase means the slot is free everywhere; chunk i is fetched once, by CTA i % csize,
+                    // and multicast to the whole cluster (every CTA arms its own full barrier).
                     mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
                     mbar_arrive_expect_tx(&a_full[slot], kATile);
-                    tma_load_3d(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0);
+                    if (!MCAST)
+                        tma_load_3d(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0);
+                    else if ((i % csize) == c)
+                        tma_load_3d_mcast(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0,
+                                          all_mask);
                 }
+                TL_MARK(1);
             }
             __syncwarp();
             cluster_sync_b();
@@ -163,18 +181,22 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         __syncwarp();
         for (int s = 0; s < T; ++s) {
             if (lane == 0 && s > 0) {
-                for (int kc = 0; kc < nkc; ++kc, ++am) {
+                for (int i = 0; i < nkc; ++i, ++am) {
+                    const int kc = i;
                     const int slot = am % kARing;
                     mbar_wait(&a_full[slot], (am / kARing) & 1);
+                    if (i == 0) TL_MARK(2);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kATile), 16, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
 #pragma unroll
                     for (int k = 0; k < LK / 16; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
-                    umma_commit(&a_empty[slot]);
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) != 0);
+                    if (MCAST) umma_commit_mcast(&a_empty[slot], all_mask);
+                    else umma_commit(&a_empty[slot]);
                 }
                 umma_commit(tmem_full);
+                TL_MARK(3);
             }
             __syncwarp();
             cluster_sync_b();
@@ -199,9 +221,18 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
             ChunkIn cur, nxt;
             load_chunk(cur, grow, crow, cprow, dhrow, 0, valid);
+            if (valid && s + 1 < T) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
+                const int tn = dir ? t + 1 : t - 1;
+                const size_t rn = ((size_t)dir * T + tn) * B + b;
+                prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128);
+                prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128 + 64);
+                prefetch_l2(p.csave + rn * H + 32 * c);
+                prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * c);
+            }
             uint32_t acc[32];
             if (s > 0) {
                 mbar_wait(tmem_full, (s - 1) & 1);
+                if (threadIdx.x == 64) TL_MARK(4);
                 tc_fence_after();
                 tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16), acc);
                 tmem_ld_wait();
@@ -247,11 +278,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 if (q < 3) cur = nxt;
             }
+            if (threadIdx.x == 64) TL_MARK(5);
             tc_fence_before();
-            fence_proxy_async_all();   // dG_t stores before the other CTAs' TMA reads
+            fence_proxy_async_global();   // dG_t stores before the other CTAs' TMA reads
             cluster_sync_b();
+            if (threadIdx.x == 64) TL_MARK(6);
         }
     }
+    if (MCAST) cluster_sync_b();   // no CTA leaves while peers may still signal its barriers
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -259,7 +293,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
 }
 
-size_t bwd_smem_bytes(int H) { return 1024 + (size_t)(4 * H / LK) * kWTile + kARing * kATile + 256; }
+size_t bwd_smem_bytes(int H, int ring) { return 1024 + (size_t)(4 * H / LK) * kWTile + (size_t)ring * kATile + 256; }
 
 // column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
 __global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, long long rows, int cols,
@@ -282,36 +316,22 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long l
     }
 }
 
-// hprev^T for the dW_hh GEMM: out[dir][u][b*T + t] = hcat[b, t -/+ 1, dir*H + u] (0 at the first
-// step of that direction), i.e. the h that multiplied W_hh when gates_t were formed.
-__global__ void hprev_transpose_kernel(const __nv_bfloat16 *__restrict__ hcat, __nv_bfloat16 *__restrict__ out,
-                                       long long ldo, int B, int T, int H) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int dir = blockIdx.z;
-    const long long BT = (long long)B * T;
-    const long long r0 = (long long)blockIdx.y * 64;   // rows of (b,t)
-    const int u0 = blockIdx.x * 64;
-    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-        const long long r = r0 + i;
-        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
-            const int u = u0 + j;
-            __nv_bfloat16 v = __float2bfloat16(0.f);
-            if (r < BT && u < H) {
-                const long long b = r / T;
-                const int t = (int)(r - b * T);
-                const int tp = dir ? t + 1 : t - 1;
-                if (tp >= 0 && tp < T) v = hcat[(b * T + tp) * 2 * H + (long long)dir * H + u];
-            }
-            tile[i][j] = v;
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-        const int u = u0 + i;
-        for (int j = threadIdx.x; j < 64; j += blockDim.x) {
-            const long long r = r0 + j;
-            if (r < BT && u < H) out[((long long)dir * H + u) * ldo + r] = tile[j][i];
-        }
+// hprev for the dW_hh GEMM: out[b, t, dir*H + u] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H + u], zero at
+// the first step of that direction: the h that multiplied W_hh when gates_t were formed.
+__global__ void hprev_shift_kernel(const uint4 *__restrict__ hcat, uint4 *__restrict__ out, int B, int T, int H) {
+    const int vec_per_row = 2 * H / 8;           // uint4 = 8 bf16
+    const int vec_per_dir = H / 8;
+    const long long total = (long long)B * T * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec_per_row);
+        const long long bt = i / vec_per_row;
+        const int t = (int)(bt % T);
+        const int dir = v / vec_per_dir;
+        const int tp = dir ? t + 1 : t - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (tp >= 0 && tp < T) val = hcat[(bt + (tp - t)) * vec_per_row + v];
+        out[i] = val;
     }
 }
 
@@ -359,12 +379,17 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.csave = c_save;
     p.dhcat = dhcat;
     p.dG = (__nv_bfloat16 *)dG;
+    p.tl = debug_timeline();
     const int csize = H / 32;
     const int ntiles = (B + LB - 1) / LB;
-    const size_t smem = bwd_smem_bytes(H);
+    static const int ring = getenv("RCNN_BWD_RING") ? atoi(getenv("RCNN_BWD_RING")) : 3;
+    static const bool stagger = getenv("RCNN_MCAST") ? atoi(getenv("RCNN_MCAST")) != 0 : true;
+    const size_t smem = bwd_smem_bytes(H, ring == 6 ? 6 : 3);
     cudaStream_t s = (cudaStream_t)stream;
-    RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (csize > 8) RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    auto kern = ring == 6 ? (stagger ? lstm_bwd_kernel<6, true> : lstm_bwd_kernel<6, false>)
+                          : (stagger ? lstm_bwd_kernel<3, true> : lstm_bwd_kernel<3, false>);
+    RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(csize * ntiles * 2));
     cfg.blockDim = dim3(kThreads);
@@ -378,7 +403,7 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_BWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, tg, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, tg, p));
     count_launch();
     return RCNN_OK;
 }
@@ -398,16 +423,15 @@ extern "C" int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int c
     return RCNN_OK;
 }
 
-extern "C" int rcnn_lstm_hprev_t(const void *hcat, void *out, int64_t ldo, int B, int T, int H, rcnn_stream_t stream) {
+extern "C" int rcnn_lstm_hprev(const void *hcat, void *out, int B, int T, int H, rcnn_stream_t stream) {
     using namespace rcnn;
-    RCNN_CHECK_ARG(B >= 0 && T >= 0 && H > 0, "hprev_t: bad shape");
+    RCNN_CHECK_ARG(B >= 0 && T >= 0 && H > 0 && H % 8 == 0, "hprev: bad shape");
     if (B == 0 || T == 0) return RCNN_OK;
-    RCNN_CHECK_ARG(hcat && out && ldo >= (int64_t)B * T, "hprev_t: null pointer or ldo < B*T");
-    const long long BT = (long long)B * T;
-    dim3 block(32, 8), grid((H + 63) / 64, (unsigned)((BT + 63) / 64), 2);
-    RCNN_CHECK_ARG(grid.y <= 65535, "hprev_t: B*T too large");
-    hprev_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)hcat, (__nv_bfloat16 *)out, ldo, B, T, H);
-    RCNN_LAUNCH_CHECK("hprev_transpose_kernel");
+    RCNN_CHECK_ARG(hcat && out, "hprev: null pointer");
+    const long long total = (long long)B * T * (2 * H / 8);
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    hprev_shift_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)hcat, (uint4 *)out, B, T, H);
+    RCNN_LAUNCH_CHECK("hprev_shift_kernel");
     return RCNN_OK;
 }
 

@@ -118,7 +118,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const int t = dir ? T - 1 - s : s;
                 if (s > 0) {
                     const int tprev = dir ? t + 1 : t - 1;
-                    fence_proxy_async_all();  // h_{t-1} was written through the generic proxy
+                    fence_proxy_async_global();  // h_{t-1} was written through the generic proxy
                     for (int kc = 0; kc < nkc; ++kc, ++an) {
                         const int slot = an % kARing;
                         mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
@@ -250,7 +250,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
             }
             tc_fence_before();
-            fence_proxy_async_all();  // order the h_t stores before the other CTAs' TMA reads
+            fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
             cluster_sync_all();
         }
     }

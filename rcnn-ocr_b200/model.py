@@ -64,26 +64,22 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         dob = ops.cast_bf16_3d(dout)                                   # [B,T,O] bf16
         dob2 = dob.view(BT, O)
         # ---- linear: dhcat = dout W, dW = dout^T hcat, db = colsum(dout) --------------------
-        lin_wt = ops.transpose_bf16(lin_wb)                            # [2H, O]
+        lin_wt = ops.transpose_bf16(lin_wb)                            # [2H, O] (weights only: small)
         dhcat = ops.gemm_bf16(dob2, lin_wt, None, torch.float32).view(B, T, 2 * H)
-        dob_t = ops.transpose_bf16(dob2)                               # [O, BT]
-        hcat_t = ops.transpose_bf16(hcat.view(BT, 2 * H))              # [2H, BT]
-        d_lin_w = ops.gemm_bf16(dob_t, hcat_t, None, torch.float32)    # [O, 2H]
+        d_lin_w = ops.gemm_bf16_atb(dob2, hcat.view(BT, 2 * H))        # [O, 2H] = dout^T hcat
         d_lin_b = ops.colsum_bf16(dob2)
-        del dob_t, hcat_t
         # ---- recurrence ---------------------------------------------------------------------
         dG = ops.lstm_backward(packed, gates, csave, dhcat, B, T)      # [B,T,8H] bf16
         dG2 = dG.view(BT, 8 * H)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm_bf16(dG2, packed.wih_pt, None, torch.float32).view(B, T, I).to(ctx.x_dtype)
-        dG_t = ops.transpose_bf16(dG2)                                 # [8H, BT]
-        xb_t = ops.transpose_bf16(xb.view(BT, I))                      # [I, BT]
-        dwih_p = ops.gemm_bf16(dG_t, xb_t, None, torch.float32)        # [8H, I]
-        hprev_t = ops.lstm_hprev_t(hcat)                               # [2, H, BT]
+        dwih_p = ops.gemm_bf16_atb(dG2, xb.view(BT, I))                # [8H, I] = dG^T x
+        hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
         dwhh_p = torch.empty((8 * H, H), dtype=torch.float32, device=dG.device)
-        for d in range(2):
-            ops.gemm_bf16(dG_t[d * 4 * H:(d + 1) * 4 * H], hprev_t[d], None, out=dwhh_p[d * 4 * H:(d + 1) * 4 * H])
+        for d in range(2):                                             # [4H, H] = dG_d^T h_prev_d
+            ops.gemm_bf16_atb(dG2[:, d * 4 * H:(d + 1) * 4 * H], hprev[:, d * H:(d + 1) * H],
+                              out=dwhh_p[d * 4 * H:(d + 1) * 4 * H])
         db_p = ops.colsum_bf16(dG2)
         g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
         return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None)
@@ -170,7 +166,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = ops.transpose_bf16(wb)                        # [K, N]
             dx = ops.gemm_bf16(dob, wt, None, torch.float32).view(*dout.shape[:-1], K).to(ctx.x_dtype)
-        dw = ops.gemm_bf16(ops.transpose_bf16(dob), ops.transpose_bf16(xb), None, torch.float32)
+        dw = ops.gemm_bf16_atb(dob, xb)                         # [N, K] = dout^T x
         db = ops.colsum_bf16(dob) if ctx.has_bias else None
         return dx, dw, db, None
 

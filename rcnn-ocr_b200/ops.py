@@ -44,6 +44,30 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None
     return out
 
 
+def gemm_bf16_atb(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None,
+                  accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= a[K,M]^T @ b[K,N] in fp32 (weight-gradient shape of kernel K1; the contraction
+    index is the row of both row-major bf16 operands, so nothing is transposed)."""
+    _lib.require_cuda(a, "a")
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.shape[0] == b.shape[0], (a.shape, b.shape)
+    if a.stride(1) != 1 or a.stride(0) % 8 or a.data_ptr() % 16:
+        a = _repitch(a)
+    if b.stride(1) != 1 or b.stride(0) % 8 or b.data_ptr() % 16:
+        b = _repitch(b)
+    K, M = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        accumulate = False
+    assert out.shape == (M, N) and out.dtype == torch.float32 and out.stride(1) == 1
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().rcnn_gemm_bf16_atb(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                           out.stride(0), M, N, K, int(accumulate), _lib.stream_ptr())
+        _lib.check(rc, "rcnn_gemm_bf16_atb")
+    return out
+
+
 class PackedLSTMWeights:
     """bf16 views of one block's nn.LSTM parameters in the kernels' layouts (see
     rcnn_lstm_pack_weights in include/rcnn_ocr_b200.h)."""
@@ -175,15 +199,15 @@ def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def lstm_hprev_t(hcat: torch.Tensor) -> torch.Tensor:
-    """[B,T,2H] bf16 -> [2, H, B*T]: previous-step h of each direction, transposed."""
+def lstm_hprev(hcat: torch.Tensor) -> torch.Tensor:
+    """[B,T,2H] bf16 -> [B,T,2H]: each direction's previous-step h (zero at its first step)."""
     B, T, H2 = hcat.shape
-    ldo = _pad8(B * T)
+    assert hcat.is_contiguous() and hcat.dtype == torch.bfloat16
     with torch.cuda.device(hcat.device):
-        out = torch.empty((2, H2 // 2, ldo), dtype=torch.bfloat16, device=hcat.device)
-        rc = _lib.lib().rcnn_lstm_hprev_t(hcat.data_ptr(), out.data_ptr(), ldo, B, T, H2 // 2, _lib.stream_ptr())
-        _lib.check(rc, "rcnn_lstm_hprev_t")
-    return out[:, :, :B * T]
+        out = torch.empty_like(hcat)
+        rc = _lib.lib().rcnn_lstm_hprev(hcat.data_ptr(), out.data_ptr(), B, T, H2 // 2, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_hprev")
+    return out
 
 
 def lstm_unpack_grads(dwih_p, dwhh_p, db_p, I: int, H: int):

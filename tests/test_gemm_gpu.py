@@ -50,3 +50,27 @@ def test_gemm_exact_small_integers():
     b = torch.randint(-4, 5, (256, 320), device="cuda", generator=g).bfloat16()
     got = ops.gemm_bf16(a, b)
     assert torch.equal(got, _ref(a, b, None))
+
+
+@pytest.mark.parametrize("K,M,N", [(64, 128, 128), (128, 128, 128), (256, 64, 64), (16384, 4096, 512), (16384, 512, 1024),
+                                   (16384, 195, 512), (1000, 200, 72), (99, 130, 40), (4096, 2048, 512)])
+def test_gemm_atb_matches_fp32(K, M, N):
+    """Weight-gradient shape D = A^T B with MN-major operands and split-K."""
+    g = torch.Generator(device="cuda").manual_seed(K + M + N)
+    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()
+    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    got = ops.gemm_bf16_atb(a, b)
+    want = a.float().t() @ b.float()
+    scale = float(want.abs().max())
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-4 * scale)
+    got2 = ops.gemm_bf16_atb(a, b, out=got.clone(), accumulate=True)
+    torch.testing.assert_close(got2, 2 * want, rtol=1e-4, atol=4e-4 * scale)
+
+
+def test_gemm_atb_exact_small_integers_and_strided():
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a_big = torch.randint(-3, 4, (320, 512), device="cuda", generator=g).bfloat16()
+    b = torch.randint(-3, 4, (320, 192), device="cuda", generator=g).bfloat16()
+    a = a_big[:, 128:384]                                     # column slice: lda = 512, M = 256
+    got = ops.gemm_bf16_atb(a, b)
+    assert torch.equal(got, a.float().t() @ b.float())

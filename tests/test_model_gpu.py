@@ -1,0 +1,90 @@
+"""GPU checks of the drop-in surface above the kernels: CTC head, RCNN (reference constructor /
+forward signature / state-dict keys), the fused train step and the inference API."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import rcnn_ocr_b200 as R
+from oracle import lstm_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ctc_head_matches_fp64_linear_with_odd_class_count():
+    torch.manual_seed(0)
+    head = R.CTCHead(64, 195).cuda()
+    x = torch.randn(7, 9, 64, device="cuda", requires_grad=True)
+    w = torch.randn(7, 9, 195, device="cuda")
+    y = head(x)
+    (y * w).sum().backward()
+    xd = x.detach().double().cpu().requires_grad_(True)
+    Wd = head.weight.detach().double().cpu().requires_grad_(True)
+    bd = head.bias.detach().double().cpu().requires_grad_(True)
+    yd = xd @ Wd.t() + bd
+    (yd * w.double().cpu()).sum().backward()
+    assert (y.detach().cpu().double() - yd.detach()).abs().max() < 1e-2
+    for got, ref in ((x.grad, xd.grad), (head.weight.grad, Wd.grad), (head.bias.grad, bd.grad)):
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= 2e-2 * ref.abs().max().item() + 1e-6
+
+
+def test_rcnn_signature_and_forward():
+    torch.manual_seed(0)
+    m = R.RCNN(num_classes=194, hidden_size=256).cuda().eval()
+    x = torch.rand(4, 3, 32, 128, device="cuda") * 2 - 1
+    with torch.no_grad():
+        logits = m(x, text=None, is_train=False, batch_max_length=25)
+        enc = m.encode(x)
+    assert logits.shape == (4, 16, 195) and enc.shape == (4, 16, 256)       # T = img_w / 8
+    # encoder part against the float64 oracle fed with the same CNN features
+    with torch.no_grad():
+        f = m.cnn(x).mean(dim=2).permute(0, 2, 1)
+    params = {k: v.detach().double().cpu() for k, v in m.enc_rnn.state_dict().items()}
+    want = lstm_ref.enc_rnn(f.double().cpu(), params)
+    assert (enc.cpu().double() - want).abs().max().item() < 1e-2
+    texts, seqs = R.ctc_greedy_decoder(logits, [chr(0x430 + i % 60) for i in range(194)], batch_first=True)
+    assert len(texts) == 4 and all(len(s) <= 16 for s in seqs)
+
+
+def test_fused_train_step_loss_matches_oracle_and_decreases():
+    """enc_rnn -> head -> fused CTC; the loss equals the oracle's CTC on the kernel's own logits
+    (1e-4) and a few Adam steps on one batch reduce it."""
+    torch.manual_seed(0)
+    enc = R.make_enc_rnn(128, 64).cuda()
+    head = R.CTCHead(64, 40).cuda()
+    opt = torch.optim.Adam(list(enc.parameters()) + list(head.parameters()), lr=3e-3)
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(24, 20, 128, generator=g).cuda()
+    tl = torch.randint(1, 6, (24,), generator=g)
+    tg = torch.randint(1, 40, (24, 5), generator=g)
+    il = torch.full((24,), 20)
+    hist = []
+    for it in range(12):
+        opt.zero_grad(set_to_none=True)
+        logits = head(enc(feats))
+        loss = R.ctc_loss_from_logits(logits.permute(1, 0, 2), tg.cuda(), il, tl, 0, "mean", True)
+        if it == 0:
+            want, _ = oracle.ctc_loss(logits.detach().permute(1, 0, 2).cpu().numpy().astype(np.float64),
+                                      tg.numpy(), il.numpy(), tl.numpy(), 0, "mean", True, want_grad=False)
+            np.testing.assert_allclose(loss.item(), want, rtol=1e-4)
+        loss.backward()
+        opt.step()
+        hist.append(loss.item())
+    assert hist[-1] < 0.8 * hist[0], hist
+
+
+def test_inference_api_shapes(tmp_path):
+    cs = tmp_path / "charset.txt"
+    cs.write_text("<PAD>\n<SOS>\n<EOS>\n \n" + "\n".join("abcdefghij") + "\n", encoding="utf-8")
+    torch.manual_seed(0)
+    model = R.RCNN(num_classes=14, hidden_size=64)
+    ocr = R.OCRInference(charset_path=str(cs), model=model, img_h=32, img_w=64)
+    imgs = [torch.rand(3, 32, 64) * 2 - 1 for _ in range(5)]
+    out = ocr.predict(imgs, batch_size=2)
+    assert isinstance(out, list) and len(out) == 5 and all(isinstance(s, str) for s in out)
+    one = ocr.predict(imgs[0], return_confidence=True)
+    assert isinstance(one, tuple) and isinstance(one[0], str) and 0.0 <= one[1] <= 1.0
+    assert one[0] == out[0]
+    with pytest.raises(TypeError):
+        ocr.predict(["/not/a/tensor.png"])
