@@ -79,6 +79,19 @@ __device__ __forceinline__ uint4 ld_ro_v4(const void *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// 256-bit (one full 32-byte sector per lane) global accesses, sm_100+
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ void st_v8(void *p, const U8 &a) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]),
+                 "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]) : "memory");
+}
+__device__ __forceinline__ U8 ld_ro_v8(const void *p) {
+    U8 a;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.v[0]), "=r"(a.v[1]), "=r"(a.v[2]), "=r"(a.v[3]), "=r"(a.v[4]), "=r"(a.v[5]), "=r"(a.v[6]), "=r"(a.v[7])
+                 : "l"(p));
+    return a;
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

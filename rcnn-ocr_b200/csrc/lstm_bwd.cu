@@ -32,7 +32,7 @@ constexpr int LK = 64;
 constexpr int kMaxRing = 6;
 constexpr uint32_t kATile = LB * LK * 2;   // 16 KB
 constexpr uint32_t kWTile = LU * LK * 2;   // 4 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct BwdParams {
     int B, T, H;
@@ -65,37 +65,23 @@ __device__ __forceinline__ float tanh_fast_b(float x) {
 }
 
 struct ChunkIn {     // saved state of 8 units of one sequence at one step
-    uint4 g[4];      // 32 halves: (i,f,g,o) x 8 units
-    float4 c[2], cp[2], dh[2];
+    U8 g[2];         // 32 halves: (i,f,g,o) x 8 units
+    U8 c, cp, dh;    // 8 floats each
 };
 
 __device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, const float *crow, const float *cprow,
                                            const float *dhrow, int q, bool valid) {
+    U8 z;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z.v[k] = 0u;
     if (valid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ci.g[j] = ld_ro_v4(grow + q * 32 + j * 8);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const uint4 a = ld_ro_v4(crow + q * 8 + j * 4);
-            ci.c[j] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-            const uint4 d = ld_ro_v4(dhrow + q * 8 + j * 4);
-            ci.dh[j] = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z), __uint_as_float(d.w));
-            if (cprow) {
-                const uint4 b = ld_ro_v4(cprow + q * 8 + j * 4);
-                ci.cp[j] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
-            } else {
-                ci.cp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+        ci.g[0] = ld_ro_v8(grow + q * 32);
+        ci.g[1] = ld_ro_v8(grow + q * 32 + 16);
+        ci.c = ld_ro_v8(crow + q * 8);
+        ci.dh = ld_ro_v8(dhrow + q * 8);
+        ci.cp = cprow ? ld_ro_v8(cprow + q * 8) : z;
     } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ci.g[j] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            ci.c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ci.cp[j] = ci.c[j];
-            ci.dh[j] = ci.c[j];
-        }
+        ci.g[0] = z; ci.g[1] = z; ci.c = z; ci.cp = z; ci.dh = z;
     }
 }
 
@@ -202,13 +188,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             cluster_sync_b();
         }
     } else {
-        const int qd = warp & 3;
+        const int qd = warp & 3;            // TMEM lane quadrant
+        const int hf = (warp - 2) >> 2;     // half of the CTA's units handled by this warp (16 units)
         const int row = qd * 32 + lane;
         const int b = b0 + row;
         const bool valid = b < B;
-        float dc[32];
+        float dc[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dc[i] = 0.f;
+        for (int i = 0; i < 16; ++i) dc[i] = 0.f;
         for (int s = 0; s < T; ++s) {
             const int t = dir ? s : T - 1 - s;
             const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
@@ -220,8 +207,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128;
 
             ChunkIn cur, nxt;
-            load_chunk(cur, grow, crow, cprow, dhrow, 0, valid);
-            if (valid && s + 1 < T) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
+            load_chunk(cur, grow, crow, cprow, dhrow, hf * 2, valid);
+            load_chunk(nxt, grow, crow, cprow, dhrow, hf * 2 + 1, valid);
+            if (valid && s + 1 < T && hf == 0) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
                 const int tn = dir ? t + 1 : t - 1;
                 const size_t rn = ((size_t)dir * T + tn) * B + b;
                 prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128);
@@ -229,35 +217,40 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 prefetch_l2(p.csave + rn * H + 32 * c);
                 prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * c);
             }
-            uint32_t acc[32];
+            uint32_t acc[16];
             if (s > 0) {
                 mbar_wait(tmem_full, (s - 1) & 1);
                 if (threadIdx.x == 64) TL_MARK(4);
                 tc_fence_after();
-                tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16), acc);
+                tmem_ld_32x16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 16), acc);
                 tmem_ld_wait();
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = 0u;
+                for (int i = 0; i < 16; ++i) acc[i] = 0u;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q < 3) load_chunk(nxt, grow, crow, cprow, dhrow, q + 1, valid);
-                const __half2 *gh = reinterpret_cast<const __half2 *>(cur.g);
-                const float cc[8] = {cur.c[0].x, cur.c[0].y, cur.c[0].z, cur.c[0].w, cur.c[1].x, cur.c[1].y, cur.c[1].z, cur.c[1].w};
-                const float cp[8] = {cur.cp[0].x, cur.cp[0].y, cur.cp[0].z, cur.cp[0].w, cur.cp[1].x, cur.cp[1].y, cur.cp[1].z, cur.cp[1].w};
-                const float dhu[8] = {cur.dh[0].x, cur.dh[0].y, cur.dh[0].z, cur.dh[0].w, cur.dh[1].x, cur.dh[1].y, cur.dh[1].z, cur.dh[1].w};
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = hf * 2 + qq;
+                const ChunkIn &ci = qq ? nxt : cur;
+                const __half2 *gh = reinterpret_cast<const __half2 *>(ci.g);
+                float cc[8], cp[8], dhu[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    cc[k] = __uint_as_float(ci.c.v[k]);
+                    cp[k] = __uint_as_float(ci.cp.v[k]);
+                    dhu[k] = __uint_as_float(ci.dh.v[k]);
+                }
                 float o32[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 if_ = __half22float2(gh[2 * j]);       // (i, f)
                     const float2 go_ = __half22float2(gh[2 * j + 1]);   // (g, o)
                     const float ig = if_.x, fg = if_.y, gg = go_.x, og = go_.y;
-                    const float dh = dhu[j] + __uint_as_float(acc[q * 8 + j]);
+                    const float dh = dhu[j] + __uint_as_float(acc[qq * 8 + j]);
                     const float tc = tanh_fast_b(cc[j]);
                     const float d_o = dh * tc;
-                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[q * 8 + j]);
-                    dc[q * 8 + j] = dct * fg;
+                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[qq * 8 + j]);
+                    dc[qq * 8 + j] = dct * fg;
                     o32[4 * j] = dct * gg * ig * (1.f - ig);
                     o32[4 * j + 1] = dct * cp[j] * fg * (1.f - fg);
                     o32[4 * j + 2] = dct * ig * (1.f - gg * gg);
@@ -265,18 +258,16 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 v;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(o32[8 * j], o32[8 * j + 1]);
-                        __nv_bfloat162 h1 = __floats2bfloat162_rn(o32[8 * j + 2], o32[8 * j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o32[8 * j + 4], o32[8 * j + 5]);
-                        __nv_bfloat162 h3 = __floats2bfloat162_rn(o32[8 * j + 6], o32[8 * j + 7]);
-                        v.x = *reinterpret_cast<uint32_t *>(&h0); v.y = *reinterpret_cast<uint32_t *>(&h1);
-                        v.z = *reinterpret_cast<uint32_t *>(&h2); v.w = *reinterpret_cast<uint32_t *>(&h3);
-                        *reinterpret_cast<uint4 *>(dgrow + q * 32 + j * 8) = v;
+                    for (int j = 0; j < 2; ++j) {
+                        U8 v;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o32[16 * j + 2 * k], o32[16 * j + 2 * k + 1]);
+                            v.v[k] = *reinterpret_cast<uint32_t *>(&h2);
+                        }
+                        st_v8(dgrow + q * 32 + j * 16, v);
                     }
                 }
-                if (q < 3) cur = nxt;
             }
             if (threadIdx.x == 64) TL_MARK(5);
             tc_fence_before();
@@ -383,7 +374,7 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     const int csize = H / 32;
     const int ntiles = (B + LB - 1) / LB;
     static const int ring = getenv("RCNN_BWD_RING") ? atoi(getenv("RCNN_BWD_RING")) : 3;
-    static const bool stagger = getenv("RCNN_MCAST") ? atoi(getenv("RCNN_MCAST")) != 0 : true;
+    static const bool stagger = getenv("RCNN_MCAST") ? atoi(getenv("RCNN_MCAST")) != 0 : false;
     const size_t smem = bwd_smem_bytes(H, ring == 6 ? 6 : 3);
     cudaStream_t s = (cudaStream_t)stream;
     auto kern = ring == 6 ? (stagger ? lstm_bwd_kernel<6, true> : lstm_bwd_kernel<6, false>)

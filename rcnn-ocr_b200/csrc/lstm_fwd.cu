@@ -13,7 +13,8 @@
 //   warp 0  (TMA)      streams h_{t-1}[128 seq, H] (bf16, straight out of the block's output
 //                      tensor, 64-column chunks, 3-slot ring) and prefetches the next xp tiles;
 //   warp 1  (MMA)      tcgen05.mma  D[128 seq, 128 gate cols] += h_chunk * W_chunk^T, fp32 in TMEM;
-//   warps 2-5 (cell)   tcgen05.ld the accumulator row of "their" sequence, add xp, sigmoid/tanh,
+//   warps 2-9 (cell)   two warps per TMEM lane quadrant; a thread owns one sequence and 16 of the
+//                      CTA's 32 units: tcgen05.ld its accumulator columns, add xp, sigmoid/tanh,
 //                      update c (fp32, in registers for the whole sequence), write h_t (bf16) and,
 //                      for training, the activated gates (fp16) and c_t (fp32);
 //   all               barrier.cluster (release/acquire): h_t of every unit slice is visible to
@@ -33,14 +34,16 @@ constexpr int LN = 128;   // gate columns per CTA: 32 units x 4 gates (UMMA N)
 constexpr int LK = 64;    // K chunk (one 128-byte swizzle row of bf16)
 constexpr int kARing = 3, kXRing = 3;
 constexpr uint32_t kTile = 16384;  // every staged tile is 16 KB: 128x64 bf16 or 128x32 fp32
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct FwdParams {
     int B, T, H;
     __nv_bfloat16 *hcat;  // [B, T, 2H]
     __half *gates;        // [2, T, B, 4H] packed column order, activated (training only)
     float *csave;         // [2, T, B, H]  (training only)
+    long long *tl;        // debug timeline or nullptr
 };
+#define TL_MARK(k) do { if (tl) tl[s * 8 + (k)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -52,6 +55,8 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
     asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
@@ -86,6 +91,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int cid = (int)cluster_id_x();
     const int dir = cid & 1, tile = cid >> 1;
     const int b0 = tile * LB;
+    long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
 
     if (warp == 1) {
         if (lane == 0) {
@@ -118,6 +124,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const int t = dir ? T - 1 - s : s;
                 if (s > 0) {
                     const int tprev = dir ? t + 1 : t - 1;
+                    TL_MARK(0);
                     fence_proxy_async_global();  // h_{t-1} was written through the generic proxy
                     for (int kc = 0; kc < nkc; ++kc, ++an) {
                         const int slot = an % kARing;
@@ -125,6 +132,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         mbar_arrive_expect_tx(&a_full[slot], kTile);
                         tma_load_3d(a_s + slot * kTile, &tmH, &a_full[slot], dir * H + kc * LK, tprev, b0);
                     }
+                    TL_MARK(1);
                 }
                 // keep the xp ring full: chunks of this step first, then the next step's
                 while (xn < xtotal && xn < 4 * (s + 1) + kXRing) {
@@ -151,6 +159,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 for (int kc = 0; kc < nkc; ++kc, ++am) {
                     const int slot = am % kARing;
                     mbar_wait(&a_full[slot], (am / kARing) & 1);
+                    if (kc == 0) TL_MARK(2);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kTile), 16, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kTile), 16, 1024);
@@ -160,6 +169,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     umma_commit(&a_empty[slot]);
                 }
                 umma_commit(tmem_full);
+                TL_MARK(3);
             }
             __syncwarp();
             cluster_sync_all();
@@ -167,24 +177,28 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     } else {
         // ===== cell update (one thread per sequence of the tile) ================================
         const int qd = warp & 3;            // TMEM lane quadrant of this warp
+        const int hf = (warp - 2) >> 2;     // which half of the CTA's gate columns (units hf*16 .. +16)
         const int row = qd * 32 + lane;     // sequence within the tile == accumulator row
         const int b = b0 + row;
         const bool valid = b < B;
-        float cst[32];
+        float cst[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cst[i] = 0.f;
-        int xm = 0;
+        for (int i = 0; i < 16; ++i) cst[i] = 0.f;
         for (int s = 0; s < T; ++s) {
             const int t = dir ? T - 1 - s : s;
             if (s > 0) {
                 mbar_wait(tmem_full, (s - 1) & 1);
+                if (threadIdx.x == 64) TL_MARK(4);
                 tc_fence_after();
             }
             __nv_bfloat16 *hrow = p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c;
             __half *grow = SAVE ? p.gates + (((size_t)dir * T + t) * B + b) * 4 * H + (size_t)c * LN : nullptr;
             float *crow = SAVE ? p.csave + (((size_t)dir * T + t) * B + b) * H + 32 * c : nullptr;
+            U8 gsave[2][2], csv[2];   // training: activated gates / c of both chunks, stored AFTER the barrier arrive
 #pragma unroll
-            for (int q = 0; q < 4; ++q, ++xm) {
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = hf * 2 + qq;          // 32-column chunk of the accumulator / xp tile
+                const int xm = 4 * s + q;           // running xp chunk number (ring position)
                 const int slot = xm % kXRing;
                 uint32_t acc[32];
                 if (s > 0) {
@@ -218,8 +232,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const float fg = sigmoid_fast(pre[4 * j + 1]);
                     const float gg = tanh_fast(pre[4 * j + 2]);
                     const float og = sigmoid_fast(pre[4 * j + 3]);
-                    const float cn = fmaf(fg, cst[q * 8 + j], ig * gg);
-                    cst[q * 8 + j] = cn;
+                    const float cn = fmaf(fg, cst[qq * 8 + j], ig * gg);
+                    cst[qq * 8 + j] = cn;
                     hv[j] = og * tanh_fast(cn);
                     pre[4 * j] = ig; pre[4 * j + 1] = fg; pre[4 * j + 2] = gg; pre[4 * j + 3] = og;
                 }
@@ -230,28 +244,36 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     hq.x = *reinterpret_cast<uint32_t *>(&h0); hq.y = *reinterpret_cast<uint32_t *>(&h1);
                     hq.z = *reinterpret_cast<uint32_t *>(&h2); hq.w = *reinterpret_cast<uint32_t *>(&h3);
                     *reinterpret_cast<uint4 *>(hrow + q * 8) = hq;
-                    if (SAVE) {
+                }
+                if (SAVE) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 gq;
-                            __half2 g0 = __floats2half2_rn(pre[8 * j], pre[8 * j + 1]);
-                            __half2 g1 = __floats2half2_rn(pre[8 * j + 2], pre[8 * j + 3]);
-                            __half2 g2 = __floats2half2_rn(pre[8 * j + 4], pre[8 * j + 5]);
-                            __half2 g3 = __floats2half2_rn(pre[8 * j + 6], pre[8 * j + 7]);
-                            gq.x = *reinterpret_cast<uint32_t *>(&g0); gq.y = *reinterpret_cast<uint32_t *>(&g1);
-                            gq.z = *reinterpret_cast<uint32_t *>(&g2); gq.w = *reinterpret_cast<uint32_t *>(&g3);
-                            *reinterpret_cast<uint4 *>(grow + q * 32 + j * 8) = gq;
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            __half2 g2 = __floats2half2_rn(pre[16 * j + 2 * k], pre[16 * j + 2 * k + 1]);
+                            gsave[qq][j].v[k] = *reinterpret_cast<uint32_t *>(&g2);
                         }
-                        *reinterpret_cast<float4 *>(crow + q * 8) =
-                            make_float4(cst[q * 8], cst[q * 8 + 1], cst[q * 8 + 2], cst[q * 8 + 3]);
-                        *reinterpret_cast<float4 *>(crow + q * 8 + 4) =
-                            make_float4(cst[q * 8 + 4], cst[q * 8 + 5], cst[q * 8 + 6], cst[q * 8 + 7]);
-                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) csv[qq].v[k] = __float_as_uint(cst[qq * 8 + k]);
                 }
             }
+            if (threadIdx.x == 64) TL_MARK(5);
             tc_fence_before();
             fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
-            cluster_sync_all();
+            cluster_arrive();            // release: its MEMBAR only has the two h stores to wait for
+            if (SAVE && valid) {
+                // The saved tensors are not needed until the backward pass: issue their stores after
+                // the arrive so they drain while this CTA waits and during the next step's MMA phase.
+#pragma unroll
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int q = hf * 2 + qq;
+                    st_v8(grow + q * 32, gsave[qq][0]);
+                    st_v8(grow + q * 32 + 16, gsave[qq][1]);
+                    st_v8(crow + q * 8, csv[qq]);
+                }
+            }
+            cluster_wait();
+            if (threadIdx.x == 64) TL_MARK(6);
         }
     }
     __syncthreads();
@@ -314,6 +336,7 @@ extern "C" int rcnn_lstm_forward(const float *xp, const void *whh_packed, int B,
     p.hcat = (__nv_bfloat16 *)hcat;
     p.gates = (__half *)gates_save;
     p.csave = c_save;
+    p.tl = debug_timeline();
     cudaStream_t s = (cudaStream_t)stream;
     return gates_save ? launch_fwd<true>(tw, th, tx, p, s) : launch_fwd<false>(tw, th, tx, p, s);
 }
