@@ -6,9 +6,10 @@
 //
 // Mapping: a group of G warps owns one sequence (G = 8 for small batches so that the
 // 148 SMs are covered, G = 1 -- warp per sequence -- once the batch alone fills the chip).
-// A warp takes whole frames: the C logits of a frame are read with a peeled head (scalar,
-// up to the first 16-byte boundary), a 128-bit vector body and a scalar tail, because a
-// row of C=195 floats is 780 B and only 4-byte aligned.  The per-frame argmax goes to
+// A warp works on 4 frames at once, 8 lanes per frame: the C logits of a frame are read with a
+// peeled head (scalar, up to the first 16-byte boundary), a 128-bit vector body (all loads
+// issued before the first compare) and a scalar tail, because a row of C=195 floats is 780 B
+// and only 4-byte aligned; the argmax reduction is 3 shuffle steps shared by the 4 frames.  The per-frame argmax goes to
 // shared memory; the first warp of the group then collapses the T predictions with
 // ballot/popc compaction.  HBM-bound: T*C*sizeof(logit) bytes in, (T+1)*4 bytes out per
 // sequence.
@@ -52,47 +53,71 @@ template <> struct Elem<__nv_bfloat16> {
     }
 };
 
-// torch.argmax semantics over one frame, computed by a full warp: the first maximal index
-// wins; NaN is maximal (first NaN wins).  Every lane returns the result.
+// torch.argmax semantics over one frame, computed by 8 consecutive lanes (a warp works on 4
+// frames at once): the first maximal index wins; NaN is maximal (first NaN wins).  `row` may be
+// nullptr for a lane group without a frame; all 32 lanes must call (shuffles use the full mask).
+// All loads of the frame are issued before the first compare (7 x 128-bit per lane for C = 195).
 template <typename T>
-__device__ __forceinline__ int frame_argmax(const T *__restrict__ row, int C, int lane, float *best_val) {
+__device__ __forceinline__ int frame_argmax8(const T *__restrict__ row, int C, int sub, float *best_val) {
     constexpr int VEC = Elem<T>::VEC;
+    constexpr int MAXV = 8;
     float bv = -INFINITY;
     int bi = INT_MAX, ni = INT_MAX;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(row);
-    int head = (int)(((16u - (unsigned)(a & 15u)) & 15u) / sizeof(T));
-    head = min(head, C);
-    if (lane < head) consider(Elem<T>::ld(row + lane), lane, bv, bi, ni);
-    const int nvec = (C - head) / VEC;
-    const uint4 *vp = reinterpret_cast<const uint4 *>(row + head);
-#pragma unroll 2
-    for (int i = lane; i < nvec; i += 32) {
-        const uint4 q = ld_nc_v4(vp + i);
-        float f[VEC];
-        Elem<T>::unpack(q, f);
-        const int base = head + i * VEC;
+    if (row != nullptr) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+        int head = (int)(((16u - (unsigned)(a & 15u)) & 15u) / sizeof(T));
+        head = min(head, C);
+        const int nvec = (C - head) / VEC;
+        const int tail0 = head + nvec * VEC;
+        const uint4 *vp = reinterpret_cast<const uint4 *>(row + head);
+        // head (< VEC elements) and tail (< VEC elements): one scalar element per lane each
+        float hvl = -INFINITY, tvl = -INFINITY;
+        const bool has_h = sub < head, has_t = tail0 + sub < C;
+        if (has_h) hvl = Elem<T>::ld(row + sub);
+        if (has_t) tvl = Elem<T>::ld(row + tail0 + sub);
+        if (has_h) consider(hvl, sub, bv, bi, ni);
+        for (int base = 0; base < nvec; base += 8 * MAXV) {
+            uint4 q[MAXV];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) consider(f[j], base + j, bv, bi, ni);
+            for (int j = 0; j < MAXV; ++j) {
+                const int i = base + sub + 8 * j;
+                if (i < nvec) q[j] = ld_nc_v4(vp + i);
+            }
+#pragma unroll
+            for (int j = 0; j < MAXV; ++j) {
+                const int i = base + sub + 8 * j;
+                if (i < nvec) {
+                    float f[VEC];
+                    Elem<T>::unpack(q[j], f);
+                    const int e0 = head + i * VEC;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) consider(f[k], e0 + k, bv, bi, ni);
+                }
+            }
+        }
+        if (has_t) consider(tvl, tail0 + sub, bv, bi, ni);
     }
-    const int ti = head + nvec * VEC + lane;  // tail: fewer than VEC (<= 8) elements
-    if (ti < C) consider(Elem<T>::ld(row + ti), ti, bv, bi, ni);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 4; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(FULL, bv, o);
         const int oi = __shfl_xor_sync(FULL, bi, o);
+        const int on = __shfl_xor_sync(FULL, ni, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        ni = min(ni, on);
     }
-    ni = warp_min_int(ni);
     if (best_val) *best_val = (ni != INT_MAX) ? NAN : bv;
     return (ni != INT_MAX) ? ni : (bi == INT_MAX ? 0 : bi);
 }
 
-// sum_c exp(x_c - m) over one frame (second pass, only when a confidence is requested)
+// sum_c exp(x_c - m) over one frame by 8 lanes (second pass, only when a confidence is requested)
 template <typename T>
-__device__ __forceinline__ float frame_sumexp(const T *__restrict__ row, int C, int lane, float m) {
+__device__ __forceinline__ float frame_sumexp8(const T *__restrict__ row, int C, int sub, float m) {
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += ex2((Elem<T>::ld(row + c) - m) * kLog2e);
-    return warp_sum(s);
+    if (row != nullptr)
+        for (int c = sub; c < C; c += 8) s += ex2((Elem<T>::ld(row + c) - m) * kLog2e);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    return s;
 }
 
 __device__ __forceinline__ void group_sync(int G, int group) {
@@ -113,13 +138,15 @@ ctc_greedy_kernel(const T *__restrict__ logits, int B, int Tn, int C, long long 
     float *pmax = reinterpret_cast<float *>(preds + Tn);
     if (b < B) {
         const T *seq = logits + (long long)b * sb;
-        for (int t = wig; t < Tn; t += G) {
-            const T *row = seq + (long long)t * st;
+        const int sub = lane & 7, fr = lane >> 3;        // 8 lanes per frame, 4 frames per warp pass
+        for (int t0 = wig * 4; t0 < Tn; t0 += G * 4) {
+            const int t = t0 + fr;
+            const T *row = t < Tn ? seq + (long long)t * st : nullptr;
             float bv;
-            const int p = frame_argmax<T>(row, C, lane, &bv);
+            const int p = frame_argmax8<T>(row, C, sub, &bv);
             float pm = 0.f;
-            if (CONF) pm = 1.f / frame_sumexp<T>(row, C, lane, bv);
-            if (lane == 0) {
+            if (CONF) pm = 1.f / frame_sumexp8<T>(row, C, sub, bv);
+            if (sub == 0 && t < Tn) {
                 preds[t] = p;
                 if (CONF) pmax[t] = pm;
             }
@@ -178,7 +205,7 @@ int dispatch_greedy(const void *logits, int B, int Tn, int C, long long sb, long
     // warps than it has frames.
     const long long warps_wanted = 16LL * num_sms();
     int G = 8;
-    while (G > 1 && ((long long)B * G > 2 * warps_wanted || G > Tn)) G >>= 1;
+    while (G > 1 && ((long long)B * G > 2 * warps_wanted || G * 4 > Tn + 3)) G >>= 1;
     switch (G) {
         case 8: return launch_greedy<T, 8>(logits, B, Tn, C, sb, st, blank, ids, lens, conf, stream);
         case 4: return launch_greedy<T, 4>(logits, B, Tn, C, sb, st, blank, ids, lens, conf, stream);
