@@ -10,8 +10,8 @@
 //
 // Same cluster decomposition as the forward kernel: CTA c owns hidden units [32c, 32c+32).
 // Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for H=512) and
-// the streamed operand is the full dG_{t'} tile [128 seq, 4H] (64-column chunks through a
-// 6-slot TMA ring), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
+// the streamed operand is the full dG_{t'} tile [128 seq, 4H] (two 64-column TMA boxes per slot of a
+// 3-slot ring, so one barrier round trip covers K = 128), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
 // threads (one per sequence) keep dc in registers for the whole sequence, read the saved gates
 // / cell states / upstream dh directly from global memory (prefetched one 8-unit chunk ahead)
 // and write dG_t in the packed column order, which is at once the next step's MMA operand and
@@ -30,7 +30,9 @@ constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
 constexpr int LU = 32;    // hidden units per CTA (UMMA N)
 constexpr int LK = 64;
 constexpr int kMaxRing = 6;
-constexpr uint32_t kATile = LB * LK * 2;   // 16 KB
+constexpr uint32_t kABox = LB * LK * 2;    // one TMA box: 128 seq x 64 k bf16 = 16 KB
+constexpr int kBoxes = 2;                  // boxes per ring slot: one barrier round trip per K = 128
+constexpr uint32_t kATile = kBoxes * kABox; // 32 KB ring slot
 constexpr uint32_t kWTile = LU * LK * 2;   // 4 KB
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
@@ -85,7 +87,10 @@ __device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, cons
     }
 }
 
-template <int kARing, bool MCAST>
+// TWO_SM: the cluster is 8 CTA pairs; a pair runs one cta_group::2 MMA of M = 128 sequences (64 per
+// CTA) x N = 64 units (32 per CTA), so each SM streams only HALF of the dG tile (the per-SM L2 read
+// port, ~40 B/clk, is what bounds this kernel).  A CTA then owns 64 sequences x the pair's 64 units.
+template <int kARing, bool TWO_SM>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -106,54 +111,66 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int dir = cid & 1, tile = cid >> 1;
     const int b0 = tile * LB;
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
-    const int csize = H / 32;
-    const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
+    const bool leader = (c & 1) == 0;
+    const uint16_t pair_mask = (uint16_t)(3u << (c & ~1));
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], MCAST ? csize : 1); }
+            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<LU>(tmem_slot);
+        if (TWO_SM) tmem_alloc_2sm<LU>(tmem_slot); else tmem_alloc<LU>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (MCAST) cluster_sync_b();   // every CTA's barriers exist before any remote arrive / multicast lands
+    if (TWO_SM) {
+        // the resident W^T slice of BOTH CTAs must be in place, and the peer's barriers initialised,
+        // before the leader issues the first pair MMA / the peer's TMA signals the leader's barrier
+        if (warp == 0 && lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
+            for (int kc = 0; kc < nkc; ++kc)
+                tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
+        }
+        if (warp == 1 && lane == 0) mbar_wait(w_full, 0);
+        __syncwarp();
+        cluster_sync_b();
+    }
 
     // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
     // reverse direction from t = 0 up to T-1.
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && !TWO_SM) {
             tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmG);
             mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
             for (int kc = 0; kc < nkc; ++kc)
                 tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
         }
-        int an = 0;
+        int pslot = 0;
+        uint32_t pphase = 0;
         for (int s = 0; s < T; ++s) {
             if (lane == 0 && s > 0) {
                 const int t = dir ? s : T - 1 - s;
                 const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
                 TL_MARK(0);
                 fence_proxy_async_global();
-                for (int i = 0; i < nkc; ++i, ++an) {
-                    const int kc = i;
-                    const int slot = an % kARing;
-                    // MCAST: a_empty counts the commits of ALL CTAs of the cluster, so a completed
-                    // phase means the slot is free everywhere; chunk i is fetched once, by CTA i % csize,
-                    // and multicast to the whole cluster (every CTA arms its own full barrier).
-                    mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&a_full[slot], kATile);
-                    if (!MCAST)
-                        tma_load_3d(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0);
-                    else if ((i % csize) == c)
-                        tma_load_3d_mcast(a_s + slot * kATile, &tmG, &a_full[slot], dir * 4 * H + kc * LK, tsrc, b0,
-                                          all_mask);
+                for (int g = 0; g < nkc / kBoxes; ++g) {
+                    mbar_wait(&a_empty[pslot], pphase ^ 1);
+                    if (!TWO_SM || leader) mbar_arrive_expect_tx(&a_full[pslot], kATile);
+#pragma unroll
+                    for (int j = 0; j < kBoxes; ++j) {
+                        const int kc = g * kBoxes + j;
+                        unsigned char *dst = a_s + pslot * kATile + j * kABox;
+                        if (!TWO_SM)
+                            tma_load_3d(dst, &tmG, &a_full[pslot], dir * 4 * H + kc * LK, tsrc, b0);
+                        else   // each CTA fetches its own 64 sequences; both halves complete on the LEADER's barrier
+                            tma_load_3d_2sm(dst, &tmG, &a_full[pslot], dir * 4 * H + kc * LK, tsrc, b0 + 64 * (c & 1));
+                    }
+                    if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
                 }
                 TL_MARK(1);
             }
@@ -161,27 +178,36 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             cluster_sync_b();
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(LB, LU);
-        int am = 0;
-        if (lane == 0) mbar_wait(w_full, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(LB, TWO_SM ? 2 * LU : LU);
+        int mslot = 0;
+        uint32_t mphase = 0;
+        if (lane == 0 && !TWO_SM) mbar_wait(w_full, 0);
         __syncwarp();
         for (int s = 0; s < T; ++s) {
-            if (lane == 0 && s > 0) {
-                for (int i = 0; i < nkc; ++i, ++am) {
-                    const int kc = i;
-                    const int slot = am % kARing;
-                    mbar_wait(&a_full[slot], (am / kARing) & 1);
-                    if (i == 0) TL_MARK(2);
+            if (lane == 0 && s > 0 && (!TWO_SM || leader)) {
+                for (int g = 0; g < nkc / kBoxes; ++g) {
+                    mbar_wait(&a_full[mslot], mphase);
+                    if (g == 0) TL_MARK(2);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kATile), 16, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < LK / 16; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) != 0);
-                    if (MCAST) umma_commit_mcast(&a_empty[slot], all_mask);
-                    else umma_commit(&a_empty[slot]);
+                    for (int j = 0; j < kBoxes; ++j) {
+                        const int kc = g * kBoxes + j;
+                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kATile + j * kABox), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < LK / 16; ++k) {
+                            if (TWO_SM)
+                                umma_bf16_2sm(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                            else
+                                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                        }
+                    }
+                    if (TWO_SM) umma_commit_2sm(&a_empty[mslot], pair_mask);   // frees the slot in both CTAs
+                    else umma_commit(&a_empty[mslot]);
+                    if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
                 }
-                umma_commit(tmem_full);
+                if (TWO_SM) umma_commit_2sm(tmem_full, pair_mask);
+                else umma_commit(tmem_full);
                 TL_MARK(3);
             }
             __syncwarp();
@@ -189,8 +215,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
     } else {
         const int qd = warp & 3;            // TMEM lane quadrant
-        const int hf = (warp - 2) >> 2;     // half of the CTA's units handled by this warp (16 units)
-        const int row = qd * 32 + lane;
+        const int hf = (warp - 2) >> 2;     // which 16 of a 32-unit slice this warp handles
+        // 1-SM: the CTA owns 128 sequences x its own 32-unit slice c.  TWO_SM: it owns 64 sequences x
+        // both slices of the pair; TMEM lanes 0-63 hold slice 2p, lanes 64-127 slice 2p+1 ("2x2" layout).
+        const int row = TWO_SM ? 64 * (c & 1) + (qd & 1) * 32 + lane : qd * 32 + lane;
+        const int cs = TWO_SM ? (c & ~1) + (qd >> 1) : c;     // unit slice this thread works on
         const int b = b0 + row;
         const bool valid = b < B;
         float dc[16];
@@ -200,11 +229,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const int t = dir ? s : T - 1 - s;
             const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
             const size_t rtb = ((size_t)dir * T + t) * B + b;
-            const __half *grow = p.gates + rtb * 4 * H + (size_t)c * 128;
-            const float *crow = p.csave + rtb * H + 32 * c;
-            const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c : nullptr;
-            const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c;
-            __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128;
+            const __half *grow = p.gates + rtb * 4 * H + (size_t)cs * 128;
+            const float *crow = p.csave + rtb * H + 32 * cs;
+            const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * cs : nullptr;
+            const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * cs;
+            __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)cs * 128;
 
             ChunkIn cur, nxt;
             load_chunk(cur, grow, crow, cprow, dhrow, hf * 2, valid);
@@ -212,10 +241,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (valid && s + 1 < T && hf == 0) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
                 const int tn = dir ? t + 1 : t - 1;
                 const size_t rn = ((size_t)dir * T + tn) * B + b;
-                prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128);
-                prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128 + 64);
-                prefetch_l2(p.csave + rn * H + 32 * c);
-                prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * c);
+                prefetch_l2(p.gates + rn * 4 * H + (size_t)cs * 128);
+                prefetch_l2(p.gates + rn * 4 * H + (size_t)cs * 128 + 64);
+                prefetch_l2(p.csave + rn * H + 32 * cs);
+                prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * cs);
             }
             uint32_t acc[16];
             if (s > 0) {
@@ -276,11 +305,11 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (threadIdx.x == 64) TL_MARK(6);
         }
     }
-    if (MCAST) cluster_sync_b();   // no CTA leaves while peers may still signal its barriers
+    if (TWO_SM) cluster_sync_b();   // no CTA leaves while its peer may still signal its barriers / use its TMEM
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<LU>(tmem_base);
+        if (TWO_SM) tmem_dealloc_2sm<LU>(tmem_base); else tmem_dealloc<LU>(tmem_base);
     }
 }
 
@@ -362,7 +391,9 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     CUtensorMap tw, tg;
     int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, LU, LK, 1);
     if (rc) return rc;
-    rc = make_tmap_3d(&tg, dG, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, LB, 1, LK, 1);
+    static const bool two_sm = getenv("RCNN_BWD_2SM") ? atoi(getenv("RCNN_BWD_2SM")) != 0 : false;
+    rc = make_tmap_3d(&tg, dG, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2,
+                      two_sm ? LB / 2 : LB, 1, LK, 1);
     if (rc) return rc;
     BwdParams p;
     p.B = B; p.T = T; p.H = H;
@@ -373,12 +404,10 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.tl = debug_timeline();
     const int csize = H / 32;
     const int ntiles = (B + LB - 1) / LB;
-    static const int ring = getenv("RCNN_BWD_RING") ? atoi(getenv("RCNN_BWD_RING")) : 3;
-    static const bool stagger = getenv("RCNN_MCAST") ? atoi(getenv("RCNN_MCAST")) != 0 : false;
-    const size_t smem = bwd_smem_bytes(H, ring == 6 ? 6 : 3);
+    const bool stagger = two_sm;
+    const size_t smem = bwd_smem_bytes(H, 3);
     cudaStream_t s = (cudaStream_t)stream;
-    auto kern = ring == 6 ? (stagger ? lstm_bwd_kernel<6, true> : lstm_bwd_kernel<6, false>)
-                          : (stagger ? lstm_bwd_kernel<3, true> : lstm_bwd_kernel<3, false>);
+    auto kern = stagger ? lstm_bwd_kernel<3, true> : lstm_bwd_kernel<3, false>;
     RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (csize > 8) RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
