@@ -34,6 +34,7 @@ extern "C" {
 /* element types */
 #define RCNN_F32 0
 #define RCNN_BF16 1
+#define RCNN_F16 2
 
 /* CTC reductions (torch.nn.CTCLoss `reduction`) */
 #define RCNN_REDUCE_NONE 0
@@ -110,7 +111,7 @@ int rcnn_ctc_scale_grad(float *grad, int T, int N, int C, int64_t gstride_t, int
  * backward pass, for dX and dW.
  *   A [M,K], B [N,K]  bf16 row-major, leading dimensions lda/ldb in elements (multiples of 8,
  *                     16-byte aligned bases)
- *   D [M,N]           row-major, ldd in elements, out_dtype RCNN_F32 or RCNN_BF16
+ *   D [M,N]           row-major, ldd in elements, out_dtype RCNN_F32, RCNN_BF16 or RCNN_F16
  *   bias [N]          float32 or NULL
  * ------------------------------------------------------------------------------------- */
 int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd,
@@ -137,7 +138,9 @@ int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, f
  *     whh_pt bf16 [2, H, 4H]  per-direction transpose of whh_p   (resident operand, backward)
  *     wih_pt bf16 [I, 2*4H]   transpose of wih_p                 (B operand of the dX GEMM)
  * rcnn_lstm_forward: the T dependent steps of both directions in one persistent kernel.
- *   xp        f32  [B*T, 2*4H]  x W_ih^T + b for every (b,t) (row b*T+t), columns in P order
+ *   xp        f16  [B*T, 2*4H]  x W_ih^T + b for every (b,t) (row b*T+t), columns in P order
+ *                               (fp16: 11-bit mantissa keeps the pre-activation error ~5e-4 and
+ *                               halves the bytes every step streams into the SM)
  *   whh_p     the whh_p view of `packed`
  *   hcat      bf16 [B, T, 2H]   output: h_t of the forward (cols [0,H)) and reverse ([H,2H))
  *                               direction; also the buffer h_{t-1} is re-read from
@@ -149,7 +152,7 @@ size_t rcnn_lstm_packed_bytes(int I, int H);
 int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
                            const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
                            int I, int H, void *packed, rcnn_stream_t stream);
-int rcnn_lstm_forward(const float *xp, const void *whh_p, int B, int T, int H, void *hcat,
+int rcnn_lstm_forward(const void *xp, const void *whh_p, int B, int T, int H, void *hcat,
                       void *gates_save, float *c_save, rcnn_stream_t stream);
 
 /* rcnn_lstm_backward: BPTT through the recurrence of both directions (autograd of nn.LSTM in the

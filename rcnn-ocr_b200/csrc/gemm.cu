@@ -12,6 +12,7 @@
 // TMEM lane quadrant: tcgen05.ld -> +bias -> convert -> global).  Three smem stages of 32 KB
 // so that two CTAs share an SM and one CTA's epilogue overlaps the other's main loop.
 // M / N / K tails: TMA zero-fills out-of-bounds rows and columns; stores are masked.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -44,7 +45,9 @@ static int encode(CUtensorMap *out, const void *base, int elem_bytes, int rank, 
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=(%llu,%llu) pitch=%llu box=(%u,%u)", (int)r,
@@ -108,6 +111,24 @@ __device__ __forceinline__ void store_row_chunk(__nv_bfloat16 *dst, const float 
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
+__device__ __forceinline__ void store_row_chunk(__half *dst, const float (&v)[32], int ncols, bool vec_ok) {
+    if (vec_ok && ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+            q.x = *reinterpret_cast<uint32_t *>(&h0); q.y = *reinterpret_cast<uint32_t *>(&h1);
+            q.z = *reinterpret_cast<uint32_t *>(&h2); q.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(dst + j) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) dst[j] = __float2half_rn(v[j]);
     }
 }
 
@@ -343,7 +364,7 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
                               int out_dtype, const float *bias, int M, int N, int K, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
-    RCNN_CHECK_ARG(out_dtype == RCNN_F32 || out_dtype == RCNN_BF16, "gemm: bad out dtype %d", out_dtype);
+    RCNN_CHECK_ARG(out_dtype == RCNN_F32 || out_dtype == RCNN_BF16 || out_dtype == RCNN_F16, "gemm: bad out dtype %d", out_dtype);
     if (M == 0 || N == 0) return RCNN_OK;
     RCNN_CHECK_ARG(A && B && D, "gemm: null pointer");
     RCNN_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension smaller than the row");
@@ -356,6 +377,7 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     if (out_dtype == RCNN_F32) return launch_gemm<float>(ta, tb, D, ldd, bias, M, N, K, s);
+    if (out_dtype == RCNN_F16) return launch_gemm<__half>(ta, tb, D, ldd, bias, M, N, K, s);
     return launch_gemm<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
 }
 

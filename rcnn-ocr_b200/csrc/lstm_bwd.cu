@@ -56,6 +56,15 @@ __device__ __forceinline__ uint32_t cluster_id_x_b() {
     asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ void cluster_arrive_relaxed_b() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_b() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+// one gpu-scope release per CTA for the cell warps' dG stores (see lstm_fwd.cu: cell_publish_arrive)
+__device__ __forceinline__ void cell_publish_sync_b() {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 64) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    else cluster_arrive_relaxed_b();
+    cluster_wait_b();
+}
 __device__ __forceinline__ void cluster_sync_b() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
@@ -175,7 +184,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 TL_MARK(1);
             }
             __syncwarp();
-            cluster_sync_b();
+            cluster_arrive_relaxed_b();
+            cluster_wait_b();
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc_bf16(LB, TWO_SM ? 2 * LU : LU);
@@ -211,7 +221,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 TL_MARK(3);
             }
             __syncwarp();
-            cluster_sync_b();
+            cluster_arrive_relaxed_b();
+            cluster_wait_b();
         }
     } else {
         const int qd = warp & 3;            // TMEM lane quadrant
@@ -301,7 +312,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (threadIdx.x == 64) TL_MARK(5);
             tc_fence_before();
             fence_proxy_async_global();   // dG_t stores before the other CTAs' TMA reads
-            cluster_sync_b();
+            cell_publish_sync_b();
             if (threadIdx.x == 64) TL_MARK(6);
         }
     }

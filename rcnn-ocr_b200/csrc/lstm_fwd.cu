@@ -11,7 +11,8 @@
 // (bf16, 128 KB for H=512) is loaded ONCE by TMA and stays resident in shared memory for all T
 // steps.  Per timestep:
 //   warp 0  (TMA)      streams h_{t-1}[128 seq, H] (bf16, straight out of the block's output
-//                      tensor, 64-column chunks, 3-slot ring) and prefetches the next xp tiles;
+//                      tensor, two 64-column boxes per ring slot) and prefetches the next step's
+//                      xp tile (fp16, four 32-column chunks, all resident);
 //   warp 1  (MMA)      tcgen05.mma  D[128 seq, 128 gate cols] += h_chunk * W_chunk^T, fp32 in TMEM;
 //   warps 2-9 (cell)   two warps per TMEM lane quadrant; a thread owns one sequence and 16 of the
 //                      CTA's 32 units: tcgen05.ld its accumulator columns, add xp, sigmoid/tanh,
@@ -32,8 +33,12 @@ using namespace sm100;
 constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
 constexpr int LN = 128;   // gate columns per CTA: 32 units x 4 gates (UMMA N)
 constexpr int LK = 64;    // K chunk (one 128-byte swizzle row of bf16)
-constexpr int kARing = 3, kXRing = 3;
-constexpr uint32_t kTile = 16384;  // every staged tile is 16 KB: 128x64 bf16 or 128x32 fp32
+constexpr uint32_t kTile = 16384;   // one operand TMA box: 128 x 64 bf16 (h chunk or W chunk) = 16 KB
+constexpr int kBoxes = 2;           // h boxes per ring slot: one barrier round trip per K = 128
+constexpr int kARing = 2;           // ring slots of kBoxes * 16 KB
+constexpr uint32_t kASlot = kBoxes * kTile;
+constexpr int kXRing = 4;           // one slot per 32-column xp chunk: the whole step's tile is resident
+constexpr uint32_t kXTile = LB * 32 * 2;   // 128 seq x 32 cols fp16 = 8 KB, 64-byte swizzle
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct FwdParams {
@@ -56,6 +61,15 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
     return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+// Publish the cell warps' global stores with ONE gpu-scope release per CTA (the pattern of a
+// cooperative-groups grid sync): CTA barrier among the 256 cell threads, then one thread arrives with
+// release semantics (its MEMBAR is cumulative over the stores it observed through the barrier) while the
+// others arrive relaxed.
+__device__ __forceinline__ void cell_publish_arrive() {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 64) cluster_arrive(); else cluster_arrive_relaxed();
+}
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
@@ -77,9 +91,9 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int H = p.H, T = p.T, B = p.B;
     const int nkc = H / LK;
     unsigned char *w_s = smem;                          // nkc tiles [128 n x 64 k] bf16, SW128
-    unsigned char *a_s = w_s + (size_t)nkc * kTile;     // kARing tiles [128 b x 64 k] bf16, SW128
-    unsigned char *x_s = a_s + kARing * kTile;          // kXRing tiles [128 b x 32 col] fp32, SW128
-    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + kXRing * kTile);
+    unsigned char *a_s = w_s + (size_t)nkc * kTile;     // kARing slots of kBoxes tiles [128 b x 64 k] bf16, SW128
+    unsigned char *x_s = a_s + kARing * kASlot;         // kXRing tiles [128 b x 32 col] fp16, SW64
+    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + kXRing * kXTile);
     uint64_t *w_full = bars;
     uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
     uint64_t *x_full = a_empty + kARing, *x_empty = x_full + kXRing;
@@ -117,8 +131,19 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kc = 0; kc < nkc; ++kc)
                 tma_load_2d(w_s + (size_t)kc * kTile, &tmW, w_full, kc * LK, dir * 4 * H + c * LN);
         }
-        int an = 0, xn = 0;
-        const int xtotal = 4 * T;
+        int pslot = 0;
+        uint32_t pphase = 0;
+        // xp chunk q of step s lives in slot q; phase parity = s & 1.  Step 0 is loaded up front, step
+        // s+1 while step s runs (each slot is refilled as soon as the cell warps released it).
+        auto load_x = [&](int xs) {
+            const int xt = dir ? T - 1 - xs : xs;
+            for (int q = 0; q < kXRing; ++q) {
+                mbar_wait(&x_empty[q], (xs & 1) ^ 1);
+                mbar_arrive_expect_tx(&x_full[q], kXTile);
+                tma_load_3d(x_s + q * kXTile, &tmX, &x_full[q], dir * 4 * H + c * LN + q * 32, xt, b0);
+            }
+        };
+        if (lane == 0 && T > 0) load_x(0);
         for (int s = 0; s < T; ++s) {
             if (lane == 0) {
                 const int t = dir ? T - 1 - s : s;
@@ -126,53 +151,54 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const int tprev = dir ? t + 1 : t - 1;
                     TL_MARK(0);
                     fence_proxy_async_global();  // h_{t-1} was written through the generic proxy
-                    for (int kc = 0; kc < nkc; ++kc, ++an) {
-                        const int slot = an % kARing;
-                        mbar_wait(&a_empty[slot], ((an / kARing) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&a_full[slot], kTile);
-                        tma_load_3d(a_s + slot * kTile, &tmH, &a_full[slot], dir * H + kc * LK, tprev, b0);
+                    for (int g = 0; g * kBoxes < nkc; ++g) {
+                        const int nb = min(kBoxes, nkc - g * kBoxes);     // H = 64 has a single box
+                        mbar_wait(&a_empty[pslot], pphase ^ 1);
+                        mbar_arrive_expect_tx(&a_full[pslot], (uint32_t)nb * kTile);
+                        for (int j = 0; j < nb; ++j)
+                            tma_load_3d(a_s + pslot * kASlot + j * kTile, &tmH, &a_full[pslot],
+                                        dir * H + (g * kBoxes + j) * LK, tprev, b0);
+                        if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
                     }
                     TL_MARK(1);
                 }
-                // keep the xp ring full: chunks of this step first, then the next step's
-                while (xn < xtotal && xn < 4 * (s + 1) + kXRing) {
-                    const int slot = xn % kXRing;
-                    const int xs = xn >> 2, q = xn & 3;
-                    const int xt = dir ? T - 1 - xs : xs;
-                    mbar_wait(&x_empty[slot], ((xn / kXRing) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&x_full[slot], kTile);
-                    tma_load_3d(x_s + slot * kTile, &tmX, &x_full[slot], dir * 4 * H + c * LN + q * 32, xt, b0);
-                    ++xn;
-                }
+                if (s + 1 < T) load_x(s + 1);
             }
             __syncwarp();
-            cluster_sync_all();
+            cluster_arrive_relaxed();
+            cluster_wait();
         }
     } else if (warp == 1) {
         // ===== MMA issuer ========================================================================
         constexpr uint32_t idesc = make_idesc_bf16(LB, LN);
-        int am = 0;
+        int mslot = 0;
+        uint32_t mphase = 0;
         if (lane == 0) mbar_wait(w_full, 0);
         __syncwarp();
         for (int s = 0; s < T; ++s) {
             if (lane == 0 && s > 0) {
-                for (int kc = 0; kc < nkc; ++kc, ++am) {
-                    const int slot = am % kARing;
-                    mbar_wait(&a_full[slot], (am / kARing) & 1);
-                    if (kc == 0) TL_MARK(2);
+                for (int g = 0; g * kBoxes < nkc; ++g) {
+                    const int nb = min(kBoxes, nkc - g * kBoxes);
+                    mbar_wait(&a_full[mslot], mphase);
+                    if (g == 0) TL_MARK(2);
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + slot * kTile), 16, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kTile), 16, 1024);
+                    for (int j = 0; j < nb; ++j) {
+                        const int kc = g * kBoxes + j;
+                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kASlot + j * kTile), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kTile), 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < LK / 16; ++k)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
-                    umma_commit(&a_empty[slot]);
+                        for (int k = 0; k < LK / 16; ++k)
+                            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                    }
+                    umma_commit(&a_empty[mslot]);
+                    if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
                 }
                 umma_commit(tmem_full);
                 TL_MARK(3);
             }
             __syncwarp();
-            cluster_sync_all();
+            cluster_arrive_relaxed();
+            cluster_wait();
         }
     } else {
         // ===== cell update (one thread per sequence of the tile) ================================
@@ -198,8 +224,6 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
                 const int q = hf * 2 + qq;          // 32-column chunk of the accumulator / xp tile
-                const int xm = 4 * s + q;           // running xp chunk number (ring position)
-                const int slot = xm % kXRing;
                 uint32_t acc[32];
                 if (s > 0) {
                     tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(q * 32), acc);
@@ -207,21 +231,28 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0u;
                 }
-                mbar_wait(&x_full[slot], (xm / kXRing) & 1);
-                const unsigned char *xrow = x_s + slot * kTile + row * 128;
+                mbar_wait(&x_full[q], s & 1);
+                // fp16 tile, 64-byte rows, TMA SWIZZLE_64B: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)
+                const unsigned char *xrow = x_s + q * kXTile + row * 64;
                 float pre[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 v = *reinterpret_cast<const float4 *>(xrow + ((j ^ (row & 7)) << 4));
-                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(xrow + ((j ^ ((row >> 1) & 3)) << 4));
+                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = __half22float2(h2[k]);
+                        pre[8 * j + 2 * k] = f.x;
+                        pre[8 * j + 2 * k + 1] = f.y;
+                    }
                 }
                 // Free the slot only once every lane's loads have RETURNED: fold one word of each
                 // 16-byte load into a value the arrive depends on, and vote it across the warp.
                 uint32_t dep = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dep |= __float_as_uint(pre[4 * j]);
+                for (int j = 0; j < 4; ++j) dep |= __float_as_uint(pre[8 * j]);
                 dep = __any_sync(FULL, dep != 0u) ? 1u : 0u;
-                if (lane == 0) mbar_arrive_after(&x_empty[slot], dep);
+                if (lane == 0) mbar_arrive_after(&x_empty[q], dep);
                 if (s > 0) tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);
@@ -260,7 +291,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (threadIdx.x == 64) TL_MARK(5);
             tc_fence_before();
             fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
-            cluster_arrive();            // release: its MEMBAR only has the two h stores to wait for
+            cell_publish_arrive();       // one release per CTA; its MEMBAR only has the h stores to wait for
             if (SAVE && valid) {
                 // The saved tensors are not needed until the backward pass: issue their stores after
                 // the arrive so they drain while this CTA waits and during the next step's MMA phase.
@@ -283,7 +314,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
 }
 
-size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK + kARing + kXRing) * kTile + 256; }
+size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK) * kTile + kARing * kASlot + kXRing * kXTile + 256; }
 
 template <bool SAVE>
 int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &tx, const FwdParams &p,
@@ -315,7 +346,7 @@ int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &
 }  // namespace
 }  // namespace rcnn
 
-extern "C" int rcnn_lstm_forward(const float *xp, const void *whh_packed, int B, int T, int H, void *hcat,
+extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, int T, int H, void *hcat,
                                  void *gates_save, float *c_save, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_forward: bad shape B=%d T=%d", B, T);
@@ -329,7 +360,7 @@ extern "C" int rcnn_lstm_forward(const float *xp, const void *whh_packed, int B,
     if (rc) return rc;
     rc = make_tmap_3d(&th, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, LB, 1, LK, 1);
     if (rc) return rc;
-    rc = make_tmap_3d(&tx, xp, 4, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 4, 8ull * H * 4, LB, 1, 32, 1);
+    rc = make_tmap_3d(&tx, xp, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, LB, 1, 32, 2);
     if (rc) return rc;
     FwdParams p;
     p.B = B; p.T = T; p.H = H;

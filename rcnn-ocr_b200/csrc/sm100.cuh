@@ -244,7 +244,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 
 }  // namespace sm100
 
-// Host: build a 2-D bf16/f32 tiled tensor map (driver entry point fetched through the runtime,
+// Host: build a 2-D / 3-D tiled tensor map; swizzle128: 0 = none, 1 = 128-byte, 2 = 64-byte swizzle (driver entry point fetched through the runtime,
 // so the library does not link libcuda).
 int make_tmap_2d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle128);

@@ -6,7 +6,7 @@ names and shapes (``rnn.weight_ih_l0`` ... ``rnn.bias_hh_l0_reverse``, ``linear.
 encoder part of reference checkpoints works (model/model.py:151-163, training/utils.py:116).
 Forward and backward run entirely in the sm_100a kernels:
 
-    x --cast--> bf16 --K1 GEMM (W_ih, both directions)--> xp --K2 recurrence--> hcat (bf16)
+    x --cast--> bf16 --K1 GEMM (W_ih, both directions)--> xp (fp16) --K2 recurrence--> hcat (bf16)
       --K1 GEMM (linear)--> out                                         [forward]
     dout --K1 GEMMs--> dhcat, dW_lin --K2 BPTT--> dG --K1 GEMMs--> dX, dW_ih, dW_hh, db   [backward]
 
@@ -43,7 +43,7 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         O = lin_w.shape[0]
         packed = ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         xb = ops.cast_bf16_3d(x)
-        xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float32)
+        xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
         hcat, gates, csave = ops.lstm_forward(xp, packed, B, T, save)
         del xp
         lin_wb = _cast2d(lin_w)

@@ -5,7 +5,7 @@ import torch
 
 from . import _lib
 
-_OUT = {torch.float32: 0, torch.bfloat16: 1}
+_OUT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 
 def _repitch(m: torch.Tensor) -> torch.Tensor:
@@ -141,10 +141,10 @@ def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool, hcat=None):
-    """Recurrence of both directions (kernel K2).  xp: float32 [B*T, 8H] in packed column order.
+    """Recurrence of both directions (kernel K2).  xp: float16 [B*T, 8H] in packed column order.
     Returns (hcat bf16 [B,T,2H], gates f16 [2,T,B,4H] | None, c f32 [2,T,B,H] | None)."""
     H = packed.H
-    assert xp.dtype == torch.float32 and xp.shape == (B * T, 8 * H) and xp.is_contiguous()
+    assert xp.dtype == torch.float16 and xp.shape == (B * T, 8 * H) and xp.is_contiguous()
     dev = xp.device
     with torch.cuda.device(dev):
         if hcat is None:

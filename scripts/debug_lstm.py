@@ -13,7 +13,7 @@ def run(B, T, I, H):
     packed = ops.lstm_pack(*[pc["rnn." + n + sfx] for sfx in ("", "_reverse")
                              for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")])
     xb = ops.cast_bf16_3d(x.cuda())
-    xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p)
+    xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
     for rep in range(4):
         save = rep >= 2
         hcat = torch.full((B, T, 2 * H), float("nan"), dtype=torch.bfloat16, device="cuda")

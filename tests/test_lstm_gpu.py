@@ -48,7 +48,7 @@ def test_recurrent_forward_matches_oracle(B, T, I, H):
     packed = ops.lstm_pack(*[pc["rnn." + n + sfx] for sfx in ("", "_reverse")
                              for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")])
     xb = ops.cast_bf16_3d(x.cuda())
-    xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p)
+    xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
     for save in (False, True):
         hcat, gates, cs = ops.lstm_forward(xp, packed, B, T, save)
         err = (hcat.float().cpu().double() - want).abs().max().item()
