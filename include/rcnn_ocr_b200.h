@@ -123,6 +123,12 @@ int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, void 
  * nn.Linear / nn.LSTM weights in the reference, model/model.py:154-157). */
 int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
                        int M, int N, int K, int accumulate, rcnn_stream_t stream);
+/* `groups` independent problems of the same shape in one launch: group g reads columns
+ * [g*a_gcols, +M) of A and [g*b_gcols, +N) of B and writes D + g*d_goff (the two directions'
+ * dW_hh = dG_d^T h_prev_d are one launch). */
+int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcols, const void *B, int64_t ldb, int b_gcols,
+                               float *D, int64_t ldd, int64_t d_goff, int groups, int M, int N, int K,
+                               int accumulate, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K2  BidirectionalLSTM recurrence (model/model.py:151-163: nn.LSTM(bidirectional=True,

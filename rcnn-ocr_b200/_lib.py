@@ -56,6 +56,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_transpose_bf16.argtypes = [vp, i64, vp, i64, i, i, vp]
     L.rcnn_gemm_bf16_atb.restype = i
     L.rcnn_gemm_bf16_atb.argtypes = [vp, i64, vp, i64, vp, i64, i, i, i, i, vp]
+    L.rcnn_gemm_bf16_atb_grouped.restype = i
+    L.rcnn_gemm_bf16_atb_grouped.argtypes = [vp, i64, i, vp, i64, i, vp, i64, i64, i, i, i, i, i, vp]
     L.rcnn_prof_enable.restype = i
     L.rcnn_prof_enable.argtypes = [i]
     L.rcnn_prof_reset.restype = i

@@ -247,7 +247,8 @@ __device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c
 
 __global__ void __launch_bounds__(kThreads)
 gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                float *__restrict__ D, long long ldd, int M, int N, int K, int kb_per_split) {
+                float *__restrict__ D, long long ldd, int M, int N, int K, int kb_per_split, int splits,
+                int a_gcols, int b_gcols, long long d_goff) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *tiles = smem;
@@ -259,9 +260,12 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_n = blockIdx.x, tile_m = blockIdx.y;
     const int total_kb = (K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * kb_per_split;
+    const int grp = blockIdx.z / splits;              // independent problems sharing one launch
+    const int kb0 = (blockIdx.z % splits) * kb_per_split;
     const int num_kb = min(kb_per_split, total_kb - kb0);
     if (num_kb <= 0) return;
+    const int a_c0 = grp * a_gcols + tile_m * BM, b_c0 = grp * b_gcols + tile_n * BN;
+    D += grp * d_goff;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1) {
@@ -287,10 +291,10 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_arrive_expect_tx(&full[s], kStageBytes);
                 unsigned char *st = tiles + s * kStageBytes;
                 const int k0 = (kb0 + kb) * BK;
-                tma_load_2d(st, &tmA, &full[s], tile_m * BM, k0);
-                tma_load_2d(st + kHalf, &tmA, &full[s], tile_m * BM + 64, k0);
-                tma_load_2d(st + kABytes, &tmB, &full[s], tile_n * BN, k0);
-                tma_load_2d(st + kABytes + kHalf, &tmB, &full[s], tile_n * BN + 64, k0);
+                tma_load_2d(st, &tmA, &full[s], a_c0, k0);
+                tma_load_2d(st + kHalf, &tmA, &full[s], a_c0 + 64, k0);
+                tma_load_2d(st + kABytes, &tmB, &full[s], b_c0, k0);
+                tma_load_2d(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, k0);
             }
         }
     } else if (warp == 1) {
@@ -381,34 +385,44 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     return launch_gemm<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
 }
 
-extern "C" int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
-                                  int M, int N, int K, int accumulate, rcnn_stream_t stream) {
+extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcols, const void *B, int64_t ldb, int b_gcols,
+                                          float *D, int64_t ldd, int64_t d_goff, int groups, int M, int N, int K,
+                                          int accumulate, rcnn_stream_t stream) {
     using namespace rcnn;
-    RCNN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "gemm_atb: bad shape M=%d N=%d K=%d", M, N, K);
+    RCNN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && groups >= 1, "gemm_atb: bad shape M=%d N=%d K=%d groups=%d", M, N, K, groups);
     if (M == 0 || N == 0) return RCNN_OK;
     RCNN_CHECK_ARG(D && ldd >= N, "gemm_atb: bad output");
     cudaStream_t s = (cudaStream_t)stream;
-    if (!accumulate) RCNN_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, s));
+    if (!accumulate)
+        for (int g = 0; g < groups; ++g)
+            RCNN_CUDA(cudaMemset2DAsync(D + g * d_goff, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, s));
     if (K == 0) return RCNN_OK;
     RCNN_CHECK_ARG(A && B, "gemm_atb: null pointer");
-    RCNN_CHECK_ARG(lda >= M && ldb >= N, "gemm_atb: leading dimension smaller than the row");
+    const long long a_cols = (long long)(groups - 1) * a_gcols + M, b_cols = (long long)(groups - 1) * b_gcols + N;
+    RCNN_CHECK_ARG(lda >= a_cols && ldb >= b_cols, "gemm_atb: leading dimension smaller than the row");
     RCNN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0,
                    "gemm_atb: A/B rows must be 16-byte aligned (lda=%lld ldb=%lld)", (long long)lda, (long long)ldb);
     CUtensorMap ta, tb;
-    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, 64, 1);
+    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)a_cols, (uint64_t)lda * 2, BK, 64, 1);
     if (rc) return rc;
-    rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, 64, 1);
+    rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)b_cols, (uint64_t)ldb * 2, BK, 64, 1);
     if (rc) return rc;
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
     const int total_kb = (K + BK - 1) / BK;
     int splits = (2 * num_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
     splits = splits < 1 ? 1 : (splits > total_kb ? total_kb : splits);
     const int kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per_split - 1) / kb_per_split;
     RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits * groups);
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_atb_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split);
+    gemm_atb_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split, splits, a_gcols, b_gcols,
+                                                     (long long)d_goff);
     RCNN_LAUNCH_CHECK("gemm_atb_kernel");
     return RCNN_OK;
+}
+
+extern "C" int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
+                                  int M, int N, int K, int accumulate, rcnn_stream_t stream) {
+    return rcnn_gemm_bf16_atb_grouped(A, lda, 0, B, ldb, 0, D, ldd, 0, 1, M, N, K, accumulate, stream);
 }

@@ -27,25 +27,41 @@ __device__ __forceinline__ int torch_row(int p, int H) {
     return g * H + 32 * c + j;
 }
 
-// one block per packed row (dir, p)
-__global__ void lstm_pack_kernel(const PackArgs a) {
+// row-major views: one block per packed row (dir, p); reads and writes are both coalesced
+__global__ void lstm_pack_rows_kernel(const PackArgs a) {
     const int H = a.H, I = a.I;
     const int dir = blockIdx.x / (4 * H), p = blockIdx.x % (4 * H);
     const int r = torch_row(p, H);
     const float *wi = a.w_ih[dir] + (size_t)r * I;
     const float *wh = a.w_hh[dir] + (size_t)r * H;
     const size_t prow = (size_t)dir * 4 * H + p;
-    for (int k = threadIdx.x; k < I; k += blockDim.x) {
-        const __nv_bfloat16 v = __float2bfloat16_rn(wi[k]);
-        a.wih_p[prow * I + k] = v;
-        a.wih_pt[(size_t)k * 8 * H + prow] = v;
-    }
-    for (int k = threadIdx.x; k < H; k += blockDim.x) {
-        const __nv_bfloat16 v = __float2bfloat16_rn(wh[k]);
-        a.whh_p[prow * H + k] = v;
-        a.whh_pt[((size_t)dir * H + k) * 4 * H + p] = v;
-    }
+    for (int k = threadIdx.x; k < I; k += blockDim.x) a.wih_p[prow * I + k] = __float2bfloat16_rn(wi[k]);
+    for (int k = threadIdx.x; k < H; k += blockDim.x) a.whh_p[prow * H + k] = __float2bfloat16_rn(wh[k]);
     if (threadIdx.x == 0) a.bias_p[prow] = a.b_ih[dir][r] + a.b_hh[dir][r];
+}
+
+// transposed views through a 32x32 shared-memory tile: which = 0 -> wih_pt [I, 8H], 1 -> whh_pt [2, H, 4H]
+__global__ void lstm_pack_transposed_kernel(const PackArgs a) {
+    __shared__ float tile[32][33];
+    const int H = a.H;
+    const int which = blockIdx.z >> 1, dir = blockIdx.z & 1;
+    const int K = which ? H : a.I;
+    const int p0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    if (k0 >= K) return;
+    const float *src = which ? a.w_hh[dir] : a.w_ih[dir];
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + threadIdx.x;
+        tile[i][threadIdx.x] = k < K ? src[(size_t)torch_row(p0 + i, H) * K + k] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, p = p0 + threadIdx.x;
+        if (k < K) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(tile[threadIdx.x][i]);
+            if (which) a.whh_pt[((size_t)dir * H + k) * 4 * H + p] = v;
+            else a.wih_pt[(size_t)k * 8 * H + (size_t)dir * 4 * H + p] = v;
+        }
+    }
 }
 
 // fp32 [R, C] (row stride ld) -> bf16 [R, ldd] (columns [C, ldd) zero-filled)
@@ -143,8 +159,12 @@ extern "C" int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, 
     a.whh_p = (__nv_bfloat16 *)p;  p += H8 * H * 2;
     a.whh_pt = (__nv_bfloat16 *)p; p += H8 * H * 2;
     a.wih_pt = (__nv_bfloat16 *)p;
-    lstm_pack_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
-    RCNN_LAUNCH_CHECK("lstm_pack_kernel");
+    lstm_pack_rows_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
+    RCNN_LAUNCH_CHECK("lstm_pack_rows_kernel");
+    const int kmax = I > H ? I : H;
+    dim3 grid((kmax + 31) / 32, 4 * H / 32, 4), block(32, 8);
+    lstm_pack_transposed_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+    RCNN_LAUNCH_CHECK("lstm_pack_transposed_kernel");
     return RCNN_OK;
 }
 

@@ -73,13 +73,11 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         dG2 = dG.view(BT, 8 * H)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm_bf16(dG2, packed.wih_pt, None, torch.float32).view(B, T, I).to(ctx.x_dtype)
+            dx_dtype = torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32
+            dx = ops.gemm_bf16(dG2, packed.wih_pt, None, dx_dtype).view(B, T, I).to(ctx.x_dtype)
         dwih_p = ops.gemm_bf16_atb(dG2, xb.view(BT, I))                # [8H, I] = dG^T x
         hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
-        dwhh_p = torch.empty((8 * H, H), dtype=torch.float32, device=dG.device)
-        for d in range(2):                                             # [4H, H] = dG_d^T h_prev_d
-            ops.gemm_bf16_atb(dG2[:, d * 4 * H:(d + 1) * 4 * H], hprev[:, d * H:(d + 1) * H],
-                              out=dwhh_p[d * 4 * H:(d + 1) * 4 * H])
+        dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
         db_p = ops.colsum_bf16(dG2)
         g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
         return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None)
@@ -134,7 +132,9 @@ class BidirectionalLSTM(nn.Module):
 
 def make_enc_rnn(enc_dim: int, hidden_size: int) -> nn.Sequential:
     """RCNN.enc_rnn (model/model.py:195-198): two stacked blocks, state-dict keys '0.*', '1.*'."""
-    return nn.Sequential(BidirectionalLSTM(enc_dim, hidden_size, hidden_size),
+    # the first block hands bf16 straight to the second (which would cast its input anyway); the
+    # stack's output stays fp32 like the reference's
+    return nn.Sequential(BidirectionalLSTM(enc_dim, hidden_size, hidden_size, out_dtype=torch.bfloat16),
                          BidirectionalLSTM(hidden_size, hidden_size, hidden_size))
 
 

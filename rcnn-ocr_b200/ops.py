@@ -68,6 +68,19 @@ def gemm_bf16_atb(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = N
     return out
 
 
+def gemm_bf16_atb_grouped(a: torch.Tensor, b: torch.Tensor, groups: int, M: int, N: int) -> torch.Tensor:
+    """out[g] = a[:, g*M:(g+1)*M]^T @ b[:, g*N:(g+1)*N] for g < groups, one launch; returns [groups*M, N] fp32."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[0] == b.shape[0]
+    assert a.shape[1] == groups * M and b.shape[1] == groups * N and a.stride(1) == 1 and b.stride(1) == 1
+    K = a.shape[0]
+    with torch.cuda.device(a.device):
+        out = torch.empty((groups * M, N), dtype=torch.float32, device=a.device)
+        rc = _lib.lib().rcnn_gemm_bf16_atb_grouped(a.data_ptr(), a.stride(0), M, b.data_ptr(), b.stride(0), N,
+                                                   out.data_ptr(), N, M * N, groups, M, N, K, 0, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_gemm_bf16_atb_grouped")
+    return out
+
+
 class PackedLSTMWeights:
     """bf16 views of one block's nn.LSTM parameters in the kernels' layouts (see
     rcnn_lstm_pack_weights in include/rcnn_ocr_b200.h)."""

@@ -74,3 +74,16 @@ def test_gemm_atb_exact_small_integers_and_strided():
     a = a_big[:, 128:384]                                     # column slice: lda = 512, M = 256
     got = ops.gemm_bf16_atb(a, b)
     assert torch.equal(got, a.float().t() @ b.float())
+
+
+def test_gemm_atb_grouped_and_colsum():
+    g = torch.Generator(device="cuda").manual_seed(6)
+    a = torch.randint(-3, 4, (700, 2 * 256), device="cuda", generator=g).bfloat16()
+    b = torch.randint(-3, 4, (700, 2 * 64), device="cuda", generator=g).bfloat16()
+    got = ops.gemm_bf16_atb_grouped(a, b, 2, 256, 64)
+    for d in range(2):
+        want = a[:, d * 256:(d + 1) * 256].float().t() @ b[:, d * 64:(d + 1) * 64].float()
+        assert torch.equal(got[d * 256:(d + 1) * 256], want)
+    for rows, cols in ((700, 512), (1000, 200), (33, 195)):
+        x = torch.randn(rows, cols, device="cuda", generator=g).bfloat16()
+        torch.testing.assert_close(ops.colsum_bf16(x), x.float().sum(0), rtol=1e-4, atol=1e-3)
