@@ -7,7 +7,9 @@
 // nn.LSTM at model/model.py:154-156,161, M = T*B rows), the block's nn.Linear(2H -> H)
 // (model/model.py:157,162) and the CTC head; the backward pass reuses it for dX and dW.
 //
-// Tile 128 x 128 x 64 per CTA, warp-specialised: warp 0 = TMA producer (one elected lane),
+// Tile 128 x 128 x 64 per CTA, warp-specialised: warps 0 and 6 = TMA producers (one elected lane
+// each, one operand box each: a single thread gets one 16 KB box per ~410 cycles out of the TMA
+// unit, independent issuers run in parallel -- see profiles/tma_rate_r01.txt),
 // warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (one warp per
 // TMEM lane quadrant: tcgen05.ld -> +bias -> convert -> global).  Three smem stages of 32 KB
 // so that two CTAs share an SM and one CTA's epilogue overlaps the other's main loop.
@@ -81,7 +83,7 @@ using namespace sm100;
 
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
 constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kThreads = 288;   // warp 0,6,7,8 TMA producers, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + BN * sizeof(float);
@@ -155,15 +157,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
         tmem_alloc<BN>(tmem_slot);
     }
-    if (warp >= 2) {
-        for (int j = threadIdx.x - 64; j < BN; j += kThreads - 64) {
+    if (warp >= 2 && warp < 6) {
+        for (int j = threadIdx.x - 64; j < BN; j += 128) {
             const int col = tile_n * BN + j;
             bias_s[j] = (bias != nullptr && col < N) ? bias[col] : 0.f;
         }
@@ -173,15 +175,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 6) {
         if (elect_one()) {
+            const bool isA = warp == 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], kStageBytes);
-                tma_load_2d(tiles + s * kStageBytes, &tmA, &full[s], kb * BK, tile_m * BM);
-                tma_load_2d(tiles + s * kStageBytes + kABytes, &tmB, &full[s], kb * BK, tile_n * BN);
+                mbar_arrive_expect_tx(&full[s], isA ? kABytes : kBBytes);
+                if (isA) tma_load_2d(tiles + s * kStageBytes, &tmA, &full[s], kb * BK, tile_m * BM);
+                else tma_load_2d(tiles + s * kStageBytes + kABytes, &tmB, &full[s], kb * BK, tile_n * BN);
             }
         }
     } else if (warp == 1) {
@@ -201,7 +204,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             umma_commit(tmem_full);
         }
-    } else {
+    } else if (warp < 6) {
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -270,7 +273,7 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
@@ -282,19 +285,20 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp >= 6) {
         if (elect_one()) {
+            const int which = warp == 0 ? 0 : warp - 5;      // 0,1: the two A halves; 2,3: the two B halves
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                mbar_arrive_expect_tx(&full[s], kHalf);
                 unsigned char *st = tiles + s * kStageBytes;
                 const int k0 = (kb0 + kb) * BK;
-                tma_load_2d(st, &tmA, &full[s], a_c0, k0);
-                tma_load_2d(st + kHalf, &tmA, &full[s], a_c0 + 64, k0);
-                tma_load_2d(st + kABytes, &tmB, &full[s], b_c0, k0);
-                tma_load_2d(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, k0);
+                if (which == 0) tma_load_2d(st, &tmA, &full[s], a_c0, k0);
+                else if (which == 1) tma_load_2d(st + kHalf, &tmA, &full[s], a_c0 + 64, k0);
+                else if (which == 2) tma_load_2d(st + kABytes, &tmB, &full[s], b_c0, k0);
+                else tma_load_2d(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, k0);
             }
         }
     } else if (warp == 1) {
@@ -314,7 +318,7 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             umma_commit(tmem_full);
         }
-    } else {
+    } else if (warp < 6) {
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
