@@ -7,12 +7,12 @@
 // nn.LSTM at model/model.py:154-156,161, M = T*B rows), the block's nn.Linear(2H -> H)
 // (model/model.py:157,162) and the CTC head; the backward pass reuses it for dX and dW.
 //
-// Tile 128 x 128 x 64 per CTA, warp-specialised: warps 0 and 6 = TMA producers (one elected lane
-// each, one operand box each: a single thread gets one 16 KB box per ~410 cycles out of the TMA
-// unit, independent issuers run in parallel -- see profiles/tma_rate_r01.txt),
-// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-5 = epilogue (one warp per
-// TMEM lane quadrant: tcgen05.ld -> +bias -> convert -> global).  Three smem stages of 32 KB
-// so that two CTAs share an SM and one CTA's epilogue overlaps the other's main loop.
+// 128 x 128 output tiles, warp-specialised: warps 0 and 6 = TMA producers (one elected lane each,
+// one operand each: a single thread gets one 16 KB box per ~410 cycles out of the TMA unit,
+// independent issuers run in parallel -- see profiles/tma_rate_r01.txt), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2-5 = epilogue (one warp per TMEM lane quadrant:
+// tcgen05.ld -> +bias -> convert -> global).  The main kernel is persistent with two TMEM
+// accumulators (see gemm_tn_kernel); the weight-gradient kernel (gemm_atb_kernel) is split-K.
 // M / N / K tails: TMA zero-fills out-of-bounds rows and columns; stores are masked.
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -88,10 +88,16 @@ constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + BN * sizeof(float);
 
+// vec_ok: 32-byte aligned row chunks -> 256-bit stores (full sectors per lane)
 __device__ __forceinline__ void store_row_chunk(float *dst, const float (&v)[32], int ncols, bool vec_ok) {
     if (vec_ok && ncols == 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; j += 8) {
+            U8 q;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q.v[k] = __float_as_uint(v[j + k]);
+            st_v8(dst + j, q);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -101,13 +107,14 @@ __device__ __forceinline__ void store_row_chunk(float *dst, const float (&v)[32]
 __device__ __forceinline__ void store_row_chunk(__nv_bfloat16 *dst, const float (&v)[32], int ncols, bool vec_ok) {
     if (vec_ok && ncols == 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            q.x = *reinterpret_cast<uint32_t *>(&h0); q.y = *reinterpret_cast<uint32_t *>(&h1);
-            q.z = *reinterpret_cast<uint32_t *>(&h2); q.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(dst + j) = q;
+        for (int j = 0; j < 32; j += 16) {
+            U8 q;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * k], v[j + 2 * k + 1]);
+                q.v[k] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            st_v8(dst + j, q);
         }
     } else {
 #pragma unroll
@@ -119,13 +126,14 @@ __device__ __forceinline__ void store_row_chunk(__nv_bfloat16 *dst, const float 
 __device__ __forceinline__ void store_row_chunk(__half *dst, const float (&v)[32], int ncols, bool vec_ok) {
     if (vec_ok && ncols == 32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-            q.x = *reinterpret_cast<uint32_t *>(&h0); q.y = *reinterpret_cast<uint32_t *>(&h1);
-            q.z = *reinterpret_cast<uint32_t *>(&h2); q.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(dst + j) = q;
+        for (int j = 0; j < 32; j += 16) {
+            U8 q;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                __half2 h = __floats2half2_rn(v[j + 2 * k], v[j + 2 * k + 1]);
+                q.v[k] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            st_v8(dst + j, q);
         }
     } else {
 #pragma unroll
@@ -134,41 +142,47 @@ __device__ __forceinline__ void store_row_chunk(__half *dst, const float (&v)[32
     }
 }
 
+// Persistent main kernel.  One CTA per SM walks a static list of 128 x 128 output tiles (tile_n
+// fastest, so neighbouring CTAs share A row-blocks in L2).  A pipeline stage holds K = 128 (two TMA
+// boxes per operand, 64 KB): one barrier round trip then feeds eight tcgen05.mma -- with K = 64 per
+// round the issuing thread spent as long on wait/commit bookkeeping as the tensor pipe spent on
+// the four MMAs (profiles/timeline_r01.txt).  Two 128-column TMEM accumulators alternate between
+// tiles, so the epilogue warps drain tile i while the MMA warp is already on tile i+1.
+constexpr int kPStages = 3;
+constexpr int kPBoxes = 2;                                   // k-boxes of 64 per stage
+constexpr uint32_t kPOperand = kPBoxes * kABytes;            // 32 KB per operand per stage
+constexpr uint32_t kPStage = 2 * kPOperand;                  // 64 KB
+constexpr int kPThreads = 224;                               // warps: 0 A-TMA, 1 MMA, 2-5 epilogue, 6 B-TMA
+constexpr size_t kPSmem = 1024 + kPStages * kPStage + 256 + 2 * BN * sizeof(float);
+
 template <typename OutT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *tiles = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
-    uint64_t *empty = full + kStages;
-    uint64_t *tmem_full = empty + kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
-    float *bias_s = reinterpret_cast<float *>(smem + kStages * kStageBytes + 256);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kPStages * kPStage);
+    uint64_t *empty = full + kPStages;
+    uint64_t *tmem_full = empty + kPStages;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;        // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + kPStages * kPStage + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    const int num_kb = (K + BK - 1) / BK;
+    const int ntn = (N + BN - 1) / BN, ntm = (M + BM - 1) / BM;
+    const int num_tiles = ntn * ntm;
+    const int rounds = (K + kPBoxes * BK - 1) / (kPBoxes * BK);
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-            mbar_init(tmem_full, 1);
+            for (int s = 0; s < kPStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<BN>(tmem_slot);
-    }
-    if (warp >= 2 && warp < 6) {
-        for (int j = threadIdx.x - 64; j < BN; j += 128) {
-            const int col = tile_n * BN + j;
-            bias_s[j] = (bias != nullptr && col < N) ? bias[col] : 0.f;
-        }
+        tmem_alloc<2 * BN>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -176,63 +190,92 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 || warp == 6) {
+        // ===== TMA producers: warp 0 streams A, warp 6 streams B (independent issuers) =============
         if (elect_one()) {
             const bool isA = warp == 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], isA ? kABytes : kBBytes);
-                if (isA) tma_load_2d(tiles + s * kStageBytes, &tmA, &full[s], kb * BK, tile_m * BM);
-                else tma_load_2d(tiles + s * kStageBytes + kABytes, &tmB, &full[s], kb * BK, tile_n * BN);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = isA ? (tile / ntn) * BM : (tile % ntn) * BN;
+                for (int r = 0; r < rounds; ++r) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[st], kPOperand);
+                    unsigned char *dst = tiles + st * kPStage + (isA ? 0 : kPOperand);
+#pragma unroll
+                    for (int j = 0; j < kPBoxes; ++j)
+                        tma_load_2d(dst + j * kABytes, isA ? &tmA : &tmB, &full[st], (r * kPBoxes + j) * BK, row0);
+                    if (++st == kPStages) { st = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
+        // ===== MMA issuer ==========================================================================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&full[s], ph);
+            int st = 0, it = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
                 tc_fence_after();
-                const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes), 16, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + s * kStageBytes + kABytes), 16, 1024);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int r = 0; r < rounds; ++r) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < BK / UK; ++k)  // +32 bytes along K inside the 128-byte swizzle row
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                    for (int j = 0; j < kPBoxes; ++j) {
+                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + st * kPStage + j * kABytes), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + st * kPStage + kPOperand + j * kABytes), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (r | j | k) != 0);
+                    }
+                    umma_commit(&empty[st]);
+                    if (++st == kPStages) { st = 0; ph ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
             }
-            umma_commit(tmem_full);
         }
     } else if (warp < 6) {
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int row = tile_m * BM + q * 32 + lane;
-        const bool vec_ok = (ldd % (16 / (long long)sizeof(OutT)) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
-            const int col0 = tile_n * BN + c0;
-            if (row < M && col0 < N) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
-                store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
+        // ===== epilogue: TMEM -> registers -> (+bias, convert) -> global ============================
+        const int q = warp & 3;
+        const bool vec_ok = (ldd % (32 / (long long)sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(D) & 31) == 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int tile_m = tile / ntn, tile_n = tile % ntn;
+            {   // this tile's 128 bias values -> shared memory (broadcast reads below)
+                const int j = threadIdx.x - 64, col = tile_n * BN + j;
+                bias_s[acc * BN + j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
             }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");   // bias_s visible to the four epilogue warps
+            tc_fence_after();
+            const int row = tile_m * BM + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                tmem_ld_wait();
+                const int col0 = tile_n * BN + c0;
+                if (row < M && col0 < N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * BN + c0 + j];
+                    store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
 }
-
 
 // ---- D[M,N] += A[K,M]^T * B[K,N]  (weight-gradient shape) -------------------------------------
 // Both operands are "MN-major": the contraction index k is the ROW of the row-major global
@@ -357,10 +400,11 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <typename OutT>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
                 int N, int K, cudaStream_t s) {
-    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+    const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_tn_kernel<OutT><<<grid, kThreads, kSmemBytes, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
+    gemm_tn_kernel<OutT><<<grid, kPThreads, kPSmem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
     RCNN_LAUNCH_CHECK("gemm_tn_kernel");
     return RCNN_OK;
 }
