@@ -36,6 +36,31 @@ long long *debug_timeline() { return g_timeline; }
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
+// ---- group-barrier counters for the recurrent kernels -------------------------------------------
+static const int kCounterRegion = 128, kCounterRegions = 64, kMaxDevices = 32;
+static unsigned int *g_counters[kMaxDevices] = {};
+static unsigned int g_counter_next[kMaxDevices] = {};
+
+unsigned int *group_counters(int n, cudaStream_t s) {
+    int dev = 0;
+    if (n > kCounterRegion || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        set_error("group_counters: n=%d device=%d unsupported", n, dev);
+        return nullptr;
+    }
+    if (!g_counters[dev]) {   // one-time 32 KB per device (like a library handle's workspace)
+        if (cudaMalloc(&g_counters[dev], sizeof(unsigned int) * kCounterRegion * kCounterRegions) != cudaSuccess) {
+            set_error("group_counters: cudaMalloc failed");
+            return nullptr;
+        }
+    }
+    unsigned int *p = g_counters[dev] + (size_t)(g_counter_next[dev]++ % kCounterRegions) * kCounterRegion;
+    if (cudaMemsetAsync(p, 0, sizeof(unsigned int) * kCounterRegion, s) != cudaSuccess) {
+        set_error("group_counters: cudaMemsetAsync failed");
+        return nullptr;
+    }
+    return p;
+}
+
 // ---- per-kernel event timing -----------------------------------------------------------
 static const int kProfSlots = 16384;
 static bool g_prof_on = false;

@@ -36,6 +36,9 @@ int num_sms();
 // optional per-step clock64 timeline of cluster 0 / CTA 0 of the recurrent kernels (debug aid)
 long long *debug_timeline();
 void count_launch();
+// `n` zeroed 32-bit counters (zeroed on `s`, in stream order) for the recurrent kernels' group barriers.
+// The storage is a per-device ring of regions allocated once; a region is reused only after 64 later calls.
+unsigned int *group_counters(int n, cudaStream_t s);
 
 // Optional per-kernel event timing (see rcnn_prof_* in the header).
 int prof_begin(int kernel, cudaStream_t s);

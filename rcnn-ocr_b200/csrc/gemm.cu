@@ -44,7 +44,7 @@ static int encode(CUtensorMap *out, const void *base, int elem_bytes, int rank, 
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return RCNN_ERR_DEVICE;
     }
-    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -75,6 +75,16 @@ int make_tmap_3d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t d2
     const cuuint64_t gstride[2] = {row_pitch_bytes, pitch2_bytes};
     const cuuint32_t box[3] = {box_cols, box_rows, box2};
     return encode(out, base, elem_bytes, 3, gdim, gstride, box, swizzle128);
+}
+
+// 4-D map with caller-given dimension order (dims[0] innermost, strides[i] = byte stride of dims[i+1]):
+// lets one TMA operation gather several K chunks of a row tile into consecutive UMMA-shaped boxes.
+int make_tmap_4d(CUtensorMap *out, const void *base, int elem_bytes, const uint64_t dims[4], const uint64_t strides[3],
+                 const uint32_t box[4], int swizzle128) {
+    const cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+    const cuuint64_t gstride[3] = {strides[0], strides[1], strides[2]};
+    const cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+    return encode(out, base, elem_bytes, 4, gdim, gstride, b, swizzle128);
 }
 
 namespace {

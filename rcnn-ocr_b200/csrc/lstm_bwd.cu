@@ -8,14 +8,17 @@
 //     dG_t   = [di*i(1-i), df*f(1-f), dg*(1-g^2), do*o(1-o)]   (pre-activation gradients)
 // dW_ih, dW_hh, db and dX are GEMMs / reductions over dG after the loop (host side).
 //
-// Same cluster decomposition as the forward kernel: CTA c owns hidden units [32c, 32c+32).
-// Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for H=512) and
-// the streamed operand is the full dG_{t'} tile [128 seq, 4H] (two 64-column TMA boxes per slot of a
-// 3-slot ring, so one barrier round trip covers K = 128), accumulated by tcgen05.mma into a 128 x 32 fp32 TMEM tile.  The cell
-// threads (one per sequence) keep dc in registers for the whole sequence, read the saved gates
-// / cell states / upstream dh directly from global memory (prefetched one 8-unit chunk ahead)
-// and write dG_t in the packed column order, which is at once the next step's MMA operand and
-// the operand of the dX / dW GEMMs.
+// Same decomposition as the forward kernel: a GROUP of H/32 CTAs owns one work item = (direction,
+// tile of 64 sequences) at a time, CTA c owns hidden units [32c, 32c+32); groups synchronise per step
+// through a counter in global memory (red.release / relaxed poll) and the kernel is launched
+// cooperatively.  Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for
+// H=512) and the streamed operand is the full dG_{t'} tile [64 seq, 4H]: one TMA operation brings
+// four K chunks (a 32 KB slot of a 3-slot ring, 4-D tensor map), accumulated by tcgen05.mma (M = 64)
+// into a 64 x 32 fp32 TMEM tile.  The cell threads (16 rows per TMEM lane quadrant, the two half-warps
+// of a warp split the columns) keep dc in registers for the whole sequence, read the saved gates /
+// cell states / upstream dh directly from global memory (issued before the MMA wait) and write dG_t
+// in the packed column order, which is at once the next step's MMA operand and the operand of the
+// dX / dW GEMMs.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -26,53 +29,50 @@ namespace {
 
 using namespace sm100;
 
-constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
+constexpr int LB = 64;    // sequences per work item (UMMA M)
 constexpr int LU = 32;    // hidden units per CTA (UMMA N)
 constexpr int LK = 64;
-constexpr int kMaxRing = 6;
-constexpr uint32_t kABox = LB * LK * 2;    // one TMA box: 128 seq x 64 k bf16 = 16 KB
-constexpr int kBoxes = 2;                  // boxes per ring slot: one barrier round trip per K = 128
-constexpr uint32_t kATile = kBoxes * kABox; // 32 KB ring slot
-constexpr uint32_t kWTile = LU * LK * 2;   // 4 KB
+constexpr int kARing = 3;
+constexpr int kChunks = 4;                   // K chunks per TMA operation / ring slot
+constexpr uint32_t kABox = LB * LK * 2;      // [64 seq x 64 k] bf16 = 8 KB
+constexpr uint32_t kATile = kChunks * kABox; // 32 KB ring slot
+constexpr uint32_t kWTile = LU * LK * 2;     // 4 KB
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct BwdParams {
     int B, T, H;
+    int nitems, ngroups;
     const __half *gates;       // [2, T, B, 4H] activated gates, packed order
     const float *csave;        // [2, T, B, H]
     const float *dhcat;        // [B, T, 2H] upstream gradient of the block's LSTM output
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
+    unsigned int *sync;        // [ngroups] zeroed before the launch
     long long *tl;             // debug timeline or nullptr
 };
-#define TL_MARK(k) do { if (tl) tl[s * 8 + (k)] = clock64(); } while (0)
+#define TL_MARK(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
 
-__device__ __forceinline__ uint32_t cluster_ctarank_b() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_id_x_b() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_arrive_relaxed_b() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_b() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
-// one gpu-scope release per CTA for the cell warps' dG stores (see lstm_fwd.cu: cell_publish_arrive)
-__device__ __forceinline__ void cell_publish_sync_b() {
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x == 64) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-    else cluster_arrive_relaxed_b();
-    cluster_wait_b();
-}
-__device__ __forceinline__ void cluster_sync_b() {
-    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
 __device__ __forceinline__ float tanh_fast_b(float x) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+__device__ __forceinline__ void red_release_gpu_inc_b(unsigned int *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_b(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_counter_b(const unsigned int *p, unsigned int target) {
+    if (ld_relaxed_gpu_b(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_relaxed_gpu_b(p) < target) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("rcnn-ocr_b200: lstm_bwd group counter timed out (block %d)\n", blockIdx.x);
+            __trap();
+        }
+    }
 }
 
 struct ChunkIn {     // saved state of 8 units of one sequence at one step
@@ -81,33 +81,31 @@ struct ChunkIn {     // saved state of 8 units of one sequence at one step
 };
 
 __device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, const float *crow, const float *cprow,
-                                           const float *dhrow, int q, bool valid) {
+                                           const float *dhrow, bool valid) {
     U8 z;
 #pragma unroll
     for (int k = 0; k < 8; ++k) z.v[k] = 0u;
     if (valid) {
-        ci.g[0] = ld_ro_v8(grow + q * 32);
-        ci.g[1] = ld_ro_v8(grow + q * 32 + 16);
-        ci.c = ld_ro_v8(crow + q * 8);
-        ci.dh = ld_ro_v8(dhrow + q * 8);
-        ci.cp = cprow ? ld_ro_v8(cprow + q * 8) : z;
+        ci.g[0] = ld_ro_v8(grow);
+        ci.g[1] = ld_ro_v8(grow + 16);
+        ci.c = ld_ro_v8(crow);
+        ci.dh = ld_ro_v8(dhrow);
+        ci.cp = cprow ? ld_ro_v8(cprow) : z;
     } else {
         ci.g[0] = z; ci.g[1] = z; ci.c = z; ci.cp = z; ci.dh = z;
     }
 }
 
-// TWO_SM: the cluster is 8 CTA pairs; a pair runs one cta_group::2 MMA of M = 128 sequences (64 per
-// CTA) x N = 64 units (32 per CTA), so each SM streams only HALF of the dG tile (the per-SM L2 read
-// port, ~40 B/clk, is what bounds this kernel).  A CTA then owns 64 sequences x the pair's 64 units.
-template <int kARing, bool TWO_SM>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
     const int nkc = 4 * H / LK;
+    const int nslots = nkc / kChunks;          // ring slots consumed per step
+    const int gsize = H / 32;
     unsigned char *w_s = smem;                          // nkc tiles [32 n x 64 k] bf16, SW128
-    unsigned char *a_s = w_s + (size_t)nkc * kWTile;    // kARing tiles [128 b x 64 k] bf16, SW128
+    unsigned char *a_s = w_s + (size_t)nkc * kWTile;    // kARing slots of kChunks boxes [64 seq x 64 k] bf16, SW128
     uint64_t *bars = reinterpret_cast<uint64_t *>(a_s + kARing * kATile);
     uint64_t *w_full = bars;
     uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
@@ -115,13 +113,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = (int)cluster_ctarank_b();
-    const int cid = (int)cluster_id_x_b();
-    const int dir = cid & 1, tile = cid >> 1;
-    const int b0 = tile * LB;
+    const int group = blockIdx.x / gsize;
+    const int c = blockIdx.x % gsize;
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
-    const bool leader = (c & 1) == 0;
-    const uint16_t pair_mask = (uint16_t)(3u << (c & ~1));
+    unsigned int *counter = p.sync + group;
 
     if (warp == 1) {
         if (lane == 0) {
@@ -131,168 +126,148 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             fence_barrier_init();
         }
         __syncwarp();
-        if (TWO_SM) tmem_alloc_2sm<LU>(tmem_slot); else tmem_alloc<LU>(tmem_slot);
+        tmem_alloc<LU>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (TWO_SM) {
-        // the resident W^T slice of BOTH CTAs must be in place, and the peer's barriers initialised,
-        // before the leader issues the first pair MMA / the peer's TMA signals the leader's barrier
-        if (warp == 0 && lane == 0) {
-            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
-            for (int kc = 0; kc < nkc; ++kc)
-                tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
-        }
-        if (warp == 1 && lane == 0) mbar_wait(w_full, 0);
-        __syncwarp();
-        cluster_sync_b();
-    }
 
     // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
     // reverse direction from t = 0 up to T-1.
     if (warp == 0) {
-        if (lane == 0 && !TWO_SM) {
+        // ===== TMA producer (one elected thread) =================================================
+        if (elect_one()) {
             tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmG);
-            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
-            for (int kc = 0; kc < nkc; ++kc)
-                tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
-        }
-        int pslot = 0;
-        uint32_t pphase = 0;
-        for (int s = 0; s < T; ++s) {
-            if (lane == 0 && s > 0) {
-                const int t = dir ? s : T - 1 - s;
-                const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
-                TL_MARK(0);
-                fence_proxy_async_global();
-                for (int g = 0; g < nkc / kBoxes; ++g) {
-                    mbar_wait(&a_empty[pslot], pphase ^ 1);
-                    if (!TWO_SM || leader) mbar_arrive_expect_tx(&a_full[pslot], kATile);
-#pragma unroll
-                    for (int j = 0; j < kBoxes; ++j) {
-                        const int kc = g * kBoxes + j;
-                        unsigned char *dst = a_s + pslot * kATile + j * kABox;
-                        if (!TWO_SM)
-                            tma_load_3d(dst, &tmG, &a_full[pslot], dir * 4 * H + kc * LK, tsrc, b0);
-                        else   // each CTA fetches its own 64 sequences; both halves complete on the LEADER's barrier
-                            tma_load_3d_2sm(dst, &tmG, &a_full[pslot], dir * 4 * H + kc * LK, tsrc, b0 + 64 * (c & 1));
-                    }
-                    if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
+            int cur_dir = -1;
+            int pslot = 0;
+            uint32_t pphase = 0;
+            unsigned int published = 0;
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1, b0 = (item >> 1) * LB;
+                if (dir != cur_dir) {
+                    mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
+                    for (int kc = 0; kc < nkc; ++kc)
+                        tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
+                    cur_dir = dir;
                 }
-                TL_MARK(1);
+                for (int s = 1; s < T; ++s) {
+                    const int t = dir ? s : T - 1 - s;
+                    const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
+                    TL_MARK(7);
+                    wait_counter_b(counter, (published + (unsigned)s) * (unsigned)gsize);
+                    TL_MARK(0);
+                    fence_proxy_async_global();
+                    for (int g = 0; g < nslots; ++g) {
+                        mbar_wait(&a_empty[pslot], pphase ^ 1);
+                        mbar_arrive_expect_tx(&a_full[pslot], kATile);
+                        tma_load_4d(a_s + pslot * kATile, &tmG, &a_full[pslot], 0, b0, dir * nkc + g * kChunks, tsrc);
+                        if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
+                    }
+                    TL_MARK(1);
+                }
+                published += (unsigned)T;
             }
-            __syncwarp();
-            cluster_arrive_relaxed_b();
-            cluster_wait_b();
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_bf16(LB, TWO_SM ? 2 * LU : LU);
-        int mslot = 0;
-        uint32_t mphase = 0;
-        if (lane == 0 && !TWO_SM) mbar_wait(w_full, 0);
-        __syncwarp();
-        for (int s = 0; s < T; ++s) {
-            if (lane == 0 && s > 0 && (!TWO_SM || leader)) {
-                for (int g = 0; g < nkc / kBoxes; ++g) {
-                    mbar_wait(&a_full[mslot], mphase);
-                    if (g == 0) TL_MARK(2);
-                    tc_fence_after();
+        // ===== MMA issuer (one elected thread) ===================================================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(LB, LU);
+            int cur_dir = -1;
+            int mslot = 0;
+            uint32_t mphase = 0, wphase = 0;
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1;
+                if (dir != cur_dir) { mbar_wait(w_full, wphase); wphase ^= 1; cur_dir = dir; }
+                for (int s = 1; s < T; ++s) {
+                    for (int g = 0; g < nslots; ++g) {
+                        mbar_wait(&a_full[mslot], mphase);
+                        if (g == 0) TL_MARK(2);
+                        tc_fence_after();
 #pragma unroll
-                    for (int j = 0; j < kBoxes; ++j) {
-                        const int kc = g * kBoxes + j;
-                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kATile + j * kABox), 16, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+                        for (int j = 0; j < kChunks; ++j) {
+                            const int kc = g * kChunks + j;
+                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kATile + j * kABox), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < LK / 16; ++k) {
-                            if (TWO_SM)
-                                umma_bf16_2sm(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
-                            else
+                            for (int k = 0; k < LK / 16; ++k)
                                 umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
                         }
+                        umma_commit(&a_empty[mslot]);
+                        if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
                     }
-                    if (TWO_SM) umma_commit_2sm(&a_empty[mslot], pair_mask);   // frees the slot in both CTAs
-                    else umma_commit(&a_empty[mslot]);
-                    if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
+                    umma_commit(tmem_full);
+                    TL_MARK(3);
                 }
-                if (TWO_SM) umma_commit_2sm(tmem_full, pair_mask);
-                else umma_commit(tmem_full);
-                TL_MARK(3);
             }
-            __syncwarp();
-            cluster_arrive_relaxed_b();
-            cluster_wait_b();
         }
     } else {
-        const int qd = warp & 3;            // TMEM lane quadrant
-        const int hf = (warp - 2) >> 2;     // which 16 of a 32-unit slice this warp handles
-        // 1-SM: the CTA owns 128 sequences x its own 32-unit slice c.  TWO_SM: it owns 64 sequences x
-        // both slices of the pair; TMEM lanes 0-63 hold slice 2p, lanes 64-127 slice 2p+1 ("2x2" layout).
-        const int row = TWO_SM ? 64 * (c & 1) + (qd & 1) * 32 + lane : qd * 32 + lane;
-        const int cs = TWO_SM ? (c & ~1) + (qd >> 1) : c;     // unit slice this thread works on
-        const int b = b0 + row;
-        const bool valid = b < B;
-        float dc[16];
+        // ===== cell update ========================================================================
+        // M = 64 accumulator layout: row m sits in TMEM lane 32*(m/16) + m%16, so warp quadrant qd reads
+        // rows 16qd .. 16qd+15 in its lanes 0-15; the upper half-warp takes over 8 of the 16 columns.
+        const int qd = warp & 3;
+        const int hf = (warp - 2) >> 2;                   // which 16 of the CTA's 32 units this warp handles
+        const int row = qd * 16 + (lane & 15);            // sequence within the tile
+        const int u0 = hf * 16 + (lane >> 4) * 8;         // first of this thread's 8 units (within the CTA)
+        unsigned int mcount = 0;
+        for (int item = group; item < p.nitems; item += p.ngroups) {
+            const int dir = item & 1, b0 = (item >> 1) * LB;
+            const int b = b0 + row;
+            const bool valid = b < B;
+            float dc[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dc[i] = 0.f;
-        for (int s = 0; s < T; ++s) {
-            const int t = dir ? s : T - 1 - s;
-            const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
-            const size_t rtb = ((size_t)dir * T + t) * B + b;
-            const __half *grow = p.gates + rtb * 4 * H + (size_t)cs * 128;
-            const float *crow = p.csave + rtb * H + 32 * cs;
-            const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * cs : nullptr;
-            const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * cs;
-            __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)cs * 128;
+            for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+            for (int s = 0; s < T; ++s) {
+                const int t = dir ? s : T - 1 - s;
+                const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
+                const size_t rtb = ((size_t)dir * T + t) * B + b;
+                const __half *grow = p.gates + rtb * 4 * H + (size_t)c * 128 + u0 * 4;
+                const float *crow = p.csave + rtb * H + 32 * c + u0;
+                const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c + u0 : nullptr;
+                const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + u0;
+                __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128 + u0 * 4;
 
-            ChunkIn cur, nxt;
-            load_chunk(cur, grow, crow, cprow, dhrow, hf * 2, valid);
-            load_chunk(nxt, grow, crow, cprow, dhrow, hf * 2 + 1, valid);
-            if (valid && s + 1 < T && hf == 0) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
-                const int tn = dir ? t + 1 : t - 1;
-                const size_t rn = ((size_t)dir * T + tn) * B + b;
-                prefetch_l2(p.gates + rn * 4 * H + (size_t)cs * 128);
-                prefetch_l2(p.gates + rn * 4 * H + (size_t)cs * 128 + 64);
-                prefetch_l2(p.csave + rn * H + 32 * cs);
-                prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * cs);
-            }
-            uint32_t acc[16];
-            if (s > 0) {
-                mbar_wait(tmem_full, (s - 1) & 1);
-                if (threadIdx.x == 64) TL_MARK(4);
-                tc_fence_after();
-                tmem_ld_32x16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 16), acc);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0u;
-            }
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-                const int q = hf * 2 + qq;
-                const ChunkIn &ci = qq ? nxt : cur;
-                const __half2 *gh = reinterpret_cast<const __half2 *>(ci.g);
-                float cc[8], cp[8], dhu[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    cc[k] = __uint_as_float(ci.c.v[k]);
-                    cp[k] = __uint_as_float(ci.cp.v[k]);
-                    dhu[k] = __uint_as_float(ci.dh.v[k]);
+                ChunkIn ci;
+                load_chunk(ci, grow, crow, cprow, dhrow, valid);
+                if (valid && s + 1 < T) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
+                    const int tn = dir ? t + 1 : t - 1;
+                    const size_t rn = ((size_t)dir * T + tn) * B + b;
+                    prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128 + u0 * 4);
+                    prefetch_l2(p.csave + rn * H + 32 * c + u0);
+                    prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * c + u0);
                 }
+                float rec[8];   // dG_{t'} W_hh for this thread's 8 units
+                if (s > 0) {
+                    uint32_t acc[16];
+                    mbar_wait(tmem_full, mcount & 1);
+                    ++mcount;
+                    if (threadIdx.x == 64) TL_MARK(4);
+                    tc_fence_after();
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 16), acc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t hi = __shfl_sync(FULL, acc[8 + j], lane & 15);
+                        rec[j] = __uint_as_float(lane < 16 ? acc[j] : hi);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rec[j] = 0.f;
+                }
+                const __half2 *gh = reinterpret_cast<const __half2 *>(ci.g);
                 float o32[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 if_ = __half22float2(gh[2 * j]);       // (i, f)
                     const float2 go_ = __half22float2(gh[2 * j + 1]);   // (g, o)
                     const float ig = if_.x, fg = if_.y, gg = go_.x, og = go_.y;
-                    const float dh = dhu[j] + __uint_as_float(acc[qq * 8 + j]);
-                    const float tc = tanh_fast_b(cc[j]);
+                    const float dh = __uint_as_float(ci.dh.v[j]) + rec[j];
+                    const float tc = tanh_fast_b(__uint_as_float(ci.c.v[j]));
                     const float d_o = dh * tc;
-                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[qq * 8 + j]);
-                    dc[qq * 8 + j] = dct * fg;
+                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[j]);
+                    dc[j] = dct * fg;
                     o32[4 * j] = dct * gg * ig * (1.f - ig);
-                    o32[4 * j + 1] = dct * cp[j] * fg * (1.f - fg);
+                    o32[4 * j + 1] = dct * __uint_as_float(ci.cp.v[j]) * fg * (1.f - fg);
                     o32[4 * j + 2] = dct * ig * (1.f - gg * gg);
                     o32[4 * j + 3] = d_o * og * (1.f - og);
                 }
@@ -305,26 +280,28 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(o32[16 * j + 2 * k], o32[16 * j + 2 * k + 1]);
                             v.v[k] = *reinterpret_cast<uint32_t *>(&h2);
                         }
-                        st_v8(dgrow + q * 32 + j * 16, v);
+                        st_v8(dgrow + j * 16, v);
                     }
                 }
+                if (threadIdx.x == 64) TL_MARK(5);
+                tc_fence_before();
+                fence_proxy_async_global();   // dG_t stores before the other CTAs' TMA reads
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 64) {      // one gpu-scope release per CTA
+                    red_release_gpu_inc_b(counter);
+                    TL_MARK(6);
+                }
             }
-            if (threadIdx.x == 64) TL_MARK(5);
-            tc_fence_before();
-            fence_proxy_async_global();   // dG_t stores before the other CTAs' TMA reads
-            cell_publish_sync_b();
-            if (threadIdx.x == 64) TL_MARK(6);
         }
     }
-    if (TWO_SM) cluster_sync_b();   // no CTA leaves while its peer may still signal its barriers / use its TMEM
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        if (TWO_SM) tmem_dealloc_2sm<LU>(tmem_base); else tmem_dealloc<LU>(tmem_base);
+        tmem_dealloc<LU>(tmem_base);
     }
 }
 
-size_t bwd_smem_bytes(int H, int ring) { return 1024 + (size_t)(4 * H / LK) * kWTile + (size_t)ring * kATile + 256; }
+size_t bwd_smem_bytes(int H) { return 1024 + (size_t)(4 * H / LK) * kWTile + (size_t)kARing * kATile + 256; }
 
 // column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
 __global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, long long rows, int cols,
@@ -435,10 +412,13 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     CUtensorMap tw, tg;
     int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, LU, LK, 1);
     if (rc) return rc;
-    static const bool two_sm = getenv("RCNN_BWD_2SM") ? atoi(getenv("RCNN_BWD_2SM")) != 0 : false;
-    rc = make_tmap_3d(&tg, dG, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2,
-                      two_sm ? LB / 2 : LB, 1, LK, 1);
-    if (rc) return rc;
+    {   // dG [B, T, 8H] seen as (k within chunk, b, chunk, t): one box = kChunks chunks of [64 seq x 64 k]
+        const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 8ull * H / LK, (uint64_t)T};
+        const uint64_t strides[3] = {(uint64_t)T * 8 * H * 2, (uint64_t)LK * 2, 8ull * H * 2};
+        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)LB, (uint32_t)kChunks, 1u};
+        rc = make_tmap_4d(&tg, dG, 2, dims, strides, box, 1);
+        if (rc) return rc;
+    }
     BwdParams p;
     p.B = B; p.T = T; p.H = H;
     p.gates = (const __half *)gates_save;
@@ -446,28 +426,28 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.dhcat = dhcat;
     p.dG = (__nv_bfloat16 *)dG;
     p.tl = debug_timeline();
-    const int csize = H / 32;
-    const int ntiles = (B + LB - 1) / LB;
-    const bool stagger = two_sm;
-    const size_t smem = bwd_smem_bytes(H, 3);
+    const int gsize = H / 32;
+    const size_t smem = bwd_smem_bytes(H);
     cudaStream_t s = (cudaStream_t)stream;
-    auto kern = stagger ? lstm_bwd_kernel<3, true> : lstm_bwd_kernel<3, false>;
-    RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (csize > 8) RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.nitems = 2 * ((B + LB - 1) / LB);
+    const int max_groups = num_sms() / gsize;    // one CTA per SM (shared memory)
+    p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
+    if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;   // even: a group keeps its direction
+    p.sync = group_counters(p.ngroups, s);
+    if (!p.sync) return RCNN_ERR_CUDA_BASE;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(csize * ntiles * 2));
+    cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the groups spin on each other
+    attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_BWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, tg, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, tg, p));
     count_launch();
     return RCNN_OK;
 }

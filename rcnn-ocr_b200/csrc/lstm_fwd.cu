@@ -5,23 +5,31 @@
 // c = f*c + i*g, h = o*tanh(c), h_0 = c_0 = 0, gate order i,f,g,o.  The input projection
 // xp = x W_ih^T + b_ih + b_hh for all timesteps comes from the tcgen05 GEMM (gemm.cu).
 //
-// Decomposition.  One thread-block CLUSTER owns (direction, tile of 128 sequences).  CTA c of
-// the cluster owns hidden units [32c, 32c+32) with all four gates, so cluster size = H/32
-// (16 CTAs for H=512 -- a non-portable cluster -- 8 for H=256).  Its 128 x H slice of W_hh
-// (bf16, 128 KB for H=512) is loaded ONCE by TMA and stays resident in shared memory for all T
-// steps.  Per timestep:
-//   warp 0  (TMA)      streams h_{t-1}[128 seq, H] (bf16, straight out of the block's output
-//                      tensor, two 64-column boxes per ring slot) and prefetches the next step's
-//                      xp tile (fp16, four 32-column chunks, all resident);
-//   warp 1  (MMA)      tcgen05.mma  D[128 seq, 128 gate cols] += h_chunk * W_chunk^T, fp32 in TMEM;
-//   warps 2-9 (cell)   two warps per TMEM lane quadrant; a thread owns one sequence and 16 of the
-//                      CTA's 32 units: tcgen05.ld its accumulator columns, add xp, sigmoid/tanh,
-//                      update c (fp32, in registers for the whole sequence), write h_t (bf16) and,
-//                      for training, the activated gates (fp16) and c_t (fp32);
-//   all               barrier.cluster (release/acquire): h_t of every unit slice is visible to
-//                      the other CTAs' TMA loads of the next step.
-// Only h crosses CTAs, through L2; nothing is exchanged between clusters.
+// Decomposition.  A GROUP of H/32 CTAs (16 for H=512) owns one work item = (direction, tile of 64
+// sequences) at a time; CTA c of the group owns hidden units [32c, 32c+32) with all four gates.
+// Its 128 x H slice of W_hh (bf16, 128 KB for H=512) is loaded ONCE by TMA and stays resident in
+// shared memory.  The product is computed TRANSPOSED, D^T[128 gate rows, 64 seq] = W_slice h^T, so
+// the resident weights are the M = 128 operand (full tensor-pipe rate) and the sequence tile is the
+// N operand: a 64-sequence tile keeps the per-step ingest of a CTA at 64 KB of h (all of it in
+// flight at once: the whole tile has its own shared-memory slots) and lets a B = 256 batch spread
+// over 8 groups = 128 SMs.  Per timestep:
+//   warp 0  (TMA)      waits until all CTAs of the group have published h_{t-1} (a counter in global
+//                      memory, red.release / ld.acquire at gpu scope: groups are not clusters, so any
+//                      number of them fits the machine), then streams h_{t-1}[64 seq, H] (bf16,
+//                      straight out of the block's output tensor); prefetches the next step's xp
+//                      tile (fp16) and, for training, TMA-stores the previous step's activated gates;
+//   warp 1  (MMA)      tcgen05.mma  D^T[128, 64] += W_chunk * h_chunk^T, fp32 in TMEM;
+//   warps 2-9 (cell)   a thread owns one gate row (TMEM lane) and 32 sequences: tcgen05.ld, add xp,
+//                      one MUFU.TANH per gate value (sigmoid through tanh with per-lane constants),
+//                      4x4 register transposes across the 4 lanes of a unit (warp shuffles) so that each
+//                      lane has i,f,g,o of 8 (unit, sequence) cells, cell update (c stays in registers
+//                      for the whole sequence), 8x8 shuffle transpose of the bf16 h values so that each
+//                      lane stores 16 contiguous bytes of h_t; then ONE gpu-scope release per CTA.
+// Only h crosses CTAs, through L2; nothing is exchanged between groups.  The kernel is launched
+// cooperatively (all CTAs co-resident), groups loop over work items when there are more items than
+// groups.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -30,93 +38,99 @@ namespace {
 
 using namespace sm100;
 
-constexpr int LB = 128;   // sequences per cluster tile (UMMA M)
-constexpr int LN = 128;   // gate columns per CTA: 32 units x 4 gates (UMMA N)
+constexpr int NS = 64;    // sequences per work item (UMMA N)
+constexpr int GR = 128;   // gate rows per CTA: 32 units x 4 gates (UMMA M)
 constexpr int LK = 64;    // K chunk (one 128-byte swizzle row of bf16)
-constexpr uint32_t kTile = 16384;   // one operand TMA box: 128 x 64 bf16 (h chunk or W chunk) = 16 KB
-constexpr int kBoxes = 2;           // h boxes per ring slot: one barrier round trip per K = 128
-constexpr int kARing = 2;           // ring slots of kBoxes * 16 KB
-constexpr uint32_t kASlot = kBoxes * kTile;
-constexpr int kXRing = 4;           // one slot per 32-column xp chunk: the whole step's tile is resident
-constexpr uint32_t kXTile = LB * 32 * 2;   // 128 seq x 32 cols fp16 = 8 KB, 64-byte swizzle
+constexpr uint32_t kWTile = GR * LK * 2;   // 16 KB: [128 gate rows x 64 k] bf16, SW128
+constexpr uint32_t kHBox = NS * LK * 2;    //  8 KB: [64 seq x 64 k] bf16, SW128
+constexpr uint32_t kXTile = NS * GR * 2;   // 16 KB: [64 seq x 128 gate cols] fp16, no swizzle
+constexpr int kMaxHBars = 2;               // h_{t-1} arrives as (at most) two TMA operations of H/128 chunks each
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct FwdParams {
     int B, T, H;
+    int nitems, ngroups;
+    int csize;            // CTAs per cluster (1, 2 or 4): the h tile is fetched once per cluster and multicast
     __nv_bfloat16 *hcat;  // [B, T, 2H]
-    __half *gates;        // [2, T, B, 4H] packed column order, activated (training only)
     float *csave;         // [2, T, B, H]  (training only)
+    unsigned int *sync;   // [ngroups] zeroed before the launch
     long long *tl;        // debug timeline or nullptr
 };
-#define TL_MARK(k) do { if (tl) tl[s * 8 + (k)] = clock64(); } while (0)
+#define TL_MARK(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_id_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
-// Publish the cell warps' global stores with ONE gpu-scope release per CTA (the pattern of a
-// cooperative-groups grid sync): CTA barrier among the 256 cell threads, then one thread arrives with
-// release semantics (its MEMBAR is cumulative over the stores it observed through the barrier) while the
-// others arrive relaxed.
-__device__ __forceinline__ void cell_publish_arrive() {
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x == 64) cluster_arrive(); else cluster_arrive_relaxed();
-}
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
 __device__ __forceinline__ float tanh_fast(float x) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ void red_release_gpu_inc(unsigned int *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// The counter is only polled; what it guards (h_{t-1}) is read by TMA (async proxy, straight from L2), so a
+// relaxed gpu-scope load + fence.proxy.async is enough and spares the L1 invalidate of an acquire per poll.
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Bounded spin on the group counter: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_counter(const unsigned int *p, unsigned int target) {
+    if (ld_acquire_gpu(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(p) < target) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("rcnn-ocr_b200: lstm_fwd group counter timed out (block %d)\n", blockIdx.x);
+            __trap();
+        }
+    }
+}
 
 template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
-                const __grid_constant__ CUtensorMap tmX, const FwdParams p) {
+                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
     const int nkc = H / LK;
-    unsigned char *w_s = smem;                          // nkc tiles [128 n x 64 k] bf16, SW128
-    unsigned char *a_s = w_s + (size_t)nkc * kTile;     // kARing slots of kBoxes tiles [128 b x 64 k] bf16, SW128
-    unsigned char *x_s = a_s + kARing * kASlot;         // kXRing tiles [128 b x 32 col] fp16, SW64
-    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + kXRing * kXTile);
+    const int cpb = nkc >= 2 ? nkc / 2 : 1;        // K chunks per barrier
+    const int nhb = nkc / cpb;                     // h barriers per step (2; 1 for H = 64)
+    const int cpc = nkc / p.csize;                 // K chunks this CTA fetches for its whole cluster
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int gsize = H / 32;
+    unsigned char *w_s = smem;                          // nkc tiles [128 gate rows x 64 k] bf16, SW128
+    unsigned char *h_s = w_s + (size_t)nkc * kWTile;    // nkc boxes [64 seq x 64 k] bf16, SW128
+    unsigned char *x_s = h_s + (size_t)nkc * kHBox;     // 2 tiles [64 seq x 128 cols] fp16
+    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + 2 * kXTile);
     uint64_t *w_full = bars;
-    uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
-    uint64_t *x_full = a_empty + kARing, *x_empty = x_full + kXRing;
-    uint64_t *tmem_full = x_empty + kXRing;
+    uint64_t *h_full = bars + 1;                        // kMaxHBars
+    uint64_t *x_full = h_full + kMaxHBars;              // 2
+    uint64_t *x_free = x_full + 2;                      // 2: slot may be overwritten by the next xp load
+    uint64_t *g_ready = x_free + 2;                     // 2: (training) activated gates are in the slot
+    uint64_t *tmem_full = g_ready + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = (int)cluster_ctarank();        // unit slice
-    const int cid = (int)cluster_id_x();
-    const int dir = cid & 1, tile = cid >> 1;
-    const int b0 = tile * LB;
+    const int group = blockIdx.x / gsize;
+    const int c = blockIdx.x % gsize;            // unit slice
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
+    unsigned int *counter = p.sync + group;
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-            for (int i = 0; i < kXRing; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 4); }
+            for (int i = 0; i < kMaxHBars; ++i) mbar_init(&h_full[i], 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&x_full[i], 1);
+                mbar_init(&x_free[i], SAVE ? 1 : 8);
+                mbar_init(&g_ready[i], 8);
+            }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<LN>(tmem_slot);
+        tmem_alloc<NS>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -124,221 +138,289 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer ======================================================================
-        if (lane == 0) {
+        // ===== TMA producer (one elected thread: elect.sync keeps operands in uniform registers) =
+        if (elect_one()) {
             tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
-            mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kTile);
-            for (int kc = 0; kc < nkc; ++kc)
-                tma_load_2d(w_s + (size_t)kc * kTile, &tmW, w_full, kc * LK, dir * 4 * H + c * LN);
-        }
-        int pslot = 0;
-        uint32_t pphase = 0;
-        // xp chunk q of step s lives in slot q; phase parity = s & 1.  Step 0 is loaded up front, step
-        // s+1 while step s runs (each slot is refilled as soon as the cell warps released it).
-        auto load_x = [&](int xs) {
-            const int xt = dir ? T - 1 - xs : xs;
-            for (int q = 0; q < kXRing; ++q) {
-                mbar_wait(&x_empty[q], (xs & 1) ^ 1);
-                mbar_arrive_expect_tx(&x_full[q], kXTile);
-                tma_load_3d(x_s + q * kXTile, &tmX, &x_full[q], dir * 4 * H + c * LN + q * 32, xt, b0);
-            }
-        };
-        if (lane == 0 && T > 0) load_x(0);
-        for (int s = 0; s < T; ++s) {
-            if (lane == 0) {
-                const int t = dir ? T - 1 - s : s;
-                if (s > 0) {
-                    const int tprev = dir ? t + 1 : t - 1;
-                    TL_MARK(0);
-                    fence_proxy_async_global();  // h_{t-1} was written through the generic proxy
-                    for (int g = 0; g * kBoxes < nkc; ++g) {
-                        const int nb = min(kBoxes, nkc - g * kBoxes);     // H = 64 has a single box
-                        mbar_wait(&a_empty[pslot], pphase ^ 1);
-                        mbar_arrive_expect_tx(&a_full[pslot], (uint32_t)nb * kTile);
-                        for (int j = 0; j < nb; ++j)
-                            tma_load_3d(a_s + pslot * kASlot + j * kTile, &tmH, &a_full[pslot],
-                                        dir * H + (g * kBoxes + j) * LK, tprev, b0);
-                        if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
-                    }
-                    TL_MARK(1);
+            if (SAVE) tma_prefetch_desc(&tmG);
+            int cur_dir = -1;
+            unsigned int xidx = 0;       // xp tiles requested so far (slot = xidx & 1)
+            unsigned int gidx = 0;       // gate tiles stored so far
+            unsigned int published = 0;  // steps this group has completed before the current one
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1, b0 = (item >> 1) * NS;
+                if (dir != cur_dir) {
+                    // every MMA that read the old slice has completed: its step was published
+                    mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
+                    for (int kc = 0; kc < nkc; ++kc)
+                        tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * 4 * H + c * GR);
+                    cur_dir = dir;
                 }
-                if (s + 1 < T) load_x(s + 1);
+                auto load_x = [&](int xs) {
+                    const int slot = xidx & 1;
+                    mbar_wait(&x_free[slot], ((xidx >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&x_full[slot], kXTile);
+                    tma_load_3d(x_s + slot * kXTile, &tmX, &x_full[slot], dir * 4 * H + c * GR, dir ? T - 1 - xs : xs, b0);
+                    ++xidx;
+                };
+                auto store_gates = [&](int gs) {   // activated gates of step gs: shared memory -> gates_save
+                    const int slot = gidx & 1;
+                    mbar_wait(&g_ready[slot], (gidx >> 1) & 1);
+                    tma_store_3d(&tmG, x_s + slot * kXTile, c * GR, b0, dir * T + (dir ? T - 1 - gs : gs));
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&x_free[slot]);
+                    ++gidx;
+                };
+                load_x(0);
+                for (int s = 0; s < T; ++s) {
+                    if (s > 0) {
+                        const int t = dir ? T - 1 - s : s;
+                        const int tprev = dir ? t + 1 : t - 1;
+                        TL_MARK(7);
+                        wait_counter(counter, (published + (unsigned)s) * (unsigned)gsize);
+                        TL_MARK(0);
+                        fence_proxy_async_global();  // h_{t-1} was written through the generic proxy
+                        // Every CTA of the cluster expects the whole tile and fetches 1/csize of it (cpc boxes
+                        // [64 seq x 64 k], chunk-major) for all of them: L2 is read once per cluster.  The peers'
+                        // slots are free: they published step s-1 after their MMAs had consumed the old tile.
+                        for (int g = 0; g < nhb; ++g) mbar_arrive_expect_tx(&h_full[g], (uint32_t)cpb * kHBox);
+                        const int bxc = cpc < cpb ? cpc : cpb;      // chunks per TMA operation (= the map's box)
+                        for (int kc0 = (int)crank * cpc; kc0 < ((int)crank + 1) * cpc; kc0 += bxc) {
+                            if (p.csize > 1)
+                                tma_load_4d_mcast(h_s + (size_t)kc0 * kHBox, &tmH, &h_full[kc0 / cpb], 0, b0, dir * nkc + kc0,
+                                                  tprev, (uint16_t)((1u << p.csize) - 1u));
+                            else
+                                tma_load_4d(h_s + (size_t)kc0 * kHBox, &tmH, &h_full[kc0 / cpb], 0, b0, dir * nkc + kc0, tprev);
+                        }
+                        TL_MARK(1);
+                        if (SAVE) store_gates(s - 1);
+                    }
+                    if (s + 1 < T) load_x(s + 1);
+                }
+                if (SAVE) store_gates(T - 1);
+                published += (unsigned)T;
             }
-            __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();
+            if (SAVE) tma_store_wait<0>();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer ========================================================================
-        constexpr uint32_t idesc = make_idesc_bf16(LB, LN);
-        int mslot = 0;
-        uint32_t mphase = 0;
-        if (lane == 0) mbar_wait(w_full, 0);
-        __syncwarp();
-        for (int s = 0; s < T; ++s) {
-            if (lane == 0 && s > 0) {
-                for (int g = 0; g * kBoxes < nkc; ++g) {
-                    const int nb = min(kBoxes, nkc - g * kBoxes);
-                    mbar_wait(&a_full[mslot], mphase);
-                    if (g == 0) TL_MARK(2);
-                    tc_fence_after();
-                    for (int j = 0; j < nb; ++j) {
-                        const int kc = g * kBoxes + j;
-                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kASlot + j * kTile), 16, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kTile), 16, 1024);
+        // ===== MMA issuer (one elected thread) ===================================================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(GR, NS);
+            int cur_dir = -1;
+            uint32_t wphase = 0, hphase = 0;
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1;
+                if (dir != cur_dir) { mbar_wait(w_full, wphase); wphase ^= 1; cur_dir = dir; }
+                for (int s = 1; s < T; ++s) {
+                    for (int g = 0; g < nhb; ++g) {
+                        mbar_wait(&h_full[g], hphase);
+                        if (g == 0) TL_MARK(2);
+                        tc_fence_after();
+                        for (int j = 0; j < cpb; ++j) {
+                            const int kc = g * cpb + j;
+                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)kc * kHBox), 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < LK / 16; ++k)
-                            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                            for (int k = 0; k < LK / 16; ++k)
+                                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                        }
                     }
-                    umma_commit(&a_empty[mslot]);
-                    if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
+                    umma_commit(tmem_full);
+                    TL_MARK(3);
+                    hphase ^= 1;
                 }
-                umma_commit(tmem_full);
-                TL_MARK(3);
             }
-            __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();
         }
     } else {
-        // ===== cell update (one thread per sequence of the tile) ================================
+        // ===== cell update ========================================================================
         const int qd = warp & 3;            // TMEM lane quadrant of this warp
-        const int hf = (warp - 2) >> 2;     // which half of the CTA's gate columns (units hf*16 .. +16)
-        const int row = qd * 32 + lane;     // sequence within the tile == accumulator row
-        const int b = b0 + row;
-        const bool valid = b < B;
-        float cst[16];
+        const int ch = (warp - 2) >> 2;     // which 32 of the tile's 64 sequences
+        const int r = qd * 32 + lane;       // gate row within the CTA == accumulator lane: unit r>>2, gate r&3
+        const int g = lane & 3, ul = lane >> 2;
+        const bool g0 = g & 1, g1 = (g >> 1) & 1;
+        const float a_scale = (g == 2) ? 1.f : 0.5f;     // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5
+        const float a_shift = (g == 2) ? 0.f : 0.5f;
+        const bool o0 = ul & 1, o1 = (ul >> 1) & 1, o2 = (ul >> 2) & 1;
+        unsigned int xidx = 0, mcount = 0;
+        for (int item = group; item < p.nitems; item += p.ngroups) {
+            const int dir = item & 1, b0 = (item >> 1) * NS;
+            float cst[8];   // cell state of unit 8*qd+ul for sequences 32ch + 4k + g
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cst[i] = 0.f;
-        for (int s = 0; s < T; ++s) {
-            const int t = dir ? T - 1 - s : s;
-            if (s > 0) {
-                mbar_wait(tmem_full, (s - 1) & 1);
-                if (threadIdx.x == 64) TL_MARK(4);
-                tc_fence_after();
-            }
-            __nv_bfloat16 *hrow = p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c;
-            __half *grow = SAVE ? p.gates + (((size_t)dir * T + t) * B + b) * 4 * H + (size_t)c * LN : nullptr;
-            float *crow = SAVE ? p.csave + (((size_t)dir * T + t) * B + b) * H + 32 * c : nullptr;
-            U8 gsave[2][2], csv[2];   // training: activated gates / c of both chunks, stored AFTER the barrier arrive
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-                const int q = hf * 2 + qq;          // 32-column chunk of the accumulator / xp tile
-                uint32_t acc[32];
-                if (s > 0) {
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(q * 32), acc);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = 0u;
-                }
-                mbar_wait(&x_full[q], s & 1);
-                // fp16 tile, 64-byte rows, TMA SWIZZLE_64B: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)
-                const unsigned char *xrow = x_s + q * kXTile + row * 64;
+            for (int k = 0; k < 8; ++k) cst[k] = 0.f;
+            for (int s = 0; s < T; ++s) {
+                const int t = dir ? T - 1 - s : s;
+                const int slot = xidx & 1;
+                unsigned char *xs = x_s + slot * kXTile + (size_t)(32 * ch) * (GR * 2) + 2 * r;
                 float pre[32];
+                mbar_wait(&x_full[slot], (xidx >> 1) & 1);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(xrow + ((j ^ ((row >> 1) & 3)) << 4));
-                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&v);
+                for (int i = 0; i < 32; ++i) pre[i] = __half2float(*reinterpret_cast<const __half *>(xs + i * (GR * 2)));
+                if (!SAVE) {
+                    // Free the slot only once every lane's loads have RETURNED (an mbarrier arrive is not
+                    // ordered behind shared-memory loads still in flight): make the arrive data-dependent.
+                    uint32_t dep = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 f = __half22float2(h2[k]);
-                        pre[8 * j + 2 * k] = f.x;
-                        pre[8 * j + 2 * k + 1] = f.y;
-                    }
+                    for (int i = 0; i < 32; i += 8) dep |= __float_as_uint(pre[i]);
+                    dep = __any_sync(FULL, dep != 0u) ? 1u : 0u;
+                    if (lane == 0) mbar_arrive_after(&x_free[slot], dep);
                 }
-                // Free the slot only once every lane's loads have RETURNED: fold one word of each
-                // 16-byte load into a value the arrive depends on, and vote it across the warp.
-                uint32_t dep = 0;
+                if (s > 0) {
+                    uint32_t acc[32];
+                    mbar_wait(tmem_full, mcount & 1);
+                    ++mcount;
+                    if (threadIdx.x == 64) TL_MARK(4);
+                    tc_fence_after();
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), acc);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dep |= __float_as_uint(pre[8 * j]);
-                dep = __any_sync(FULL, dep != 0u) ? 1u : 0u;
-                if (lane == 0) mbar_arrive_after(&x_empty[q], dep);
-                if (s > 0) tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);
-                float hv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float ig = sigmoid_fast(pre[4 * j]);
-                    const float fg = sigmoid_fast(pre[4 * j + 1]);
-                    const float gg = tanh_fast(pre[4 * j + 2]);
-                    const float og = sigmoid_fast(pre[4 * j + 3]);
-                    const float cn = fmaf(fg, cst[qq * 8 + j], ig * gg);
-                    cst[qq * 8 + j] = cn;
-                    hv[j] = og * tanh_fast(cn);
-                    pre[4 * j] = ig; pre[4 * j + 1] = fg; pre[4 * j + 2] = gg; pre[4 * j + 3] = og;
+                    for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);
                 }
-                if (valid) {
-                    uint4 hq;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(hv[0], hv[1]), h1 = __floats2bfloat162_rn(hv[2], hv[3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(hv[4], hv[5]), h3 = __floats2bfloat162_rn(hv[6], hv[7]);
-                    hq.x = *reinterpret_cast<uint32_t *>(&h0); hq.y = *reinterpret_cast<uint32_t *>(&h1);
-                    hq.z = *reinterpret_cast<uint32_t *>(&h2); hq.w = *reinterpret_cast<uint32_t *>(&h3);
-                    *reinterpret_cast<uint4 *>(hrow + q * 8) = hq;
-                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pre[i] = fmaf(tanh_fast(pre[i] * a_scale), a_scale, a_shift);
+                uint32_t gsv[16];   // (training) activated gates as fp16 pairs, stashed after the publish
                 if (SAVE) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            __half2 g2 = __floats2half2_rn(pre[16 * j + 2 * k], pre[16 * j + 2 * k + 1]);
-                            gsave[qq][j].v[k] = *reinterpret_cast<uint32_t *>(&g2);
-                        }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) csv[qq].v[k] = __float_as_uint(cst[qq * 8 + k]);
+                    for (int i = 0; i < 16; ++i) {
+                        const __half2 h2 = __floats2half2_rn(pre[2 * i], pre[2 * i + 1]);
+                        gsv[i] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
                 }
-            }
-            if (threadIdx.x == 64) TL_MARK(5);
-            tc_fence_before();
-            fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
-            cell_publish_arrive();       // one release per CTA; its MEMBAR only has the h stores to wait for
-            if (SAVE && valid) {
-                // The saved tensors are not needed until the backward pass: issue their stores after
-                // the arrive so they drain while this CTA waits and during the next step's MMA phase.
+                uint32_t hb[8];
 #pragma unroll
-                for (int qq = 0; qq < 2; ++qq) {
-                    const int q = hf * 2 + qq;
-                    st_v8(grow + q * 32, gsave[qq][0]);
-                    st_v8(grow + q * 32 + 16, gsave[qq][1]);
-                    st_v8(crow + q * 8, csv[qq]);
+                for (int k = 0; k < 8; ++k) {
+                    // 4x4 transpose across the four lanes of a unit: in = my gate for sequences 4k..4k+3,
+                    // out = gates i,f,g,o for sequence 4k + g
+                    const float v0 = pre[4 * k], v1 = pre[4 * k + 1], v2 = pre[4 * k + 2], v3 = pre[4 * k + 3];
+                    const float ra0 = __shfl_xor_sync(FULL, g0 ? v0 : v1, 1);
+                    const float ra1 = __shfl_xor_sync(FULL, g0 ? v2 : v3, 1);
+                    const float w0 = g0 ? ra0 : v0, w1 = g0 ? v1 : ra0, w2 = g0 ? ra1 : v2, w3 = g0 ? v3 : ra1;
+                    const float rb0 = __shfl_xor_sync(FULL, g1 ? w0 : w2, 2);
+                    const float rb1 = __shfl_xor_sync(FULL, g1 ? w1 : w3, 2);
+                    const float ig = g1 ? rb0 : w0, fg = g1 ? rb1 : w1, gg = g1 ? w2 : rb0, og = g1 ? w3 : rb1;
+                    const float cn = fmaf(fg, cst[k], ig * gg);
+                    cst[k] = cn;
+                    const __nv_bfloat16 hv = __float2bfloat16_rn(og * tanh_fast(cn));
+                    hb[k] = (uint32_t)__bfloat16_as_ushort(hv);
                 }
+                // 8x8 transpose across the eight lanes with the same g: in = my unit's h for sequences
+                // 4k + g (k = 0..7), out = units 8qd .. 8qd+7 for sequence 4*ul + g = lane
+                uint32_t p1[4];
+                {
+                    uint32_t keep[4], send[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { keep[j] = o0 ? hb[2 * j + 1] : hb[2 * j]; send[j] = o0 ? hb[2 * j] : hb[2 * j + 1]; }
+                    const uint32_t r0 = __shfl_xor_sync(FULL, send[0] | (send[1] << 16), 4);
+                    const uint32_t r1 = __shfl_xor_sync(FULL, send[2] | (send[3] << 16), 4);
+                    const uint32_t recv[4] = {r0 & 0xffffu, r0 >> 16, r1 & 0xffffu, r1 >> 16};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) p1[j] = o0 ? (recv[j] | (keep[j] << 16)) : (keep[j] | (recv[j] << 16));
+                }
+                uint32_t q2[2][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t keep = o1 ? p1[2 * i + 1] : p1[2 * i], send = o1 ? p1[2 * i] : p1[2 * i + 1];
+                    const uint32_t rr = __shfl_xor_sync(FULL, send, 8);
+                    q2[i][0] = o1 ? rr : keep;
+                    q2[i][1] = o1 ? keep : rr;
+                }
+                uint4 hq;
+                {
+                    const uint32_t k0 = o2 ? q2[1][0] : q2[0][0], k1 = o2 ? q2[1][1] : q2[0][1];
+                    const uint32_t s0 = o2 ? q2[0][0] : q2[1][0], s1 = o2 ? q2[0][1] : q2[1][1];
+                    const uint32_t r0 = __shfl_xor_sync(FULL, s0, 16), r1 = __shfl_xor_sync(FULL, s1, 16);
+                    hq.x = o2 ? r0 : k0; hq.y = o2 ? r1 : k1; hq.z = o2 ? k0 : r0; hq.w = o2 ? k1 : r1;
+                }
+                const int bh = b0 + 32 * ch + lane;
+                if (bh < B)
+                    *reinterpret_cast<uint4 *>(p.hcat + ((size_t)bh * T + t) * 2 * H + (size_t)dir * H + 32 * c + 8 * qd) = hq;
+                if (threadIdx.x == 64) TL_MARK(5);
+                tc_fence_before();
+                fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 64) {     // one release per CTA, cumulative over the stores seen through the barrier
+                    red_release_gpu_inc(counter);
+                    TL_MARK(6);
+                }
+                if (SAVE) {
+                    // activated gates back into the xp slot (same addresses this thread read), then out by TMA
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        *reinterpret_cast<uint16_t *>(xs + (2 * i) * (GR * 2)) = (uint16_t)(gsv[i] & 0xffffu);
+                        *reinterpret_cast<uint16_t *>(xs + (2 * i + 1) * (GR * 2)) = (uint16_t)(gsv[i] >> 16);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&g_ready[slot]);
+                    // c_t is not needed until the backward pass: stored after the publish
+                    float *crow = p.csave + (((size_t)dir * T + t) * B) * H + 32 * c + 8 * qd + ul;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int bc = b0 + 32 * ch + 4 * k + g;
+                        if (bc < B) crow[(size_t)bc * H] = cst[k];
+                    }
+                }
+                ++xidx;
             }
-            cluster_wait();
-            if (threadIdx.x == 64) TL_MARK(6);
         }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<LN>(tmem_base);
+        tmem_dealloc<NS>(tmem_base);
     }
 }
 
-size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK) * kTile + kARing * kASlot + kXRing * kXTile + 256; }
+int fwd_cluster_size(int nkc) {
+    static const int want = getenv("RCNN_FWD_CLUSTER") ? atoi(getenv("RCNN_FWD_CLUSTER")) : 1;
+    return want >= 4 && nkc >= 4 ? 4 : (want >= 2 && nkc >= 2 ? 2 : 1);
+}
+
+size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK) * (kWTile + kHBox) + 2 * kXTile + 256; }
 
 template <bool SAVE>
-int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &tx, const FwdParams &p,
-               cudaStream_t s) {
-    const int csize = p.H / 32;
-    const int ntiles = (p.B + LB - 1) / LB;
+int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &tx, const CUtensorMap &tg,
+               FwdParams &p, cudaStream_t s) {
+    const int gsize = p.H / 32;
+    const int nkc = p.H / LK;
+    // cluster = multicast domain for the h tile; it divides the group.  Measured on B200 (B=256, H=512): with
+    // multicast the step is ~7% SLOWER (the tile's first half then waits for two CTAs' polls), L2 read
+    // bandwidth is not the limiter, so the default is no cluster; RCNN_FWD_CLUSTER=4 turns it on.
+    p.csize = fwd_cluster_size(nkc);
+    p.nitems = 2 * ((p.B + NS - 1) / NS);
     const size_t smem = fwd_smem_bytes(p.H);
     RCNN_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (csize > 8)
-        RCNN_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<SAVE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(csize * ntiles * 2));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the groups spin on each other
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)p.csize;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
+    static thread_local int max_clusters[2][4] = {};   // [SAVE][log2 H/64], per calling thread (device assumed fixed per thread)
+    int &mc = max_clusters[SAVE ? 1 : 0][p.H == 64 ? 0 : p.H == 128 ? 1 : p.H == 256 ? 2 : 3];
+    if (mc == 0) {
+        cfg.gridDim = dim3((unsigned)(p.csize * 1024));
+        RCNN_CUDA(cudaOccupancyMaxActiveClusters(&mc, lstm_fwd_kernel<SAVE>, &cfg));
+        if (mc * p.csize < gsize) {
+            set_error("lstm_forward: only %d clusters of %d CTAs fit the device, a group needs %d CTAs", mc, p.csize, gsize);
+            mc = 0;
+            return RCNN_ERR_DEVICE;
+        }
+    }
+    const int max_groups = mc * p.csize / gsize;
+    p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
+    if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;   // even: a group keeps its direction (and W slice)
+    p.sync = group_counters(p.ngroups, s);
+    if (!p.sync) return RCNN_ERR_CUDA_BASE;
+    cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
     ProfScope prof(RCNN_K_LSTM_FWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, tg, p));
     count_launch();
     return RCNN_OK;
 }
@@ -355,19 +437,31 @@ extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, 
     if (B == 0 || T == 0) return RCNN_OK;
     RCNN_CHECK_ARG(xp && whh_packed && hcat, "lstm_forward: null pointer");
     RCNN_CHECK_ARG((gates_save == nullptr) == (c_save == nullptr), "lstm_forward: gates_save and c_save go together");
-    CUtensorMap tw, th, tx;
-    int rc = make_tmap_2d(&tw, whh_packed, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, LN, LK, 1);
+    CUtensorMap tw, th, tx, tg;
+    int rc = make_tmap_2d(&tw, whh_packed, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, GR, LK, 1);
     if (rc) return rc;
-    rc = make_tmap_3d(&th, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, LB, 1, LK, 1);
+    {   // hcat [B, T, 2H] seen as (k within chunk, b, chunk, t): one box = cpc chunks of [64 seq x 64 k],
+        // the share one CTA of a cluster fetches (see launch_fwd: csize = min(4, nkc))
+        const int nkc = H / LK, cpb = nkc >= 2 ? nkc / 2 : 1;
+        const int cpc = nkc / fwd_cluster_size(nkc) < cpb ? nkc / fwd_cluster_size(nkc) : cpb;
+        const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 2ull * nkc, (uint64_t)T};
+        const uint64_t strides[3] = {(uint64_t)T * 2 * H * 2, (uint64_t)LK * 2, 2ull * H * 2};
+        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)NS, (uint32_t)cpc, 1u};
+        rc = make_tmap_4d(&th, hcat, 2, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    rc = make_tmap_3d(&tx, xp, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, NS, 1, GR, 0);
     if (rc) return rc;
-    rc = make_tmap_3d(&tx, xp, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, LB, 1, 32, 2);
-    if (rc) return rc;
+    tg = tx;
+    if (gates_save) {
+        rc = make_tmap_3d(&tg, gates_save, 2, 2ull * T, (uint64_t)B, 4ull * H, (uint64_t)B * 4 * H * 2, 4ull * H * 2, 1, NS, GR, 0);
+        if (rc) return rc;
+    }
     FwdParams p;
     p.B = B; p.T = T; p.H = H;
     p.hcat = (__nv_bfloat16 *)hcat;
-    p.gates = (__half *)gates_save;
     p.csave = c_save;
     p.tl = debug_timeline();
     cudaStream_t s = (cudaStream_t)stream;
-    return gates_save ? launch_fwd<true>(tw, th, tx, p, s) : launch_fwd<false>(tw, th, tx, p, s);
+    return gates_save ? launch_fwd<true>(tw, th, tx, tg, p, s) : launch_fwd<false>(tw, th, tx, tg, p, s);
 }

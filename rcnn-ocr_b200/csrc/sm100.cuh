@@ -97,6 +97,21 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mcast(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
+                                                  int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+          "h"(cta_mask)
+        : "memory");
+}
 // Multicast variant: the tile (and its complete_tx) lands at the same shared-memory offset of every
 // CTA of the cluster whose bit is set in cta_mask.
 __device__ __forceinline__ void tma_load_3d_mcast(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
@@ -111,6 +126,11 @@ __device__ __forceinline__ void tma_load_3d_mcast(void *dst, const CUtensorMap *
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -251,5 +271,7 @@ int make_tmap_2d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t ro
 int make_tmap_3d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t d2, uint64_t rows, uint64_t cols,
                  uint64_t pitch2_bytes, uint64_t row_pitch_bytes, uint32_t box2, uint32_t box_rows,
                  uint32_t box_cols, int swizzle128);
+int make_tmap_4d(CUtensorMap *out, const void *base, int elem_bytes, const uint64_t dims[4], const uint64_t strides[3],
+                 const uint32_t box[4], int swizzle128);
 
 }  // namespace rcnn
