@@ -37,7 +37,7 @@ static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
 // ---- group-barrier counters for the recurrent kernels -------------------------------------------
-static const int kCounterRegion = 128, kCounterRegions = 64, kMaxDevices = 32;
+static const int kCounterRegion = 256, kCounterRegions = 64, kMaxDevices = 32;
 static unsigned int *g_counters[kMaxDevices] = {};
 static unsigned int g_counter_next[kMaxDevices] = {};
 
@@ -47,7 +47,7 @@ unsigned int *group_counters(int n, cudaStream_t s) {
         set_error("group_counters: n=%d device=%d unsupported", n, dev);
         return nullptr;
     }
-    if (!g_counters[dev]) {   // one-time 32 KB per device (like a library handle's workspace)
+    if (!g_counters[dev]) {   // one-time 64 KB per device (like a library handle's workspace)
         if (cudaMalloc(&g_counters[dev], sizeof(unsigned int) * kCounterRegion * kCounterRegions) != cudaSuccess) {
             set_error("group_counters: cudaMalloc failed");
             return nullptr;

@@ -46,6 +46,7 @@ struct BwdParams {
     const float *csave;        // [2, T, B, H]
     const float *dhcat;        // [B, T, 2H] upstream gradient of the block's LSTM output
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
+    float *db;                 // [2*4H] out or nullptr: column sums of dG (bias gradient), zeroed before the launch
     unsigned int *sync;        // [ngroups] zeroed before the launch
     long long *tl;             // debug timeline or nullptr
 };
@@ -217,6 +218,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             float dc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+            float dbacc[32];   // this sequence's contribution to the bias gradient of the thread's 32 gate columns
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbacc[i] = 0.f;
             for (int s = 0; s < T; ++s) {
                 const int t = dir ? s : T - 1 - s;
                 const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
@@ -273,6 +277,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 if (valid) {
 #pragma unroll
+                    for (int i = 0; i < 32; ++i) dbacc[i] += o32[i];
+#pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         U8 v;
 #pragma unroll
@@ -290,6 +296,21 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (threadIdx.x == 64) {      // one gpu-scope release per CTA
                     red_release_gpu_inc_b(counter);
                     TL_MARK(6);
+                }
+            }
+            if (p.db != nullptr) {
+                // db: sum over the 16 sequences of the half-warp, then one atomic per column and half-warp
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = dbacc[i];
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                    dbacc[i] = v;
+                }
+                if ((lane & 15) == 0) {
+                    float *dst = p.db + (size_t)dir * 4 * H + (size_t)c * 128 + u0 * 4;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) atomicAdd(dst + i, dbacc[i]);
                 }
             }
         }
@@ -402,11 +423,12 @@ __global__ void lstm_unpack_grads_kernel(const UnpackArgs a) {
 }  // namespace rcnn
 
 extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
-                                  int B, int T, int H, void *dG, rcnn_stream_t stream) {
+                                  int B, int T, int H, void *dG, float *db, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_backward: bad shape B=%d T=%d", B, T);
     RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
                    "lstm_backward: hidden size %d unsupported (64, 128, 256 or 512)", H);
+    if (db) RCNN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 8 * (size_t)H, (cudaStream_t)stream));
     if (B == 0 || T == 0) return RCNN_OK;
     RCNN_CHECK_ARG(whh_pt && gates_save && c_save && dhcat && dG, "lstm_backward: null pointer");
     CUtensorMap tw, tg;
@@ -425,6 +447,7 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.csave = c_save;
     p.dhcat = dhcat;
     p.dG = (__nv_bfloat16 *)dG;
+    p.db = db;
     p.tl = debug_timeline();
     const int gsize = H / 32;
     const size_t smem = bwd_smem_bytes(H);

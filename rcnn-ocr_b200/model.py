@@ -69,7 +69,7 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         d_lin_w = ops.gemm_bf16_atb(dob2, hcat.view(BT, 2 * H))        # [O, 2H] = dout^T hcat
         d_lin_b = ops.colsum_bf16(dob2)
         # ---- recurrence ---------------------------------------------------------------------
-        dG = ops.lstm_backward(packed, gates, csave, dhcat, B, T)      # [B,T,8H] bf16
+        dG, db_p = ops.lstm_backward(packed, gates, csave, dhcat, B, T)   # [B,T,8H] bf16, [8H] f32
         dG2 = dG.view(BT, 8 * H)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -78,7 +78,6 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         dwih_p = ops.gemm_bf16_atb(dG2, xb.view(BT, I))                # [8H, I] = dG^T x
         hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
         dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
-        db_p = ops.colsum_bf16(dG2)
         g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
         return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None)
 

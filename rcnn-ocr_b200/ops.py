@@ -173,15 +173,17 @@ def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, sa
 
 def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int):
     """BPTT of both directions (kernel K2 backward).  dhcat: float32 [B,T,2H] contiguous.
-    Returns dG bf16 [B,T,8H] (gradient w.r.t. the gate pre-activations, packed column order)."""
+    Returns (dG bf16 [B,T,8H]: gradient w.r.t. the gate pre-activations, packed column order;
+    db f32 [8H]: its column sums = the packed-order bias gradient, accumulated inside the kernel)."""
     H = packed.H
     assert dhcat.dtype == torch.float32 and dhcat.is_contiguous() and dhcat.shape == (B, T, 2 * H)
     with torch.cuda.device(dhcat.device):
         dG = torch.empty((B, T, 8 * H), dtype=torch.bfloat16, device=dhcat.device)
+        db = torch.empty((8 * H,), dtype=torch.float32, device=dhcat.device)
         rc = _lib.lib().rcnn_lstm_backward(packed.whh_pt.data_ptr(), gates.data_ptr(), csave.data_ptr(),
-                                           dhcat.data_ptr(), B, T, H, dG.data_ptr(), _lib.stream_ptr())
+                                           dhcat.data_ptr(), B, T, H, dG.data_ptr(), db.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_backward")
-    return dG
+    return dG, db
 
 
 def cast_bf16_2d(x: torch.Tensor) -> torch.Tensor:
