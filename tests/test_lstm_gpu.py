@@ -38,8 +38,11 @@ def _hcat_oracle(x, p):
     return torch.cat([hf, hr], 2)
 
 
+# (300, 4, 64, 512) and (2500, 3, 64, 64) have more (direction, 64-sequence) work items than CTA groups fit
+# the device: groups loop over items and carry the step flags across them
 @pytest.mark.parametrize("B,T,I,H", [(4, 3, 64, 64), (128, 5, 64, 64), (130, 7, 96, 128), (32, 16, 512, 256),
-                                     (256, 64, 512, 512), (1, 1, 64, 64), (3, 33, 128, 512)])
+                                     (256, 64, 512, 512), (1, 1, 64, 64), (3, 33, 128, 512), (300, 4, 64, 512),
+                                     (2500, 3, 64, 64), (65, 2, 64, 256)])
 def test_recurrent_forward_matches_oracle(B, T, I, H):
     p = _params(I, H, H, seed=B + T + H)
     x = torch.randn(B, T, I, generator=torch.Generator().manual_seed(1))
@@ -70,7 +73,8 @@ def _block_and_oracle(I, H, O, seed):
 
 
 @pytest.mark.parametrize("B,T,I,H,O", [(5, 4, 64, 64, 64), (130, 6, 64, 128, 32), (32, 16, 512, 256, 256),
-                                       (256, 64, 512, 512, 512), (3, 33, 128, 512, 200)])
+                                       (256, 64, 512, 512, 512), (3, 33, 128, 512, 200), (300, 4, 64, 512, 64),
+                                       (2500, 2, 64, 64, 64), (1, 1, 64, 64, 8)])
 def test_block_forward_backward_matches_oracle(B, T, I, H, O):
     """Whole block (cast, K1 GEMMs, K2 fwd/bwd, linear) against float64 autograd of the
     explicit-equation oracle.  Outputs: 1e-2 absolute (north_star).  Gradients: bf16 operands and
