@@ -33,6 +33,16 @@ CFG = dict(T=64, IN=512, H=512, C=195, LMAX=32, B=256)
 L2_BYTES = 126 * 1024 * 1024
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (None if absent)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -331,7 +341,8 @@ def run_ours(args, rank, world, local_rank):
         if dom in ("lstm_fwd", "lstm_bwd"):
             ach = rec_flops / (per_launch_ms * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sus"],
-                    "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": load_traffic(dom),
+                    "traffic_note": "DRAM bytes per launch, ncu --set full capture at this config (profiles/ncu_traffic_r01.json)",
                     "algorithmic": f"2*B*T*H*4H*2dirs = {rec_flops / 1e9:.1f} GFLOP per launch (one block)",
                     "us_per_timestep": round(per_launch_ms * 1e3 / T, 3), "peak_source": peaks["src"]}
         elif dom == "gemm":
