@@ -182,7 +182,7 @@ class TrainStep:
         self.enc = R.make_enc_rnn(CFG["IN"], CFG["H"]).to(device)
         self.head = R.CTCHead(CFG["H"], CFG["C"]).to(device)
         self.params = list(self.enc.parameters()) + list(self.head.parameters())
-        self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True)
+        self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True, capturable=True)
         self.reducer = GradAllReducer(self.params) if world > 1 else None
         self.world = world
 
@@ -260,14 +260,20 @@ def run_ours(args, rank, world, local_rank):
     dev = [[t.to(device) for t in b] for b in host]
     step = TrainStep(device, world, rank)
     infer = InferStep(step)
+    use_graph = args.graph and world == 1
+    # One CUDA-graph replay per step (rcnn_ocr_b200.GraphedStep): the step function is the same eager
+    # code; inputs are copied into the graph's static tensors inside the timed region.
+    gstep = step.R.GraphedStep(step, dev[0]) if use_graph else step
 
     # ---- device-resident train step (headline `value`) -----------------------------------------
-    clocks = ClockSampler(local_rank)
     l0 = ops.launch_count()
+    step(*dev[0])                                        # one eager step: counts this library's launches per step
+    sync()
+    launches = ops.launch_count() - l0                   # (a graph replay runs exactly the kernels captured from it)
+    clocks = ClockSampler(local_rank)
     clocks.start()
-    ms_train = timed(lambda i: step(*dev[i % RING]), args.steps, args.warmup, sync, barrier)
+    ms_train = timed(lambda i: gstep(*dev[i % RING]), args.steps, args.warmup, sync, barrier)
     clk = clocks.stop()
-    launches = (ops.launch_count() - l0) / (args.steps + args.warmup)
     ms_train = max_over_ranks(ms_train)
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------
@@ -293,7 +299,7 @@ def run_ours(args, rank, world, local_rank):
             e2e_train.primed = True
         stage(i + 1)                                    # overlap the next step's H2D with this step
         torch.cuda.current_stream().wait_event(ready[s])
-        loss = step(*slots[s])
+        loss = gstep(*slots[s])                         # (graph: d2d copy of the staged inputs + one replay)
         freed[s].record()
         losses.append(loss.item())                      # D2H read of the result, every step
 
@@ -304,35 +310,64 @@ def run_ours(args, rank, world, local_rank):
     sync()
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    # ---- greedy inference (same encoder, decode on device) --------------------------------------
-    ms_inf = max_over_ranks(timed(lambda i: infer.device(dev[i % RING][0]), args.steps, args.warmup, sync, barrier))
+    # ---- greedy inference (same encoder, decode on device); eval() as inference.py:88 does -------
+    step.enc.eval(); step.head.eval()
+    ginfer = step.R.GraphedStep(infer.device, [dev[0][0]]) if use_graph else infer.device
+    ms_inf = max_over_ranks(timed(lambda i: ginfer(dev[i % RING][0]), args.steps, args.warmup, sync, barrier))
 
-    def e2e_infer(i):
-        texts, _ = infer.e2e(host[i % RING][0])          # pinned host features in, python strings out
+    def stage_inf(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            slots[s][0].copy_(host[i % RING][0], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_infer(i):                                    # pinned host features in, python strings out
+        s = i % 2
+        if e2e_infer.primed is False:
+            stage_inf(i)
+            e2e_infer.primed = True
+        stage_inf(i + 1)                                 # next batch's H2D overlaps this batch's kernels
+        torch.cuda.current_stream().wait_event(ready[s])
+        ids, lens = ginfer(slots[s][0])
+        freed[s].record()
+        texts, _ = step.R.ids_to_text(ids, lens, infer.alphabet)   # D2H of ids/len + charset mapping
         return texts
 
+    e2e_infer.primed = False
+    for f in freed:
+        f.record()
     ms_inf_e2e = max_over_ranks(timed(e2e_infer, args.steps, args.warmup, sync, barrier))
+    step.enc.train(); step.head.train()
 
     # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
     _lib.prof_enable(True)
     for i in range(args.steps):
         step(*dev[i % RING])
     sync()
-    names = {0: "decode", 1: "ctc", 2: "gemm", 3: "lstm_fwd", 4: "lstm_bwd"}
+    names = {0: "decode", 1: "ctc", 2: "gemm_tn", 3: "lstm_fwd", 4: "lstm_bwd", 5: "gemm_atb"}
     kern = {}
     for kid, name in names.items():
         ms, n = _lib.prof_read(kid)
         if n:
             kern[name] = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps}
     _lib.lib().rcnn_prof_reset()
+    step.enc.eval(); step.head.eval()
     for i in range(args.steps):
         infer.device(dev[i % RING][0])
     sync()
+    step.enc.train(); step.head.train()
     ms_dec, n_dec = _lib.prof_read(0)
     _lib.prof_enable(False)
 
     T, H, C, IN = CFG["T"], CFG["H"], CFG["C"], CFG["IN"]
     rec_flops = 2.0 * B * T * H * 4 * H * 2                 # recurrent matmuls of one block, both directions
+    BT = 2.0 * B * T
+    gemm_flops = {   # per train step (block 1 has no dX: its input needs no gradient)
+        "gemm_tn": BT * (IN * 8 * H + 2 * H * H + H * 8 * H + 2 * H * H + H * C)      # forward: xp, linear (x2 blocks), head
+                   + BT * (2 * (H * 2 * H) + H * 8 * H + C * H),                      # backward: dhcat (x2), dX of block 2, d enc
+        "gemm_atb": BT * (IN * 8 * H + H * 8 * H + 2 * (H * 8 * H) + 2 * (2 * H * H) + C * H),   # dW_ih, dW_hh, dW_lin, dW_head
+    }
     roof = None
     if kern:
         dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
@@ -345,13 +380,11 @@ def run_ours(args, rank, world, local_rank):
                     "traffic_note": "DRAM bytes per launch, ncu --set full capture at this config (profiles/ncu_traffic_r01.json)",
                     "algorithmic": f"2*B*T*H*4H*2dirs = {rec_flops / 1e9:.1f} GFLOP per launch (one block)",
                     "us_per_timestep": round(per_launch_ms * 1e3 / T, 3), "peak_source": peaks["src"]}
-        elif dom == "gemm":
-            # all GEMMs of the step: projections, linears, head and their backward GEMMs
-            g_flops = 2.0 * B * T * (IN * 8 * H + 2 * H * H + H * 8 * H + 2 * H * H + H * C) * 3
-            ach = g_flops / (k["ms_per_step"] * 1e-3) / 1e12
+        elif dom in ("gemm_tn", "gemm_atb"):
+            ach = gemm_flops[dom] / (k["ms_per_step"] * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sus"],
                     "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": None,
-                    "algorithmic": f"{g_flops / 1e9:.1f} GFLOP over all GEMM launches of a step",
+                    "algorithmic": f"{gemm_flops[dom] / 1e9:.1f} GFLOP over the {dom} launches of a step",
                     "peak_source": peaks["src"]}
         else:
             nbytes = 2.0 * T * C * 4 * B
@@ -360,6 +393,15 @@ def run_ours(args, rank, world, local_rank):
                     "frac": round(ach / peaks["hbm"], 4), "traffic": None, "peak_source": peaks["src"]}
     kernels = {n: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"]}
                for n, v in kern.items()}
+    for n in ("gemm_tn", "gemm_atb"):
+        if n in kern:
+            kernels[n]["tflops"] = round(gemm_flops[n] / (kern[n]["ms_per_step"] * 1e-3) / 1e12, 1)
+            kernels[n]["tensor_frac"] = round(kernels[n]["tflops"] / peaks["tf_sus"], 4)
+    for n in ("lstm_fwd", "lstm_bwd"):
+        if n in kern:
+            per = kern[n]["ms_per_step"] / kern[n]["launches_per_step"]
+            kernels[n]["us_per_timestep"] = round(per * 1e3 / T, 3)
+            kernels[n]["tensor_frac"] = round(rec_flops / (per * 1e-3) / 1e12 / peaks["tf_sus"], 4)
     if "ctc" in kern:
         per = kern["ctc"]["ms_per_step"] / kern["ctc"]["launches_per_step"]
         kernels["ctc"]["hbm_frac"] = round(2.0 * T * C * 4 * B / (per * 1e-3) / 1e9 / peaks["hbm"], 4)
@@ -390,7 +432,9 @@ def run_ours(args, rank, world, local_rank):
             "infer": {"value": round(total_B / (ms_inf * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_inf, 4),
                       "e2e": {"value": round(total_B / (ms_inf_e2e * 1e-3), 1), "ms_per_step": round(ms_inf_e2e, 4),
                               "h2d_bytes_per_step": host[0][0].numel() * 4, "d2h_bytes_per_step": B * (T + 1) * 4,
-                              "note": "pinned host features in, decoded python strings out"}},
+                              "note": "pinned host features -> H2D (double-buffered on a copy stream) -> encoder + "
+                                      "greedy decode -> D2H of ids/len -> python strings"}},
+            "launch_mode": "cuda-graph replay (one graph = the whole step)" if use_graph else "eager",
             "gpu_launches": round(launches * args.steps),
             "gpu_launches_per_step": round(launches, 1),
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
@@ -410,6 +454,8 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="lines per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="lines per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel eagerly instead of replaying the captured CUDA graph (N=1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

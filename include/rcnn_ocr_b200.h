@@ -205,6 +205,7 @@ int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int
 #define RCNN_K_GEMM 2
 #define RCNN_K_LSTM_FWD 3
 #define RCNN_K_LSTM_BWD 4
+#define RCNN_K_GEMM_ATB 5   /* gemm_atb_kernel (weight-gradient shape); RCNN_K_GEMM is gemm_tn_kernel */
 #define RCNN_K_COUNT 8
 /* Debug aid: when buf != NULL the recurrent kernels record clock64() marks of cluster 0 / CTA 0 per
  * timestep into buf[step*8 + k] (int64); NULL switches it off. */

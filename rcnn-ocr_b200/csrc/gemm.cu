@@ -473,7 +473,7 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
     splits = (total_kb + kb_per_split - 1) / kb_per_split;
     RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits * groups);
-    ProfScope prof(RCNN_K_GEMM, s);
+    ProfScope prof(RCNN_K_GEMM_ATB, s);
     gemm_atb_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split, splits, a_gcols, b_gcols,
                                                      (long long)d_goff);
     RCNN_LAUNCH_CHECK("gemm_atb_kernel");

@@ -60,11 +60,9 @@ def _to_host(ids: torch.Tensor, lens: torch.Tensor):
     return arr[:, :T], arr[:, T]
 
 
-def ctc_greedy_decoder(logits: torch.Tensor, alphabet, blank: int = 0, batch_first=None):
-    """Drop-in for training/utils.py:122-150.  Returns (texts, seqs)."""
-    if batch_first is None:  # the reference's heuristic, utils.py:132-133
-        batch_first = not (logits.dim() == 3 and logits.shape[0] < logits.shape[1])
-    ids, lens = ctc_greedy_ids(logits, blank=blank, batch_first=batch_first)
+def ids_to_text(ids: torch.Tensor, lens: torch.Tensor, alphabet):
+    """Device ids [B,T] / lens [B] (as returned by ctc_greedy_ids) -> (texts, seqs): one packed D2H
+    copy, then ``alphabet[p - 1]`` per emitted class as at training/utils.py:146."""
     ids_h, lens_h = _to_host(ids, lens)
     table = np.asarray(list(alphabet), dtype=object)
     seqs, texts = [], []
@@ -73,6 +71,14 @@ def ctc_greedy_decoder(logits: torch.Tensor, alphabet, blank: int = 0, batch_fir
         seqs.append(row.tolist())
         texts.append("".join(table[row - 1]) if len(row) else "")
     return texts, seqs
+
+
+def ctc_greedy_decoder(logits: torch.Tensor, alphabet, blank: int = 0, batch_first=None):
+    """Drop-in for training/utils.py:122-150.  Returns (texts, seqs)."""
+    if batch_first is None:  # the reference's heuristic, utils.py:132-133
+        batch_first = not (logits.dim() == 3 and logits.shape[0] < logits.shape[1])
+    ids, lens = ctc_greedy_ids(logits, blank=blank, batch_first=batch_first)
+    return ids_to_text(ids, lens, alphabet)
 
 
 def decode(ctc_out, alphabet, method: str = "greedy"):

@@ -34,19 +34,20 @@ class _BiLSTMBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, lin_w, lin_b,
-                out_dtype, save):
+                out_dtype, save, prepared=None):
         _lib.require_cuda(x, "x")
         if x.dim() != 3:
             raise RuntimeError(f"BidirectionalLSTM expects [B, T, input_size], got {tuple(x.shape)}")
         B, T, I = x.shape
         H = w_hh_f.shape[1]
         O = lin_w.shape[0]
-        packed = ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        if prepared is None:    # bf16 kernel views of the parameters (cached by the module in eval mode)
+            prepared = (ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r), _cast2d(lin_w))
+        packed, lin_wb = prepared
         xb = ops.cast_bf16_3d(x)
         xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
         hcat, gates, csave = ops.lstm_forward(xp, packed, B, T, save)
         del xp
-        lin_wb = _cast2d(lin_w)
         out = ops.gemm_bf16(hcat.view(B * T, 2 * H), lin_wb, lin_b.detach().float().contiguous(), out_dtype)
         if save:
             ctx.save_for_backward(xb, hcat, gates, csave, lin_wb)
@@ -79,7 +80,7 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
         dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
         g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
-        return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None)
+        return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None, None)
 
 
 class _LSTMParameters(nn.Module):
@@ -122,11 +123,28 @@ class BidirectionalLSTM(nn.Module):
         self.rnn = _LSTMParameters(input_size, hidden_size)
         self.linear = nn.Linear(hidden_size * 2, output_size)
         self.out_dtype = out_dtype
+        self._prepared = None     # (key, (packed weights, bf16 linear weight)) while the module is in eval mode
+
+    def _prepared_weights(self):
+        """eval() mode: the packed bf16 views are rebuilt only when a parameter was replaced or
+        modified in place (storage pointer / version counter), not on every call."""
+        ws = self.rnn.ordered() + [self.linear.weight]
+        key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
+        if self._prepared is None or self._prepared[0] != key:
+            with torch.no_grad():
+                self._prepared = (key, (ops.lstm_pack(*self.rnn.ordered()), _cast2d(self.linear.weight)))
+        return self._prepared[1]
+
+    def train(self, mode: bool = True):
+        if mode:
+            self._prepared = None
+        return super().train(mode)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         save = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        prepared = self._prepared_weights() if (not self.training and x.is_cuda) else None
         return _BiLSTMBlockFn.apply(x, *self.rnn.ordered(), self.linear.weight, self.linear.bias,
-                                    self.out_dtype, save)
+                                    self.out_dtype, save, prepared)
 
 
 def make_enc_rnn(enc_dim: int, hidden_size: int) -> nn.Sequential:

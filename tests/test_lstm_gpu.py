@@ -132,3 +132,25 @@ def test_inference_matches_training_forward_and_golden_style_stack():
     params = {k: v.detach().double().cpu() for k, v in enc.state_dict().items()}
     want = lstm_ref.enc_rnn(x.detach().double().cpu(), params)
     assert (y0.cpu().double() - want).abs().max().item() < ATOL
+
+
+def test_eval_mode_weight_cache_tracks_parameter_updates():
+    """eval(): the packed bf16 weight views are cached; an in-place update (optimizer step,
+    load_state_dict) or train() must invalidate them."""
+    import rcnn_ocr_b200 as R
+    torch.manual_seed(2)
+    blk = R.BidirectionalLSTM(64, 64, 32).cuda()
+    x = torch.randn(5, 7, 64, device="cuda")
+    with torch.no_grad():
+        y_train = blk(x)
+        blk.eval()
+        y0 = blk(x)
+        y1 = blk(x)                      # served from the cache
+        assert torch.equal(y_train, y0) and torch.equal(y0, y1)
+        key0 = blk._prepared[0]
+        blk.rnn.weight_hh_l0.mul_(0.5)   # in-place update bumps the version counter
+        y2 = blk(x)
+        assert blk._prepared[0] != key0 and not torch.equal(y0, y2)
+        blk.train()
+        assert blk._prepared is None
+        assert torch.equal(blk(x), y2)
