@@ -260,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
     dev = [[t.to(device) for t in b] for b in host]
     step = TrainStep(device, world, rank)
     infer = InferStep(step)
-    use_graph = args.graph and world == 1
+    use_graph = args.graph and (world == 1 or args.graph_dp)
     # One CUDA-graph replay per step (rcnn_ocr_b200.GraphedStep): the step function is the same eager
     # code; inputs are copied into the graph's static tensors inside the timed region.
     gstep = step.R.GraphedStep(step, dev[0]) if use_graph else step
@@ -442,7 +442,16 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Captured graphs hold NCCL work: drop them before the process group; a watchdog ends the process
+        # if the teardown still blocks (the result line is already out).
+        import gc
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        del gstep, ginfer
+        gc.collect()
+        sync()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
@@ -454,6 +463,8 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="lines per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="lines per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph-dp", dest="graph_dp", action="store_false",
+                    help="N>1: launch eagerly (default: the NCCL bucket all-reduces on the side stream join the capture)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel eagerly instead of replaying the captured CUDA graph (N=1)")
     args = ap.parse_args()
