@@ -168,13 +168,17 @@ int rcnn_lstm_forward(const void *xp, const void *whh_p, int B, int T, int H, vo
  *   dhcat       f32 [B, T, 2H]  gradient w.r.t. hcat
  *   dG          bf16 [B, T, 2*4H] out: gradient w.r.t. the gate pre-activations (= w.r.t. xp),
  *               columns in P order.
+ *   workspace   rcnn_lstm_backward_workspace_bytes(B,T,H) bytes of device memory (need not be zeroed): the
+ *               bf16 partial sums of dG W_hh the CTAs of a group exchange every step
  *   db_p        f32 [2*4H] out or NULL: column sums of dG (= d b_ih = d b_hh in P order), accumulated in
  *               fp32 inside the kernel from the unrounded values.  dX = dG wih_p, dW_ih_p = dG^T X, dW_hh_p = dG^T H_prev,
  *               db_p = column sums of dG are then GEMMs / reductions (rcnn_gemm_bf16,
  *               rcnn_gemm_bf16_atb, rcnn_colsum_bf16, rcnn_lstm_hprev) and rcnn_lstm_unpack_grads scatters the
  *               P-ordered results back to torch's parameter layout. */
+size_t rcnn_lstm_backward_workspace_bytes(int B, int T, int H);
 int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
-                       int B, int T, int H, void *dG, float *db_p, rcnn_stream_t stream);
+                       int B, int T, int H, void *dG, float *db_p, void *workspace, size_t workspace_bytes,
+                       rcnn_stream_t stream);
 /* out[col] = sum over rows of src[row*ld + col]  (bf16 [rows, cols] -> f32 [cols]) */
 int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float *out, rcnn_stream_t stream);
 /* out bf16 [B, T, 2H]: out[b, t, dir*H+u] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at the

@@ -38,7 +38,9 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_lstm_forward.restype = i
     L.rcnn_lstm_forward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp]
     L.rcnn_lstm_backward.restype = i
-    L.rcnn_lstm_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, vp]
+    L.rcnn_lstm_backward.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, vp, ctypes.c_size_t, vp]
+    L.rcnn_lstm_backward_workspace_bytes.restype = ctypes.c_size_t
+    L.rcnn_lstm_backward_workspace_bytes.argtypes = [i, i, i]
     L.rcnn_colsum_bf16.restype = i
     L.rcnn_colsum_bf16.argtypes = [vp, i64, i64, i, vp, vp]
     L.rcnn_cast_bf16_2d.restype = i

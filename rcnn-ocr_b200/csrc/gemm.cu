@@ -44,7 +44,7 @@ static int encode(CUtensorMap *out, const void *base, int elem_bytes, int rank, 
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return RCNN_ERR_DEVICE;
     }
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -75,6 +75,16 @@ int make_tmap_3d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t d2
     const cuuint64_t gstride[2] = {row_pitch_bytes, pitch2_bytes};
     const cuuint32_t box[3] = {box_cols, box_rows, box2};
     return encode(out, base, elem_bytes, 3, gdim, gstride, box, swizzle128);
+}
+
+// N-D map (rank <= 5) with caller-given dimension order (dims[0] innermost, strides[i] = byte stride of dims[i+1])
+int make_tmap_nd(CUtensorMap *out, const void *base, int elem_bytes, int rank, const uint64_t *dims, const uint64_t *strides,
+                 const uint32_t *box, int swizzle128) {
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t b[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides[i];
+    return encode(out, base, elem_bytes, rank, gdim, gstride, b, swizzle128);
 }
 
 // 4-D map with caller-given dimension order (dims[0] innermost, strides[i] = byte stride of dims[i+1]):

@@ -6,19 +6,31 @@
 //     do     = dh_t * tanh(c_t)            dc += dh_t * o * (1 - tanh(c_t)^2)
 //     di = dc*g   dg = dc*i   df = dc*c_prev   dc <- dc*f
 //     dG_t   = [di*i(1-i), df*f(1-f), dg*(1-g^2), do*o(1-o)]   (pre-activation gradients)
-// dW_ih, dW_hh, db and dX are GEMMs / reductions over dG after the loop (host side).
+// dW_ih, dW_hh and dX are GEMMs over dG after the loop (host side); db is accumulated here.
 //
-// Same decomposition as the forward kernel: a GROUP of H/32 CTAs owns one work item = (direction,
-// tile of 64 sequences) at a time, CTA c owns hidden units [32c, 32c+32); groups synchronise per step
-// through a counter in global memory (red.release / relaxed poll) and the kernel is launched
-// cooperatively.  Here the resident operand is the CTA's 32 x 4H slice of W_hh^T (bf16, 128 KB for
-// H=512) and the streamed operand is the full dG_{t'} tile [64 seq, 4H]: one TMA operation brings
-// four K chunks (a 32 KB slot of a 3-slot ring, 4-D tensor map), accumulated by tcgen05.mma (M = 64)
-// into a 64 x 32 fp32 TMEM tile.  The cell threads (16 rows per TMEM lane quadrant, the two half-warps
-// of a warp split the columns) keep dc in registers for the whole sequence, read the saved gates /
-// cell states / upstream dh directly from global memory (issued before the MMA wait) and write dG_t
-// in the packed column order, which is at once the next step's MMA operand and the operand of the
-// dX / dW GEMMs.
+// Same grouping as the forward kernel: a GROUP of H/32 CTAs owns one work item = (direction, tile
+// of 64 sequences) at a time, CTA c owns hidden units [32c, 32c+32); CTAs of a group synchronise per
+// step through a counter in global memory and the kernel is launched cooperatively.
+//
+// The contraction dG_{t'} W_hh is K-LOCAL: a CTA multiplies only the 128 gate columns IT produced
+// (its own dG slice, written by its cell warps straight into shared memory as the UMMA B operand:
+// no ingest from L2) with the matching 128 rows of W_hh, for ALL H outputs:
+//     partial_c^T [H units, 64 seq] = W_hh[rows of c]^T (H x 128, resident in shared memory, bf16)
+//                                     x dG_c^T (128 x 64)
+// i.e. H/128 x 8 tcgen05.mma of M = 128, N = 64 into H/128 TMEM accumulators (an all-gather of dG
+// would need 4H/16 = 128 MMAs of N = 32 per step and 256 KB of ingest per CTA).  The partial sums are
+// exchanged through L2 as bf16 (64 KB out, 64 KB in per CTA and step), both ways by ONE TMA operation
+// on a 5-D tensor map of the exchange buffer [parity x group][src CTA][dst CTA][4][1 KB]: the drained
+// accumulators are staged in shared memory and stored, the 16 partials of the CTA's own 32 units are
+// loaded back into the same shared-memory area the next step and summed by the cell warps.
+//   warp 0      loads W once; per step: polls the group counter (relaxed gpu-scope loads), TMA-loads the
+//               partials, later TMA-stores this CTA's partials, waits for their completion and
+//               releases the counter (the only gpu-scope fence of the step is this one thread's)
+//   warp 1      MMA issuer (one elected thread)
+//   warps 2-9   cell update: warp w owns sequences 8w..8w+7 of the tile, lane = hidden unit of the
+//               CTA, so every global access of a warp is one contiguous 128/256-byte row; dc and the
+//               bias-gradient sums stay in registers for the whole sequence; after the MMA the same
+//               warps drain TMEM (lane = output unit) to the exchange buffer.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -29,15 +41,12 @@ namespace {
 
 using namespace sm100;
 
-constexpr int LB = 64;    // sequences per work item (UMMA M)
-constexpr int LU = 32;    // hidden units per CTA (UMMA N)
+constexpr int NS = 64;     // sequences per work item (UMMA N)
+constexpr int LU = 32;     // hidden units per CTA
 constexpr int LK = 64;
-constexpr int kARing = 3;
-constexpr int kChunks = 4;                   // K chunks per TMA operation / ring slot
-constexpr uint32_t kABox = LB * LK * 2;      // [64 seq x 64 k] bf16 = 8 KB
-constexpr uint32_t kATile = kChunks * kABox; // 32 KB ring slot
-constexpr uint32_t kWTile = LU * LK * 2;     // 4 KB
-constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
+constexpr uint32_t kWTile = 128 * LK * 2;   // [128 output units x 64 k] bf16, SW128 = 16 KB
+constexpr uint32_t kBChunk = NS * LK * 2;   // [64 seq x 64 k] bf16, SW128 = 8 KB
+constexpr int kThreads = 320;   // warp 0 poll/TMA, warp 1 MMA, warps 2-9 cell update
 
 struct BwdParams {
     int B, T, H;
@@ -47,6 +56,7 @@ struct BwdParams {
     const float *dhcat;        // [B, T, 2H] upstream gradient of the block's LSTM output
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
     float *db;                 // [2*4H] out or nullptr: column sums of dG (bias gradient), zeroed before the launch
+    __nv_bfloat16 *xbuf;       // exchange buffer [2][ngroups][src CTA][dst CTA][8 warps][32 units][8 seq]
     unsigned int *sync;        // [ngroups] zeroed before the launch
     long long *tl;             // debug timeline or nullptr
 };
@@ -60,11 +70,15 @@ __device__ __forceinline__ float tanh_fast_b(float x) {
 __device__ __forceinline__ void red_release_gpu_inc_b(unsigned int *p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_inc_b(unsigned int *p) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ unsigned int ld_relaxed_gpu_b(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Bounded spin on the group counter: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void wait_counter_b(const unsigned int *p, unsigned int target) {
     if (ld_relaxed_gpu_b(p) >= target) return;
     const long long t0 = clock64();
@@ -75,59 +89,55 @@ __device__ __forceinline__ void wait_counter_b(const unsigned int *p, unsigned i
         }
     }
 }
-
-struct ChunkIn {     // saved state of 8 units of one sequence at one step
-    U8 g[2];         // 32 halves: (i,f,g,o) x 8 units
-    U8 c, cp, dh;    // 8 floats each
-};
-
-__device__ __forceinline__ void load_chunk(ChunkIn &ci, const __half *grow, const float *crow, const float *cprow,
-                                           const float *dhrow, bool valid) {
-    U8 z;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) z.v[k] = 0u;
-    if (valid) {
-        ci.g[0] = ld_ro_v8(grow);
-        ci.g[1] = ld_ro_v8(grow + 16);
-        ci.c = ld_ro_v8(crow);
-        ci.dh = ld_ro_v8(dhrow);
-        ci.cp = cprow ? ld_ro_v8(cprow) : z;
-    } else {
-        ci.g[0] = z; ci.g[1] = z; ci.c = z; ci.cp = z; ci.dh = z;
-    }
+// L2-only loads / stores of the exchange buffer (it is rewritten every other step: never through L1)
+__device__ __forceinline__ uint4 ld_cg_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_cg_v4(void *p, const uint4 &v) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ro_v2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, const BwdParams p) {
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXin,
+                const __grid_constant__ CUtensorMap tmXout, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
-    const int nkc = 4 * H / LK;
-    const int nslots = nkc / kChunks;          // ring slots consumed per step
+    const int nmb = (H + 127) / 128;           // accumulators: blocks of 128 output units (H = 64: one, half used)
     const int gsize = H / 32;
-    unsigned char *w_s = smem;                          // nkc tiles [32 n x 64 k] bf16, SW128
-    unsigned char *a_s = w_s + (size_t)nkc * kWTile;    // kARing slots of kChunks boxes [64 seq x 64 k] bf16, SW128
-    uint64_t *bars = reinterpret_cast<uint64_t *>(a_s + kARing * kATile);
-    uint64_t *w_full = bars;
-    uint64_t *a_full = bars + 1, *a_empty = a_full + kARing;
-    uint64_t *tmem_full = a_empty + kARing;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    unsigned char *w_s = smem;                                  // nmb x 2 tiles [128 units x 64 k] bf16, SW128
+    unsigned char *b_s = w_s + (size_t)nmb * 2 * kWTile;        // 2 chunks [64 seq x 64 k] bf16, SW128: this CTA's dG_t
+    unsigned char *x_s = b_s + 2 * kBChunk;                     // gsize x 4 KB: partials in (by source) / out (by destination)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + (size_t)gsize * 4096);
+    uint64_t *w_full = bars, *b_ready = bars + 1, *x_ready = bars + 2;
+    uint64_t *d_full = bars + 3;     // [4] accumulator block mb complete
+    uint64_t *staged = bars + 7;     // [4] block mb drained into x_s (8 warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
     unsigned int *counter = p.sync + group;
+    // exchange buffer: [parity][group][src CTA][dst CTA][warp 8][unit 32][seq 8] bf16 (4 KB per (src, dst))
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            for (int i = 0; i < kARing; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-            mbar_init(tmem_full, 1);
+            mbar_init(b_ready, 8);
+            mbar_init(x_ready, 1);
+            for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&staged[i], 8); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<LU>(tmem_slot);
+        tmem_alloc<256>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -135,194 +145,232 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
-    // reverse direction from t = 0 up to T-1.
+    // reverse direction from t = 0 up to T-1.  Every step but an item's last publishes partial sums.
     if (warp == 0) {
-        // ===== TMA producer (one elected thread) =================================================
+        // ===== W loader + counter poller (one elected thread) ====================================
         if (elect_one()) {
-            tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmG);
+            tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmXin); tma_prefetch_desc(&tmXout);
             int cur_dir = -1;
-            int pslot = 0;
-            uint32_t pphase = 0;
-            unsigned int published = 0;
+            unsigned int published = 0, npub = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1, b0 = (item >> 1) * LB;
+                const int dir = item & 1;
                 if (dir != cur_dir) {
-                    mbar_arrive_expect_tx(w_full, (uint32_t)nkc * kWTile);
-                    for (int kc = 0; kc < nkc; ++kc)
-                        tma_load_2d(w_s + (size_t)kc * kWTile, &tmW, w_full, kc * LK, dir * H + c * LU);
+                    // rows = output units j of this direction, columns = the 128 packed gate indices of CTA c
+                    mbar_arrive_expect_tx(w_full, (uint32_t)nmb * 2 * kWTile);
+                    for (int mb = 0; mb < nmb; ++mb)
+                        for (int kc = 0; kc < 2; ++kc)
+                            tma_load_2d(w_s + (size_t)(mb * 2 + kc) * kWTile, &tmW, w_full, c * 128 + kc * LK, dir * H + mb * 128);
                     cur_dir = dir;
                 }
-                for (int s = 1; s < T; ++s) {
-                    const int t = dir ? s : T - 1 - s;
-                    const int tsrc = dir ? t - 1 : t + 1;   // step processed just before
-                    TL_MARK(7);
-                    wait_counter_b(counter, (published + (unsigned)s) * (unsigned)gsize);
-                    TL_MARK(0);
-                    fence_proxy_async_global();
-                    for (int g = 0; g < nslots; ++g) {
-                        mbar_wait(&a_empty[pslot], pphase ^ 1);
-                        mbar_arrive_expect_tx(&a_full[pslot], kATile);
-                        tma_load_4d(a_s + pslot * kATile, &tmG, &a_full[pslot], 0, b0, dir * nkc + g * kChunks, tsrc);
-                        if (++pslot == kARing) { pslot = 0; pphase ^= 1; }
+                for (int s = 0; s < T; ++s) {
+                    if (s > 0) {
+                        wait_counter_b(counter, (published + (unsigned)s) * (unsigned)gsize);
+                        TL_MARK(0);
+                        fence_proxy_async_global();
+                        // the 16 partials of this CTA's units, published by the group in the previous step
+                        mbar_arrive_expect_tx(x_ready, (uint32_t)gsize * 4096u);
+                        tma_load_5d(x_s, &tmXin, x_ready, 0, 0, c, 0, (int)((npub - 1) & 1) * p.ngroups + group);
                     }
-                    TL_MARK(1);
+                    if (s + 1 < T) {
+                        // block by block as the cell warps drain the accumulators: the partials for destination
+                        // CTAs 4mb .. 4mb+3 (16 KB, contiguous in shared and global memory)
+                        for (int mb = 0; mb < nmb; ++mb) {
+                            mbar_wait(&staged[mb], npub & 1);
+                            if (mb == nmb - 1) TL_MARK(7);
+                            tma_store_5d(&tmXout, x_s + (size_t)mb * 16384, 0, 0, 4 * mb, c, (int)(npub & 1) * p.ngroups + group);
+                            tma_store_commit();
+                        }
+                        tma_store_wait<0>();                      // written, not merely read out of shared memory
+                        TL_MARK(1);
+                        // the partials are in L2 and nothing else of this thread is outstanding: a relaxed increment
+                        // publishes them (readers poll relaxed and fetch with TMA, straight from L2)
+                        fence_proxy_async_global();
+                        red_relaxed_gpu_inc_b(counter);
+                        TL_MARK(6);
+                        ++npub;
+                    }
                 }
-                published += (unsigned)T;
+                published += (unsigned)(T - 1);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) ===================================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(LB, LU);
+            constexpr uint32_t idesc = make_idesc_bf16(128, NS);
             int cur_dir = -1;
-            int mslot = 0;
-            uint32_t mphase = 0, wphase = 0;
+            uint32_t wphase = 0, bphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
                 const int dir = item & 1;
                 if (dir != cur_dir) { mbar_wait(w_full, wphase); wphase ^= 1; cur_dir = dir; }
-                for (int s = 1; s < T; ++s) {
-                    for (int g = 0; g < nslots; ++g) {
-                        mbar_wait(&a_full[mslot], mphase);
-                        if (g == 0) TL_MARK(2);
-                        tc_fence_after();
+                for (int s = 0; s + 1 < T; ++s) {
+                    mbar_wait(b_ready, bphase);
+                    bphase ^= 1;
+                    TL_MARK(2);
+                    tc_fence_after();
+                    for (int mb = 0; mb < nmb; ++mb) {
 #pragma unroll
-                        for (int j = 0; j < kChunks; ++j) {
-                            const int kc = g * kChunks + j;
-                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(a_s + mslot * kATile + j * kABox), 16, 1024);
-                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+                        for (int kc = 0; kc < 2; ++kc) {
+                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)(mb * 2 + kc) * kWTile), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_s + kc * kBChunk), 16, 1024);
 #pragma unroll
                             for (int k = 0; k < LK / 16; ++k)
-                                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                                umma_bf16(tmem_base + (uint32_t)(mb * NS), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                          idesc, (kc | k) != 0);
                         }
-                        umma_commit(&a_empty[mslot]);
-                        if (++mslot == kARing) { mslot = 0; mphase ^= 1; }
+                        umma_commit(&d_full[mb]);    // the cell warps drain block mb while the next one is multiplied
                     }
-                    umma_commit(tmem_full);
                     TL_MARK(3);
                 }
             }
         }
     } else {
-        // ===== cell update ========================================================================
-        // M = 64 accumulator layout: row m sits in TMEM lane 32*(m/16) + m%16, so warp quadrant qd reads
-        // rows 16qd .. 16qd+15 in its lanes 0-15; the upper half-warp takes over 8 of the 16 columns.
-        const int qd = warp & 3;
-        const int hf = (warp - 2) >> 2;                   // which 16 of the CTA's 32 units this warp handles
-        const int row = qd * 16 + (lane & 15);            // sequence within the tile
-        const int u0 = hf * 16 + (lane >> 4) * 8;         // first of this thread's 8 units (within the CTA)
-        unsigned int mcount = 0;
+        // ===== cell update + exchange ============================================================
+        const int w = warp - 2;               // sequences 8w .. 8w+7 of the tile; lane = hidden unit 32c + lane
+        const int qd = warp & 3;              // TMEM lane quadrant (drain phase)
+        const int hq = (warp - 2) >> 2;       // which 32 of the 64 sequence columns this warp drains
+        unsigned int npub = 0, nwait = 0, nmma = 0;   // publishes so far, x_ready / d_full phases
         for (int item = group; item < p.nitems; item += p.ngroups) {
-            const int dir = item & 1, b0 = (item >> 1) * LB;
-            const int b = b0 + row;
-            const bool valid = b < B;
-            float dc[8];
+            const int dir = item & 1, b0 = (item >> 1) * NS;
+            float dc[8], dbacc[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-            float dbacc[32];   // this sequence's contribution to the bias gradient of the thread's 32 gate columns
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dbacc[i] = 0.f;
+            for (int i = 0; i < 4; ++i) dbacc[i] = 0.f;
             for (int s = 0; s < T; ++s) {
                 const int t = dir ? s : T - 1 - s;
                 const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
-                const size_t rtb = ((size_t)dir * T + t) * B + b;
-                const __half *grow = p.gates + rtb * 4 * H + (size_t)c * 128 + u0 * 4;
-                const float *crow = p.csave + rtb * H + 32 * c + u0;
-                const float *cprow = (tfp >= 0 && tfp < T) ? p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c + u0 : nullptr;
-                const float *dhrow = p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + u0;
-                __nv_bfloat16 *dgrow = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128 + u0 * 4;
-
-                ChunkIn ci;
-                load_chunk(ci, grow, crow, cprow, dhrow, valid);
-                if (valid && s + 1 < T) {   // pull the next step's saved rows from HBM into L2 while the MMA runs
-                    const int tn = dir ? t + 1 : t - 1;
-                    const size_t rn = ((size_t)dir * T + tn) * B + b;
-                    prefetch_l2(p.gates + rn * 4 * H + (size_t)c * 128 + u0 * 4);
-                    prefetch_l2(p.csave + rn * H + 32 * c + u0);
-                    prefetch_l2(p.dhcat + ((size_t)b * T + tn) * 2 * H + (size_t)dir * H + 32 * c + u0);
+                // ---- saved activations of this step (issued before anything is waited for) ----------
+                uint2 gq[8];
+                float cc[8], cp[8], dhu[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + 8 * w + i;
+                    if (b < B) {
+                        const size_t rtb = ((size_t)dir * T + t) * B + b;
+                        gq[i] = ld_ro_v2(p.gates + rtb * 4 * H + (size_t)c * 128 + 4 * lane);
+                        cc[i] = ld_nc_f32(p.csave + rtb * H + 32 * c + lane);
+                        cp[i] = (tfp >= 0 && tfp < T) ? ld_nc_f32(p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c + lane) : 0.f;
+                        dhu[i] = ld_nc_f32(p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + lane);
+                    } else {
+                        gq[i] = make_uint2(0u, 0u); cc[i] = 0.f; cp[i] = 0.f; dhu[i] = 0.f;
+                    }
                 }
-                float rec[8];   // dG_{t'} W_hh for this thread's 8 units
+                // ---- recurrent term: sum of the partials every CTA of the group published last step ---
+                float rec[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rec[i] = 0.f;
                 if (s > 0) {
-                    uint32_t acc[16];
-                    mbar_wait(tmem_full, mcount & 1);
-                    ++mcount;
-                    if (threadIdx.x == 64) TL_MARK(4);
-                    tc_fence_after();
-                    tmem_ld_32x16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 16), acc);
-                    tmem_ld_wait();
+                    mbar_wait(x_ready, nwait & 1);
+                    ++nwait;
+                    const unsigned char *src = x_s + ((size_t)w * 256 + (size_t)lane * 8) * 2;
+#pragma unroll 4
+                    for (int sc = 0; sc < gsize; ++sc) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)sc * 4096);
+                        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t hi = __shfl_sync(FULL, acc[8 + j], lane & 15);
-                        rec[j] = __uint_as_float(lane < 16 ? acc[j] : hi);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rec[j] = 0.f;
-                }
-                const __half2 *gh = reinterpret_cast<const __half2 *>(ci.g);
-                float o32[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float2 if_ = __half22float2(gh[2 * j]);       // (i, f)
-                    const float2 go_ = __half22float2(gh[2 * j + 1]);   // (g, o)
-                    const float ig = if_.x, fg = if_.y, gg = go_.x, og = go_.y;
-                    const float dh = __uint_as_float(ci.dh.v[j]) + rec[j];
-                    const float tc = tanh_fast_b(__uint_as_float(ci.c.v[j]));
-                    const float d_o = dh * tc;
-                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[j]);
-                    dc[j] = dct * fg;
-                    o32[4 * j] = dct * gg * ig * (1.f - ig);
-                    o32[4 * j + 1] = dct * __uint_as_float(ci.cp.v[j]) * fg * (1.f - fg);
-                    o32[4 * j + 2] = dct * ig * (1.f - gg * gg);
-                    o32[4 * j + 3] = d_o * og * (1.f - og);
-                }
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) dbacc[i] += o32[i];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        U8 v;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o32[16 * j + 2 * k], o32[16 * j + 2 * k + 1]);
-                            v.v[k] = *reinterpret_cast<uint32_t *>(&h2);
+                        for (int k = 0; k < 4; ++k) {
+                            rec[2 * k] += __uint_as_float(wd[k] << 16);
+                            rec[2 * k + 1] += __uint_as_float(wd[k] & 0xffff0000u);
                         }
-                        st_v8(dgrow + j * 16, v);
                     }
+                }
+                // ---- cell backward -----------------------------------------------------------------
+                uint2 dgq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 if_ = __half22float2(*reinterpret_cast<const __half2 *>(&gq[i].x));   // (i, f)
+                    const float2 go_ = __half22float2(*reinterpret_cast<const __half2 *>(&gq[i].y));   // (g, o)
+                    const float ig = if_.x, fg = if_.y, gg = go_.x, og = go_.y;
+                    const float dh = dhu[i] + rec[i];
+                    const float tc = tanh_fast_b(cc[i]);
+                    const float d_o = dh * tc;
+                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[i]);
+                    dc[i] = dct * fg;
+                    const float o0 = dct * gg * ig * (1.f - ig);
+                    const float o1 = dct * cp[i] * fg * (1.f - fg);
+                    const float o2 = dct * ig * (1.f - gg * gg);
+                    const float o3 = d_o * og * (1.f - og);
+                    dbacc[0] += o0; dbacc[1] += o1; dbacc[2] += o2; dbacc[3] += o3;   // (rows b >= B contribute zeros)
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+                    dgq[i].x = *reinterpret_cast<const uint32_t *>(&lo);
+                    dgq[i].y = *reinterpret_cast<const uint32_t *>(&hi);
+                }
+                const bool more = s + 1 < T;
+                if (more) {
+                    // dG_t of this CTA as the K-major SW128 B operand: row = sequence, k = 4*lane + gate
+                    const int chunk = lane >> 4, piece = (lane & 15) >> 1, sub = (lane & 1) * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = 8 * w + i;
+                        *reinterpret_cast<uint2 *>(b_s + chunk * kBChunk + row * 128 + ((piece ^ (row & 7)) << 4) + sub) = dgq[i];
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_ready);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = b0 + 8 * w + i;
+                    if (b < B)
+                        *reinterpret_cast<uint2 *>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128 + 4 * lane) = dgq[i];
                 }
                 if (threadIdx.x == 64) TL_MARK(5);
-                tc_fence_before();
-                fence_proxy_async_global();   // dG_t stores before the other CTAs' TMA reads
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (threadIdx.x == 64) {      // one gpu-scope release per CTA
-                    red_release_gpu_inc_b(counter);
-                    TL_MARK(6);
+                if (more) {
+                    // ---- drain the accumulators: partial^T [unit, seq] -> exchange buffer (bf16) ---------
+                    for (int mb = 0; mb < nmb; ++mb) {
+                        mbar_wait(&d_full[mb], nmma & 1);
+                        if (threadIdx.x == 64 && mb == nmb - 1) TL_MARK(4);
+                        tc_fence_after();
+                        uint32_t acc[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mb * NS + hq * 32), acc);
+                        tmem_ld_wait();
+                        const int dstc = mb * 4 + qd;                 // CTA that owns output units [128mb + 32qd, +32)
+                        if (dstc < gsize) {
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {          // 8 sequences = one reader warp's slice
+                                uint4 v;
+                                uint32_t *vw = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * g4 + 2 * k]),
+                                                                                     __uint_as_float(acc[8 * g4 + 2 * k + 1]));
+                                    vw[k] = *reinterpret_cast<const uint32_t *>(&h2);
+                                }
+                                *reinterpret_cast<uint4 *>(x_s + (size_t)dstc * 4096 + ((size_t)(hq * 4 + g4) * 256 + (size_t)lane * 8) * 2) = v;
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&staged[mb]);
+                    }
+                    tc_fence_before();
+                    ++nmma;
+                    ++npub;
                 }
             }
             if (p.db != nullptr) {
-                // db: sum over the 16 sequences of the half-warp, then one atomic per column and half-warp
+                float *dst = p.db + (size_t)dir * 4 * H + (size_t)c * 128 + 4 * lane;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = dbacc[i];
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                    dbacc[i] = v;
-                }
-                if ((lane & 15) == 0) {
-                    float *dst = p.db + (size_t)dir * 4 * H + (size_t)c * 128 + u0 * 4;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) atomicAdd(dst + i, dbacc[i]);
-                }
+                for (int i = 0; i < 4; ++i) atomicAdd(dst + i, dbacc[i]);
             }
         }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<LU>(tmem_base);
+        tmem_dealloc<256>(tmem_base);
     }
 }
 
-size_t bwd_smem_bytes(int H) { return 1024 + (size_t)(4 * H / LK) * kWTile + (size_t)kARing * kATile + 256; }
+size_t bwd_smem_bytes(int H) { return 1024 + (size_t)((H + 127) / 128) * 2 * kWTile + 2 * kBChunk + (size_t)(H / 32) * 4096 + 256; }
+
+int bwd_groups(int B, int H) {
+    const int gsize = H / 32, nitems = 2 * ((B + NS - 1) / NS);
+    const int max_groups = num_sms() / gsize;    // one CTA per SM (shared memory)
+    int ng = nitems < max_groups ? nitems : max_groups;
+    if (ng > 1 && (ng & 1) && nitems > ng) --ng;   // even: a group keeps its direction (and W slice)
+    return ng;
+}
 
 // column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
 __global__ void colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ src, long long ld, long long rows, int cols,
@@ -422,8 +470,16 @@ __global__ void lstm_unpack_grads_kernel(const UnpackArgs a) {
 }  // namespace
 }  // namespace rcnn
 
+extern "C" size_t rcnn_lstm_backward_workspace_bytes(int B, int T, int H) {
+    using namespace rcnn;
+    if (B <= 0 || T <= 0 || !(H == 64 || H == 128 || H == 256 || H == 512)) return 0;
+    const size_t gsize = H / 32;
+    return 2 * (size_t)bwd_groups(B, H) * gsize * gsize * 8 * 32 * 8 * sizeof(__nv_bfloat16);
+}
+
 extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
-                                  int B, int T, int H, void *dG, float *db, rcnn_stream_t stream) {
+                                  int B, int T, int H, void *dG, float *db, void *workspace, size_t workspace_bytes,
+                                  rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_backward: bad shape B=%d T=%d", B, T);
     RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
@@ -431,14 +487,26 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     if (db) RCNN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 8 * (size_t)H, (cudaStream_t)stream));
     if (B == 0 || T == 0) return RCNN_OK;
     RCNN_CHECK_ARG(whh_pt && gates_save && c_save && dhcat && dG, "lstm_backward: null pointer");
-    CUtensorMap tw, tg;
-    int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, LU, LK, 1);
+    if (!workspace || workspace_bytes < rcnn_lstm_backward_workspace_bytes(B, T, H)) {
+        set_error("lstm_backward: workspace of %zu bytes needed, %zu given", rcnn_lstm_backward_workspace_bytes(B, T, H),
+                  workspace ? workspace_bytes : (size_t)0);
+        return RCNN_ERR_WORKSPACE;
+    }
+    CUtensorMap tw;
+    // whh_pt [2, H, 4H]: rows = (direction, output unit j), columns = packed gate index; box = [128 units x 64 k]
+    // (H = 64: the box reads 64 rows past the direction's block or zero fill; those accumulator lanes are unused)
+    int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, 128, LK, 1);
     if (rc) return rc;
-    {   // dG [B, T, 8H] seen as (k within chunk, b, chunk, t): one box = kChunks chunks of [64 seq x 64 k]
-        const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 8ull * H / LK, (uint64_t)T};
-        const uint64_t strides[3] = {(uint64_t)T * 8 * H * 2, (uint64_t)LK * 2, 8ull * H * 2};
-        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)LB, (uint32_t)kChunks, 1u};
-        rc = make_tmap_4d(&tg, dG, 2, dims, strides, box, 1);
+    const int gsz = H / 32, ngr = bwd_groups(B, H);
+    CUtensorMap txin, txout;
+    {   // exchange buffer as float32 [2*ngroups][src][dst][4][256]: load box = all sources of one destination,
+        // store box = all destinations of one source
+        const uint64_t dims[5] = {256, 4, (uint64_t)gsz, (uint64_t)gsz, 2ull * ngr};
+        const uint64_t strides[4] = {1024, 4096, (uint64_t)gsz * 4096, (uint64_t)gsz * gsz * 4096};
+        const uint32_t box_in[5] = {256, 4, 1, (uint32_t)gsz, 1}, box_out[5] = {256, 4, (uint32_t)(gsz < 4 ? gsz : 4), 1, 1};
+        rc = make_tmap_nd(&txin, workspace, 4, 5, dims, strides, box_in, 0);
+        if (rc) return rc;
+        rc = make_tmap_nd(&txout, workspace, 4, 5, dims, strides, box_out, 0);
         if (rc) return rc;
     }
     BwdParams p;
@@ -448,15 +516,14 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.dhcat = dhcat;
     p.dG = (__nv_bfloat16 *)dG;
     p.db = db;
+    p.xbuf = (__nv_bfloat16 *)workspace;
     p.tl = debug_timeline();
     const int gsize = H / 32;
     const size_t smem = bwd_smem_bytes(H);
     cudaStream_t s = (cudaStream_t)stream;
     RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    p.nitems = 2 * ((B + LB - 1) / LB);
-    const int max_groups = num_sms() / gsize;    // one CTA per SM (shared memory)
-    p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
-    if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;   // even: a group keeps its direction
+    p.nitems = 2 * ((B + NS - 1) / NS);
+    p.ngroups = bwd_groups(B, H);
     p.sync = group_counters(p.ngroups, s);
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
     cudaLaunchConfig_t cfg = {};
@@ -470,7 +537,7 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_BWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, tg, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, txin, txout, p));
     count_launch();
     return RCNN_OK;
 }

@@ -103,6 +103,17 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_mcast(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
                                                   int c3, uint16_t cta_mask) {
     asm volatile(
@@ -273,5 +284,7 @@ int make_tmap_3d(CUtensorMap *out, const void *base, int elem_bytes, uint64_t d2
                  uint32_t box_cols, int swizzle128);
 int make_tmap_4d(CUtensorMap *out, const void *base, int elem_bytes, const uint64_t dims[4], const uint64_t strides[3],
                  const uint32_t box[4], int swizzle128);
+int make_tmap_nd(CUtensorMap *out, const void *base, int elem_bytes, int rank, const uint64_t *dims, const uint64_t *strides,
+                 const uint32_t *box, int swizzle128);
 
 }  // namespace rcnn

@@ -180,8 +180,11 @@ def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int
     with torch.cuda.device(dhcat.device):
         dG = torch.empty((B, T, 8 * H), dtype=torch.bfloat16, device=dhcat.device)
         db = torch.empty((8 * H,), dtype=torch.float32, device=dhcat.device)
+        nws = int(_lib.lib().rcnn_lstm_backward_workspace_bytes(B, T, H))
+        ws = torch.empty((max(nws, 1),), dtype=torch.uint8, device=dhcat.device)
         rc = _lib.lib().rcnn_lstm_backward(packed.whh_pt.data_ptr(), gates.data_ptr(), csave.data_ptr(),
-                                           dhcat.data_ptr(), B, T, H, dG.data_ptr(), db.data_ptr(), _lib.stream_ptr())
+                                           dhcat.data_ptr(), B, T, H, dG.data_ptr(), db.data_ptr(), ws.data_ptr(), nws,
+                                           _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_backward")
     return dG, db
 

@@ -15,9 +15,11 @@ y = blk(x); y.sum().backward()
 torch.cuda.synchronize()
 _lib.lib().rcnn_debug_timeline(None)
 a = tl.cpu().numpy().reshape(T, 8).astype(np.float64)
-names = ["P0 start issue", "P1 issued all", "M0 first full", "M1 last commit", "E0 tmem_full", "E1 cell done", "E2 after barrier"]
-print("per-step intervals (cycles), median over steps 2..T-1, relative to P0:")
-for k in range(1, 7):
+names = ["P0 counter reached", "P1 partials stored (wait_group 0)", "M0 dG tile ready: first MMA", "M1 last MMA issued",
+         "E0 accumulators complete", "E1 cell done (dG stored)", "E2 counter released", "S0 partials staged in smem"]
+print("per-step intervals (cycles), median over steps 2..T-2, relative to P0 (K-local backward):")
+a = a[:-1]   # the last step publishes nothing
+for k in (2, 5, 3, 4, 7, 1, 6):
     d = a[2:, k] - a[2:, 0]
-    print(f"  {names[k]:18s} {np.median(d):9.0f}  (min {d.min():.0f} max {d.max():.0f})")
+    print(f"  {names[k]:36s} {np.median(d):9.0f}  (min {d.min():.0f} max {d.max():.0f})")
 print("  step period       ", np.median(np.diff(a[2:, 0])))
