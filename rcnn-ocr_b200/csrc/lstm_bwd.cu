@@ -137,7 +137,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<256>(tmem_slot);
+        tmem_alloc<512>(tmem_slot);   // [0, 256): W_hh^T blocks as A operands (64 columns each); [256, 512): accumulators
     }
     tc_fence_before();
     __syncthreads();
@@ -201,7 +201,19 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             uint32_t wphase = 0, bphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
                 const int dir = item & 1;
-                if (dir != cur_dir) { mbar_wait(w_full, wphase); wphase ^= 1; cur_dir = dir; }
+                if (dir != cur_dir) {
+                    // weights: shared memory -> tensor memory, one K = 16 slice per copy (in issue order with the MMAs)
+                    mbar_wait(w_full, wphase);
+                    wphase ^= 1;
+                    cur_dir = dir;
+                    tc_fence_after();
+                    for (int t2 = 0; t2 < nmb * 2; ++t2) {
+                        const uint64_t wdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)t2 * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < LK / 16; ++k)
+                            tmem_cp_128x256b(tmem_base + (uint32_t)(8 * (t2 * (LK / 16) + k)), wdesc + (uint64_t)(2 * k));
+                    }
+                }
                 for (int s = 0; s + 1 < T; ++s) {
                     mbar_wait(b_ready, bphase);
                     bphase ^= 1;
@@ -210,12 +222,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     for (int mb = 0; mb < nmb; ++mb) {
 #pragma unroll
                         for (int kc = 0; kc < 2; ++kc) {
-                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)(mb * 2 + kc) * kWTile), 16, 1024);
                             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_s + kc * kBChunk), 16, 1024);
 #pragma unroll
                             for (int k = 0; k < LK / 16; ++k)
-                                umma_bf16(tmem_base + (uint32_t)(mb * NS), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                          idesc, (kc | k) != 0);
+                                umma_bf16_ts(tmem_base + 256u + (uint32_t)(mb * NS),
+                                             tmem_base + (uint32_t)(8 * ((mb * 2 + kc) * (LK / 16) + k)),
+                                             bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
                         }
                         umma_commit(&d_full[mb]);    // the cell warps drain block mb while the next one is multiplied
                     }
@@ -263,14 +275,19 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     mbar_wait(x_ready, nwait & 1);
                     ++nwait;
                     const unsigned char *src = x_s + ((size_t)w * 256 + (size_t)lane * 8) * 2;
-#pragma unroll 4
-                    for (int sc = 0; sc < gsize; ++sc) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)sc * 4096);
-                        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+                    for (int sc = 0; sc < gsize; sc += 8) {     // 8 shared-memory loads in flight per round
+                        uint4 v[8];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            rec[2 * k] += __uint_as_float(wd[k] << 16);
-                            rec[2 * k + 1] += __uint_as_float(wd[k] & 0xffff0000u);
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = sc + u < gsize ? *reinterpret_cast<const uint4 *>(src + (size_t)(sc + u) * 4096) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                rec[2 * k] += __uint_as_float(wd[k] << 16);
+                                rec[2 * k + 1] += __uint_as_float(wd[k] & 0xffff0000u);
+                            }
                         }
                     }
                 }
@@ -322,7 +339,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         if (threadIdx.x == 64 && mb == nmb - 1) TL_MARK(4);
                         tc_fence_after();
                         uint32_t acc[32];
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(mb * NS + hq * 32), acc);
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(mb * NS + hq * 32), acc);
                         tmem_ld_wait();
                         const int dstc = mb * 4 + qd;                 // CTA that owns output units [128mb + 32qd, +32)
                         if (dstc < gsize) {
@@ -358,7 +375,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 

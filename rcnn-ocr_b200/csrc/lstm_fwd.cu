@@ -130,7 +130,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<NS>(tmem_slot);
+        tmem_alloc<512>(tmem_slot);   // [0, 256): the W_hh slice as the A operand (H/2 columns); [256, 320): accumulator
     }
     tc_fence_before();
     __syncthreads();
@@ -210,7 +210,19 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             uint32_t wphase = 0, hphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
                 const int dir = item & 1;
-                if (dir != cur_dir) { mbar_wait(w_full, wphase); wphase ^= 1; cur_dir = dir; }
+                if (dir != cur_dir) {
+                    // weights: shared memory -> tensor memory, one K = 16 slice per copy (in issue order with the MMAs)
+                    mbar_wait(w_full, wphase);
+                    wphase ^= 1;
+                    cur_dir = dir;
+                    tc_fence_after();
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        const uint64_t wdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < LK / 16; ++k)
+                            tmem_cp_128x256b(tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), wdesc + (uint64_t)(2 * k));
+                    }
+                }
                 for (int s = 1; s < T; ++s) {
                     for (int g = 0; g < nhb; ++g) {
                         mbar_wait(&h_full[g], hphase);
@@ -218,11 +230,11 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         tc_fence_after();
                         for (int j = 0; j < cpb; ++j) {
                             const int kc = g * cpb + j;
-                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
                             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)kc * kHBox), 16, 1024);
 #pragma unroll
                             for (int k = 0; k < LK / 16; ++k)
-                                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
+                                umma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)),
+                                             bdesc + (uint64_t)(2 * k), idesc, (g | j | k) != 0);
                         }
                     }
                     umma_commit(tmem_full);
@@ -270,7 +282,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     ++mcount;
                     if (threadIdx.x == 64) TL_MARK(4);
                     tc_fence_after();
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ch * 32), acc);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(ch * 32), acc);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) pre[i] += __uint_as_float(acc[i]);
@@ -366,7 +378,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<NS>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
