@@ -63,8 +63,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ void red_release_gpu_inc(unsigned int *p) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ void red_relaxed_gpu_inc(unsigned int *p) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 // The counter is only polled; what it guards (h_{t-1}) is read by TMA (async proxy, straight from L2), so a
 // relaxed gpu-scope load + fence.proxy.async is enough and spares the L1 invalidate of an acquire per poll.
@@ -88,7 +88,8 @@ __device__ __forceinline__ void wait_counter(const unsigned int *p, unsigned int
 template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
-                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const FwdParams p) {
+                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                const __grid_constant__ CUtensorMap tmHs, const FwdParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
@@ -109,7 +110,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     uint64_t *x_free = x_full + 2;                      // 2: slot may be overwritten by the next xp load
     uint64_t *g_ready = x_free + 2;                     // 2: (training) activated gates are in the slot
     uint64_t *tmem_full = g_ready + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *h_staged = tmem_full + 1;                 // the 8 cell warps put h_t into shared memory
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_staged + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
@@ -127,6 +129,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 mbar_init(&g_ready[i], 8);
             }
             mbar_init(tmem_full, 1);
+            mbar_init(h_staged, 8);
             fence_barrier_init();
         }
         __syncwarp();
@@ -207,9 +210,24 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(GR, NS);
             int cur_dir = -1;
-            uint32_t wphase = 0, hphase = 0;
+            uint32_t wphase = 0, hphase = 0, sphase = 0;
+            tma_prefetch_desc(&tmHs);
+            // h_t of this CTA's 32 units leaves by ONE TMA store (staged by the cell warps in the idle h tile);
+            // its completion is awaited by this thread alone and followed by a relaxed counter increment: no
+            // gpu-scope fence over 256 threads' stores in the step's critical path.
+            auto publish = [&](int dir, int b0, int s) {
+                const int t = dir ? T - 1 - s : s;
+                mbar_wait(h_staged, sphase);
+                sphase ^= 1;
+                tma_store_3d(&tmHs, h_s, dir * H + 32 * c, t, b0);
+                tma_store_commit();
+                tma_store_wait<0>();
+                fence_proxy_async_global();
+                red_relaxed_gpu_inc(counter);
+                TL_MARK(6);
+            };
             for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1;
+                const int dir = item & 1, b0 = (item >> 1) * NS;
                 if (dir != cur_dir) {
                     // weights: shared memory -> tensor memory, one K = 16 slice per copy (in issue order with the MMAs)
                     mbar_wait(w_full, wphase);
@@ -223,6 +241,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                             tmem_cp_128x256b(tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), wdesc + (uint64_t)(2 * k));
                     }
                 }
+                if (T > 0) publish(dir, b0, 0);
                 for (int s = 1; s < T; ++s) {
                     for (int g = 0; g < nhb; ++g) {
                         mbar_wait(&h_full[g], hphase);
@@ -240,6 +259,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     umma_commit(tmem_full);
                     TL_MARK(3);
                     hphase ^= 1;
+                    publish(dir, b0, s);
                 }
             }
         }
@@ -342,17 +362,14 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const uint32_t r0 = __shfl_xor_sync(FULL, s0, 16), r1 = __shfl_xor_sync(FULL, s1, 16);
                     hq.x = o2 ? r0 : k0; hq.y = o2 ? r1 : k1; hq.z = o2 ? k0 : r0; hq.w = o2 ? k1 : r1;
                 }
-                const int bh = b0 + 32 * ch + lane;
-                if (bh < B)
-                    *reinterpret_cast<uint4 *>(p.hcat + ((size_t)bh * T + t) * 2 * H + (size_t)dir * H + 32 * c + 8 * qd) = hq;
-                if (threadIdx.x == 64) TL_MARK(5);
+                // stage h_t [64 seq x 32 units] in the (now idle) h tile: row = sequence, 64 bytes per row; the MMA
+                // warp's thread stores it with TMA (rows >= B are clipped by the tensor map) and publishes the step
+                *reinterpret_cast<uint4 *>(h_s + (size_t)(32 * ch + lane) * 64 + qd * 16) = hq;
                 tc_fence_before();
-                fence_proxy_async_global();  // order the h_t stores before the other CTAs' TMA reads
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (threadIdx.x == 64) {     // one release per CTA, cumulative over the stores seen through the barrier
-                    red_release_gpu_inc(counter);
-                    TL_MARK(6);
-                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_staged);
+                if (threadIdx.x == 64) TL_MARK(5);
                 if (SAVE) {
                     // activated gates back into the xp slot (same addresses this thread read), then out by TMA
 #pragma unroll
@@ -391,7 +408,7 @@ size_t fwd_smem_bytes(int H) { return 1024 + (size_t)(H / LK) * (kWTile + kHBox)
 
 template <bool SAVE>
 int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &tx, const CUtensorMap &tg,
-               FwdParams &p, cudaStream_t s) {
+               const CUtensorMap &ths, FwdParams &p, cudaStream_t s) {
     const int gsize = p.H / 32;
     const int nkc = p.H / LK;
     // cluster = multicast domain for the h tile; it divides the group.  Measured on B200 (B=256, H=512): with
@@ -432,7 +449,7 @@ int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
     ProfScope prof(RCNN_K_LSTM_FWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, tg, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_kernel<SAVE>, tw, th, tx, tg, ths, p));
     count_launch();
     return RCNN_OK;
 }
@@ -449,7 +466,7 @@ extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, 
     if (B == 0 || T == 0) return RCNN_OK;
     RCNN_CHECK_ARG(xp && whh_packed && hcat, "lstm_forward: null pointer");
     RCNN_CHECK_ARG((gates_save == nullptr) == (c_save == nullptr), "lstm_forward: gates_save and c_save go together");
-    CUtensorMap tw, th, tx, tg;
+    CUtensorMap tw, th, tx, tg, ths;
     int rc = make_tmap_2d(&tw, whh_packed, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, GR, LK, 1);
     if (rc) return rc;
     {   // hcat [B, T, 2H] seen as (k within chunk, b, chunk, t): one box = cpc chunks of [64 seq x 64 k],
@@ -462,6 +479,9 @@ extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, 
         rc = make_tmap_4d(&th, hcat, 2, dims, strides, box, 1);
         if (rc) return rc;
     }
+    // store view of hcat: box = [64 seq x 1 t x 32 units] (this CTA's slice of h_t), plain rows of 64 bytes
+    rc = make_tmap_3d(&ths, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, NS, 1, 32, 0);
+    if (rc) return rc;
     rc = make_tmap_3d(&tx, xp, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 8 * H * 2, 8ull * H * 2, NS, 1, GR, 0);
     if (rc) return rc;
     tg = tx;
@@ -475,5 +495,5 @@ extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, 
     p.csave = c_save;
     p.tl = debug_timeline();
     cudaStream_t s = (cudaStream_t)stream;
-    return gates_save ? launch_fwd<true>(tw, th, tx, tg, p, s) : launch_fwd<false>(tw, th, tx, tg, p, s);
+    return gates_save ? launch_fwd<true>(tw, th, tx, tg, ths, p, s) : launch_fwd<false>(tw, th, tx, tg, ths, p, s);
 }
