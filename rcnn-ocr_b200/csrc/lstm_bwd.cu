@@ -475,8 +475,15 @@ __global__ void lstm_unpack_grads_kernel(const UnpackArgs a) {
     const int cc = pidx >> 7, j = (pidx >> 2) & 31, g = pidx & 3;
     const int r = g * H + 32 * cc + j;
     const size_t prow = (size_t)dir * 4 * H + pidx;
-    for (int k = threadIdx.x; k < I; k += blockDim.x) a.dw_ih[dir][(size_t)r * I + k] = a.dwih_p[prow * I + k];
-    for (int k = threadIdx.x; k < H; k += blockDim.x) a.dw_hh[dir][(size_t)r * H + k] = a.dwhh_p[prow * H + k];
+    if ((I & 3) == 0 && (H & 3) == 0) {
+        for (int k = 4 * threadIdx.x; k < I; k += 4 * blockDim.x)
+            *reinterpret_cast<float4 *>(a.dw_ih[dir] + (size_t)r * I + k) = *reinterpret_cast<const float4 *>(a.dwih_p + prow * I + k);
+        for (int k = 4 * threadIdx.x; k < H; k += 4 * blockDim.x)
+            *reinterpret_cast<float4 *>(a.dw_hh[dir] + (size_t)r * H + k) = *reinterpret_cast<const float4 *>(a.dwhh_p + prow * H + k);
+    } else {
+        for (int k = threadIdx.x; k < I; k += blockDim.x) a.dw_ih[dir][(size_t)r * I + k] = a.dwih_p[prow * I + k];
+        for (int k = threadIdx.x; k < H; k += blockDim.x) a.dw_hh[dir][(size_t)r * H + k] = a.dwhh_p[prow * H + k];
+    }
     if (threadIdx.x == 0) {
         const float v = a.db_p[prow];
         a.db_ih[dir][r] = v;

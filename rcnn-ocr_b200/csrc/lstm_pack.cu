@@ -35,32 +35,70 @@ __global__ void lstm_pack_rows_kernel(const PackArgs a) {
     const float *wi = a.w_ih[dir] + (size_t)r * I;
     const float *wh = a.w_hh[dir] + (size_t)r * H;
     const size_t prow = (size_t)dir * 4 * H + p;
-    for (int k = threadIdx.x; k < I; k += blockDim.x) a.wih_p[prow * I + k] = __float2bfloat16_rn(wi[k]);
-    for (int k = threadIdx.x; k < H; k += blockDim.x) a.whh_p[prow * H + k] = __float2bfloat16_rn(wh[k]);
+    if ((I & 3) == 0 && (H & 3) == 0) {   // rows are 16-byte aligned: 128-bit loads, 64-bit stores
+        for (int k = 4 * threadIdx.x; k < I; k += 4 * blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4 *>(wi + k);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            *reinterpret_cast<uint2 *>(a.wih_p + prow * I + k) =
+                make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+        }
+        for (int k = 4 * threadIdx.x; k < H; k += 4 * blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4 *>(wh + k);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            *reinterpret_cast<uint2 *>(a.whh_p + prow * H + k) =
+                make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+        }
+    } else {
+        for (int k = threadIdx.x; k < I; k += blockDim.x) a.wih_p[prow * I + k] = __float2bfloat16_rn(wi[k]);
+        for (int k = threadIdx.x; k < H; k += blockDim.x) a.whh_p[prow * H + k] = __float2bfloat16_rn(wh[k]);
+    }
     if (threadIdx.x == 0) a.bias_p[prow] = a.b_ih[dir][r] + a.b_hh[dir][r];
 }
 
-// transposed views through a 32x32 shared-memory tile: which = 0 -> wih_pt [I, 8H], 1 -> whh_pt [2, H, 4H]
+// transposed views through a [32 k][64 p] shared-memory tile: which = 0 -> wih_pt [I, 8H], 1 -> whh_pt [2, H, 4H].
+// Reads are 128-byte row pieces of the fp32 source, writes 128-byte pieces (64 bf16) of the transposed views.
 __global__ void lstm_pack_transposed_kernel(const PackArgs a) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][33];
     const int H = a.H;
     const int which = blockIdx.z >> 1, dir = blockIdx.z & 1;
     const int K = which ? H : a.I;
-    const int p0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int p0 = blockIdx.y * 64, k0 = blockIdx.x * 32;
     if (k0 >= K) return;
     const float *src = which ? a.w_hh[dir] : a.w_ih[dir];
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
         const int k = k0 + threadIdx.x;
         tile[i][threadIdx.x] = k < K ? src[(size_t)torch_row(p0 + i, H) * K + k] : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int k = k0 + i, p = p0 + threadIdx.x;
+        const int k = k0 + i, p = p0 + 2 * threadIdx.x;
         if (k < K) {
-            const __nv_bfloat16 v = __float2bfloat16_rn(tile[threadIdx.x][i]);
-            if (which) a.whh_pt[((size_t)dir * H + k) * 4 * H + p] = v;
-            else a.wih_pt[(size_t)k * 8 * H + (size_t)dir * 4 * H + p] = v;
+            const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * threadIdx.x][i], tile[2 * threadIdx.x + 1][i]);
+            if (which) *reinterpret_cast<__nv_bfloat162 *>(a.whh_pt + ((size_t)dir * H + k) * 4 * H + p) = v;
+            else *reinterpret_cast<__nv_bfloat162 *>(a.wih_pt + (size_t)k * 8 * H + (size_t)dir * 4 * H + p) = v;
         }
+    }
+}
+
+// contiguous-channel fast path of the 3-D cast: 8 elements per thread (two 128-bit loads, one 128-bit store)
+__global__ void cast3_bf16_vec_kernel(const float *__restrict__ src, long long sb, long long st,
+                                      __nv_bfloat16 *__restrict__ dst, int B, int T, int C8) {
+    const long long total = (long long)B * T * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const long long bt = i / C8;
+        const int t = (int)(bt % T);
+        const long long b = bt / T;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + b * sb + (long long)t * st + 8 * c8);
+        const uint4 u0 = ld_nc_v4(s4), u1 = ld_nc_v4(s4 + 1);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(u0.x), __uint_as_float(u0.y));
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(u0.z), __uint_as_float(u0.w));
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(u1.x), __uint_as_float(u1.y));
+        const __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(u1.z), __uint_as_float(u1.w));
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&h0); o.y = *reinterpret_cast<const uint32_t *>(&h1);
+        o.z = *reinterpret_cast<const uint32_t *>(&h2); o.w = *reinterpret_cast<const uint32_t *>(&h3);
+        *reinterpret_cast<uint4 *>(dst + (bt * C8 + c8) * 8) = o;
     }
 }
 
@@ -162,7 +200,7 @@ extern "C" int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, 
     lstm_pack_rows_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
     RCNN_LAUNCH_CHECK("lstm_pack_rows_kernel");
     const int kmax = I > H ? I : H;
-    dim3 grid((kmax + 31) / 32, 4 * H / 32, 4), block(32, 8);
+    dim3 grid((kmax + 31) / 32, 4 * H / 64, 4), block(32, 8);
     lstm_pack_transposed_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
     RCNN_LAUNCH_CHECK("lstm_pack_transposed_kernel");
     return RCNN_OK;
@@ -174,6 +212,13 @@ extern "C" int rcnn_cast_bf16_3d(const float *src, int64_t sb, int64_t st, int64
     RCNN_CHECK_ARG(B >= 0 && T >= 0 && C >= 0, "cast_bf16_3d: bad shape");
     if (B == 0 || T == 0 || C == 0) return RCNN_OK;
     RCNN_CHECK_ARG(src && dst, "cast_bf16_3d: null pointer");
+    if (sc == 1 && (C & 7) == 0 && (sb & 3) == 0 && (st & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        const long long total = (long long)B * T * (C / 8);
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        cast3_bf16_vec_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, sb, st, (__nv_bfloat16 *)dst, B, T, C / 8);
+        RCNN_LAUNCH_CHECK("cast3_bf16_vec_kernel");
+        return RCNN_OK;
+    }
     RCNN_CHECK_ARG(B <= 65535, "cast_bf16_3d: batch %d exceeds the grid limit", B);
     dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
     cast3_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, sb, st, sc, (__nv_bfloat16 *)dst, B, T, C);
