@@ -44,7 +44,7 @@ constexpr int LK = 64;    // K chunk (one 128-byte swizzle row of bf16)
 constexpr uint32_t kWTile = GR * LK * 2;   // 16 KB: [128 gate rows x 64 k] bf16, SW128
 constexpr uint32_t kHBox = NS * LK * 2;    //  8 KB: [64 seq x 64 k] bf16, SW128
 constexpr uint32_t kXTile = NS * GR * 2;   // 16 KB: [64 seq x 128 gate cols] fp16, no swizzle
-constexpr int kMaxHBars = 2;               // h_{t-1} arrives as (at most) two TMA operations of H/128 chunks each
+constexpr int kMaxHBars = 4;               // h_{t-1} arrives as (at most) four TMA operations of H/256 chunks each
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
 
 struct FwdParams {
@@ -94,8 +94,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, B = p.B;
     const int nkc = H / LK;
-    const int cpb = nkc >= 2 ? nkc / 2 : 1;        // K chunks per barrier
-    const int nhb = nkc / cpb;                     // h barriers per step (2; 1 for H = 64)
+    const int cpb = nkc >= 4 ? nkc / 4 : 1;        // K chunks per barrier / TMA operation
+    const int nhb = nkc / cpb;                     // h barriers per step (4; 2 for H = 128, 1 for H = 64)
     const int cpc = nkc / p.csize;                 // K chunks this CTA fetches for its whole cluster
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -471,7 +471,7 @@ extern "C" int rcnn_lstm_forward(const void *xp, const void *whh_packed, int B, 
     if (rc) return rc;
     {   // hcat [B, T, 2H] seen as (k within chunk, b, chunk, t): one box = cpc chunks of [64 seq x 64 k],
         // the share one CTA of a cluster fetches (see launch_fwd: csize = min(4, nkc))
-        const int nkc = H / LK, cpb = nkc >= 2 ? nkc / 2 : 1;
+        const int nkc = H / LK, cpb = nkc >= 4 ? nkc / 4 : 1;
         const int cpc = nkc / fwd_cluster_size(nkc) < cpb ? nkc / fwd_cluster_size(nkc) : cpb;
         const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 2ull * nkc, (uint64_t)T};
         const uint64_t strides[3] = {(uint64_t)T * 2 * H * 2, (uint64_t)LK * 2, 2ull * H * 2};
