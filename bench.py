@@ -338,6 +338,14 @@ def run_ours(args, rank, world, local_rank):
     for f in freed:
         f.record()
     ms_inf_e2e = max_over_ranks(timed(e2e_infer, args.steps, args.warmup, sync, barrier))
+    # ---- validation metrics of one batch on the device (K5): decode ids vs the CTC targets ---------------
+    table = step.R.CharsetTable(infer.alphabet, device)
+    v_ids, v_lens = [t.clone() for t in ginfer(dev[0][0])]
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        val = step.R.validation_metrics(v_ids, v_lens, dev[0][1], dev[0][3], table)
+    ms_val = (time.perf_counter() - t0) / 10 * 1e3
     step.enc.train(); step.head.train()
 
     # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
@@ -433,7 +441,11 @@ def run_ours(args, rank, world, local_rank):
                       "e2e": {"value": round(total_B / (ms_inf_e2e * 1e-3), 1), "ms_per_step": round(ms_inf_e2e, 4),
                               "h2d_bytes_per_step": host[0][0].numel() * 4, "d2h_bytes_per_step": B * (T + 1) * 4,
                               "note": "pinned host features -> H2D (double-buffered on a copy stream) -> encoder + "
-                                      "greedy decode -> D2H of ids/len -> python strings"}},
+                                      "greedy decode -> D2H of ids/len -> python strings"},
+                      "val_metrics": {"ms_per_batch": round(ms_val, 3), "cer": round(val["cer"], 4),
+                                      "accuracy": val["accuracy"],
+                                      "note": "CER/WER/accuracy of one decoded batch on the device (K5 edit distance), "
+                                              "wall clock incl. the D2H of the per-pair integers"}},
             "launch_mode": "cuda-graph replay (one graph = the whole step)" if use_graph else "eager",
             "gpu_launches": round(launches * args.steps),
             "gpu_launches_per_step": round(launches, 1),

@@ -200,6 +200,23 @@ int rcnn_cast_bf16_2d(const float *src, int64_t ld_src, void *dst, int64_t ld_ds
 int rcnn_transpose_bf16(const void *src, int64_t ld, void *dst, int64_t ldo, int R, int C, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K5  batched edit distance for the validation metrics (training/metrics.py:5-32 as used at
+ * training/train.py:582-598 and evaluate_dataset.py:104-119: CER = Levenshtein / len(reference)
+ * on characters, WER on words, accuracy = exact match).
+ *   hyp_ids   int32 [N, hyp_stride]  class ids left by rcnn_ctc_greedy (-1 padded), hyp_len int32 [N]
+ *   ref_ids   int64 flat class ids (CTC targets), ref_off int64 [N] start of pair n, ref_len int64 [N]
+ *   cp_off    int32 [C+1], cp int32: class k expands to the Unicode code points cp[cp_off[k]..cp_off[k+1])
+ *             (class 0 = blank = empty; class k = itos[k-1], training/utils.py:146)
+ *   words     0: distance over code points; 1: over words (split on U+0020, empty words dropped)
+ *   dist_out, nref_out, nhyp_out  int32 [N]: distance and the two symbol counts; dist = -1 when a
+ *             sequence expands to more than 320 symbols
+ * ------------------------------------------------------------------------------------- */
+int rcnn_edit_distance(const int32_t *hyp_ids, int64_t hyp_stride, const int32_t *hyp_len,
+                       const int64_t *ref_ids, const int64_t *ref_off, const int64_t *ref_len, int N,
+                       const int32_t *cp_off, const int32_t *cp, int C, int words,
+                       int32_t *dist_out, int32_t *nref_out, int32_t *nhyp_out, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

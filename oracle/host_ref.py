@@ -8,6 +8,7 @@ missing), so they are restated from the source:
   decode_tokens           data/transforms.py:196-206
   character_error_rate    training/metrics.py:5-13   (own Levenshtein DP)
   compute_accuracy        training/metrics.py:23-32
+  word_error_rate         training/metrics.py:16-21  (jiwer default word split, restated)
 """
 from __future__ import annotations
 
@@ -56,3 +57,16 @@ def compute_accuracy(references, hypotheses) -> float:
     if len(references) == 0:
         return 0.0
     return sum(1 for r, h in zip(references, hypotheses) if r == h) / len(references)
+
+
+def word_error_rate(reference: str, hypothesis: str) -> float:
+    """training/metrics.py:16-21 calls jiwer.wer(reference, hypothesis) (jiwer is not installed in this
+    image: third-party, pinned by requirements.txt as ``jiwer``).  Its default transform collapses runs
+    of whitespace, strips the ends and splits on " "; WER = word-level Levenshtein / number of reference
+    words.  jiwer raises ValueError for an empty reference; the restatement (and the device kernel) use
+    the CER convention there: inf for a non-empty hypothesis, 0 for two empty strings."""
+    ref_words = [w for w in reference.split(" ") if w != ""]
+    hyp_words = [w for w in hypothesis.split(" ") if w != ""]
+    if len(ref_words) == 0:
+        return float("inf") if len(hyp_words) > 0 else 0.0
+    return levenshtein(ref_words, hyp_words) / len(ref_words)

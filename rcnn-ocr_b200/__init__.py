@@ -10,6 +10,7 @@ Surface (mirrors the reference; citations are path:line under the reference tree
   CTCLoss, ctc_loss              nn.CTCLoss call site at training/train.py:289,503-505
   ctc_greedy_decoder, decode     training/utils.py:122-162
   load_charset, decode_tokens    data/transforms.py:39-59, 196-206
+  validation_metrics, ...        training/metrics.py:5-32 as used at training/train.py:582-598
 """
 from ._lib import lib, library_path, LibraryMissing  # noqa: F401
 from .charset import load_charset, decode_tokens, ctc_alphabet  # noqa: F401
@@ -18,5 +19,6 @@ from .ctc import CTCLoss, ctc_loss, ctc_loss_from_logits  # noqa: F401
 from .model import BidirectionalLSTM, CTCHead, RCNN, SEResNet31, make_enc_rnn  # noqa: F401
 from .inference import OCRInference  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
+from .metrics import CharsetTable, edit_stats, character_error_rates, word_error_rates, validation_metrics  # noqa: F401
 
 __version__ = "0.1.0"

@@ -45,6 +45,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_colsum_bf16.argtypes = [vp, i64, i64, i, vp, vp]
     L.rcnn_cast_bf16_2d.restype = i
     L.rcnn_cast_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i, vp]
+    L.rcnn_edit_distance.restype = i
+    L.rcnn_edit_distance.argtypes = [vp, i64, vp, vp, vp, vp, i, vp, vp, i, i, vp, vp, vp, vp]
     L.rcnn_launch_count.restype = ctypes.c_ulonglong
     L.rcnn_debug_timeline.restype = i
     L.rcnn_debug_timeline.argtypes = [vp]

@@ -40,6 +40,15 @@ def test_argument_errors_do_not_need_a_gpu():
                            None, None, None, 0, 0, None, 0, None) == 1
 
 
+def test_new_entry_points_validate_arguments():
+    L = R.lib()
+    assert L.rcnn_edit_distance(None, 0, None, None, None, None, 4, None, None, 5, 0, None, None, None, None) == 1
+    assert b"null pointer" in L.rcnn_last_error()
+    assert L.rcnn_edit_distance(None, 0, None, None, None, None, 0, None, None, 5, 0, None, None, None, None) == 0
+    assert L.rcnn_lstm_backward_workspace_bytes(256, 64, 512) == 2 * 8 * 16 * 16 * 4096
+    assert L.rcnn_lstm_backward_workspace_bytes(256, 64, 100) == 0
+
+
 def test_workspace_sizes():
     L = R.lib()
     small = L.rcnn_ctc_workspace_bytes(64, 256, 195, 32)

@@ -134,3 +134,7 @@ def test_host_ref_charset_and_metrics(tmp_path):
     assert host_ref.character_error_rate("", "") == 0.0
     assert host_ref.compute_accuracy(["a", "b"], ["a", "c"]) == 0.5
     assert host_ref.compute_accuracy([], []) == 0.0
+    # jiwer's documented example: one substitution in four reference words
+    assert host_ref.word_error_rate("hello world how are", "hello duck how are") == 0.25
+    assert host_ref.word_error_rate("  a   b ", "a b") == 0.0           # whitespace runs collapse, ends are stripped
+    assert host_ref.word_error_rate("a b", "a b c d") == 1.0            # insertions can push WER past 1
