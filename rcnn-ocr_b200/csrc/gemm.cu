@@ -15,6 +15,7 @@
 // accumulators (see gemm_tn_kernel); the weight-gradient kernel (gemm_atb_kernel) is split-K.
 // M / N / K tails: TMA zero-fills out-of-bounds rows and columns; stores are masked.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -168,41 +169,52 @@ __device__ __forceinline__ void store_row_chunk(__half *dst, const float (&v)[32
 // round the issuing thread spent as long on wait/commit bookkeeping as the tensor pipe spent on
 // the four MMAs (profiles/timeline_r01.txt).  Two 128-column TMEM accumulators alternate between
 // tiles, so the epilogue warps drain tile i while the MMA warp is already on tile i+1.
-constexpr int kPStages = 3;
-constexpr int kPBoxes = 2;                                   // k-boxes of 64 per stage
-constexpr uint32_t kPOperand = kPBoxes * kABytes;            // 32 KB per operand per stage
-constexpr uint32_t kPStage = 2 * kPOperand;                  // 64 KB
-constexpr int kPThreads = 224;                               // warps: 0 A-TMA, 1 MMA, 2-5 epilogue, 6 B-TMA
-constexpr size_t kPSmem = 1024 + kPStages * kPStage + 256 + 2 * BN * sizeof(float);
+// Tile width TN: 128 (K = 128 per stage, 3 stages) or 256 (K = 64 per stage, 4 stages).  With 128 x 128 tiles
+// every tile re-reads (128 + 128) x K operand elements for 128 x 128 x K MACs = 64 FLOP per L2 byte, and the
+// large GEMMs of the step then sit exactly at the L2 -> SM bandwidth (~12.5 TB/s: 830 TFLOP/s); 128 x 256
+// tiles raise that to 85 FLOP per byte and need half as many tcgen05.mma instructions (N = 256 each).
+constexpr int kPThreads = 352;                               // warps: 0 A-TMA, 1 MMA, 2-5 and 7-10 epilogue, 6 B-TMA
+template <int TN> struct PCfg {
+    static constexpr int kBoxes = TN == 128 ? 2 : 1;                       // k-boxes of 64 per stage
+    static constexpr int kStages = TN == 128 ? 3 : 4;
+    static constexpr uint32_t kAOp = kBoxes * kABytes;                     // A bytes per stage
+    static constexpr uint32_t kBBox = TN * BK * 2;                         // one B box [TN x 64] bf16
+    static constexpr uint32_t kBOp = kBoxes * kBBox;
+    static constexpr uint32_t kStage = kAOp + kBOp;
+    static constexpr size_t kSmem = 1024 + kStages * kStage + 256 + 2 * TN * sizeof(float);
+};
 
-template <typename OutT>
+template <typename OutT, int TN>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using C = PCfg<TN>;
+    constexpr int kPStages = C::kStages, kPBoxes = C::kBoxes;
+    constexpr uint32_t kPStage = C::kStage, kPAOp = C::kAOp, kPBBox = C::kBBox;
     unsigned char *tiles = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kPStages * kPStage);
     uint64_t *empty = full + kPStages;
     uint64_t *tmem_full = empty + kPStages;      // [2]
     uint64_t *tmem_empty = tmem_full + 2;        // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    float *bias_s = reinterpret_cast<float *>(smem + kPStages * kPStage + 256);   // [2][BN]
+    float *bias_s = reinterpret_cast<float *>(smem + kPStages * kPStage + 256);   // [2][TN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntn = (N + BN - 1) / BN, ntm = (M + BM - 1) / BM;
+    const int ntn = (N + TN - 1) / TN, ntm = (M + BM - 1) / BM;
     const int num_tiles = ntn * ntm;
-    const int rounds = (K + kPBoxes * BK - 1) / (kPBoxes * BK);
+    const int rounds = (K + PCfg<TN>::kBoxes * BK - 1) / (PCfg<TN>::kBoxes * BK);
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kPStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<2 * BN>(tmem_slot);
+        tmem_alloc<2 * TN>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -216,14 +228,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int st = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int row0 = isA ? (tile / ntn) * BM : (tile % ntn) * BN;
+                const int row0 = isA ? (tile / ntn) * BM : (tile % ntn) * TN;
                 for (int r = 0; r < rounds; ++r) {
                     mbar_wait(&empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[st], kPOperand);
-                    unsigned char *dst = tiles + st * kPStage + (isA ? 0 : kPOperand);
+                    mbar_arrive_expect_tx(&full[st], isA ? kPAOp : C::kBOp);
+                    unsigned char *dst = tiles + st * kPStage + (isA ? 0 : kPAOp);
 #pragma unroll
                     for (int j = 0; j < kPBoxes; ++j)
-                        tma_load_2d(dst + j * kABytes, isA ? &tmA : &tmB, &full[st], (r * kPBoxes + j) * BK, row0);
+                        tma_load_2d(dst + j * (isA ? kABytes : kPBBox), isA ? &tmA : &tmB, &full[st], (r * kPBoxes + j) * BK, row0);
                     if (++st == kPStages) { st = 0; ph ^= 1; }
                 }
             }
@@ -231,21 +243,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===== MMA issuer ==========================================================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, TN);
             int st = 0, it = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
                 for (int r = 0; r < rounds; ++r) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
 #pragma unroll
                     for (int j = 0; j < kPBoxes; ++j) {
                         const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + st * kPStage + j * kABytes), 16, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + st * kPStage + kPOperand + j * kABytes), 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + st * kPStage + kPAOp + j * kPBBox), 16, 1024);
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k)
                             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (r | j | k) != 0);
@@ -256,32 +268,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(&tmem_full[acc]);
             }
         }
-    } else if (warp < 6) {
-        // ===== epilogue: TMEM -> registers -> (+bias, convert) -> global ============================
+    } else if (warp != 6) {
+        // ===== epilogue: TMEM -> registers -> (+bias, convert) -> global.  Eight warps: two per TMEM lane
+        // quadrant (warp % 4), each draining half of the tile's columns -- with K = 512 a tile is only
+        // 32 MMAs (~2,000 cycles) and four warps took about as long to drain it. =====================
         const int q = warp & 3;
+        const int chalf = warp >= 7 ? 1 : 0;
+        const int etid = warp < 6 ? threadIdx.x - 64 : threadIdx.x - 96;    // 0..255 over the epilogue threads
         const bool vec_ok = (ldd % (32 / (long long)sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(D) & 31) == 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int tile_m = tile / ntn, tile_n = tile % ntn;
             {   // this tile's 128 bias values -> shared memory (broadcast reads below)
-                const int j = threadIdx.x - 64, col = tile_n * BN + j;
-                bias_s[acc * BN + j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+                const int j = etid, col = tile_n * TN + j;
+                if (j < TN) bias_s[acc * TN + j] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
             }
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-            asm volatile("bar.sync 2, 128;" ::: "memory");   // bias_s visible to the four epilogue warps
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // bias_s visible to the eight epilogue warps
             tc_fence_after();
             const int row = tile_m * BM + q * 32 + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = chalf * (TN / 2); c0 < (chalf + 1) * (TN / 2); c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
                 tmem_ld_wait();
-                const int col0 = tile_n * BN + c0;
+                const int col0 = tile_n * TN + c0;
                 if (row < M && col0 < N) {
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * BN + c0 + j];
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
                     store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
                 }
             }
@@ -293,7 +309,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem_base);
+        tmem_dealloc<2 * TN>(tmem_base);
     }
 }
 
@@ -417,14 +433,15 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
-template <typename OutT>
+template <typename OutT, int TN>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
                 int N, int K, cudaStream_t s) {
-    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
-    const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+    constexpr size_t smem = PCfg<TN>::kSmem;
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = ((N + TN - 1) / TN) * ((M + BM - 1) / BM);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_tn_kernel<OutT><<<grid, kPThreads, kPSmem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
+    gemm_tn_kernel<OutT, TN><<<grid, kPThreads, smem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
     RCNN_LAUNCH_CHECK("gemm_tn_kernel");
     return RCNN_OK;
 }
@@ -445,12 +462,19 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     CUtensorMap ta, tb;
     int rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, BM, BK, 1);
     if (rc) return rc;
-    rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, BN, BK, 1);
+    static const int force_tn = getenv("RCNN_GEMM_TN") ? atoi(getenv("RCNN_GEMM_TN")) : 0;
+    const int tn = force_tn == 128 || force_tn == 256 ? force_tn : (N > 128 ? 256 : 128);
+    rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, (uint32_t)tn, BK, 1);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (out_dtype == RCNN_F32) return launch_gemm<float>(ta, tb, D, ldd, bias, M, N, K, s);
-    if (out_dtype == RCNN_F16) return launch_gemm<__half>(ta, tb, D, ldd, bias, M, N, K, s);
-    return launch_gemm<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
+    if (tn == 256) {
+        if (out_dtype == RCNN_F32) return launch_gemm<float, 256>(ta, tb, D, ldd, bias, M, N, K, s);
+        if (out_dtype == RCNN_F16) return launch_gemm<__half, 256>(ta, tb, D, ldd, bias, M, N, K, s);
+        return launch_gemm<__nv_bfloat16, 256>(ta, tb, D, ldd, bias, M, N, K, s);
+    }
+    if (out_dtype == RCNN_F32) return launch_gemm<float, 128>(ta, tb, D, ldd, bias, M, N, K, s);
+    if (out_dtype == RCNN_F16) return launch_gemm<__half, 128>(ta, tb, D, ldd, bias, M, N, K, s);
+    return launch_gemm<__nv_bfloat16, 128>(ta, tb, D, ldd, bias, M, N, K, s);
 }
 
 extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcols, const void *B, int64_t ldb, int b_gcols,
