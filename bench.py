@@ -346,6 +346,30 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(10):
         val = step.R.validation_metrics(v_ids, v_lens, dev[0][1], dev[0][3], table)
     ms_val = (time.perf_counter() - t0) / 10 * 1e3
+    # ---- attention decoder (section 8f-1, the reference's live decoder): greedy decode of one batch ------
+    attn_res = None
+    if not args.no_attention:
+        torch.manual_seed(1)
+        attn = step.R.Attention(CFG["H"], CFG["H"], CFG["C"] - 1, 1, 2, 0, 3).to(device).eval()
+        encs = [torch.randn(B, CFG["T"], CFG["H"], device=device) for _ in range(RING)]
+        decode = lambda e: attn(e, is_train=False, batch_max_length=25)
+        gdec = step.R.GraphedStep(decode, [encs[0]]) if use_graph else decode
+        ms_attn = max_over_ranks(timed(lambda i: gdec(encs[i % RING]), args.steps, args.warmup, sync, barrier))
+        attn_res = {"value": round(B * world / (ms_attn * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms_attn, 4),
+                    "config": {"B": B, "T_enc": CFG["T"], "hidden": CFG["H"], "classes": CFG["C"] - 1, "steps": 26},
+                    "note": "Attention._greedy_decode (model/model.py:89-108) on the device: hoisted i2h GEMM + 26 x "
+                            "(h2h GEMM, score/softmax/context, gate GEMM, LSTMCell, generator GEMM, mask+argmax)"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle.ref_port import RefAttention
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref = RefAttention(CFG["H"], CFG["H"], CFG["C"] - 1).eval()
+            xb = torch.randn(32, CFG["T"], CFG["H"])
+            ref.greedy(xb[:4])
+            t0 = time.perf_counter()
+            ref.greedy(xb)
+            dt = time.perf_counter() - t0
+            attn_res["cpu_baseline"] = {"value": round(32 / dt, 1), "unit": "lines/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "32 lines x 26 steps, oracle/ref_port.RefAttention (the reference's op sequence)"}
     step.enc.train(); step.head.train()
 
     # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
@@ -445,7 +469,8 @@ def run_ours(args, rank, world, local_rank):
                       "val_metrics": {"ms_per_batch": round(ms_val, 3), "cer": round(val["cer"], 4),
                                       "accuracy": val["accuracy"],
                                       "note": "CER/WER/accuracy of one decoded batch on the device (K5 edit distance), "
-                                              "wall clock incl. the D2H of the per-pair integers"}},
+                                              "wall clock incl. the D2H of the per-pair integers"},
+                      "attention_decoder": attn_res},
             "launch_mode": "cuda-graph replay (one graph = the whole step)" if use_graph else "eager",
             "gpu_launches": round(launches * args.steps),
             "gpu_launches_per_step": round(launches, 1),
@@ -475,6 +500,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="lines per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="lines per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-attention", action="store_true", help="skip the attention-decoder (section 8f-1) measurement")
     ap.add_argument("--no-graph-dp", dest="graph_dp", action="store_false",
                     help="N>1: launch eagerly (default: the NCCL bucket all-reduces on the side stream join the capture)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",

@@ -217,6 +217,30 @@ int rcnn_edit_distance(const int32_t *hyp_ids, int64_t hyp_stride, const int32_t
                        int32_t *dist_out, int32_t *nref_out, int32_t *nhyp_out, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K6  per-step kernels of the attention decoder (model/model.py:23-148, inference path); the
+ * matrix products of a step (h2h, the LSTMCell gates, generator) go through rcnn_gemm_bf16 and
+ * i2h(batch_H) is computed once.
+ * rcnn_attn_score_context (model/model.py:35-45): e = score(tanh(proj_H + proj_h)), alpha =
+ *   softmax over the T encoder frames, context = alpha^T enc.
+ *     projH f32 [B,T,H], projh f32 [B,H], v f32 [H] (score.weight), enc f32 [B,T,C] addressed as
+ *     enc[b*stride_b + t*stride_t + c]; alpha_out f32 [B,T] or NULL; the context is written as
+ *     bf16 into xcat[b*ldx + 0..C) -- the first half of the LSTMCell GEMM operand [context | h].
+ * rcnn_attn_cell (nn.LSTMCell at model/model.py:46, gate order i,f,g,o): gates f32 [B,4H] = the GEMM
+ *   over [context | h_{t-1}], embT f32 [V,4H] = columns C.. of rnn.weight_ih transposed (the one-hot
+ *   input of :44 is a row gather by y int64 [B]); c f32 [B,H] updated in place; h_t is written as
+ *   bf16 into xcat[b*ldx + C + j] and (if hid_out != NULL) as f32 into hid_out[b*hid_ld + j].
+ * rcnn_attn_argmax (model/model.py:104-108): logits[:, blank] = -1e4 (blank < 0: no mask), the
+ *   masked row is copied to probs[b*probs_ld + k] (if probs != NULL), y[b] = argmax (first maximum).
+ * ------------------------------------------------------------------------------------- */
+int rcnn_attn_score_context(const float *projH, const float *projh, const float *v, const float *enc,
+                            int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                            float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream);
+int rcnn_attn_cell(const float *gates, const float *embT, const int64_t *y, int B, int H, int V, float *c,
+                   void *xcat, int64_t ldx, int C, float *hid_out, int64_t hid_ld, rcnn_stream_t stream);
+int rcnn_attn_argmax(const float *logits, int B, int V, int blank, float *probs, int64_t probs_ld,
+                     int64_t *y, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

@@ -68,3 +68,43 @@ def train_step(encoder, head, feats, targets, in_len, tg_len, blank=0):
 def infer_step(encoder, head, feats, alphabet, blank=0):
     logits = head(encoder(feats))
     return greedy_decode_loop(logits, alphabet, blank)
+
+
+class RefAttention(nn.Module):
+    """The reference's attention decoder restated as its torch op sequence (model/model.py:23-108, eval
+    mode, greedy path), parameter names as in the reference so state dicts interchange.  Pinned against the
+    reference module's own outputs (tests/golden/attn_*.npz, tests/test_oracle_golden.py)."""
+
+    def __init__(self, input_size, hidden_size, num_classes, sos_id=1, blank_id=3):
+        super().__init__()
+        cell = nn.Module()
+        cell.i2h = nn.Linear(input_size, hidden_size, bias=False)
+        cell.h2h = nn.Linear(hidden_size, hidden_size)
+        cell.score = nn.Linear(hidden_size, 1, bias=False)
+        cell.rnn = nn.LSTMCell(input_size + num_classes, hidden_size)
+        self.attention_cell = cell
+        self.generator = nn.Linear(hidden_size, num_classes)
+        self.hidden_size, self.num_classes, self.sos_id, self.blank_id = hidden_size, num_classes, sos_id, blank_id
+
+    @torch.no_grad()
+    def greedy(self, batch_H, batch_max_length=25):
+        cell = self.attention_cell
+        B = batch_H.size(0)
+        steps = batch_max_length + 1
+        h = batch_H.new_zeros(B, self.hidden_size)
+        c = batch_H.new_zeros(B, self.hidden_size)
+        y = torch.full((B,), self.sos_id, dtype=torch.long)
+        probs = batch_H.new_zeros(B, steps, self.num_classes)
+        for t in range(steps):
+            onehot = F.one_hot(y, self.num_classes).to(batch_H.dtype)
+            proj_H = cell.i2h(batch_H)                                   # recomputed every step, as the reference does
+            e = cell.score(torch.tanh(proj_H + cell.h2h(h).unsqueeze(1)))
+            alpha = F.softmax(e, dim=1)
+            context = torch.bmm(alpha.transpose(1, 2), batch_H).squeeze(1)
+            h, c = cell.rnn(torch.cat([context, onehot], 1), (h, c))
+            logits = self.generator(h)
+            if self.blank_id is not None:
+                logits[:, self.blank_id] = -1e4
+            probs[:, t] = logits
+            y = logits.argmax(1)
+        return probs

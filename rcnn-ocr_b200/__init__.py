@@ -7,6 +7,7 @@ if the library is missing or the tensors are not on a CUDA device.
 
 Surface (mirrors the reference; citations are path:line under the reference tree):
   BidirectionalLSTM, RCNN        model/model.py:151-163, 166-227
+  Attention (inference)          model/model.py:23-148
   CTCLoss, ctc_loss              nn.CTCLoss call site at training/train.py:289,503-505
   ctc_greedy_decoder, decode     training/utils.py:122-162
   load_charset, decode_tokens    data/transforms.py:39-59, 196-206
@@ -19,6 +20,7 @@ from .ctc import CTCLoss, ctc_loss, ctc_loss_from_logits  # noqa: F401
 from .model import BidirectionalLSTM, CTCHead, RCNN, SEResNet31, make_enc_rnn  # noqa: F401
 from .inference import OCRInference  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
+from .attention import Attention, AttentionCell  # noqa: F401
 from .metrics import CharsetTable, edit_stats, character_error_rates, word_error_rates, validation_metrics  # noqa: F401
 
 __version__ = "0.1.0"

@@ -47,6 +47,12 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_cast_bf16_2d.argtypes = [vp, i64, vp, i64, i64, i, vp]
     L.rcnn_edit_distance.restype = i
     L.rcnn_edit_distance.argtypes = [vp, i64, vp, vp, vp, vp, i, vp, vp, i, i, vp, vp, vp, vp]
+    L.rcnn_attn_score_context.restype = i
+    L.rcnn_attn_score_context.argtypes = [vp, vp, vp, vp, i64, i64, i, i, i, i, vp, vp, i64, vp]
+    L.rcnn_attn_cell.restype = i
+    L.rcnn_attn_cell.argtypes = [vp, vp, vp, i, i, i, vp, vp, i64, i, vp, i64, vp]
+    L.rcnn_attn_argmax.restype = i
+    L.rcnn_attn_argmax.argtypes = [vp, i, i, i, vp, i64, vp, vp]
     L.rcnn_launch_count.restype = ctypes.c_ulonglong
     L.rcnn_debug_timeline.restype = i
     L.rcnn_debug_timeline.argtypes = [vp]

@@ -1,0 +1,143 @@
+"""Attention decoder of the reference (model/model.py:23-148) on the device, inference path.
+
+``Attention`` keeps the reference's constructor, parameter names and shapes
+(``attention_cell.i2h/h2h/score/rnn.*``, ``generator.*``), so ``attn.*`` of a reference checkpoint
+loads with ``load_state_dict(strict=True)``.  ``forward(batch_H, text=None, is_train=True,
+batch_max_length=25)`` returns what the reference returns: greedy-decoded ``probs [B, steps, V]``
+for ``is_train=False`` (model/model.py:89-108), teacher-forced logits for ``is_train=True``
+(:110-148).  The step loop runs on the tcgen05 GEMM (K1) plus three small kernels (K6, csrc/attn.cu);
+``i2h(batch_H)`` is hoisted out of the loop.  Not covered in this round: the backward pass and
+dropout (training of the attention decoder): the module must be in ``eval()`` mode or have
+``dropout_p == 0``, and it does not record an autograd graph.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class AttentionCell(nn.Module):
+    """Parameter holder with the reference's names (model/model.py:23-31)."""
+
+    def __init__(self, input_size, hidden_size, num_embeddings, dropout_p=0.1):
+        super().__init__()
+        self.i2h = nn.Linear(input_size, hidden_size, bias=False)
+        self.h2h = nn.Linear(hidden_size, hidden_size)
+        self.score = nn.Linear(hidden_size, 1, bias=False)
+        self.rnn = nn.LSTMCell(input_size + num_embeddings, hidden_size)
+        self.hidden_size = hidden_size
+        self.dropout_p = dropout_p
+
+
+class Attention(nn.Module):
+    def __init__(self, input_size, hidden_size, num_classes, sos_id: int, eos_id: int, pad_id: int,
+                 blank_id=None, dropout_p: float = 0.1, sampling_prob: float = 0.0):
+        super().__init__()
+        if input_size % 8 or hidden_size % 8:
+            raise ValueError("input_size and hidden_size must be multiples of 8 (16-byte bf16 rows)")
+        self.attention_cell = AttentionCell(input_size, hidden_size, num_classes, dropout_p=dropout_p)
+        self.input_size, self.hidden_size, self.num_classes = input_size, hidden_size, num_classes
+        self.sos_id, self.eos_id, self.pad_id, self.blank_id = sos_id, eos_id, pad_id, blank_id
+        self.generator = nn.Linear(hidden_size, num_classes)
+        self.dropout_p = dropout_p
+        self.sampling_prob = sampling_prob
+        self._prepared = None
+
+    # ---- bf16 / transposed views of the parameters, rebuilt only when a parameter changed ------------
+    def _weights(self):
+        cell = self.attention_cell
+        ps = [cell.i2h.weight, cell.h2h.weight, cell.h2h.bias, cell.score.weight, cell.rnn.weight_ih,
+              cell.rnn.weight_hh, cell.rnn.bias_ih, cell.rnn.bias_hh, self.generator.weight, self.generator.bias]
+        key = tuple((p.data_ptr(), p._version, p.device) for p in ps)
+        if self._prepared is None or self._prepared[0] != key:
+            C = self.input_size
+            with torch.no_grad():
+                w = {
+                    "i2h": ops.cast_bf16_2d(cell.i2h.weight.detach()),                                    # [H, C]
+                    "h2h": ops.cast_bf16_2d(cell.h2h.weight.detach()),                                    # [H, H]
+                    "h2h_b": cell.h2h.bias.detach().float().contiguous(),
+                    "v": cell.score.weight.detach().float().reshape(-1).contiguous(),                     # [H]
+                    # gates = [context, h] @ [W_ih[:, :C] | W_hh]^T + (b_ih + b_hh) + W_ih[:, C + y]
+                    "wcat": ops.cast_bf16_2d(torch.cat([cell.rnn.weight_ih.detach()[:, :C],
+                                                        cell.rnn.weight_hh.detach()], 1).contiguous()),   # [4H, C+H]
+                    "bcat": (cell.rnn.bias_ih.detach() + cell.rnn.bias_hh.detach()).float().contiguous(),
+                    "embT": cell.rnn.weight_ih.detach()[:, C:].t().float().contiguous(),                  # [V, 4H]
+                    "gen": ops.cast_bf16_2d(self.generator.weight.detach()),                              # [V, H]
+                    "gen_b": self.generator.bias.detach().float().contiguous(),
+                }
+            self._prepared = (key, w)
+        return self._prepared[1]
+
+    @torch.no_grad()
+    def _decode(self, batch_H, steps, text):
+        """Both paths of model/model.py:89-148.  text is None: greedy (returns probs [B,steps,V]);
+        else teacher forcing with targets text[:, t] (returns generator(out_hid), blank-masked)."""
+        _lib.require_cuda(batch_H, "batch_H")
+        if batch_H.dim() != 3 or batch_H.shape[2] != self.input_size:
+            raise RuntimeError(f"Attention expects [B, T, {self.input_size}], got {tuple(batch_H.shape)}")
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError("the attention decoder runs in eval() mode only (dropout / training are "
+                                      "outside this round's scope)")
+        B, T, C = batch_H.shape
+        H, V = self.hidden_size, self.num_classes
+        dev = batch_H.device
+        w = self._weights()
+        L = _lib.lib()
+        blank = -1 if self.blank_id is None else int(self.blank_id)
+        enc = batch_H.float()
+        if enc.stride(2) != 1:
+            enc = enc.contiguous()
+        with torch.cuda.device(dev):
+            encb = ops.cast_bf16_3d(enc)
+            projH = ops.gemm_bf16(encb.view(B * T, C), w["i2h"], None, torch.float32)          # hoisted i2h(batch_H)
+            xcat = torch.zeros((B, C + H), dtype=torch.bfloat16, device=dev)                    # [context | h], h_0 = 0
+            hview = xcat[:, C:]
+            c = torch.zeros((B, H), dtype=torch.float32, device=dev)
+            projh = torch.empty((B, H), dtype=torch.float32, device=dev)
+            gates = torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
+            logits = torch.empty((B, V), dtype=torch.float32, device=dev)
+            greedy = text is None
+            probs = torch.zeros((B, steps, V), dtype=torch.float32, device=dev) if greedy else None
+            out_hid = None if greedy else torch.zeros((B, steps, H), dtype=torch.float32, device=dev)
+            y = torch.full((B,), int(self.sos_id), dtype=torch.int64, device=dev) if greedy else None
+            if not greedy:
+                text = text.to(device=dev, dtype=torch.int64).contiguous()
+            s = _lib.stream_ptr()
+            for t in range(steps):
+                yt = y if greedy else text[:, t].contiguous()
+                ops.gemm_bf16(hview, w["h2h"], w["h2h_b"], torch.float32, out=projh)
+                _lib.check(L.rcnn_attn_score_context(projH.data_ptr(), projh.data_ptr(), w["v"].data_ptr(), enc.data_ptr(),
+                                                     enc.stride(0), enc.stride(1), B, T, H, C, None, xcat.data_ptr(),
+                                                     xcat.stride(0), s), "rcnn_attn_score_context")
+                ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
+                hid = out_hid[:, t] if out_hid is not None else None
+                _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), yt.data_ptr(), B, H, V, c.data_ptr(),
+                                            xcat.data_ptr(), xcat.stride(0), C,
+                                            hid.data_ptr() if hid is not None else None,
+                                            out_hid.stride(0) if out_hid is not None else 0, s), "rcnn_attn_cell")
+                if greedy:
+                    ops.gemm_bf16(hview, w["gen"], w["gen_b"], torch.float32, out=logits)
+                    pt = probs[:, t]
+                    _lib.check(L.rcnn_attn_argmax(logits.data_ptr(), B, V, blank, pt.data_ptr(), probs.stride(0),
+                                                  y.data_ptr(), s), "rcnn_attn_argmax")
+            if greedy:
+                return probs
+            # teacher forcing: logits = generator(out_hid) in one GEMM, then the blank mask (model/model.py:146-148)
+            out = ops.gemm_bf16(ops.cast_bf16_2d(out_hid.view(B * steps, H)), w["gen"], w["gen_b"], torch.float32)
+            out = out.view(B, steps, V)
+            if blank >= 0:
+                out[:, :, blank] = -1e4
+            return out
+
+    def forward(self, batch_H, text=None, is_train=True, batch_max_length=25):
+        steps = batch_max_length + 1
+        if not is_train:
+            return self._decode(batch_H, steps, None)
+        assert text is not None, "For training, `text` with <SOS> at text[:,0] is required"
+        if self.sampling_prob > 0 and self.training:
+            raise NotImplementedError("scheduled sampling belongs to the training path (out of scope)")
+        if text.shape[1] < steps:
+            raise RuntimeError(f"text has {text.shape[1]} columns, {steps} steps need text[:, :{steps}]")
+        return self._decode(batch_H, steps, text)

@@ -1,0 +1,168 @@
+// K6: per-step kernels of the reference's attention decoder (model/model.py:23-148), inference path.
+//
+// One decoding step of AttentionCell.forward + Attention._greedy_decode (model/model.py:33-47, 100-108):
+//     proj_h  = h2h(h_{t-1})                                   -> tcgen05 GEMM (gemm.cu)
+//     e       = score(tanh(proj_H + proj_h)),  alpha = softmax_T(e),  context = alpha^T batch_H   (K6a)
+//     gates   = [context, h_{t-1}] [W_ih[:, :C] | W_hh]^T + b_ih + b_hh   -> tcgen05 GEMM
+//               + W_ih[:, C + y_{t-1}]  (the one-hot half of the LSTMCell input is a column gather)
+//     c, h    = LSTMCell pointwise                                                                 (K6b)
+//     logits  = generator(h)                                   -> tcgen05 GEMM
+//     logits[:, blank] = -1e4;  probs[:, t] = logits;  y_t = argmax                                (K6c)
+// proj_H = i2h(batch_H) does not depend on the step and is hoisted out of the loop (the reference
+// recomputes it every step, model/model.py:35).  Sequences are independent: no exchange between CTAs.
+#include "common.cuh"
+
+namespace rcnn {
+namespace {
+
+__device__ __forceinline__ float tanh_fast_a(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast_a(float x) { return fmaf(tanh_fast_a(0.5f * x), 0.5f, 0.5f); }
+
+// K6a: one CTA per sequence.  proj_H [B,T,H] f32, proj_h [B,H] f32, v [H] f32, enc [B,T,C] f32 (strided rows)
+// -> alpha [B,T] f32 (optional), context as bf16 into xcat[b, 0:C] (row pitch ldx elements)
+__global__ void __launch_bounds__(256) attn_score_context_kernel(
+    const float *__restrict__ projH, const float *__restrict__ projh, const float *__restrict__ v,
+    const float *__restrict__ enc, long long enc_sb, long long enc_st, int T, int H, int C,
+    float *__restrict__ alpha_out, __nv_bfloat16 *__restrict__ xcat, long long ldx) {
+    extern __shared__ float sm[];
+    float *ph = sm, *vs = sm + H, *e = sm + 2 * H;          // [H], [H], [T]
+    __shared__ float red[2];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) { ph[j] = projh[(size_t)b * H + j]; vs[j] = v[j]; }
+    __syncthreads();
+    for (int t = warp; t < T; t += nw) {
+        const float *row = projH + ((size_t)b * T + t) * H;
+        float s = 0.f;
+        for (int j = lane; j < H; j += 32) s = fmaf(vs[j], tanh_fast_a(row[j] + ph[j]), s);
+        s = warp_sum(s);
+        if (lane == 0) e[t] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {                                          // softmax over the T encoder frames
+        float m = -INFINITY;
+        for (int t = lane; t < T; t += 32) m = fmaxf(m, e[t]);
+        m = warp_max(m);
+        float z = 0.f;
+        for (int t = lane; t < T; t += 32) z += __expf(e[t] - m);
+        z = warp_sum(z);
+        if (lane == 0) { red[0] = m; red[1] = 1.f / z; }
+    }
+    __syncthreads();
+    const float m = red[0], iz = red[1];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const float a = __expf(e[t] - m) * iz;
+        e[t] = a;
+        if (alpha_out) alpha_out[(size_t)b * T + t] = a;
+    }
+    __syncthreads();
+    const float *eb = enc + (size_t)b * enc_sb;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(e[t], eb[(size_t)t * enc_st + c], acc);
+        xcat[(size_t)b * ldx + c] = __float2bfloat16_rn(acc);
+    }
+}
+
+// K6b: LSTMCell pointwise.  gates [B,4H] f32 (torch order i,f,g,o), embT [V,4H] f32 (column C+v of W_ih),
+// y [B] int64 previous tokens; c [B,H] f32 in place; h -> bf16 xcat[b, C + j], f32 hid_out[b*hid_ld + j] (optional)
+__global__ void attn_cell_kernel(const float *__restrict__ gates, const float *__restrict__ embT,
+                                 const long long *__restrict__ y, int B, int H, int V, float *__restrict__ c,
+                                 __nv_bfloat16 *__restrict__ xcat, long long ldx, int C,
+                                 float *__restrict__ hid_out, long long hid_ld) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * H) return;
+    const int b = (int)(idx / H), j = (int)(idx % H);
+    long long tok = y[b];
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    const float *g = gates + (size_t)b * 4 * H, *em = embT + (size_t)tok * 4 * H;
+    const float ig = sigmoid_fast_a(g[j] + em[j]);
+    const float fg = sigmoid_fast_a(g[H + j] + em[H + j]);
+    const float gg = tanh_fast_a(g[2 * H + j] + em[2 * H + j]);
+    const float og = sigmoid_fast_a(g[3 * H + j] + em[3 * H + j]);
+    const float cn = fmaf(fg, c[idx], ig * gg);
+    c[idx] = cn;
+    const float hn = og * tanh_fast_a(cn);
+    xcat[(size_t)b * ldx + C + j] = __float2bfloat16_rn(hn);
+    if (hid_out) hid_out[(size_t)b * hid_ld + j] = hn;
+}
+
+// K6c: one warp per sequence: mask the blank class, copy the row into probs[:, t, :], argmax (first maximum,
+// NaN counts as maximal: torch.argmax)
+__global__ void __launch_bounds__(128) attn_argmax_kernel(const float *__restrict__ logits, int B, int V, int blank,
+                                                          float *__restrict__ probs, long long probs_ld,
+                                                          long long *__restrict__ y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + warp;
+    if (b >= B) return;
+    const float *row = logits + (size_t)b * V;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    bool nan = false;
+    for (int k = lane; k < V; k += 32) {
+        float x = row[k];
+        if (k == blank) x = -1e4f;
+        if (probs) probs[(size_t)b * probs_ld + k] = x;
+        const bool xn = x != x;
+        if (!nan && (xn || x > best || arg == 0x7fffffff)) { best = x; arg = k; nan = xn; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int oa = __shfl_xor_sync(FULL, arg, o);
+        const bool on = __shfl_xor_sync(FULL, (int)nan, o) != 0;
+        bool take;
+        if (nan != on) take = on;                                 // a NaN beats any number
+        else if (nan) take = oa < arg;                            // two NaNs: the first index
+        else take = ob > best || (ob == best && oa < arg);
+        if (take) { best = ob; arg = oa; nan = on; }
+    }
+    if (lane == 0 && y) y[b] = arg == 0x7fffffff ? 0 : arg;
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" int rcnn_attn_score_context(const float *projH, const float *projh, const float *v, const float *enc,
+                                       int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                                       float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && C >= 1 && ldx >= C, "attn_score_context: bad shape");
+    if (B == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(projH && projh && v && enc && xcat, "attn_score_context: null pointer");
+    const size_t smem = sizeof(float) * (2 * (size_t)H + T);
+    RCNN_CHECK_ARG(smem <= 200 * 1024, "attn_score_context: T=%d, H=%d exceed shared memory", T, H);
+    if (smem > 48 * 1024)
+        RCNN_CUDA(cudaFuncSetAttribute(attn_score_context_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_score_context_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(projH, projh, v, enc, enc_stride_b, enc_stride_t, T, H, C,
+                                                                    alpha_out, (__nv_bfloat16 *)xcat, ldx);
+    RCNN_LAUNCH_CHECK("attn_score_context_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_attn_cell(const float *gates, const float *embT, const int64_t *y, int B, int H, int V, float *c,
+                              void *xcat, int64_t ldx, int C, float *hid_out, int64_t hid_ld, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && H >= 1 && V >= 1 && ldx >= (int64_t)C + H, "attn_cell: bad shape");
+    if (B == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(gates && embT && y && c && xcat, "attn_cell: null pointer");
+    const long long total = (long long)B * H;
+    attn_cell_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        gates, embT, (const long long *)y, B, H, V, c, (__nv_bfloat16 *)xcat, ldx, C, hid_out, hid_ld);
+    RCNN_LAUNCH_CHECK("attn_cell_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_attn_argmax(const float *logits, int B, int V, int blank, float *probs, int64_t probs_ld,
+                                int64_t *y, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && V >= 1, "attn_argmax: bad shape");
+    if (B == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(logits, "attn_argmax: null pointer");
+    attn_argmax_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(logits, B, V, blank, probs, probs_ld, (long long *)y);
+    RCNN_LAUNCH_CHECK("attn_argmax_kernel");
+    return RCNN_OK;
+}

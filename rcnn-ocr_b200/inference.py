@@ -1,5 +1,7 @@
-"""Inference surface mirroring inference.py:12-194 of the reference (``OCRInference.predict``)
-for the CTC path: batch loop -> model -> greedy CTC decode on the device -> strings.
+"""Inference surface mirroring inference.py:12-194 of the reference (``OCRInference.predict``):
+batch loop -> model -> decode -> strings.  decoder="ctc" (default): greedy CTC decode on the device (K4);
+decoder="attention": the reference's own path -- greedy attention decoding on the device (K6), argmax,
+``decode_tokens`` (inference.py:166-180), so existing reference checkpoints predict unchanged.
 
 Image file / PIL preprocessing (cv2 + albumentations, inference.py:93-124) is host-side I/O
 outside the hot path; ``predict`` takes preprocessed tensors
@@ -10,14 +12,14 @@ from typing import List, Union
 
 import torch
 
-from .charset import ctc_alphabet, load_charset
+from .charset import ctc_alphabet, decode_tokens, load_charset
 from .decode import _to_host, ctc_greedy_ids
 from .model import RCNN
 
 
 class OCRInference:
     def __init__(self, model_path=None, charset_path=None, device: str = "auto", img_h: int = 64,
-                 img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256):
+                 img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256, decoder: str = "ctc"):
         if device == "auto":
             device = "cuda"
         self.device = torch.device(device)
@@ -26,10 +28,12 @@ class OCRInference:
         self.img_h, self.img_w = img_h, img_w
         self.itos, self.stoi = load_charset(charset_path)
         self.alphabet, self.num_ctc_classes, self.blank = ctc_alphabet(self.itos)
+        self.pad_id, self.eos_id = self.stoi.get("<PAD>", 0), self.stoi.get("<EOS>", 2)
+        self.blank_id = self.stoi.get("<BLANK>")
         if model is None:
             model = RCNN(num_classes=len(self.itos), hidden_size=hidden_size,
-                         sos_id=self.stoi.get("<SOS>", 1), eos_id=self.stoi.get("<EOS>", 2),
-                         pad_id=self.stoi.get("<PAD>", 0), blank_id=self.stoi.get("<BLANK>"))
+                         sos_id=self.stoi.get("<SOS>", 1), eos_id=self.eos_id,
+                         pad_id=self.pad_id, blank_id=self.blank_id, decoder=decoder)
             if model_path is not None:
                 state = torch.load(model_path, map_location="cpu")
                 if isinstance(state, dict) and "model_state" in state:
@@ -60,6 +64,17 @@ class OCRInference:
             if not chunk.is_cuda:
                 chunk = chunk.pin_memory().to(self.device, non_blocking=True)
             logits = self.model(chunk, is_train=False, batch_max_length=max_length)
+            if getattr(self.model, "attn", None) is not None:     # the reference's decode step, inference.py:167-189
+                pred = logits.argmax(dim=-1)
+                if return_confidence:
+                    maxp = torch.softmax(logits, dim=-1).max(dim=-1)[0]
+                    valid = (pred != self.pad_id) & (pred != self.eos_id)
+                    conf = torch.where(valid.sum(1) > 0, (maxp * valid).sum(1) / valid.sum(1).clamp(min=1),
+                                       torch.zeros_like(maxp[:, 0])).cpu().tolist()
+                for j, row in enumerate(pred.cpu()):
+                    text = decode_tokens(row, self.itos, pad_id=self.pad_id, eos_id=self.eos_id, blank_id=self.blank_id)
+                    results.append((text, conf[j]) if return_confidence else text)
+                continue
             out = ctc_greedy_ids(logits, blank=self.blank, return_confidence=return_confidence)
             ids_h, lens_h = _to_host(out[0], out[1])
             conf_h = out[2].cpu().tolist() if return_confidence else None

@@ -279,8 +279,12 @@ class RCNN(nn.Module):
     """
 
     def __init__(self, num_classes, hidden_size=256, sos_id: int = 1, eos_id: int = 2, pad_id: int = 0,
-                 blank_id=3, enc_dropout_p: float = 0.1, dropblock_p: float = 0.0, dropblock_block_size: int = 5):
+                 blank_id=3, enc_dropout_p: float = 0.1, dropblock_p: float = 0.0, dropblock_block_size: int = 5,
+                 decoder: str = "ctc"):
         super().__init__()
+        if decoder not in ("ctc", "attention"):
+            raise ValueError(f"decoder must be 'ctc' or 'attention', got {decoder!r}")
+        self.decoder = decoder
         self.num_classes = num_classes
         self.hidden_size = hidden_size
         self.sos_id, self.eos_id, self.pad_id, self.blank_id = sos_id, eos_id, pad_id, blank_id
@@ -290,6 +294,13 @@ class RCNN(nn.Module):
         self.enc_rnn = make_enc_rnn(self.cnn.out_channels, hidden_size)
         self.enc_dropout = nn.Dropout(enc_dropout_p)
         self.ctc_head = CTCHead(hidden_size, self.num_ctc_classes)
+        # decoder="attention": the reference's own decoder (model/model.py:204-214), inference path on the device;
+        # forward() then returns what the reference's forward returns and attn.* of a checkpoint is loaded too
+        self.attn = None
+        if decoder == "attention":
+            from .attention import Attention
+            self.attn = Attention(input_size=hidden_size, hidden_size=hidden_size, num_classes=num_classes, sos_id=sos_id,
+                                  eos_id=eos_id, pad_id=pad_id, blank_id=blank_id, dropout_p=0.1, sampling_prob=0.0)
 
     def encode_features(self, feats: torch.Tensor) -> torch.Tensor:
         """[B, T, 512] feature columns -> [B, T, H] (the hot path without the backbone)."""
@@ -300,15 +311,19 @@ class RCNN(nn.Module):
         return self.encode_features(f.permute(0, 2, 1))
 
     def forward(self, x, text=None, is_train=True, batch_max_length=25):
-        return self.ctc_head(self.encode(x))
+        enc = self.encode(x)
+        if self.attn is not None:
+            return self.attn(enc, text=text, is_train=is_train, batch_max_length=batch_max_length)
+        return self.ctc_head(enc)
 
     def load_reference_state_dict(self, state_dict, strict_encoder: bool = True):
-        """Load ``cnn.*`` and ``enc_rnn.*`` from a reference checkpoint; its attention decoder
-        (``attn.*``) has no counterpart here and the CTC head keeps its own weights."""
+        """Load ``cnn.*`` and ``enc_rnn.*`` (and ``attn.*`` when built with decoder="attention") from a
+        reference checkpoint; the CTC head keeps its own weights.  Returns the keys that were not used."""
         own = self.state_dict()
-        picked = {k: v for k, v in state_dict.items() if k.startswith(("cnn.", "enc_rnn."))}
+        prefixes = ("cnn.", "enc_rnn.", "attn.") if self.attn is not None else ("cnn.", "enc_rnn.")
+        picked = {k: v for k, v in state_dict.items() if k.startswith(prefixes)}
         if strict_encoder:
-            missing = [k for k in own if k.startswith(("cnn.", "enc_rnn.")) and k not in picked]
+            missing = [k for k in own if k.startswith(prefixes) and k not in picked]
             if missing:
                 raise KeyError(f"reference state dict lacks encoder keys: {missing[:5]}...")
         own.update(picked)

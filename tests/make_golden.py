@@ -6,6 +6,7 @@ the GPU box):   python tests/make_golden.py
   decode_*.npz   training/utils.py:122-150  ctc_greedy_decoder  (reference code, imported)
   bilstm_*.npz   model/model.py:151-163     BidirectionalLSTM   (reference code, imported)
   encrnn_*.npz   model/model.py:195-198     Sequential of two blocks, outputs + all grads
+  attn_*.npz     model/model.py:50-148      Attention (reference code, imported), eval mode
   ctc_*.npz      torch.nn.functional.ctc_loss, CPU float64 (the reference has no CTC code;
                  SURVEY.md section 0) -- loss per reduction and the gradient AT THE LOGITS.
 """
@@ -150,9 +151,51 @@ def gen_ctc():
     case("cfgb", 64, 3, 195, 32, big=True)                # cfg-B geometry, reduced batch
 
 
+def gen_attention():
+    """model/model.py:50-148  Attention (reference code, imported): greedy probs and teacher-forced logits
+    in eval() mode, float32 CPU, plus the state dict the outputs were made with."""
+    from model.model import Attention
+
+    def case(name, B, T, C, H, V, steps, seed, blank=3, scale=1.0, store_weights=True):
+        torch.manual_seed(seed)
+        m = Attention(input_size=C, hidden_size=H, num_classes=V, sos_id=1, eos_id=2, pad_id=0, blank_id=blank,
+                      dropout_p=0.1, sampling_prob=0.0).eval()
+        with torch.no_grad():
+            for p in m.parameters():          # larger weights: peaky attention and well separated argmax margins
+                p.mul_(scale)
+        g = torch.Generator().manual_seed(seed + 1)
+        batch_H = torch.randn(B, T, C, generator=g)
+        text = torch.randint(0, V, (B, steps), generator=g)
+        text[:, 0] = 1
+        with torch.no_grad():
+            probs = m(batch_H, is_train=False, batch_max_length=steps - 1)
+            logits = m(batch_H, text=text, is_train=True, batch_max_length=steps - 1)
+        out = {"batch_H": batch_H.numpy(), "text": text.numpy(), "probs": probs.numpy(), "logits": logits.numpy(),
+               "dims": np.array([B, T, C, H, V, steps, -1 if blank is None else blank])}
+        if store_weights:
+            for k, v in m.state_dict().items():
+                out["sd." + k] = v.numpy()
+        else:
+            # large case: the weights are re-created from the seed by the build's own module, whose parameter
+            # registration order (hence default init) equals the reference's -- checked here, once
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+            import rcnn_ocr_b200 as R
+            torch.manual_seed(seed)
+            ours = R.Attention(C, H, V, 1, 2, 0, blank, dropout_p=0.1)
+            for k, v in m.state_dict().items():
+                assert torch.equal(ours.state_dict()[k] * scale, v), k
+            out["seed_scale"] = np.array([seed, scale], dtype=np.float64)
+        np.savez_compressed(os.path.join(OUT, f"attn_{name}.npz"), **out)
+
+    case("tiny", 3, 5, 64, 64, 20, 6, seed=11, scale=3.0)
+    case("cfga", 16, 16, 256, 256, 194, 26, seed=12, scale=2.0, store_weights=False)   # configs/config.json geometry
+    case("noblank", 5, 7, 64, 128, 30, 4, seed=13, blank=None, scale=3.0)
+
+
 if __name__ == "__main__":
     gen_decode()
     gen_bilstm()
     gen_ctc()
+    gen_attention()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")

@@ -88,3 +88,30 @@ def test_inference_api_shapes(tmp_path):
     assert one[0] == out[0]
     with pytest.raises(TypeError):
         ocr.predict(["/not/a/tensor.png"])
+
+
+def test_rcnn_with_the_reference_attention_decoder(tmp_path):
+    """decoder="attention": forward() returns the reference's outputs (greedy probs [B, steps, V] for
+    is_train=False, model/model.py:223-227), attn.* keys/shapes follow the reference's module tree, and
+    OCRInference decodes through argmax + decode_tokens as inference.py:166-180 does."""
+    torch.manual_seed(0)
+    model = R.RCNN(num_classes=14, hidden_size=64, decoder="attention").cuda().eval()
+    sd = model.state_dict()
+    assert sd["attn.attention_cell.rnn.weight_ih"].shape == (256, 64 + 14)
+    assert sd["attn.generator.weight"].shape == (14, 64) and sd["attn.attention_cell.score.weight"].shape == (1, 64)
+    x = torch.rand(3, 3, 32, 64, device="cuda") * 2 - 1
+    with torch.no_grad():
+        probs = model(x, is_train=False, batch_max_length=6)
+    assert probs.shape == (3, 7, 14) and torch.isfinite(probs).all()
+    assert (probs[:, :, 3] == -1e4).all()                              # blank_id = 3 is masked (model/model.py:82-88)
+    # a reference checkpoint (cnn.*, enc_rnn.*, attn.*) loads; the CTC head is the only extra
+    ref_like = {k: v.clone() for k, v in sd.items() if not k.startswith("ctc_head.")}
+    unused = model.load_reference_state_dict(ref_like)
+    assert unused == []
+    cs = tmp_path / "charset.txt"
+    cs.write_text("<PAD>\n<SOS>\n<EOS>\n \n" + "\n".join("abcdefghij") + "\n", encoding="utf-8")
+    ocr = R.OCRInference(charset_path=str(cs), model=model, img_h=32, img_w=64)
+    out = ocr.predict([t for t in x.cpu()], max_length=6, return_confidence=True)
+    assert len(out) == 3 and all(isinstance(t, str) and 0.0 <= c <= 1.0 for t, c in out)
+    want = [R.decode_tokens(row, ocr.itos, pad_id=0, eos_id=2, blank_id=None) for row in probs.argmax(-1).cpu()]
+    assert [t for t, _ in out] == want

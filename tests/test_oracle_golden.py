@@ -138,3 +138,25 @@ def test_host_ref_charset_and_metrics(tmp_path):
     assert host_ref.word_error_rate("hello world how are", "hello duck how are") == 0.25
     assert host_ref.word_error_rate("  a   b ", "a b") == 0.0           # whitespace runs collapse, ends are stripped
     assert host_ref.word_error_rate("a b", "a b c d") == 1.0            # insertions can push WER past 1
+
+
+def test_attention_port_matches_reference_module_outputs():
+    """oracle/ref_port.RefAttention (the CPU baseline of the attention decoder) against the reference module's
+    own greedy outputs (tests/golden/attn_*.npz, made by importing model/model.py in the build container)."""
+    import glob, os
+    import numpy as np
+    import torch
+    from conftest import GOLDEN
+    from oracle.ref_port import RefAttention
+    n = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "attn_*.npz"))):
+        d = np.load(path)
+        if "seed_scale" in d.files:
+            continue
+        B, T, C, H, V, steps, blank = [int(v) for v in d["dims"]]
+        m = RefAttention(C, H, V, sos_id=1, blank_id=None if blank < 0 else blank).eval()
+        m.load_state_dict({k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd.")}, strict=True)
+        got = m.greedy(torch.from_numpy(d["batch_H"]), steps - 1).numpy()
+        np.testing.assert_allclose(got, d["probs"], rtol=1e-5, atol=1e-5)
+        n += 1
+    assert n >= 2
