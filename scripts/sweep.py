@@ -76,4 +76,24 @@ for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
                               "seq_per_s_kernel": round(B / (ms_k * 1e-3)), "GBps_kernel": round(alg / ms_k / 1e6, 1),
                               "hbm_frac_kernel": round(alg / ms_k / 1e6 / peaks["hbm"], 4), "buffers": nbuf})
         del xs
+# ---- BASELINE configs[4]: greedy inference throughput over the batch size (encoder 2xBiLSTM(512) + head + decode,
+# eval mode, device-resident features), eager launches and one CUDA-graph replay per batch; plus the train step.
+out["inference"], out["train"] = [], []
+step = bench.TrainStep(dev, 1, 0)
+infer = bench.InferStep(step)
+step.enc.eval(); step.head.eval()
+for B in (1, 8, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+    nbuf = max(2, min(8, (160 << 20) // (B * T * 512 * 4) + 1))
+    feats = [torch.randn(B, T, 512, device=dev) for _ in range(nbuf)]
+    ms_eager = time_ms(lambda i: infer.device(feats[i]), nbuf, reps=20)
+    gi = R.GraphedStep(infer.device, [feats[0]])
+    ms_graph = time_ms(lambda i: gi(feats[i]), nbuf, reps=20)
+    out["inference"].append({"B": B, "ms_eager": round(ms_eager, 4), "ms_graph": round(ms_graph, 4),
+                             "lines_per_s_graph": round(B / (ms_graph * 1e-3), 1)})
+    del gi, feats
+step.enc.train(); step.head.train()
+for B in (64, 128, 256, 512, 1024):
+    batches = [[t.to(dev) for t in bench.make_batch(B, 77 + i)] for i in range(3)]
+    ms = time_ms(lambda i: step(*batches[i]), 3, reps=10, warm=3)
+    out["train"].append({"B": B, "ms_eager": round(ms, 4), "lines_per_s": round(B / (ms * 1e-3), 1)})
 print(json.dumps(out, indent=1))
