@@ -313,6 +313,147 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2, 256 x 256 output tile per pair ----------------------------
+// The two CTAs of a cluster compute one 256 x 256 tile: CTA r holds A rows [128r, 128r+128) and HALF of the B
+// tile (N rows [128r, 128r+128)); the leader (even CTA) issues M = 256, N = 256 MMAs that read both CTAs'
+// shared memory, each CTA accumulates its own 128 rows x 256 columns in its own TMEM.  Per stage (K = 64) a
+// CTA ingests 32 KB for 128 x 256 x 64 MACs: 128 FLOP per L2 byte, twice the single-CTA 128 x 256 tile --
+// the large GEMMs of the step are bound by L2 -> SM bandwidth, not by the tensor pipe.
+constexpr int kQStages = 6;
+constexpr uint32_t kQStage = 2 * kABytes;                          // A box + B-half box, 16 KB each
+constexpr size_t kQSmem = 1024 + kQStages * kQStage + 256 + 2 * 256 * sizeof(float);
+
+template <typename OutT>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int TN = 256;
+    unsigned char *tiles = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kQStages * kQStage);   // used in the leader only
+    uint64_t *empty = full + kQStages;
+    uint64_t *tmem_full = empty + kQStages;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;        // [2], used in the leader only (16 arrivals: both CTAs' epilogue warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(smem + kQStages * kQStage + 256);  // [2][TN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int ntn = (N + TN - 1) / TN, ntm = (M + 255) / 256;
+    const int num_tiles = ntn * ntm;
+    const int rounds = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kQStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_2sm<2 * TN>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    // both CTAs' barriers and TMEM allocations exist before either signals the other
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 || warp == 6) {
+        // ===== TMA producers (both CTAs): warp 0 its A rows, warp 6 its half of the B tile; every load
+        // completes on the LEADER's full barrier, which the leader's two producers arm for both CTAs =====
+        if (elect_one()) {
+            const bool isA = warp == 0;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = pid; tile < num_tiles; tile += npairs) {
+                const int row0 = isA ? (tile / ntn) * 256 + (int)rank * 128 : (tile % ntn) * TN + (int)rank * 128;
+                for (int r = 0; r < rounds; ++r) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full[st], 2 * kABytes);      // this operand: own box + the peer's
+                    tma_load_2d_2sm(tiles + st * kQStage + (isA ? 0 : kABytes), isA ? &tmA : &tmB, &full[st], r * BK, row0);
+                    if (++st == kQStages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's elected thread drives both tensor cores =======================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, TN);
+            int st = 0, it = 0;
+            uint32_t ph = 0;
+            for (int tile = pid; tile < num_tiles; tile += npairs, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);     // both epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+                for (int r = 0; r < rounds; ++r) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + st * kQStage), 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + st * kQStage + kABytes), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (r | k) != 0);
+                    umma_commit_2sm(&empty[st], (uint16_t)3);          // frees the stage in both CTAs
+                    if (++st == kQStages) { st = 0; ph ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc], (uint16_t)3);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows x 256 columns ==========================================
+        const int q = warp & 3;
+        const int chalf = warp >= 7 ? 1 : 0;
+        const int etid = warp < 6 ? threadIdx.x - 64 : threadIdx.x - 96;    // 0..255 over the epilogue threads
+        const bool vec_ok = (ldd % (32 / (long long)sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(D) & 31) == 0);
+        int it = 0;
+        for (int tile = pid; tile < num_tiles; tile += npairs, ++it) {
+            const int acc = it & 1;
+            const int tile_m = tile / ntn, tile_n = tile % ntn;
+            {
+                const int col = tile_n * TN + etid;
+                bias_s[acc * TN + etid] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            tc_fence_after();
+            const int row = tile_m * 256 + (int)rank * 128 + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = chalf * (TN / 2); c0 < (chalf + 1) * (TN / 2); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
+                tmem_ld_wait();
+                const int col0 = tile_n * TN + c0;
+                if (row < M && col0 < N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
+                    store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        }
+    }
+    // no CTA leaves while its peer may still read its shared memory / signal its barriers
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<2 * TN>(tmem_base);
+    }
+}
+
 // ---- D[M,N] += A[K,M]^T * B[K,N]  (weight-gradient shape) -------------------------------------
 // Both operands are "MN-major": the contraction index k is the ROW of the row-major global
 // arrays, so no transposed copies are needed for dW = dY^T X.  A k-block of 64 rows is staged as
@@ -446,6 +587,30 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long
     return RCNN_OK;
 }
 
+template <typename OutT>
+int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
+                     int N, int K, cudaStream_t s) {
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmem));
+    const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
+    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kPThreads);
+    cfg.dynamicSmemBytes = kQSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(RCNN_K_GEMM, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel<OutT>, ta, tb, (OutT *)D, ldd, bias, M, N, K));
+    count_launch();
+    return RCNN_OK;
+}
+
 }  // namespace
 }  // namespace rcnn
 
@@ -463,10 +628,18 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     int rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, BM, BK, 1);
     if (rc) return rc;
     static const int force_tn = getenv("RCNN_GEMM_TN") ? atoi(getenv("RCNN_GEMM_TN")) : 0;
+    static const int use_pair = getenv("RCNN_GEMM_PAIR") ? atoi(getenv("RCNN_GEMM_PAIR")) : 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (use_pair && !force_tn && M >= 512 && N >= 256) {      // CTA-pair kernel: 256 x 256 tiles, each CTA loads 128 B rows
+        rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 128, BK, 1);
+        if (rc) return rc;
+        if (out_dtype == RCNN_F32) return launch_gemm_pair<float>(ta, tb, D, ldd, bias, M, N, K, s);
+        if (out_dtype == RCNN_F16) return launch_gemm_pair<__half>(ta, tb, D, ldd, bias, M, N, K, s);
+        return launch_gemm_pair<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
+    }
     const int tn = force_tn == 128 || force_tn == 256 ? force_tn : (N > 128 ? 256 : 128);
     rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, (uint32_t)tn, BK, 1);
     if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
     if (tn == 256) {
         if (out_dtype == RCNN_F32) return launch_gemm<float, 256>(ta, tb, D, ldd, bias, M, N, K, s);
         if (out_dtype == RCNN_F16) return launch_gemm<__half, 256>(ta, tb, D, ldd, bias, M, N, K, s);

@@ -239,6 +239,18 @@ __device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *m,
         : "memory");
 }
 
+// 2-D variant of the pair load (operand tiles of the CTA-pair GEMM)
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the barrier at the same offset in the EVEN CTA of the pair (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // 32 lanes x 32 consecutive columns (fp32) -> 32 registers per thread (thread = lane/row).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
