@@ -313,36 +313,56 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<float>(float a, float) { return __float_as_uint(a); }
+
 // ---- CTA-pair variant: tcgen05.mma.cta_group::2, 256 x 256 output tile per pair ----------------------------
 // The two CTAs of a cluster compute one 256 x 256 tile: CTA r holds A rows [128r, 128r+128) and HALF of the B
 // tile (N rows [128r, 128r+128)); the leader (even CTA) issues M = 256, N = 256 MMAs that read both CTAs'
 // shared memory, each CTA accumulates its own 128 rows x 256 columns in its own TMEM.  Per stage (K = 64) a
 // CTA ingests 32 KB for 128 x 256 x 64 MACs: 128 FLOP per L2 byte, twice the single-CTA 128 x 256 tile --
 // the large GEMMs of the step are bound by L2 -> SM bandwidth, not by the tensor pipe.
-constexpr int kQStages = 6;
+// Epilogue: a thread owns one accumulator row, so direct stores touch 32 different rows per instruction and the
+// LSU, not HBM, bounded the kernel (7,100 cycles to drain a tile against 4,400 cycles of MMAs, measured with
+// scripts/timeline_gemm.py).  Each epilogue warp therefore stages its [32 rows x 32 columns] chunks in shared
+// memory (swizzled, conflict-free) and hands them to TMA stores, which also clip the M / N tails.
+constexpr int kQStages = 4;
 constexpr uint32_t kQStage = 2 * kABytes;                          // A box + B-half box, 16 KB each
-constexpr size_t kQSmem = 1024 + kQStages * kQStage + 256 + 2 * 256 * sizeof(float);
+constexpr uint32_t kQOutBuf = 4096;                                // one staged chunk: 32 rows x 32 columns x <= 4 bytes
+constexpr size_t kQSmem = 1024 + kQStages * kQStage + 8 * 2 * kQOutBuf + 256 + 2 * 256 * sizeof(float);
 
 template <typename OutT>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
+                    OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K,
+                    long long *tlbuf, const __grid_constant__ CUtensorMap tmD, int tma_out) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int TN = 256;
     unsigned char *tiles = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kQStages * kQStage);   // used in the leader only
+    unsigned char *outbuf = smem + kQStages * kQStage;                            // [8 warps][2] staged output chunks
+    uint64_t *full = reinterpret_cast<uint64_t *>(outbuf + 8 * 2 * kQOutBuf);    // used in the leader only
     uint64_t *empty = full + kQStages;
     uint64_t *tmem_full = empty + kQStages;      // [2]
     uint64_t *tmem_empty = tmem_full + 2;        // [2], used in the leader only (16 arrivals: both CTAs' epilogue warps)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    float *bias_s = reinterpret_cast<float *>(smem + kQStages * kQStage + 256);  // [2][TN]
+    float *bias_s = reinterpret_cast<float *>(outbuf + 8 * 2 * kQOutBuf + 256);  // [2][TN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const bool leader = rank == 0;
     const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    long long *tl = blockIdx.x == 0 ? tlbuf : nullptr;       // debug: per-tile clock64 marks of CTA 0 (see rcnn_debug_timeline)
+#define GT_MARK(k) do { if (tl && it < 64) tl[it * 8 + (k)] = clock64(); } while (0)
     const int ntn = (N + TN - 1) / TN, ntm = (M + 255) / 256;
     const int num_tiles = ntn * ntm;
     const int rounds = (K + BK - 1) / BK;
@@ -390,11 +410,14 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t ph = 0;
             for (int tile = pid; tile < num_tiles; tile += npairs, ++it) {
                 const int acc = it & 1;
+                GT_MARK(0);
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);     // both epilogues drained this accumulator
+                GT_MARK(1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
                 for (int r = 0; r < rounds; ++r) {
                     mbar_wait(&full[st], ph);
+                    if (r == 0) GT_MARK(2);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + st * kQStage), 16, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + st * kQStage + kABytes), 16, 1024);
@@ -405,6 +428,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++st == kQStages) { st = 0; ph ^= 1; }
                 }
                 umma_commit_2sm(&tmem_full[acc], (uint16_t)3);
+                GT_MARK(3);
             }
         }
     } else {
@@ -422,27 +446,65 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 bias_s[acc * TN + etid] = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
             }
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            if (threadIdx.x == 64) GT_MARK(4);
             asm volatile("bar.sync 2, 256;" ::: "memory");
             tc_fence_after();
             const int row = tile_m * 256 + (int)rank * 128 + q * 32 + lane;
+            const int ew = etid >> 5;                                   // epilogue warp 0..7
+            int nchunk = 0;
 #pragma unroll 1
-            for (int c0 = chalf * (TN / 2); c0 < (chalf + 1) * (TN / 2); c0 += 32) {
+            for (int c0 = chalf * (TN / 2); c0 < (chalf + 1) * (TN / 2); c0 += 32, ++nchunk) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
                 tmem_ld_wait();
+                if (c0 + 32 == (chalf + 1) * (TN / 2)) {                // accumulator fully read: hand it back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+                }
                 const int col0 = tile_n * TN + c0;
-                if (row < M && col0 < N) {
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
+                if (tma_out) {
+                    if (col0 < N && tile_m * 256 + (int)rank * 128 + q * 32 < M) {
+                        unsigned char *buf = outbuf + (size_t)(ew * 2 + (nchunk & 1)) * kQOutBuf;
+                        if (lane == 0) tma_store_wait_read<1>();        // the store that last used this buffer has read it
+                        __syncwarp();
+                        if (sizeof(OutT) == 2) {                        // 64-byte rows, SWIZZLE_64B: piece j of row r at j ^ ((r >> 1) & 3)
+                            unsigned char *rowp = buf + lane * 64;
+                            const int sw = (lane >> 1) & 3;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) ow[k] = pack2<OutT>(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                                *reinterpret_cast<uint4 *>(rowp + ((j ^ sw) << 4)) = o;
+                            }
+                        } else {                                        // 128-byte rows, SWIZZLE_128B: piece j of row r at j ^ (r & 7)
+                            unsigned char *rowp = buf + lane * 128;
+                            const int sw = lane & 7;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmD, buf, col0, tile_m * 256 + (int)rank * 128 + q * 32);
+                            tma_store_commit();
+                        }
+                    }
+                } else if (row < M && col0 < N) {
                     store_row_chunk(D + (long long)row * ldd + col0, v, min(32, N - col0), vec_ok);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (threadIdx.x == 64) GT_MARK(5);
         }
     }
+#undef GT_MARK
+    if (tma_out && warp >= 2 && warp != 6 && lane == 0) tma_store_wait<0>();
     // no CTA leaves while its peer may still read its shared memory / signal its barriers
     tc_fence_before();
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
@@ -605,8 +667,18 @@ int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // TMA-store epilogue when the output rows are 16-byte aligned (else direct stores)
+    CUtensorMap td = ta;
+    int tma_out = 0;
+    if (((uintptr_t)D & 15) == 0 && (ldd * (long long)sizeof(OutT)) % 16 == 0) {
+        const int rc = make_tmap_2d(&td, D, (int)sizeof(OutT), (uint64_t)M, (uint64_t)N, (uint64_t)ldd * sizeof(OutT), 32, 32,
+                                    sizeof(OutT) == 2 ? 2 : 1);
+        if (rc) return rc;
+        tma_out = 1;
+    }
     ProfScope prof(RCNN_K_GEMM, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel<OutT>, ta, tb, (OutT *)D, ldd, bias, M, N, K));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_pair_kernel<OutT>, ta, tb, (OutT *)D, ldd, bias, M, N, K, debug_timeline(), td,
+                                 tma_out));
     count_launch();
     return RCNN_OK;
 }
