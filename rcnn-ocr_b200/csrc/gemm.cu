@@ -108,6 +108,7 @@ constexpr int kThreads = 288;   // warp 0,6,7,8 TMA producers, warp 1 MMA, warps
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + BN * sizeof(float);
+constexpr size_t kAtbSmemBytes = kSmemBytes;   // the epilogue stages its chunks in the (by then idle) operand ring: 2 CTAs per SM
 
 // vec_ok: 32-byte aligned row chunks -> 256-bit stores (full sectors per lane)
 __device__ __forceinline__ void store_row_chunk(float *dst, const float (&v)[32], int ncols, bool vec_ok) {
@@ -533,10 +534,11 @@ __device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c
 __global__ void __launch_bounds__(kThreads)
 gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 float *__restrict__ D, long long ldd, int M, int N, int K, int kb_per_split, int splits,
-                int a_gcols, int b_gcols, long long d_goff) {
+                int a_gcols, int b_gcols, long long d_goff, const __grid_constant__ CUtensorMap tmD, int tma_out) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *tiles = smem;
+    unsigned char *outbuf = smem;          // [4 warps] staged 32 x 32 fp32 chunks: the operand ring, idle once tmem_full fired
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
     uint64_t *empty = full + kStages;
     uint64_t *tmem_full = empty + kStages;
@@ -612,7 +614,27 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
             const int col0 = tile_n * BN + c0;
-            if (row < M && col0 < N) {
+            if (tma_out) {
+                // a thread owns one accumulator row: direct red.add touches 32 rows per instruction (LSU-bound);
+                // stage the chunk (128-byte rows, SWIZZLE_128B) and let TMA do a coalesced reduce-add that also
+                // clips the M / N tails
+                if (tile_m * BM + q * 32 < M && col0 < N) {
+                    unsigned char *buf = outbuf + (warp - 2) * 4096;
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    unsigned char *rowp = buf + lane * 128;
+                    const int sw = lane & 7;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4 *>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_3d(&tmD, buf, col0, tile_m * BM + q * 32, grp);
+                        tma_store_commit();
+                    }
+                }
+            } else if (row < M && col0 < N) {
                 float *dst = D + (long long)row * ldd + col0;
                 const int ncols = min(32, N - col0);
                 if (vec_ok && ncols == 32) {
@@ -627,6 +649,7 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+        if (tma_out && lane == 0) tma_store_wait<0>();
         tc_fence_before();
     }
     __syncthreads();
@@ -750,11 +773,20 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
     splits = splits < 1 ? 1 : (splits > total_kb ? total_kb : splits);
     const int kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per_split - 1) / kb_per_split;
-    RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAtbSmemBytes));
+    // TMA reduce-add epilogue when the output rows (and the group stride) are 16-byte aligned
+    CUtensorMap td = ta;
+    int tma_out = 0;
+    if (((uintptr_t)D & 15) == 0 && (ldd % 4) == 0 && (groups == 1 || (d_goff % 4) == 0)) {
+        rc = make_tmap_3d(&td, D, 4, (uint64_t)groups, (uint64_t)M, (uint64_t)N, (uint64_t)(groups > 1 ? d_goff : (int64_t)M * ldd) * 4,
+                          (uint64_t)ldd * 4, 1, 32, 32, 1);
+        if (rc) return rc;
+        tma_out = 1;
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits * groups);
     ProfScope prof(RCNN_K_GEMM_ATB, s);
-    gemm_atb_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split, splits, a_gcols, b_gcols,
-                                                     (long long)d_goff);
+    gemm_atb_kernel<<<grid, kThreads, kAtbSmemBytes, s>>>(ta, tb, D, ldd, M, N, K, kb_per_split, splits, a_gcols, b_gcols,
+                                                        (long long)d_goff, td, tma_out);
     RCNN_LAUNCH_CHECK("gemm_atb_kernel");
     return RCNN_OK;
 }
