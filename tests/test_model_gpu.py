@@ -115,3 +115,42 @@ def test_rcnn_with_the_reference_attention_decoder(tmp_path):
     assert len(out) == 3 and all(isinstance(t, str) and 0.0 <= c <= 1.0 for t, c in out)
     want = [R.decode_tokens(row, ocr.itos, pad_id=0, eos_id=2, blank_id=None) for row in probs.argmax(-1).cpu()]
     assert [t for t, _ in out] == want
+
+
+def test_graphed_step_replays_the_eager_train_step():
+    """GraphedStep (one CUDA-graph replay per step, what bench.py times): same losses and weights as launching the
+    identical step eagerly, cooperative recurrent kernels and capturable Adam included."""
+    def make():
+        torch.manual_seed(3)
+        enc = R.make_enc_rnn(64, 64).cuda()
+        head = R.CTCHead(64, 40).cuda()
+        params = list(enc.parameters()) + list(head.parameters())
+        opt = torch.optim.Adam(params, lr=2e-3, fused=True, capturable=True)
+
+        def step(feats, tg, il, tl):
+            opt.zero_grad(set_to_none=True)
+            logits = head(enc(feats))
+            loss = R.ctc_loss_from_logits(logits.permute(1, 0, 2), tg, il, tl, 0, "mean", True, max_target_length=5)
+            loss.backward()
+            opt.step()
+            return loss
+        return step, params
+
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for _ in range(6):
+        tl = torch.randint(1, 6, (70,), generator=g)
+        batches.append([torch.randn(70, 20, 64, generator=g).cuda(), torch.randint(1, 40, (70, 5), generator=g).cuda(),
+                        torch.full((70,), 20).cuda(), tl.cuda()])
+    eager, p_e = make()
+    graphed_fn, p_g = make()
+    # GraphedStep runs 3 eager warm-up steps on its example inputs before capturing: give the eager twin the same
+    gs = R.GraphedStep(graphed_fn, batches[0], warmup=3)
+    for _ in range(3):
+        eager(*batches[0])
+    for b in batches:
+        le = eager(*b).item()
+        lg = gs(*b).item()
+        assert abs(le - lg) <= 2e-3 * max(1.0, abs(le)), (le, lg)
+    for a, b in zip(p_e, p_g):
+        assert (a - b).abs().max().item() <= 5e-3 * (a.abs().max().item() + 1e-3)
