@@ -468,32 +468,38 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
                 if (tma_out) {
-                    if (col0 < N && tile_m * 256 + (int)rank * 128 + q * 32 < M) {
-                        unsigned char *buf = outbuf + (size_t)(ew * 2 + (nchunk & 1)) * kQOutBuf;
-                        if (lane == 0) tma_store_wait_read<1>();        // the store that last used this buffer has read it
+                    // 8 KB of staging per warp = two blocks [32 rows x 128 bytes] (SWIZZLE_128B): one TMA store (3-D
+                    // map: column-in-block, row, block) writes both -- the store engine, not the LSU, is the limiter
+                    // once the rows are coalesced, so fewer and larger operations matter
+                    constexpr int kCPB = sizeof(OutT) == 2 ? 2 : 1;                 // 32-column chunks per 128-byte row block
+                    unsigned char *buf = outbuf + (size_t)ew * 2 * kQOutBuf;
+                    const int blk = (nchunk / kCPB) & 1, sub = nchunk % kCPB;
+                    if ((nchunk % (2 * kCPB)) == 0) {                               // first chunk of a store: buffer free?
+                        if (lane == 0) tma_store_wait_read<0>();
                         __syncwarp();
-                        if (sizeof(OutT) == 2) {                        // 64-byte rows, SWIZZLE_64B: piece j of row r at j ^ ((r >> 1) & 3)
-                            unsigned char *rowp = buf + lane * 64;
-                            const int sw = (lane >> 1) & 3;
+                    }
+                    unsigned char *rowp = buf + blk * kQOutBuf + lane * 128;
+                    const int sw = lane & 7;
+                    if (sizeof(OutT) == 2) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 o;
-                                uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) ow[k] = pack2<OutT>(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
-                                *reinterpret_cast<uint4 *>(rowp + ((j ^ sw) << 4)) = o;
-                            }
-                        } else {                                        // 128-byte rows, SWIZZLE_128B: piece j of row r at j ^ (r & 7)
-                            unsigned char *rowp = buf + lane * 128;
-                            const int sw = lane & 7;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int k = 0; k < 4; ++k) ow[k] = pack2<OutT>(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                            *reinterpret_cast<uint4 *>(rowp + (((sub * 4 + j) ^ sw) << 4)) = o;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4 *>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if ((nchunk % (2 * kCPB)) == 2 * kCPB - 1) {                    // both blocks staged: store
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmD, buf, col0, tile_m * 256 + (int)rank * 128 + q * 32);
+                        const int colb = (col0 + 32 - 2 * kCPB * 32) / (32 * kCPB);   // first 128-byte column block of the store
+                        if (lane == 0 && tile_m * 256 + (int)rank * 128 + q * 32 < M) {
+                            tma_store_3d(&tmD, buf, 0, tile_m * 256 + (int)rank * 128 + q * 32, colb);
                             tma_store_commit();
                         }
                     }
@@ -693,9 +699,12 @@ int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long
     // TMA-store epilogue when the output rows are 16-byte aligned (else direct stores)
     CUtensorMap td = ta;
     int tma_out = 0;
-    if (((uintptr_t)D & 15) == 0 && (ldd * (long long)sizeof(OutT)) % 16 == 0) {
-        const int rc = make_tmap_2d(&td, D, (int)sizeof(OutT), (uint64_t)M, (uint64_t)N, (uint64_t)ldd * sizeof(OutT), 32, 32,
-                                    sizeof(OutT) == 2 ? 2 : 1);
+    constexpr int kCW = 128 / (int)sizeof(OutT);         // columns per 128-byte block
+    if (((uintptr_t)D & 15) == 0 && (ldd * (long long)sizeof(OutT)) % 16 == 0 && N % kCW == 0) {
+        const uint64_t dims[3] = {(uint64_t)kCW, (uint64_t)M, (uint64_t)(N / kCW)};
+        const uint64_t strides[2] = {(uint64_t)ldd * sizeof(OutT), 128};
+        const uint32_t box[3] = {(uint32_t)kCW, 32, 2};
+        const int rc = make_tmap_nd(&td, D, (int)sizeof(OutT), 3, dims, strides, box, 1);
         if (rc) return rc;
         tma_out = 1;
     }

@@ -20,7 +20,8 @@ t = tl.cpu().numpy().reshape(64, 8).astype(np.float64)
 t = t[(t[:, 0] > 0) & (t[:, 3] > 0)]
 names = ["M0 tile start", "M1 accumulator free", "M2 first stage full", "M3 last MMA + commit issued", "E4 accumulator complete (epilogue)", "E5 drained"]
 print(f"{M}x{N}x{K}: {len(t)} tiles by CTA 0; cycles relative to the tile start (median over tiles 2..)")
-for k in range(1, 6):
+names += ["E6 first chunk read from TMEM", "E7 first chunk handed to TMA"]
+for k in (1, 2, 3, 4, 6, 7, 5):
     d = t[2:, k] - t[2:, 0]
     print(f"  {names[k]:36s} {np.median(d):9.0f}  (min {d.min():.0f} max {d.max():.0f})")
 print("  tile period", np.median(np.diff(t[2:, 0])))
