@@ -665,6 +665,136 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ---- CTA-pair weight-gradient GEMM: D[256 x 256 tile] += A^T B over a K range, tcgen05.mma.cta_group::2 ---------
+// Same operand layout as gemm_atb_kernel (MN-major boxes of 64 k-rows x 64 columns) and the same split-K +
+// TMA reduce-add output; the pair mechanics are those of gemm_tn_pair_kernel: CTA r stages its own 128 columns of
+// A (rows of D) and 128 of the tile's 256 B columns, every load completes on the leader's barrier, the leader
+// issues M = 256, N = 256 MMAs for both tensor cores.  A CTA ingests 32 KB per 128 x 256 x 64 MACs instead of
+// 32 KB per 128 x 128 x 64: the single-CTA kernel sat at the per-SM L2 ingest limit (two CTAs x 32 KB per 256
+// cycles of MMA = 125 B/clk).
+constexpr int kRStages = 5;
+constexpr uint32_t kRStage = 2 * kABytes;                                 // A: two halves, B-half: two halves (8 KB each)
+constexpr size_t kRSmem = 1024 + kRStages * kRStage + 4 * 8192 + 256;     // + one 8 KB staging buffer per epilogue warp
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_atb_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int kb_per_split, int splits,
+                     int a_gcols, int b_gcols) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tiles = smem;
+    unsigned char *outbuf = smem + kRStages * kRStage;       // [4 warps][2 blocks of 32 rows x 128 bytes]
+    uint64_t *full = reinterpret_cast<uint64_t *>(outbuf + 4 * 8192);       // used in the leader only
+    uint64_t *empty = full + kRStages;
+    uint64_t *tmem_full = empty + kRStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+    const int tile_n = blockIdx.x >> 1, tile_m = blockIdx.y;        // gridDim.x = 2 * column tiles (cluster along x)
+    const int total_kb = (K + BK - 1) / BK;
+    const int grp = blockIdx.z / splits;
+    const int kb0 = (blockIdx.z % splits) * kb_per_split;
+    const int num_kb = min(kb_per_split, total_kb - kb0);            // identical in both CTAs of the pair
+    if (num_kb <= 0) return;
+    const int a_c0 = grp * a_gcols + tile_m * 256 + (int)rank * 128, b_c0 = grp * b_gcols + tile_n * 256 + (int)rank * 128;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kRStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_2sm<256>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 || warp >= 6) {
+        if (elect_one()) {
+            const int which = warp == 0 ? 0 : warp - 5;      // 0,1: the two A halves; 2,3: the two halves of this CTA's B columns
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kRStages;
+                const uint32_t ph = (kb / kRStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (leader) mbar_arrive_expect_tx(&full[s], 2 * kHalf);          // own box + the peer's twin
+                unsigned char *st = tiles + s * kRStage;
+                const int k0 = (kb0 + kb) * BK;
+                if (which == 0) tma_load_2d_2sm(st, &tmA, &full[s], a_c0, k0);
+                else if (which == 1) tma_load_2d_2sm(st + kHalf, &tmA, &full[s], a_c0 + 64, k0);
+                else if (which == 2) tma_load_2d_2sm(st + kABytes, &tmB, &full[s], b_c0, k0);
+                else tma_load_2d_2sm(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, k0);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, 256, 1, 1);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kRStages;
+                const uint32_t ph = (kb / kRStages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem_u32(tiles + s * kRStage), kHalf, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(tiles + s * kRStage + kABytes), kHalf, 1024);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k)
+                    umma_bf16_2sm(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (kb | k) != 0);
+                umma_commit_2sm(&empty[s], (uint16_t)3);
+            }
+            umma_commit_2sm(tmem_full, (uint16_t)3);
+        }
+    } else if (warp < 6) {
+        // epilogue: this CTA's 128 rows x 256 columns, 64 columns (two 128-byte blocks) per TMA reduce-add
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        unsigned char *buf = outbuf + (warp - 2) * 8192;
+        const int row0 = tile_m * 256 + (int)rank * 128 + q * 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int blk = (c0 >> 5) & 1;
+            if (blk == 0) {
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+            }
+            unsigned char *rowp = buf + blk * 4096 + lane * 128;
+            const int sw = lane & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            if (blk == 1) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                const int col0 = tile_n * 256 + c0 - 32;
+                if (lane == 0 && row0 < M && col0 < N) {
+                    tma_reduce_add_4d(&tmD, buf, 0, row0, col0 / 32, grp);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();
+        tc_fence_before();
+    }
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<256>(tmem_base);
+    }
+}
+
 template <typename OutT, int TN>
 int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long ldd, const float *bias, int M,
                 int N, int K, cudaStream_t s) {
@@ -776,6 +906,41 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
     if (rc) return rc;
     rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)b_cols, (uint64_t)ldb * 2, BK, 64, 1);
     if (rc) return rc;
+    static const int use_pair = getenv("RCNN_GEMM_PAIR") ? atoi(getenv("RCNN_GEMM_PAIR")) : 1;
+    if (use_pair && M >= 256 && N >= 256 && (N % 32) == 0 && ((uintptr_t)D & 15) == 0 && (ldd % 4) == 0 &&
+        (groups == 1 || (d_goff % 4) == 0)) {
+        // CTA-pair kernel: 256 x 256 tiles, TMA reduce-add of [32 rows x 64 columns] pieces (4-D map: column in
+        // block, row, 32-column block, group)
+        CUtensorMap td;
+        const uint64_t dims[4] = {32, (uint64_t)M, (uint64_t)(N / 32), (uint64_t)groups};
+        const uint64_t strides[3] = {(uint64_t)ldd * 4, 128, (uint64_t)(groups > 1 ? d_goff : (int64_t)M * ldd) * 4};
+        const uint32_t box[4] = {32, 32, 2, 1};
+        rc = make_tmap_nd(&td, D, 4, 4, dims, strides, box, 1);
+        if (rc) return rc;
+        const int ptiles = ((M + 255) / 256) * ((N + 255) / 256) * groups;
+        const int tkb = (K + BK - 1) / BK;
+        int sp = (num_sms() / 2) / ptiles;                      // fill the 74 CTA pairs once
+        sp = sp < 1 ? 1 : (sp > tkb ? tkb : sp);
+        const int kbs = (tkb + sp - 1) / sp;
+        sp = (tkb + kbs - 1) / kbs;
+        RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRSmem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * ((N + 255) / 256)), (unsigned)((M + 255) / 256), (unsigned)(sp * groups));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kRSmem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ProfScope prof(RCNN_K_GEMM_ATB, s);
+        RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_atb_pair_kernel, ta, tb, td, M, N, K, kbs, sp, a_gcols, b_gcols));
+        count_launch();
+        return RCNN_OK;
+    }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
     const int total_kb = (K + BK - 1) / BK;
     int splits = (2 * num_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
