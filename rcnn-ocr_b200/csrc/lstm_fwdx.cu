@@ -1,0 +1,338 @@
+// K2 (forward, inference): recurrent LSTM kernel with the INPUT PROJECTION fused in.
+//
+// Same decomposition, exchange and cell arithmetic as lstm_fwd.cu (groups of H/32 CTAs, 64-sequence work
+// items, transposed product with the weights as the M = 128 operand, W_hh in tensor memory).  In addition the
+// CTA keeps its 128 x I slice of W_ih resident in SHARED memory and computes
+//     acc_t  = W_ih_slice x_t^T                 (K = I, operands from shared memory: x_t streams through a
+//                                                2-slot TMA ring straight out of the bf16 input tensor)
+//     acc_t += W_hh_slice h_{t-1}^T             (K = H, A from tensor memory, h tile by TMA as before)
+// into one of two alternating TMEM accumulators: the x half of step t+1 does not depend on the recurrence, so
+// its MMAs are issued right after the h half of step t and execute while the cell warps, the publish and the
+// group counter of step t are in flight -- the tensor pipe idles ~75 % of a step otherwise.  The separate xp
+// GEMM (nn.LSTM's `W_ih x_t + b` for all t, model/model.py:154-156,161), its 134 MB fp16 output and the
+// re-read of that output disappear from the inference path; the bias is a per-thread constant (a thread owns
+// one gate row).  Training keeps lstm_fwd.cu (the saved activations need the shared memory this kernel gives
+// to W_ih).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "sm100.cuh"
+#include "lstm_cell.cuh"
+
+namespace rcnn {
+namespace {
+
+using namespace sm100;
+
+constexpr int NS = 64;    // sequences per work item (UMMA N)
+constexpr int GR = 128;   // gate rows per CTA
+constexpr int LK = 64;
+constexpr uint32_t kWTile = GR * LK * 2;   // 16 KB
+constexpr uint32_t kHBox = NS * LK * 2;    //  8 KB
+constexpr int kThreads = 320;              // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
+
+struct FxParams {
+    int B, T, H, I;
+    int nitems, ngroups;
+    const float *bias;    // [2*4H] b_ih + b_hh, packed order
+    unsigned int *sync;   // [ngroups] zeroed before the launch
+};
+
+__device__ __forceinline__ void red_relaxed_gpu_inc_x(unsigned int *p) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_x(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_counter_x(const unsigned int *p, unsigned int target) {
+    if (ld_relaxed_gpu_x(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_relaxed_gpu_x(p) < target) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("rcnn-ocr_b200: lstm_fwdx group counter timed out (block %d)\n", blockIdx.x);
+            __trap();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
+                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmHs, const FxParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int H = p.H, T = p.T, I = p.I;
+    const int nkc = H / LK, nki = I / LK;
+    const int nkw = nkc > nki ? nkc : nki;        // tiles of the weight area (W_hh is staged there on its way to TMEM)
+    const int cpb = nkc >= 4 ? nkc / 4 : 1;       // h chunks per TMA operation / barrier
+    const int nhb = nkc / cpb;
+    const int xcs = nki >= 2 ? 2 : 1;             // x chunks (K = 64 each) per ring slot
+    const int nxs = nki / xcs;                    // ring slots consumed per step
+    const int gsize = H / 32;
+    unsigned char *w_s = smem;                            // nkw tiles [128 gate rows x 64 k] bf16, SW128: W_ih (resident)
+    unsigned char *h_s = w_s + (size_t)nkw * kWTile;      // nkc boxes [64 seq x 64 k]
+    unsigned char *x_s = h_s + (size_t)nkc * kHBox;       // 2 ring slots of xcs boxes [64 seq x 64 k]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + 2 * (size_t)xcs * kHBox);
+    uint64_t *wh_full = bars, *wcp_done = bars + 1, *wi_full = bars + 2;
+    uint64_t *h_full = bars + 3;                          // [4]
+    uint64_t *x_full = h_full + 4, *x_empty = x_full + 2; // [2] each
+    uint64_t *tmem_full = x_empty + 2;                    // [2]: accumulator of step parity
+    uint64_t *h_staged = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_staged + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x / gsize;
+    const int c = blockIdx.x % gsize;
+    unsigned int *counter = p.sync + group;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(wh_full, 1); mbar_init(wcp_done, 1); mbar_init(wi_full, 1);
+            for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&tmem_full[i], 1); }
+            mbar_init(h_staged, 8);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_slot);   // [0, 256): W_hh slice (A operand); [256, 320), [320, 384): the two accumulators
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer ========================================================================
+        if (elect_one()) {
+            tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWi); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
+            int cur_dir = -1;
+            unsigned int xn = 0, wn = 0, published = 0;
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1, b0 = (item >> 1) * NS;
+                if (dir != cur_dir) {
+                    // W_hh slice -> weight area -> (MMA thread) tensor memory; then W_ih takes the area for good.
+                    // (On a direction change the previous item's last x-half MMAs must have read the old W_ih.)
+                    if (xn > 0) mbar_wait(&x_empty[(xn - 1) & 1], ((xn - 1) >> 1) & 1);
+                    mbar_arrive_expect_tx(wh_full, (uint32_t)nkc * kWTile);
+                    for (int kc = 0; kc < nkc; ++kc)
+                        tma_load_2d(w_s + (size_t)kc * kWTile, &tmWh, wh_full, kc * LK, dir * 4 * H + c * GR);
+                    mbar_wait(wcp_done, wn & 1);
+                    mbar_arrive_expect_tx(wi_full, (uint32_t)nki * kWTile);
+                    for (int kc = 0; kc < nki; ++kc)
+                        tma_load_2d(w_s + (size_t)kc * kWTile, &tmWi, wi_full, kc * LK, dir * 4 * H + c * GR);
+                    ++wn;
+                    cur_dir = dir;
+                }
+                auto load_x = [&](int xs) {       // x_t of step xs: nxs ring operations of xcs K-chunks each
+                    const int t = dir ? T - 1 - xs : xs;
+                    for (int j = 0; j < nxs; ++j, ++xn) {
+                        const int slot = xn & 1;
+                        mbar_wait(&x_empty[slot], ((xn >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)xcs * kHBox);
+                        tma_load_4d(x_s + (size_t)slot * xcs * kHBox, &tmX, &x_full[slot], 0, b0, j * xcs, t);
+                    }
+                };
+                load_x(0);
+                for (int s = 0; s < T; ++s) {
+                    if (s > 0) {
+                        const int t = dir ? T - 1 - s : s;
+                        const int tprev = dir ? t + 1 : t - 1;
+                        wait_counter_x(counter, (published + (unsigned)s) * (unsigned)gsize);
+                        fence_proxy_async_global();
+                        for (int g = 0; g < nhb; ++g) {
+                            mbar_arrive_expect_tx(&h_full[g], (uint32_t)cpb * kHBox);
+                            tma_load_4d(h_s + (size_t)g * cpb * kHBox, &tmH, &h_full[g], 0, b0, dir * nkc + g * cpb, tprev);
+                        }
+                    }
+                    if (s + 1 < T) load_x(s + 1);
+                }
+                published += (unsigned)T;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer + publisher (one elected thread) ==========================================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(GR, NS);
+            int cur_dir = -1;
+            unsigned int xn = 0, wn = 0;
+            uint32_t hphase = 0, sphase = 0;
+            tma_prefetch_desc(&tmHs);
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1, b0 = (item >> 1) * NS;
+                if (dir != cur_dir) {
+                    mbar_wait(wh_full, wn & 1);
+                    tc_fence_after();
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        const uint64_t wdesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < LK / 16; ++k)
+                            tmem_cp_128x256b(tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), wdesc + (uint64_t)(2 * k));
+                    }
+                    umma_commit(wcp_done);            // the copies have read the staging area
+                    mbar_wait(wi_full, wn & 1);
+                    tc_fence_after();
+                    ++wn;
+                    cur_dir = dir;
+                }
+                // x half of a step: acc[par] = W_ih_slice x_t^T  (first MMA overwrites)
+                auto x_part = [&](int par) {
+                    const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS);
+                    for (int j = 0; j < nxs; ++j, ++xn) {
+                        const int slot = xn & 1;
+                        mbar_wait(&x_full[slot], (xn >> 1) & 1);
+                        tc_fence_after();
+                        for (int jj = 0; jj < xcs; ++jj) {
+                            const int kc = j * xcs + jj;
+                            const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(x_s + (size_t)(slot * xcs + jj) * kHBox), 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < LK / 16; ++k)
+                                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | jj | k) != 0);
+                        }
+                        umma_commit(&x_empty[slot]);
+                    }
+                };
+                x_part(0);
+                for (int s = 0; s < T; ++s) {
+                    const int par = s & 1;
+                    if (s > 0) {
+                        const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS);
+                        for (int g = 0; g < nhb; ++g) {
+                            mbar_wait(&h_full[g], hphase);
+                            tc_fence_after();
+                            for (int j = 0; j < cpb; ++j) {
+                                const int kc = g * cpb + j;
+                                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)kc * kHBox), 16, 1024);
+#pragma unroll
+                                for (int k = 0; k < LK / 16; ++k)
+                                    umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), bdesc + (uint64_t)(2 * k),
+                                                 idesc, 1u);
+                            }
+                        }
+                        hphase ^= 1;
+                    }
+                    umma_commit(&tmem_full[par]);
+                    if (s + 1 < T) x_part(par ^ 1);   // runs while step s is in its cell / publish / counter phases
+                    // publish h_t: staged by the cell warps in the idle h tile, one TMA store, relaxed counter increment
+                    const int t = dir ? T - 1 - s : s;
+                    mbar_wait(h_staged, sphase);
+                    sphase ^= 1;
+                    tma_store_3d(&tmHs, h_s, dir * H + 32 * c, t, b0);
+                    tma_store_commit();
+                    tma_store_wait<0>();
+                    fence_proxy_async_global();
+                    red_relaxed_gpu_inc_x(counter);
+                }
+            }
+        }
+    } else {
+        // ===== cell update ==========================================================================
+        const int qd = warp & 3;
+        const int ch = (warp - 2) >> 2;
+        const int r = qd * 32 + lane;
+        const CellLane CL(lane);
+        unsigned int use[2] = {0u, 0u};           // completions of tmem_full[parity] consumed so far
+        for (int item = group; item < p.nitems; item += p.ngroups) {
+            const int dir = item & 1;
+            const float bias = p.bias[(size_t)dir * 4 * H + (size_t)c * GR + r];
+            float cst[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cst[k] = 0.f;
+            for (int s = 0; s < T; ++s) {
+                const int par = s & 1;
+                uint32_t acc[32];
+                mbar_wait(&tmem_full[par], use[par] & 1);
+                ++use[par];
+                tc_fence_after();
+                tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(par * NS + ch * 32), acc);
+                tmem_ld_wait();
+                float pre[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pre[i] = __uint_as_float(acc[i]) + bias;
+                cell_activate(pre, CL);
+                const uint4 hq = cell_update(pre, cst, CL);
+                *reinterpret_cast<uint4 *>(h_s + (size_t)(32 * ch + lane) * 64 + qd * 16) = hq;
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_staged);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+size_t fwdx_smem_bytes(int H, int I) {
+    const int nkc = H / LK, nki = I / LK, nkw = nkc > nki ? nkc : nki, xcs = nki >= 2 ? 2 : 1;
+    return 1024 + (size_t)nkw * kWTile + (size_t)nkc * kHBox + 2 * (size_t)xcs * kHBox + 256;
+}
+
+}  // namespace
+}  // namespace rcnn
+
+extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const float *bias_p, const void *whh_p, int B, int T,
+                                       int I, int H, void *hcat, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_forward_fused: bad shape B=%d T=%d", B, T);
+    RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
+                   "lstm_forward_fused: hidden size %d unsupported (64, 128, 256 or 512)", H);
+    RCNN_CHECK_ARG(I >= 64 && I % 64 == 0 && I <= 512, "lstm_forward_fused: input size %d unsupported (multiple of 64, <= 512)", I);
+    if (B == 0 || T == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(x && wih_p && bias_p && whh_p && hcat, "lstm_forward_fused: null pointer");
+    CUtensorMap twh, twi, th, tx, ths;
+    int rc = make_tmap_2d(&twh, whh_p, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, GR, LK, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&twi, wih_p, 2, 8ull * H, (uint64_t)I, (uint64_t)I * 2, GR, LK, 1);
+    if (rc) return rc;
+    {   // hcat [B, T, 2H] as (k in chunk, b, chunk, t): box = cpb chunks of [64 seq x 64 k]
+        const int nkc = H / LK, cpb = nkc >= 4 ? nkc / 4 : 1;
+        const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 2ull * nkc, (uint64_t)T};
+        const uint64_t strides[3] = {(uint64_t)T * 2 * H * 2, (uint64_t)LK * 2, 2ull * H * 2};
+        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)NS, (uint32_t)cpb, 1u};
+        rc = make_tmap_4d(&th, hcat, 2, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    {   // x [B, T, I] bf16 the same way: box = xcs chunks
+        const int nki = I / LK, xcs = nki >= 2 ? 2 : 1;
+        const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, (uint64_t)nki, (uint64_t)T};
+        const uint64_t strides[3] = {(uint64_t)T * I * 2, (uint64_t)LK * 2, (uint64_t)I * 2};
+        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)NS, (uint32_t)xcs, 1u};
+        rc = make_tmap_4d(&tx, x, 2, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    rc = make_tmap_3d(&ths, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, NS, 1, 32, 0);
+    if (rc) return rc;
+    FxParams p;
+    p.B = B; p.T = T; p.H = H; p.I = I;
+    p.bias = bias_p;
+    const int gsize = H / 32;
+    p.nitems = 2 * ((B + NS - 1) / NS);
+    const int max_groups = num_sms() / gsize;
+    p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
+    if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;
+    cudaStream_t s = (cudaStream_t)stream;
+    p.sync = group_counters(p.ngroups, s);
+    if (!p.sync) return RCNN_ERR_CUDA_BASE;
+    const size_t smem = fwdx_smem_bytes(H, I);
+    RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(RCNN_K_LSTM_FWD, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel, twh, twi, th, tx, ths, p));
+    count_launch();
+    return RCNN_OK;
+}

@@ -171,6 +171,23 @@ def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, sa
     return hcat, gates, csave
 
 
+def lstm_forward_fused(xb: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int):
+    """Inference recurrence with the input projection fused in (no xp tensor, no saved activations).
+    xb: bf16 [B, T, I] contiguous, I a multiple of 64 and <= 512.  Returns hcat bf16 [B, T, 2H]."""
+    H, I = packed.H, packed.I
+    assert xb.dtype == torch.bfloat16 and xb.shape == (B, T, I) and xb.is_contiguous()
+    with torch.cuda.device(xb.device):
+        hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=xb.device)
+        rc = _lib.lib().rcnn_lstm_forward_fused(xb.data_ptr(), packed.wih_p.data_ptr(), packed.bias_p.data_ptr(),
+                                                packed.whh_p.data_ptr(), B, T, I, H, hcat.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_forward_fused")
+    return hcat
+
+
+def fused_forward_supported(I: int, H: int) -> bool:
+    return I % 64 == 0 and 64 <= I <= 512 and H in (64, 128, 256, 512)
+
+
 def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int):
     """BPTT of both directions (kernel K2 backward).  dhcat: float32 [B,T,2H] contiguous.
     Returns (dG bf16 [B,T,8H]: gradient w.r.t. the gate pre-activations, packed column order;
