@@ -161,12 +161,13 @@ int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float
 int rcnn_lstm_forward(const void *xp, const void *whh_p, int B, int T, int H, void *hcat,
                       void *gates_save, float *c_save, rcnn_stream_t stream);
 
-/* rcnn_lstm_forward_fused: inference variant of rcnn_lstm_forward with the input projection fused in: takes the
+/* rcnn_lstm_forward_fused: variant of rcnn_lstm_forward with the input projection fused in: takes the
  * block input x (bf16 [B, T, I] contiguous, I a multiple of 64 and <= 512) and the wih_p / bias_p / whh_p views
  * of `packed` instead of xp; the W_ih slice stays resident in shared memory, `W_ih x_t` of step t+1 is multiplied
- * while step t waits for its exchange.  Same hcat output; no saved activations (no backward). */
+ * while step t waits for its exchange.  Same hcat output and the same saved activations (gates_save, c_save:
+ * both NULL for inference) as rcnn_lstm_forward. */
 int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const float *bias_p, const void *whh_p, int B, int T,
-                            int I, int H, void *hcat, rcnn_stream_t stream);
+                            int I, int H, void *hcat, void *gates_save, float *c_save, rcnn_stream_t stream);
 
 /* rcnn_lstm_backward: BPTT through the recurrence of both directions (autograd of nn.LSTM in the
  * reference, model/model.py:161).

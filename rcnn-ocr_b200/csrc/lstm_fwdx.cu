@@ -11,8 +11,9 @@
 // group counter of step t are in flight -- the tensor pipe idles ~75 % of a step otherwise.  The separate xp
 // GEMM (nn.LSTM's `W_ih x_t + b` for all t, model/model.py:154-156,161), its 134 MB fp16 output and the
 // re-read of that output disappear from the inference path; the bias is a per-thread constant (a thread owns
-// one gate row).  Training keeps lstm_fwd.cu (the saved activations need the shared memory this kernel gives
-// to W_ih).
+// one gate row).  SAVE (training): the activated gates (fp16, lane pairs exchange halves so that every store is 32
+// bits) and c_t leave by plain global stores after the step is published -- off the dependent chain, and shared
+// memory has no room left for a staging tile.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -35,6 +36,8 @@ struct FxParams {
     int B, T, H, I;
     int nitems, ngroups;
     const float *bias;    // [2*4H] b_ih + b_hh, packed order
+    float *csave;         // [2, T, B, H] (training only)
+    __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
     unsigned int *sync;   // [ngroups] zeroed before the launch
 };
 
@@ -57,6 +60,7 @@ __device__ __forceinline__ void wait_counter_x(const unsigned int *p, unsigned i
     }
 }
 
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
@@ -234,8 +238,9 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         const int r = qd * 32 + lane;
         const CellLane CL(lane);
         unsigned int use[2] = {0u, 0u};           // completions of tmem_full[parity] consumed so far
+        const int g = lane & 3, ul = lane >> 2;
         for (int item = group; item < p.nitems; item += p.ngroups) {
-            const int dir = item & 1;
+            const int dir = item & 1, b0 = (item >> 1) * NS;
             const float bias = p.bias[(size_t)dir * 4 * H + (size_t)c * GR + r];
             float cst[8];
 #pragma unroll
@@ -252,12 +257,40 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pre[i] = __uint_as_float(acc[i]) + bias;
                 cell_activate(pre, CL);
+                uint32_t gsv[16];   // (training) activated gates as fp16 pairs, staged after the publish
+                if (SAVE) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __half2 h2 = __floats2half2_rn(pre[2 * i], pre[2 * i + 1]);
+                        gsv[i] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
+                }
                 const uint4 hq = cell_update(pre, cst, CL);
                 *reinterpret_cast<uint4 *>(h_s + (size_t)(32 * ch + lane) * 64 + qd * 16) = hq;
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(h_staged);
+                if (SAVE) {
+                    // gates_save [2, T, B, 4H]: this thread holds gate row r for 32 sequences; a lane pair swaps halves so
+                    // that the even lane writes rows (r, r+1) of sequence 2i and the odd lane those of sequence 2i+1.
+                    // Neither this nor c_t is needed before the backward pass.
+                    const int t = dir ? T - 1 - s : s;
+                    const int odd = lane & 1;
+                    __half *grow = p.gsave + (((size_t)dir * T + t) * p.B + b0 + 32 * ch + odd) * (size_t)(4 * H) + c * GR + (r & ~1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t pv = __shfl_xor_sync(FULL, gsv[i], 1);
+                        const uint32_t out = odd ? ((pv >> 16) | (gsv[i] & 0xffff0000u)) : ((gsv[i] & 0xffffu) | (pv << 16));
+                        if (b0 + 32 * ch + 2 * i + odd < p.B) *reinterpret_cast<uint32_t *>(grow + (size_t)(2 * i) * (4 * H)) = out;
+                    }
+                    float *crow = p.csave + (((size_t)dir * T + t) * p.B) * H + 32 * c + 8 * qd + ul;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int bc = b0 + 32 * ch + 4 * k + g;
+                        if (bc < p.B) crow[(size_t)bc * H] = cst[k];
+                    }
+                }
             }
         }
     }
@@ -268,7 +301,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     }
 }
 
-size_t fwdx_smem_bytes(int H, int I) {
+size_t fwdx_smem_bytes(int H, int I, bool save) {
+    (void)save;
     const int nkc = H / LK, nki = I / LK, nkw = nkc > nki ? nkc : nki, xcs = nki >= 2 ? 2 : 1;
     return 1024 + (size_t)nkw * kWTile + (size_t)nkc * kHBox + 2 * (size_t)xcs * kHBox + 256;
 }
@@ -277,7 +311,7 @@ size_t fwdx_smem_bytes(int H, int I) {
 }  // namespace rcnn
 
 extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const float *bias_p, const void *whh_p, int B, int T,
-                                       int I, int H, void *hcat, rcnn_stream_t stream) {
+                                       int I, int H, void *hcat, void *gates_save, float *c_save, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && T >= 0, "lstm_forward_fused: bad shape B=%d T=%d", B, T);
     RCNN_CHECK_ARG(H == 64 || H == 128 || H == 256 || H == 512,
@@ -285,6 +319,8 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     RCNN_CHECK_ARG(I >= 64 && I % 64 == 0 && I <= 512, "lstm_forward_fused: input size %d unsupported (multiple of 64, <= 512)", I);
     if (B == 0 || T == 0) return RCNN_OK;
     RCNN_CHECK_ARG(x && wih_p && bias_p && whh_p && hcat, "lstm_forward_fused: null pointer");
+    RCNN_CHECK_ARG((gates_save == nullptr) == (c_save == nullptr), "lstm_forward_fused: gates_save and c_save go together");
+    const bool save = gates_save != nullptr;
     CUtensorMap twh, twi, th, tx, ths;
     int rc = make_tmap_2d(&twh, whh_p, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, GR, LK, 1);
     if (rc) return rc;
@@ -311,6 +347,8 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     FxParams p;
     p.B = B; p.T = T; p.H = H; p.I = I;
     p.bias = bias_p;
+    p.csave = c_save;
+    p.gsave = (__half *)gates_save;
     const int gsize = H / 32;
     p.nitems = 2 * ((B + NS - 1) / NS);
     const int max_groups = num_sms() / gsize;
@@ -319,8 +357,9 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     cudaStream_t s = (cudaStream_t)stream;
     p.sync = group_counters(p.ngroups, s);
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
-    const size_t smem = fwdx_smem_bytes(H, I);
-    RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = fwdx_smem_bytes(H, I, save);
+    if (save) RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
     cfg.blockDim = dim3(kThreads);
@@ -332,7 +371,8 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_FWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel, twh, twi, th, tx, ths, p));
+    if (save) RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<true>, twh, twi, th, tx, ths, p));
+    else RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<false>, twh, twi, th, tx, ths, p));
     count_launch();
     return RCNN_OK;
 }

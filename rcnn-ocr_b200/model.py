@@ -45,9 +45,9 @@ class _BiLSTMBlockFn(torch.autograd.Function):
             prepared = (ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r), _cast2d(lin_w))
         packed, lin_wb = prepared
         xb = ops.cast_bf16_3d(x)
-        if not save and ops.fused_forward_supported(I, H):
-            # inference: the input projection runs inside the recurrent kernel (no xp tensor)
-            hcat, gates, csave = ops.lstm_forward_fused(xb, packed, B, T), None, None
+        if ops.fused_forward_supported(I, H):
+            # the input projection runs inside the recurrent kernel (no xp tensor)
+            hcat, gates, csave = ops.lstm_forward_fused(xb, packed, B, T, save)
         else:
             xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
             hcat, gates, csave = ops.lstm_forward(xp, packed, B, T, save)

@@ -171,17 +171,22 @@ def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, sa
     return hcat, gates, csave
 
 
-def lstm_forward_fused(xb: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int):
-    """Inference recurrence with the input projection fused in (no xp tensor, no saved activations).
-    xb: bf16 [B, T, I] contiguous, I a multiple of 64 and <= 512.  Returns hcat bf16 [B, T, 2H]."""
+def lstm_forward_fused(xb: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, save: bool = False):
+    """Recurrence with the input projection fused in (no xp tensor).  xb: bf16 [B, T, I] contiguous, I a
+    multiple of 64 and <= 512.  Returns (hcat bf16 [B,T,2H], gates f16 [2,T,B,4H] | None, c f32 [2,T,B,H] | None)."""
     H, I = packed.H, packed.I
     assert xb.dtype == torch.bfloat16 and xb.shape == (B, T, I) and xb.is_contiguous()
-    with torch.cuda.device(xb.device):
-        hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=xb.device)
+    dev = xb.device
+    with torch.cuda.device(dev):
+        hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
+        gates = torch.empty((2, T, B, 4 * H), dtype=torch.float16, device=dev) if save else None
+        csave = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
         rc = _lib.lib().rcnn_lstm_forward_fused(xb.data_ptr(), packed.wih_p.data_ptr(), packed.bias_p.data_ptr(),
-                                                packed.whh_p.data_ptr(), B, T, I, H, hcat.data_ptr(), _lib.stream_ptr())
+                                                packed.whh_p.data_ptr(), B, T, I, H, hcat.data_ptr(),
+                                                gates.data_ptr() if save else None, csave.data_ptr() if save else None,
+                                                _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_forward_fused")
-    return hcat
+    return hcat, gates, csave
 
 
 def fused_forward_supported(I: int, H: int) -> bool:
