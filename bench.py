@@ -179,7 +179,7 @@ class TrainStep:
         from rcnn_ocr_b200.dist import GradAllReducer
         self.R = R
         torch.manual_seed(0)
-        self.enc = R.make_enc_rnn(CFG["IN"], CFG["H"]).to(device)
+        self.enc = R.make_enc_rnn(CFG["IN"], CFG["H"], out_dtype=torch.bfloat16).to(device)   # feeds the bf16 head GEMM
         self.head = R.CTCHead(CFG["H"], CFG["C"]).to(device)
         self.params = list(self.enc.parameters()) + list(self.head.parameters())
         self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True, capturable=True)

@@ -193,6 +193,14 @@ int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float 
  * direction's first step: the h that multiplied W_hh when gates_t were formed (B operand of the
  * dW_hh GEMM). */
 int rcnn_lstm_hprev(const void *hcat, void *out, int B, int T, int H, rcnn_stream_t stream);
+/* Both weight gradients of a block in one call and in nn.LSTM's row order (gate-major), no h_prev copy and no
+ * unpack pass:  dwih[d] (4H x I) (+)= sum_{b,t} dG_d[b,t]^T x[b,t],  dwhh[d] (4H x H) (+)= sum dG_d[b,t]^T h_d[b,t-/+1]
+ * (h_{t-1} for d = 0, h_{t+1} for d = 1, zero outside the sequence -- read from hcat through a shifted tensor map).
+ * dG [B,T,8H] bf16 (packed gate order, as rcnn_lstm_backward writes it), x [B,T,I] bf16, hcat [B,T,2H] bf16;
+ * dwih [2,4H,I], dwhh [2,4H,H] fp32.  accumulate == 0 zeroes the outputs first.  H in {256, 512}, I >= 256 and a
+ * multiple of 32 (smaller blocks use rcnn_gemm_bf16_atb* + rcnn_lstm_hprev + rcnn_lstm_unpack_grads). */
+int rcnn_lstm_weight_grads(const void *dG, const void *x, const void *hcat, int B, int T, int I, int H,
+                           float *dwih, float *dwhh, int accumulate, rcnn_stream_t stream);
 int rcnn_lstm_unpack_grads(const float *dwih_p, const float *dwhh_p, const float *db_p, int I, int H,
                            float *dw_ih_f, float *dw_hh_f, float *db_ih_f, float *db_hh_f,
                            float *dw_ih_r, float *dw_hh_r, float *db_ih_r, float *db_hh_r,

@@ -672,14 +672,25 @@ gemm_atb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // issues M = 256, N = 256 MMAs for both tensor cores.  A CTA ingests 32 KB per 128 x 256 x 64 MACs instead of
 // 32 KB per 128 x 128 x 64: the single-CTA kernel sat at the per-SM L2 ingest limit (two CTAs x 32 KB per 256
 // cycles of MMA = 125 B/clk).
+//
+// The operands are read through 3-D maps (column, inner k, outer k): a flat [K, cols] matrix is (cols, K, 1); the
+// LSTM's dW_hh uses (cols, t, b) with the B operand's t shifted by -1 / +1 per group -- h_{t-1} of the forward and
+// h_{t+1} of the reverse direction straight from hcat, out-of-range rows zero-filled by TMA (x_seq.shift[]).
+// x_seq.perm: the 32 packed gate rows of an output piece (unit-major, gate-minor) are scattered to nn.LSTM's
+// gate-major row order by a 5-D reduce-add map, so the gradients land in torch layout without an unpack pass.
+struct AtbSeq {
+    int cps;        // 64-row K chunks per outer index (flat: all of them)
+    int shift[2];   // B operand: offset of the inner k coordinate for group 0 / group >= 1
+    int perm;       // output rows in packed gate order -> 5-D map (col, gate, unit, column block, group)
+};
 constexpr int kRStages = 5;
 constexpr uint32_t kRStage = 2 * kABytes;                                 // A: two halves, B-half: two halves (8 KB each)
 constexpr size_t kRSmem = 1024 + kRStages * kRStage + 4 * 8192 + 256;     // + one 8 KB staging buffer per epilogue warp
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_atb_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmD, int M, int N, int K, int kb_per_split, int splits,
-                     int a_gcols, int b_gcols) {
+                     const __grid_constant__ CUtensorMap tmD, int M, int N, int total_kb, int kb_per_split, int splits,
+                     int a_gcols, int b_gcols, const AtbSeq x_seq) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *tiles = smem;
@@ -694,7 +705,6 @@ gemm_atb_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const bool leader = rank == 0;
     const int tile_n = blockIdx.x >> 1, tile_m = blockIdx.y;        // gridDim.x = 2 * column tiles (cluster along x)
-    const int total_kb = (K + BK - 1) / BK;
     const int grp = blockIdx.z / splits;
     const int kb0 = (blockIdx.z % splits) * kb_per_split;
     const int num_kb = min(kb_per_split, total_kb - kb0);            // identical in both CTAs of the pair
@@ -721,17 +731,20 @@ gemm_atb_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 0 || warp >= 6) {
         if (elect_one()) {
             const int which = warp == 0 ? 0 : warp - 5;      // 0,1: the two A halves; 2,3: the two halves of this CTA's B columns
+            const int bshift = x_seq.shift[grp > 0 ? 1 : 0];
+            int ko = kb0 / x_seq.cps, ki = (kb0 % x_seq.cps) * BK;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kRStages;
                 const uint32_t ph = (kb / kRStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 if (leader) mbar_arrive_expect_tx(&full[s], 2 * kHalf);          // own box + the peer's twin
                 unsigned char *st = tiles + s * kRStage;
-                const int k0 = (kb0 + kb) * BK;
-                if (which == 0) tma_load_2d_2sm(st, &tmA, &full[s], a_c0, k0);
-                else if (which == 1) tma_load_2d_2sm(st + kHalf, &tmA, &full[s], a_c0 + 64, k0);
-                else if (which == 2) tma_load_2d_2sm(st + kABytes, &tmB, &full[s], b_c0, k0);
-                else tma_load_2d_2sm(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, k0);
+                if (which == 0) tma_load_3d_2sm(st, &tmA, &full[s], a_c0, ki, ko);
+                else if (which == 1) tma_load_3d_2sm(st + kHalf, &tmA, &full[s], a_c0 + 64, ki, ko);
+                else if (which == 2) tma_load_3d_2sm(st + kABytes, &tmB, &full[s], b_c0, ki + bshift, ko);
+                else tma_load_3d_2sm(st + kABytes + kHalf, &tmB, &full[s], b_c0 + 64, ki + bshift, ko);
+                ki += BK;
+                if (ki >= x_seq.cps * BK) { ki = 0; ++ko; }
             }
         }
     } else if (warp == 1) {
@@ -778,7 +791,8 @@ gemm_atb_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 __syncwarp();
                 const int col0 = tile_n * 256 + c0 - 32;
                 if (lane == 0 && row0 < M && col0 < N) {
-                    tma_reduce_add_4d(&tmD, buf, 0, row0, col0 / 32, grp);
+                    if (x_seq.perm) tma_reduce_add_5d(&tmD, buf, 0, 0, row0 >> 2, col0 / 32, grp);
+                    else tma_reduce_add_4d(&tmD, buf, 0, row0, col0 / 32, grp);
                     tma_store_commit();
                 }
             }
@@ -845,6 +859,32 @@ int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long
     return RCNN_OK;
 }
 
+int launch_atb_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &td, int M, int N, int tkb, int groups,
+                    int a_gcols, int b_gcols, const AtbSeq &seq, cudaStream_t s) {
+    const int ptiles = ((M + 255) / 256) * ((N + 255) / 256) * groups;
+    int sp = (num_sms() / 2) / ptiles;                      // fill the 74 CTA pairs once
+    sp = sp < 1 ? 1 : (sp > tkb ? tkb : sp);
+    const int kbs = (tkb + sp - 1) / sp;
+    sp = (tkb + kbs - 1) / kbs;
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRSmem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * ((N + 255) / 256)), (unsigned)((M + 255) / 256), (unsigned)(sp * groups));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kRSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope prof(RCNN_K_GEMM_ATB, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_atb_pair_kernel, ta, tb, td, M, N, tkb, kbs, sp, a_gcols, b_gcols, seq));
+    count_launch();
+    return RCNN_OK;
+}
+
 }  // namespace
 }  // namespace rcnn
 
@@ -902,45 +942,29 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
     RCNN_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0,
                    "gemm_atb: A/B rows must be 16-byte aligned (lda=%lld ldb=%lld)", (long long)lda, (long long)ldb);
     CUtensorMap ta, tb;
-    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)a_cols, (uint64_t)lda * 2, BK, 64, 1);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)b_cols, (uint64_t)ldb * 2, BK, 64, 1);
-    if (rc) return rc;
     static const int use_pair = getenv("RCNN_GEMM_PAIR") ? atoi(getenv("RCNN_GEMM_PAIR")) : 1;
     if (use_pair && M >= 256 && N >= 256 && (N % 32) == 0 && ((uintptr_t)D & 15) == 0 && (ldd % 4) == 0 &&
         (groups == 1 || (d_goff % 4) == 0)) {
         // CTA-pair kernel: 256 x 256 tiles, TMA reduce-add of [32 rows x 64 columns] pieces (4-D map: column in
-        // block, row, 32-column block, group)
+        // block, row, 32-column block, group); flat operands as (cols, K, 1)
+        int rc = make_tmap_3d(&ta, A, 2, 1, (uint64_t)K, (uint64_t)a_cols, (uint64_t)lda * 2 * (uint64_t)K, (uint64_t)lda * 2, 1, BK, 64, 1);
+        if (rc) return rc;
+        rc = make_tmap_3d(&tb, B, 2, 1, (uint64_t)K, (uint64_t)b_cols, (uint64_t)ldb * 2 * (uint64_t)K, (uint64_t)ldb * 2, 1, BK, 64, 1);
+        if (rc) return rc;
         CUtensorMap td;
         const uint64_t dims[4] = {32, (uint64_t)M, (uint64_t)(N / 32), (uint64_t)groups};
         const uint64_t strides[3] = {(uint64_t)ldd * 4, 128, (uint64_t)(groups > 1 ? d_goff : (int64_t)M * ldd) * 4};
         const uint32_t box[4] = {32, 32, 2, 1};
         rc = make_tmap_nd(&td, D, 4, 4, dims, strides, box, 1);
         if (rc) return rc;
-        const int ptiles = ((M + 255) / 256) * ((N + 255) / 256) * groups;
         const int tkb = (K + BK - 1) / BK;
-        int sp = (num_sms() / 2) / ptiles;                      // fill the 74 CTA pairs once
-        sp = sp < 1 ? 1 : (sp > tkb ? tkb : sp);
-        const int kbs = (tkb + sp - 1) / sp;
-        sp = (tkb + kbs - 1) / kbs;
-        RCNN_CUDA(cudaFuncSetAttribute(gemm_atb_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRSmem));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(2 * ((N + 255) / 256)), (unsigned)((M + 255) / 256), (unsigned)(sp * groups));
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = kRSmem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        ProfScope prof(RCNN_K_GEMM_ATB, s);
-        RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_atb_pair_kernel, ta, tb, td, M, N, K, kbs, sp, a_gcols, b_gcols));
-        count_launch();
-        return RCNN_OK;
+        const AtbSeq flat = {tkb, {0, 0}, 0};
+        return launch_atb_pair(ta, tb, td, M, N, tkb, groups, a_gcols, b_gcols, flat, s);
     }
+    int rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)a_cols, (uint64_t)lda * 2, BK, 64, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)b_cols, (uint64_t)ldb * 2, BK, 64, 1);
+    if (rc) return rc;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
     const int total_kb = (K + BK - 1) / BK;
     int splits = (2 * num_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
@@ -968,4 +992,50 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
 extern "C" int rcnn_gemm_bf16_atb(const void *A, int64_t lda, const void *B, int64_t ldb, float *D, int64_t ldd,
                                   int M, int N, int K, int accumulate, rcnn_stream_t stream) {
     return rcnn_gemm_bf16_atb_grouped(A, lda, 0, B, ldb, 0, D, ldd, 0, 1, M, N, K, accumulate, stream);
+}
+
+// Weight gradients of one bidirectional LSTM block, written in nn.LSTM's row order (see include/rcnn_ocr_b200.h)
+extern "C" int rcnn_lstm_weight_grads(const void *dG, const void *x, const void *hcat, int B, int T, int I, int H,
+                                      float *dwih, float *dwhh, int accumulate, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 1 && T >= 1 && (H == 256 || H == 512) && I >= 256 && (I % 32) == 0,
+                   "lstm_weight_grads: needs H in {256, 512} and I >= 256, a multiple of 32 (B=%d T=%d I=%d H=%d)", B, T, I, H);
+    RCNN_CHECK_ARG(dG && x && hcat && dwih && dwhh, "lstm_weight_grads: null pointer");
+    RCNN_CHECK_ARG(((uintptr_t)dG % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)hcat % 16) == 0 &&
+                   ((uintptr_t)dwih % 16) == 0 && ((uintptr_t)dwhh % 16) == 0, "lstm_weight_grads: 16-byte aligned buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int H4 = 4 * H;
+    if (!accumulate) {
+        RCNN_CUDA(cudaMemsetAsync(dwih, 0, sizeof(float) * 2 * (size_t)H4 * I, s));
+        RCNN_CUDA(cudaMemsetAsync(dwhh, 0, sizeof(float) * 2 * (size_t)H4 * H, s));
+    }
+    auto out_map = [&](CUtensorMap *td, float *D, int N) {   // (col in block, gate, unit, 32-column block, direction)
+        const uint64_t dims[5] = {32, 4, (uint64_t)H, (uint64_t)(N / 32), 2};
+        const uint64_t strides[4] = {(uint64_t)H * N * 4, (uint64_t)N * 4, 128, (uint64_t)H4 * N * 4};
+        const uint32_t box[5] = {32, 4, 8, 2, 1};
+        return make_tmap_nd(td, D, 4, 5, dims, strides, box, 1);
+    };
+    CUtensorMap ta, tb, td;
+    // dW_ih[d] = dG_d^T x: flat K = B*T rows, both directions read the same x (b_gcols = 0)
+    const uint64_t K = (uint64_t)B * T;
+    int rc = make_tmap_3d(&ta, dG, 2, 1, K, 8ull * H, K * 16ull * H, 16ull * H, 1, BK, 64, 1);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tb, x, 2, 1, K, (uint64_t)I, K * 2ull * I, 2ull * I, 1, BK, 64, 1);
+    if (rc) return rc;
+    rc = out_map(&td, dwih, I);
+    if (rc) return rc;
+    const int tkb = (int)((K + BK - 1) / BK);
+    const AtbSeq flat = {tkb, {0, 0}, 1};
+    rc = launch_atb_pair(ta, tb, td, H4, I, tkb, 2, H4, 0, flat, s);
+    if (rc) return rc;
+    // dW_hh[d] = dG_d^T h_d(t -/+ 1): K runs over (b, t) with the h rows shifted inside each sequence
+    rc = make_tmap_3d(&ta, dG, 2, (uint64_t)B, (uint64_t)T, 8ull * H, (uint64_t)T * 16ull * H, 16ull * H, 1, BK, 64, 1);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tb, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 4ull * H, 4ull * H, 1, BK, 64, 1);
+    if (rc) return rc;
+    rc = out_map(&td, dwhh, H);
+    if (rc) return rc;
+    const int cps = (T + BK - 1) / BK;
+    const AtbSeq seq = {cps, {-1, 1}, 1};
+    return launch_atb_pair(ta, tb, td, H4, H, B * cps, 2, H4, H, seq, s);
 }

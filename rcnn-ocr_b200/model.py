@@ -80,10 +80,13 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx_dtype = torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32
             dx = ops.gemm_bf16(dG2, packed.wih_pt, None, dx_dtype).view(B, T, I).to(ctx.x_dtype)
-        dwih_p = ops.gemm_bf16_atb(dG2, xb.view(BT, I))                # [8H, I] = dG^T x
-        hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
-        dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
-        g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
+        if ops.weight_grads_supported(I, H, T):
+            g = ops.lstm_weight_grads(dG, xb, hcat, db_p, B, T, I, H)  # torch layout, no h_prev copy / unpack pass
+        else:
+            dwih_p = ops.gemm_bf16_atb(dG2, xb.view(BT, I))                # [8H, I] = dG^T x
+            hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
+            dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
+            g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
         return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None, None)
 
 
@@ -151,12 +154,13 @@ class BidirectionalLSTM(nn.Module):
                                     self.out_dtype, save, prepared)
 
 
-def make_enc_rnn(enc_dim: int, hidden_size: int) -> nn.Sequential:
+def make_enc_rnn(enc_dim: int, hidden_size: int, out_dtype: torch.dtype = torch.float32) -> nn.Sequential:
     """RCNN.enc_rnn (model/model.py:195-198): two stacked blocks, state-dict keys '0.*', '1.*'."""
     # the first block hands bf16 straight to the second (which would cast its input anyway); the
-    # stack's output stays fp32 like the reference's
+    # stack's output stays fp32 like the reference's unless the caller feeds it to another bf16
+    # GEMM (the CTC head) and asks for the hand-off format: same rounding, one cast kernel fewer
     return nn.Sequential(BidirectionalLSTM(enc_dim, hidden_size, hidden_size, out_dtype=torch.bfloat16),
-                         BidirectionalLSTM(hidden_size, hidden_size, hidden_size))
+                         BidirectionalLSTM(hidden_size, hidden_size, hidden_size, out_dtype=out_dtype))
 
 
 class _LinearFn(torch.autograd.Function):
@@ -186,7 +190,8 @@ class _LinearFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wt = ops.transpose_bf16(wb)                        # [K, N]
-            dx = ops.gemm_bf16(dob, wt, None, torch.float32).view(*dout.shape[:-1], K).to(ctx.x_dtype)
+            dx_dtype = torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32
+            dx = ops.gemm_bf16(dob, wt, None, dx_dtype).view(*dout.shape[:-1], K).to(ctx.x_dtype)
         dw = ops.gemm_bf16_atb(dob, xb)                         # [N, K] = dout^T x
         db = ops.colsum_bf16(dob) if ctx.has_bias else None
         return dx, dw, db, None
@@ -295,7 +300,9 @@ class RCNN(nn.Module):
         self.ctc_blank = 0
         self.num_ctc_classes = num_classes + 1
         self.cnn = SEResNet31(3, 512, dropblock_p=dropblock_p, dropblock_block_size=dropblock_block_size)
-        self.enc_rnn = make_enc_rnn(self.cnn.out_channels, hidden_size)
+        # CTC: the head consumes bf16 (it would cast anyway); attention: fp32 like the reference's encoder output
+        self.enc_rnn = make_enc_rnn(self.cnn.out_channels, hidden_size,
+                                    out_dtype=torch.bfloat16 if decoder == "ctc" else torch.float32)
         self.enc_dropout = nn.Dropout(enc_dropout_p)
         self.ctc_head = CTCHead(hidden_size, self.num_ctc_classes)
         # decoder="attention": the reference's own decoder (model/model.py:204-214), inference path on the device;
@@ -307,15 +314,21 @@ class RCNN(nn.Module):
                                   eos_id=eos_id, pad_id=pad_id, blank_id=blank_id, dropout_p=0.1, sampling_prob=0.0)
 
     def encode_features(self, feats: torch.Tensor) -> torch.Tensor:
-        """[B, T, 512] feature columns -> [B, T, H] (the hot path without the backbone)."""
+        """[B, T, 512] feature columns -> [B, T, H] fp32 (the hot path without the backbone)."""
+        return self._encode_features(feats).float()
+
+    def _encode_features(self, feats: torch.Tensor) -> torch.Tensor:
+        # bf16 when the CTC head follows (its GEMM operand format), fp32 for the attention decoder
         return self.enc_dropout(self.enc_rnn(feats))
 
+    def _features(self, x: torch.Tensor) -> torch.Tensor:
+        return self.cnn(x).mean(dim=2).permute(0, 2, 1)   # AdaptiveAvgPool2d((1, None)) + squeeze(2): [B, W', C]
+
     def encode(self, x: torch.Tensor) -> torch.Tensor:
-        f = self.cnn(x).mean(dim=2)          # AdaptiveAvgPool2d((1, None)) + squeeze(2): [B, C, W']
-        return self.encode_features(f.permute(0, 2, 1))
+        return self.encode_features(self._features(x))
 
     def forward(self, x, text=None, is_train=True, batch_max_length=25):
-        enc = self.encode(x)
+        enc = self._encode_features(self._features(x))
         if self.attn is not None:
             return self.attn(enc, text=text, is_train=is_train, batch_max_length=batch_max_length)
         return self.ctc_head(enc)

@@ -267,6 +267,30 @@ def lstm_unpack_grads(dwih_p, dwhh_p, db_p, I: int, H: int):
     return outs
 
 
+def weight_grads_supported(I: int, H: int, T: int) -> bool:
+    """rcnn_lstm_weight_grads: the CTA-pair shapes; K chunks are 64 steps of ONE sequence, so T should fill them."""
+    return H in (256, 512) and I >= 256 and I % 32 == 0 and (-(-T // 64) * 64) <= 1.25 * T
+
+
+def lstm_weight_grads(dG: torch.Tensor, xb: torch.Tensor, hcat: torch.Tensor, db_p: torch.Tensor, B: int, T: int, I: int, H: int):
+    """dW_ih, dW_hh, db of one block straight in nn.LSTM's layout: two GEMM launches (h_{t-/+1} read from hcat
+    through a shifted tensor map, rows scattered to gate-major order by the reduce-add map) and one small copy
+    for the biases.  Returns the eight gradients in ``_LSTMParameters.ordered()`` order."""
+    assert dG.dtype == torch.bfloat16 and dG.is_contiguous() and dG.numel() == B * T * 8 * H
+    assert xb.dtype == torch.bfloat16 and xb.is_contiguous() and hcat.dtype == torch.bfloat16 and hcat.is_contiguous()
+    dev = dG.device
+    with torch.cuda.device(dev):
+        n_ih, n_hh = 2 * 4 * H * I, 2 * 4 * H * H
+        buf = torch.zeros((n_ih + n_hh,), dtype=torch.float32, device=dev)        # one fill for both outputs
+        dwih, dwhh = buf[:n_ih].view(2, 4 * H, I), buf[n_ih:].view(2, 4 * H, H)
+        rc = _lib.lib().rcnn_lstm_weight_grads(dG.data_ptr(), xb.data_ptr(), hcat.data_ptr(), B, T, I, H,
+                                               dwih.data_ptr(), dwhh.data_ptr(), 1, _lib.stream_ptr())
+        _lib.check(rc, "rcnn_lstm_weight_grads")
+        # packed bias order (unit-major, gate-minor) -> gate-major, one copy each for b_ih and b_hh (same values)
+        db = db_p.view(2, 1, H, 4).permute(0, 1, 3, 2).expand(2, 2, 4, H).reshape(2, 2, 4 * H)
+    return [dwih[0], dwhh[0], db[0, 0], db[0, 1], dwih[1], dwhh[1], db[1, 0], db[1, 1]]
+
+
 def launch_count() -> int:
     """Kernels launched by the library so far in this process."""
     return int(_lib.lib().rcnn_launch_count())

@@ -177,3 +177,28 @@ def test_eval_mode_weight_cache_tracks_parameter_updates():
         blk.train()
         assert blk._prepared is None
         assert torch.equal(blk(x), y2)
+
+
+@pytest.mark.parametrize("B,T,I,H", [(3, 64, 256, 256), (5, 80, 512, 256), (7, 128, 288, 512), (130, 5, 256, 256)])
+def test_weight_grads_in_torch_layout_exact(B, T, I, H):
+    """rcnn_lstm_weight_grads (h_{t-/+1} through a shifted tensor map, rows scattered to nn.LSTM's gate-major order
+    by the reduce-add map) on small integers: equal to the fp32 matmuls bit for bit, for T below, equal to and
+    above the 64-step K chunk."""
+    g = torch.Generator(device="cuda").manual_seed(B * T)
+    dG = torch.randint(-2, 3, (B, T, 8 * H), device="cuda", generator=g).bfloat16()
+    x = torch.randint(-2, 3, (B, T, I), device="cuda", generator=g).bfloat16()
+    hcat = torch.randint(-2, 3, (B, T, 2 * H), device="cuda", generator=g).bfloat16()
+    db_p = torch.randn(8 * H, device="cuda", generator=g)
+    got = ops.lstm_weight_grads(dG, x, hcat, db_p, B, T, I, H)
+    hprev = torch.zeros_like(hcat)
+    hprev[:, 1:, :H] = hcat[:, :-1, :H]
+    hprev[:, :-1, H:] = hcat[:, 1:, H:]
+    assert torch.equal(ops.lstm_hprev(hcat), hprev)
+    for d in range(2):
+        # packed row (unit u, gate k) = 4 u + k  ->  torch row k H + u
+        dGd = dG[..., d * 4 * H:(d + 1) * 4 * H].float().reshape(B * T, H, 4).permute(0, 2, 1).reshape(B * T, 4 * H)
+        assert torch.equal(got[4 * d + 0], dGd.t() @ x.float().reshape(B * T, I))
+        assert torch.equal(got[4 * d + 1], dGd.t() @ hprev[..., d * H:(d + 1) * H].float().reshape(B * T, H))
+        want_b = db_p[d * 4 * H:(d + 1) * 4 * H].view(H, 4).t().reshape(4 * H)
+        assert torch.equal(got[4 * d + 2], want_b) and torch.equal(got[4 * d + 3], want_b)
+        assert got[4 * d + 2].data_ptr() != got[4 * d + 3].data_ptr()
