@@ -158,6 +158,12 @@ size_t rcnn_lstm_packed_bytes(int I, int H);
 int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
                            const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
                            int I, int H, void *packed, rcnn_stream_t stream);
+/* parts: 1 = the views the forward pass reads (wih_p, bias_p, whh_p), 2 = the transposed views of the backward
+ * pass (whh_pt, wih_pt), 3 = both: lets a caller convert the backward views on another stream while the forward
+ * recurrence already runs. */
+int rcnn_lstm_pack_weights_parts(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
+                                 const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
+                                 int I, int H, void *packed, int parts, rcnn_stream_t stream);
 int rcnn_lstm_forward(const void *xp, const void *whh_p, int B, int T, int H, void *hcat,
                       void *gates_save, float *c_save, rcnn_stream_t stream);
 

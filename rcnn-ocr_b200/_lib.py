@@ -57,6 +57,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_lstm_forward_fused.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
     L.rcnn_lstm_weight_grads.restype = i
     L.rcnn_lstm_weight_grads.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, i, vp]
+    L.rcnn_lstm_pack_weights_parts.restype = i
+    L.rcnn_lstm_pack_weights_parts.argtypes = [vp] * 8 + [i, i, vp, i, vp]
     L.rcnn_launch_count.restype = ctypes.c_ulonglong
     L.rcnn_debug_timeline.restype = i
     L.rcnn_debug_timeline.argtypes = [vp]

@@ -23,7 +23,7 @@
 // on a 5-D tensor map of the exchange buffer [parity x group][src CTA][dst CTA][4][1 KB]: the drained
 // accumulators are staged in shared memory and stored, the 16 partials of the CTA's own 32 units are
 // loaded back into the same shared-memory area the next step and summed by the cell warps.
-//   warp 0      loads W once; per step: polls the group counter (relaxed gpu-scope loads), TMA-loads the
+//   warp 0      loads W once; per step: polls the group counter (acquire gpu-scope loads), TMA-loads the
 //               partials, later TMA-stores this CTA's partials, waits for their completion and
 //               releases the counter (the only gpu-scope fence of the step is this one thread's)
 //   warp 1      MMA issuer (one elected thread)
@@ -67,22 +67,24 @@ __device__ __forceinline__ float tanh_fast_b(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Publishing a step: the partials were written by TMA stores of this thread (complete: cp.async.bulk.wait_group 0,
+// then fence.proxy.async); the counter increment must be a gpu-scope RELEASE and the poll an ACQUIRE.  A relaxed
+// increment after the completed stores is NOT enough on this part: completion makes the writes visible to the
+// issuing thread only, and readers on other SMs were observed (scripts/stress_block.py, B=4736 T=3 H=128 under
+// RCNN_POISON=1) to fetch the previous contents of the slot after seeing the counter.
 __device__ __forceinline__ void red_release_gpu_inc_b(unsigned int *p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ void red_relaxed_gpu_inc_b(unsigned int *p) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_relaxed_gpu_b(const unsigned int *p) {
+__device__ __forceinline__ unsigned int ld_acquire_gpu_b(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // Bounded spin on the group counter: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void wait_counter_b(const unsigned int *p, unsigned int target) {
-    if (ld_relaxed_gpu_b(p) >= target) return;
+    if (ld_acquire_gpu_b(p) >= target) return;
     const long long t0 = clock64();
-    while (ld_relaxed_gpu_b(p) < target) {
+    while (ld_acquire_gpu_b(p) < target) {
         if (clock64() - t0 > 4000000000LL) {
             printf("rcnn-ocr_b200: lstm_bwd group counter timed out (block %d)\n", blockIdx.x);
             __trap();
@@ -182,10 +184,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         }
                         tma_store_wait<0>();                      // written, not merely read out of shared memory
                         TL_MARK(1);
-                        // the partials are in L2 and nothing else of this thread is outstanding: a relaxed increment
-                        // publishes them (readers poll relaxed and fetch with TMA, straight from L2)
+                        // the partials are complete for this thread; the release increment makes them visible to the
+                        // group (readers poll with acquire loads and fetch with TMA)
                         fence_proxy_async_global();
-                        red_relaxed_gpu_inc_b(counter);
+                        red_release_gpu_inc_b(counter);
                         TL_MARK(6);
                         ++npub;
                     }
@@ -419,15 +421,24 @@ __global__ void colsum_bf16_v8_kernel(const uint4 *__restrict__ src, long long l
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     if (c8 < cols8) {
-        for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
-            const uint4 v = ld_nc_v4(src + r * ld8 + c8);
+        const long long step = (long long)gridDim.y * 8;
+        long long r = (long long)blockIdx.y * 8 + threadIdx.y;
+        auto add = [&](const uint4 &v) {
             const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 acc[2 * k] += __uint_as_float(w[k] << 16);
                 acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
             }
+        };
+        for (; r + 7 * step < rows; r += 8 * step) {       // eight independent 128-bit loads in flight per thread
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ld_nc_v4(src + (r + j * step) * ld8 + c8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) add(v[j]);
         }
+        for (; r < rows; r += step) add(ld_nc_v4(src + r * ld8 + c8));
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) part[threadIdx.y][threadIdx.x][k] = acc[k];
@@ -577,7 +588,9 @@ extern "C" int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int c
     RCNN_CHECK_ARG(src, "colsum: null pointer");
     if (cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)src % 16) == 0) {
         const int cols8 = cols / 8;
-        const long long want = (2LL * num_sms() * 32) / cols8 + 1;   // ~2 blocks per SM in total
+        // ~1 block of 256 threads per SM: the column sums end in same-address atomics (one per block and
+        // column), which serialise in L2 -- few fat blocks with deep loads beat many thin ones
+        const long long want = ((long long)num_sms() * 32) / cols8 + 1;
         const long long maxy = (rows + 7) / 8;
         dim3 block(32, 8), grid((cols8 + 31) / 32, (unsigned)(want < maxy ? want : maxy));
         colsum_bf16_v8_kernel<<<grid, block, 0, s>>>((const uint4 *)src, ld / 8, rows, cols8, out);

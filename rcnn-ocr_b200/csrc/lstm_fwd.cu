@@ -59,14 +59,16 @@ struct FwdParams {
 };
 #define TL_MARK(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
 
-__device__ __forceinline__ void red_relaxed_gpu_inc(unsigned int *p) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+// Publishing h_t: written by a TMA store of this thread (complete: cp.async.bulk.wait_group 0 + fence.proxy.async);
+// the counter increment is a gpu-scope RELEASE and the poll an ACQUIRE.  A relaxed increment is not enough:
+// completion makes the writes visible to the issuing thread only (see lstm_bwd.cu, where readers were observed to
+// fetch the previous contents of the exchange slot after seeing the counter).
+__device__ __forceinline__ void red_release_gpu_inc(unsigned int *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-// The counter is only polled; what it guards (h_{t-1}) is read by TMA (async proxy, straight from L2), so a
-// relaxed gpu-scope load + fence.proxy.async is enough and spares the L1 invalidate of an acquire per poll.
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // Bounded spin on the group counter: a protocol bug traps instead of hanging the GPU.
@@ -209,8 +211,8 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             uint32_t wphase = 0, hphase = 0, sphase = 0;
             tma_prefetch_desc(&tmHs);
             // h_t of this CTA's 32 units leaves by ONE TMA store (staged by the cell warps in the idle h tile);
-            // its completion is awaited by this thread alone and followed by a relaxed counter increment: no
-            // gpu-scope fence over 256 threads' stores in the step's critical path.
+            // its completion is awaited by this thread alone and followed by ONE release increment of the counter
+            // (instead of a gpu-scope fence after 256 threads' stores).
             auto publish = [&](int dir, int b0, int s) {
                 const int t = dir ? T - 1 - s : s;
                 mbar_wait(h_staged, sphase);
@@ -219,7 +221,7 @@ lstm_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 tma_store_commit();
                 tma_store_wait<0>();
                 fence_proxy_async_global();
-                red_relaxed_gpu_inc(counter);
+                red_release_gpu_inc(counter);
                 TL_MARK(6);
             };
             for (int item = group; item < p.nitems; item += p.ngroups) {

@@ -41,18 +41,19 @@ struct FxParams {
     unsigned int *sync;   // [ngroups] zeroed before the launch
 };
 
-__device__ __forceinline__ void red_relaxed_gpu_inc_x(unsigned int *p) {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+// release / acquire at gpu scope around the TMA-stored h_t: see lstm_fwd.cu
+__device__ __forceinline__ void red_release_gpu_inc_x(unsigned int *p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_relaxed_gpu_x(const unsigned int *p) {
+__device__ __forceinline__ unsigned int ld_acquire_gpu_x(const unsigned int *p) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void wait_counter_x(const unsigned int *p, unsigned int target) {
-    if (ld_relaxed_gpu_x(p) >= target) return;
+    if (ld_acquire_gpu_x(p) >= target) return;
     const long long t0 = clock64();
-    while (ld_relaxed_gpu_x(p) < target) {
+    while (ld_acquire_gpu_x(p) < target) {
         if (clock64() - t0 > 4000000000LL) {
             printf("rcnn-ocr_b200: lstm_fwdx group counter timed out (block %d)\n", blockIdx.x);
             __trap();
@@ -219,7 +220,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     }
                     umma_commit(&tmem_full[par]);
                     if (s + 1 < T) x_part(par ^ 1);   // runs while step s is in its cell / publish / counter phases
-                    // publish h_t: staged by the cell warps in the idle h tile, one TMA store, relaxed counter increment
+                    // publish h_t: staged by the cell warps in the idle h tile, one TMA store, release increment of the counter
                     const int t = dir ? T - 1 - s : s;
                     mbar_wait(h_staged, sphase);
                     sphase ^= 1;
@@ -227,7 +228,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     tma_store_commit();
                     tma_store_wait<0>();
                     fence_proxy_async_global();
-                    red_relaxed_gpu_inc_x(counter);
+                    red_release_gpu_inc_x(counter);
                 }
             }
         }

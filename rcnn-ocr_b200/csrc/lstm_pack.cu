@@ -182,8 +182,15 @@ extern "C" size_t rcnn_lstm_packed_bytes(int I, int H) {
 extern "C" int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
                                       const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
                                       int I, int H, void *packed, rcnn_stream_t stream) {
+    return rcnn_lstm_pack_weights_parts(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, I, H, packed, 3, stream);
+}
+
+extern "C" int rcnn_lstm_pack_weights_parts(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
+                                            const float *w_ih_r, const float *w_hh_r, const float *b_ih_r, const float *b_hh_r,
+                                            int I, int H, void *packed, int parts, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(I > 0 && H > 0 && H % 32 == 0, "lstm_pack: bad sizes I=%d H=%d", I, H);
+    RCNN_CHECK_ARG(parts >= 1 && parts <= 3, "lstm_pack: parts must be 1 (forward views), 2 (transposed views) or 3");
     RCNN_CHECK_ARG(w_ih_f && w_hh_f && b_ih_f && b_hh_f && w_ih_r && w_hh_r && b_ih_r && b_hh_r && packed,
                    "lstm_pack: null pointer");
     PackArgs a;
@@ -197,12 +204,16 @@ extern "C" int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, 
     a.whh_p = (__nv_bfloat16 *)p;  p += H8 * H * 2;
     a.whh_pt = (__nv_bfloat16 *)p; p += H8 * H * 2;
     a.wih_pt = (__nv_bfloat16 *)p;
-    lstm_pack_rows_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
-    RCNN_LAUNCH_CHECK("lstm_pack_rows_kernel");
-    const int kmax = I > H ? I : H;
-    dim3 grid((kmax + 31) / 32, 4 * H / 64, 4), block(32, 8);
-    lstm_pack_transposed_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
-    RCNN_LAUNCH_CHECK("lstm_pack_transposed_kernel");
+    if (parts & 1) {
+        lstm_pack_rows_kernel<<<(unsigned)H8, 128, 0, (cudaStream_t)stream>>>(a);
+        RCNN_LAUNCH_CHECK("lstm_pack_rows_kernel");
+    }
+    if (parts & 2) {
+        const int kmax = I > H ? I : H;
+        dim3 grid((kmax + 31) / 32, 4 * H / 64, 4), block(32, 8);
+        lstm_pack_transposed_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);
+        RCNN_LAUNCH_CHECK("lstm_pack_transposed_kernel");
+    }
     return RCNN_OK;
 }
 

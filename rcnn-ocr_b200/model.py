@@ -16,6 +16,7 @@ fp32 (north_star tolerance: 1e-2 absolute on outputs against the fp32/fp64 refer
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -27,6 +28,38 @@ _SUPPORTED_H = (64, 128, 256, 512)
 
 def _cast2d(w: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16_3d(w.detach().unsqueeze(0))[0]
+
+
+class _Prepared:
+    """bf16 kernel views of one block's parameters.  ``rows_event`` / ``rest_event``: when the views were converted
+    on the prefetch stream (EncRNN.forward), the events the consuming stream waits on before the recurrence
+    (wih_p, bias_p, whh_p) and before the Linear / the backward pass (lin_wb, lin_wt, whh_pt, wih_pt)."""
+    __slots__ = ("packed", "lin_wb", "lin_wt", "rows_event", "rest_event")
+
+    def __init__(self, packed, lin_wb, lin_wt=None, rows_event=None, rest_event=None):
+        self.packed, self.lin_wb, self.lin_wt = packed, lin_wb, lin_wt
+        self.rows_event, self.rest_event = rows_event, rest_event
+
+    def wait_rows(self):
+        if self.rows_event is not None:
+            torch.cuda.current_stream().wait_event(self.rows_event)
+            self.rows_event = None
+
+    def wait_rest(self):
+        if self.rest_event is not None:
+            torch.cuda.current_stream().wait_event(self.rest_event)
+            self.rest_event = None
+
+
+_PREFETCH = os.environ.get("RCNN_PREFETCH", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 class _BiLSTMBlockFn(torch.autograd.Function):
@@ -42,9 +75,10 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         H = w_hh_f.shape[1]
         O = lin_w.shape[0]
         if prepared is None:    # bf16 kernel views of the parameters (cached by the module in eval mode)
-            prepared = (ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r), _cast2d(lin_w))
-        packed, lin_wb = prepared
+            prepared = _Prepared(ops.lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r), _cast2d(lin_w))
+        packed, lin_wb = prepared.packed, prepared.lin_wb
         xb = ops.cast_bf16_3d(x)
+        prepared.wait_rows()
         if ops.fused_forward_supported(I, H):
             # the input projection runs inside the recurrent kernel (no xp tensor)
             hcat, gates, csave = ops.lstm_forward_fused(xb, packed, B, T, save)
@@ -52,10 +86,12 @@ class _BiLSTMBlockFn(torch.autograd.Function):
             xp = ops.gemm_bf16(xb.view(B * T, I), packed.wih_p, packed.bias_p, torch.float16)
             hcat, gates, csave = ops.lstm_forward(xp, packed, B, T, save)
             del xp
+        prepared.wait_rest()
         out = ops.gemm_bf16(hcat.view(B * T, 2 * H), lin_wb, lin_b.detach().float().contiguous(), out_dtype)
         if save:
             ctx.save_for_backward(xb, hcat, gates, csave, lin_wb)
             ctx.packed = packed
+            ctx.lin_wt = prepared.lin_wt
             ctx.dims = (B, T, I, H, O)
             ctx.x_dtype = x.dtype
         return out.view(B, T, O)
@@ -69,7 +105,7 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         dob = ops.cast_bf16_3d(dout)                                   # [B,T,O] bf16
         dob2 = dob.view(BT, O)
         # ---- linear: dhcat = dout W, dW = dout^T hcat, db = colsum(dout) --------------------
-        lin_wt = ops.transpose_bf16(lin_wb)                            # [2H, O] (weights only: small)
+        lin_wt = ctx.lin_wt if ctx.lin_wt is not None else ops.transpose_bf16(lin_wb)   # [2H, O] (weights only: small)
         dhcat = ops.gemm_bf16(dob2, lin_wt, None, torch.float32).view(B, T, 2 * H)
         d_lin_w = ops.gemm_bf16_atb(dob2, hcat.view(BT, 2 * H))        # [O, 2H] = dout^T hcat
         d_lin_b = ops.colsum_bf16(dob2)
@@ -130,7 +166,8 @@ class BidirectionalLSTM(nn.Module):
         self.rnn = _LSTMParameters(input_size, hidden_size)
         self.linear = nn.Linear(hidden_size * 2, output_size)
         self.out_dtype = out_dtype
-        self._prepared = None     # (key, (packed weights, bf16 linear weight)) while the module is in eval mode
+        self._prepared = None     # (key, _Prepared) while the module is in eval mode
+        self._prefetched = None   # _Prepared handed over by EncRNN.forward for the next call (training)
 
     def _prepared_weights(self):
         """eval() mode: the packed bf16 views are rebuilt only when a parameter was replaced or
@@ -139,8 +176,27 @@ class BidirectionalLSTM(nn.Module):
         key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
         if self._prepared is None or self._prepared[0] != key:
             with torch.no_grad():
-                self._prepared = (key, (ops.lstm_pack(*self.rnn.ordered()), _cast2d(self.linear.weight)))
+                self._prepared = (key, _Prepared(ops.lstm_pack(*self.rnn.ordered()), _cast2d(self.linear.weight)))
         return self._prepared[1]
+
+    def prefetch_weights(self, first: bool) -> "_Prepared":
+        """Training: convert this block's parameters for the kernels on the prefetch stream, concurrently with
+        whatever the current stream runs next (the recurrent kernels leave 20 SMs idle).  ``first``: the block
+        whose recurrence starts right away -- its forward views are converted on the current stream."""
+        main = torch.cuda.current_stream()
+        side = _side_stream(self.linear.weight.device)
+        with torch.no_grad():
+            packed = ops.lstm_pack(*self.rnn.ordered(), parts=1) if first else None
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                packed = ops.lstm_pack(*self.rnn.ordered(), parts=2 if first else 3, into=packed)
+                lin_wb = _cast2d(self.linear.weight)
+                lin_wt = ops.transpose_bf16(lin_wb)
+                ev = side.record_event()
+            packed.blob.record_stream(side if first else main)
+            lin_wb.record_stream(main)
+            lin_wt.record_stream(main)
+        return _Prepared(packed, lin_wb, lin_wt, rows_event=None if first else ev, rest_event=ev)
 
     def train(self, mode: bool = True):
         if mode:
@@ -149,9 +205,23 @@ class BidirectionalLSTM(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         save = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        prepared = self._prepared_weights() if (not self.training and x.is_cuda) else None
+        prepared = self._prefetched
+        self._prefetched = None
+        if prepared is None and not self.training and x.is_cuda:
+            prepared = self._prepared_weights()
         return _BiLSTMBlockFn.apply(x, *self.rnn.ordered(), self.linear.weight, self.linear.bias,
                                     self.out_dtype, save, prepared)
+
+
+class EncRNN(nn.Sequential):
+    """nn.Sequential of BidirectionalLSTM blocks (same state-dict keys); in training the parameter conversions of
+    all blocks but the first block's forward views run on a second stream, under the first recurrence."""
+
+    def forward(self, x):
+        if _PREFETCH and self.training and x.is_cuda and torch.is_grad_enabled():
+            for i, blk in enumerate(self):
+                blk._prefetched = blk.prefetch_weights(first=(i == 0))
+        return super().forward(x)
 
 
 def make_enc_rnn(enc_dim: int, hidden_size: int, out_dtype: torch.dtype = torch.float32) -> nn.Sequential:
@@ -159,8 +229,8 @@ def make_enc_rnn(enc_dim: int, hidden_size: int, out_dtype: torch.dtype = torch.
     # the first block hands bf16 straight to the second (which would cast its input anyway); the
     # stack's output stays fp32 like the reference's unless the caller feeds it to another bf16
     # GEMM (the CTC head) and asks for the hand-off format: same rounding, one cast kernel fewer
-    return nn.Sequential(BidirectionalLSTM(enc_dim, hidden_size, hidden_size, out_dtype=torch.bfloat16),
-                         BidirectionalLSTM(hidden_size, hidden_size, hidden_size, out_dtype=out_dtype))
+    return EncRNN(BidirectionalLSTM(enc_dim, hidden_size, hidden_size, out_dtype=torch.bfloat16),
+                  BidirectionalLSTM(hidden_size, hidden_size, hidden_size, out_dtype=out_dtype))
 
 
 class _LinearFn(torch.autograd.Function):

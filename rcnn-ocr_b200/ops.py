@@ -1,11 +1,19 @@
 """Thin tensor-level wrappers over the C ABI (no autograd; see model.py for the modules)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 
 _OUT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+# RCNN_POISON=1 (debugging aid): fill the buffers the recurrent kernels exchange data through (hcat, the backward
+# workspace) with NaN patterns before the launch, so that a read that overtakes its write shows up as NaN
+# instead of as the previous call's (usually identical) values.  scripts/stress_*.py
+_POISON = os.environ.get("RCNN_POISON", "0") == "1"
 
 
 def _repitch(m: torch.Tensor) -> torch.Tensor:
@@ -103,7 +111,10 @@ class PackedLSTMWeights:
         self.wih_pt = take(H8 * I * 2, torch.bfloat16, (I, H8))
 
 
-def lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r) -> PackedLSTMWeights:
+def lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, parts: int = 3,
+              into: PackedLSTMWeights | None = None) -> PackedLSTMWeights:
+    """parts: 1 = forward views, 2 = transposed (backward) views, 3 = both; ``into`` fills an existing blob
+    (the two halves may be converted on different streams)."""
     ts = [w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r]
     for t in ts:
         _lib.require_cuda(t, "LSTM parameter")
@@ -113,10 +124,10 @@ def lstm_pack(w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r) ->
     L = _lib.lib()
     nbytes = L.rcnn_lstm_packed_bytes(I, H)
     with torch.cuda.device(ts[0].device):
-        blob = torch.empty((nbytes,), dtype=torch.uint8, device=ts[0].device)
-        rc = L.rcnn_lstm_pack_weights(*[t.data_ptr() for t in ts], I, H, blob.data_ptr(), _lib.stream_ptr())
+        blob = into.blob if into is not None else torch.empty((nbytes,), dtype=torch.uint8, device=ts[0].device)
+        rc = L.rcnn_lstm_pack_weights_parts(*[t.data_ptr() for t in ts], I, H, blob.data_ptr(), parts, _lib.stream_ptr())
         _lib.check(rc, "rcnn_lstm_pack_weights")
-    return PackedLSTMWeights(blob, I, H)
+    return into if into is not None else PackedLSTMWeights(blob, I, H)
 
 
 def cast_bf16_3d(x: torch.Tensor) -> torch.Tensor:
@@ -162,6 +173,8 @@ def lstm_forward(xp: torch.Tensor, packed: PackedLSTMWeights, B: int, T: int, sa
     with torch.cuda.device(dev):
         if hcat is None:
             hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
+            if _POISON:
+                hcat.view(torch.int16).fill_(-1)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float16, device=dev) if save else None
         csave = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
         rc = _lib.lib().rcnn_lstm_forward(xp.data_ptr(), packed.whh_p.data_ptr(), B, T, H, hcat.data_ptr(),
@@ -179,6 +192,8 @@ def lstm_forward_fused(xb: torch.Tensor, packed: PackedLSTMWeights, B: int, T: i
     dev = xb.device
     with torch.cuda.device(dev):
         hcat = torch.empty((B, T, 2 * H), dtype=torch.bfloat16, device=dev)
+        if _POISON:
+            hcat.view(torch.int16).fill_(-1)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float16, device=dev) if save else None
         csave = torch.empty((2, T, B, H), dtype=torch.float32, device=dev) if save else None
         rc = _lib.lib().rcnn_lstm_forward_fused(xb.data_ptr(), packed.wih_p.data_ptr(), packed.bias_p.data_ptr(),
@@ -204,6 +219,8 @@ def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int
         db = torch.empty((8 * H,), dtype=torch.float32, device=dhcat.device)
         nws = int(_lib.lib().rcnn_lstm_backward_workspace_bytes(B, T, H))
         ws = torch.empty((max(nws, 1),), dtype=torch.uint8, device=dhcat.device)
+        if _POISON:
+            ws.fill_(0xFF)
         rc = _lib.lib().rcnn_lstm_backward(packed.whh_pt.data_ptr(), gates.data_ptr(), csave.data_ptr(),
                                            dhcat.data_ptr(), B, T, H, dG.data_ptr(), db.data_ptr(), ws.data_ptr(), nws,
                                            _lib.stream_ptr())
