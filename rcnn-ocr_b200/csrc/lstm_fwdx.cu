@@ -38,6 +38,7 @@ struct FxParams {
     const float *bias;    // [2*4H] b_ih + b_hh, packed order
     float *csave;         // [2, T, B, H] (training only)
     __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
+    __nv_bfloat16 *hcat;  // [B, T, 2H]
     unsigned int *sync;   // [ngroups] zeroed before the launch
 };
 
@@ -65,7 +66,7 @@ template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
-                 const __grid_constant__ CUtensorMap tmHs, const FxParams p) {
+                 const FxParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int H = p.H, T = p.T, I = p.I;
@@ -163,7 +164,6 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             int cur_dir = -1;
             unsigned int xn = 0, wn = 0;
             uint32_t hphase = 0, sphase = 0;
-            tma_prefetch_desc(&tmHs);
             for (int item = group; item < p.nitems; item += p.ngroups) {
                 const int dir = item & 1, b0 = (item >> 1) * NS;
                 if (dir != cur_dir) {
@@ -220,14 +220,10 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     }
                     umma_commit(&tmem_full[par]);
                     if (s + 1 < T) x_part(par ^ 1);   // runs while step s is in its cell / publish / counter phases
-                    // publish h_t: staged by the cell warps in the idle h tile, one TMA store, release increment of the counter
-                    const int t = dir ? T - 1 - s : s;
+                    // publish h_t: the cell warps stored it to hcat themselves and arrived on h_staged; ONE gpu-scope
+                    // release (cumulative over what the barrier ordered before it) makes it visible to the group
                     mbar_wait(h_staged, sphase);
                     sphase ^= 1;
-                    tma_store_3d(&tmHs, h_s, dir * H + 32 * c, t, b0);
-                    tma_store_commit();
-                    tma_store_wait<0>();
-                    fence_proxy_async_global();
                     red_release_gpu_inc_x(counter);
                 }
             }
@@ -267,9 +263,13 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     }
                 }
                 const uint4 hq = cell_update(pre, cst, CL);
-                *reinterpret_cast<uint4 *>(h_s + (size_t)(32 * ch + lane) * 64 + qd * 16) = hq;
+                {   // h_t: 8 units (16 bytes) of sequence 32ch + lane, straight to hcat[b, t, dir*H + 32c + 8qd ..]
+                    const int t = dir ? T - 1 - s : s;
+                    const int b = b0 + 32 * ch + lane;
+                    if (b < p.B)
+                        *reinterpret_cast<uint4 *>(p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + 8 * qd) = hq;
+                }
                 tc_fence_before();
-                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(h_staged);
                 if (SAVE) {
@@ -322,7 +322,7 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     RCNN_CHECK_ARG(x && wih_p && bias_p && whh_p && hcat, "lstm_forward_fused: null pointer");
     RCNN_CHECK_ARG((gates_save == nullptr) == (c_save == nullptr), "lstm_forward_fused: gates_save and c_save go together");
     const bool save = gates_save != nullptr;
-    CUtensorMap twh, twi, th, tx, ths;
+    CUtensorMap twh, twi, th, tx;
     int rc = make_tmap_2d(&twh, whh_p, 2, 8ull * H, (uint64_t)H, (uint64_t)H * 2, GR, LK, 1);
     if (rc) return rc;
     rc = make_tmap_2d(&twi, wih_p, 2, 8ull * H, (uint64_t)I, (uint64_t)I * 2, GR, LK, 1);
@@ -343,12 +343,12 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
         rc = make_tmap_4d(&tx, x, 2, dims, strides, box, 1);
         if (rc) return rc;
     }
-    rc = make_tmap_3d(&ths, hcat, 2, (uint64_t)B, (uint64_t)T, 2ull * H, (uint64_t)T * 2 * H * 2, 2ull * H * 2, NS, 1, 32, 0);
     if (rc) return rc;
     FxParams p;
     p.B = B; p.T = T; p.H = H; p.I = I;
     p.bias = bias_p;
     p.csave = c_save;
+    p.hcat = (__nv_bfloat16 *)hcat;
     p.gsave = (__half *)gates_save;
     const int gsize = H / 32;
     p.nitems = 2 * ((B + NS - 1) / NS);
@@ -372,8 +372,8 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_FWD, s);
-    if (save) RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<true>, twh, twi, th, tx, ths, p));
-    else RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<false>, twh, twi, th, tx, ths, p));
+    if (save) RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<true>, twh, twi, th, tx, p));
+    else RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<false>, twh, twi, th, tx, p));
     count_launch();
     return RCNN_OK;
 }
