@@ -202,3 +202,37 @@ def test_weight_grads_in_torch_layout_exact(B, T, I, H):
         want_b = db_p[d * 4 * H:(d + 1) * 4 * H].view(H, 4).t().reshape(4 * H)
         assert torch.equal(got[4 * d + 2], want_b) and torch.equal(got[4 * d + 3], want_b)
         assert got[4 * d + 2].data_ptr() != got[4 * d + 3].data_ptr()
+
+
+def test_step_exchange_is_ordered_under_poisoned_buffers():
+    """Regression for the release / acquire protocol of the recurrent kernels' step exchange: several work items
+    per CTA group and few, short timesteps (the shape that exposed readers overtaking the TMA-stored partial sums
+    when the counter increment was relaxed).  The exchange buffers are NaN-poisoned before every launch
+    (ops._POISON), so a premature read cannot hide behind the previous call's identical values: hcat, the saved
+    activations and dG must come out bit-identical on every repeat and finite."""
+    B, T, I, H = 4736, 3, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    k = 1.0 / H ** 0.5
+    ws = []
+    for _ in range(2):
+        ws += [(torch.rand(4 * H, I, device="cuda", generator=g) * 2 - 1) * k, (torch.rand(4 * H, H, device="cuda", generator=g) * 2 - 1) * k,
+               (torch.rand(4 * H, device="cuda", generator=g) * 2 - 1) * k, (torch.rand(4 * H, device="cuda", generator=g) * 2 - 1) * k]
+    packed = ops.lstm_pack(*ws)
+    x = torch.randn(B, T, I, device="cuda", generator=g).bfloat16()
+    dh = torch.randn(B, T, 2 * H, device="cuda", generator=g) / (B * T) ** 0.5
+    old = ops._POISON
+    ops._POISON = True
+    try:
+        ref = None
+        for it in range(40):
+            hcat, gates, cs = ops.lstm_forward_fused(x, packed, B, T, True)
+            dG, _ = ops.lstm_backward(packed, gates, cs, dh, B, T)
+            cur = [hcat.view(torch.int16), gates.view(torch.int16), cs, dG.view(torch.int16)]
+            if ref is None:
+                ref = [c.clone() for c in cur]
+                assert torch.isfinite(hcat.float()).all() and torch.isfinite(dG.float()).all()
+            else:
+                for name, a, b in zip(("hcat", "gates", "c", "dG"), cur, ref):
+                    assert torch.equal(a, b), f"repeat {it}: {name} differs from the first run"
+    finally:
+        ops._POISON = old
