@@ -30,7 +30,7 @@ constexpr int GR = 128;   // gate rows per CTA
 constexpr int LK = 64;
 constexpr uint32_t kWTile = GR * LK * 2;   // 16 KB
 constexpr uint32_t kHBox = NS * LK * 2;    //  8 KB
-constexpr int kThreads = 320;              // warp 0 TMA, warp 1 MMA, warps 2-9 cell update
+constexpr int kThreads = 352;              // warp 0 TMA, warp 1 MMA, warps 2-9 cell update, warp 10 publisher
 
 struct FxParams {
     int B, T, H, I;
@@ -39,7 +39,7 @@ struct FxParams {
     float *csave;         // [2, T, B, H] (training only)
     __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
     __nv_bfloat16 *hcat;  // [B, T, 2H]
-    unsigned int *sync;   // [ngroups] zeroed before the launch
+    unsigned int *sync;   // [ngroups * NH] zeroed before the launch
 };
 
 // release / acquire at gpu scope around the TMA-stored h_t: see lstm_fwd.cu
@@ -62,7 +62,11 @@ __device__ __forceinline__ void wait_counter_x(const unsigned int *p, unsigned i
     }
 }
 
-template <bool SAVE>
+// NH = 2: the item's 64 sequences are two HALVES of 32 with independent dependency chains -- own h tile, own
+// accumulator columns, own counter; the cell warps were split that way already (4 warps per 32 sequences).  The
+// halves fall half a step apart, so the exchange latency of one (release, counter propagation, TMA load of h) hides
+// behind the MMAs and the cell phase of the other.  The x half of a step is still one N = 64 product.
+template <bool SAVE, int NH>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
@@ -72,33 +76,35 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     const int H = p.H, T = p.T, I = p.I;
     const int nkc = H / LK, nki = I / LK;
     const int nkw = nkc > nki ? nkc : nki;        // tiles of the weight area (W_hh is staged there on its way to TMEM)
-    const int cpb = nkc >= 4 ? nkc / 4 : 1;       // h chunks per TMA operation / barrier
+    constexpr int HS = NS / NH;                   // sequences per half
+    constexpr uint32_t kHalfBox = HS * LK * 2;    // [HS seq x 64 k] bf16
+    const int cpb = NH == 1 ? (nkc >= 4 ? nkc / 4 : 1) : (nkc >= 2 ? nkc / 2 : 1);   // h chunks per TMA operation / barrier
     const int nhb = nkc / cpb;
     const int xcs = nki >= 2 ? 2 : 1;             // x chunks (K = 64 each) per ring slot
     const int nxs = nki / xcs;                    // ring slots consumed per step
     const int gsize = H / 32;
     unsigned char *w_s = smem;                            // nkw tiles [128 gate rows x 64 k] bf16, SW128: W_ih (resident)
-    unsigned char *h_s = w_s + (size_t)nkw * kWTile;      // nkc boxes [64 seq x 64 k]
+    unsigned char *h_s = w_s + (size_t)nkw * kWTile;      // NH x nkc boxes [HS seq x 64 k]
     unsigned char *x_s = h_s + (size_t)nkc * kHBox;       // 2 ring slots of xcs boxes [64 seq x 64 k]
     uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + 2 * (size_t)xcs * kHBox);
     uint64_t *wh_full = bars, *wcp_done = bars + 1, *wi_full = bars + 2;
-    uint64_t *h_full = bars + 3;                          // [4]
-    uint64_t *x_full = h_full + 4, *x_empty = x_full + 2; // [2] each
-    uint64_t *tmem_full = x_empty + 2;                    // [2]: accumulator of step parity
-    uint64_t *h_staged = tmem_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_staged + 1);
+    uint64_t *h_full = bars + 3;                          // [2 halves][4]
+    uint64_t *x_full = h_full + 8, *x_empty = x_full + 2; // [2] each
+    uint64_t *tmem_full = x_empty + 2;                    // [2 halves][2]: accumulator columns of (half, step parity)
+    uint64_t *h_staged = tmem_full + 4;                   // [2 halves]: h_t of the half is in hcat (its cell warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_staged + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
-    unsigned int *counter = p.sync + group;
+    unsigned int *counter = p.sync + group * NH;          // one per half
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(wh_full, 1); mbar_init(wcp_done, 1); mbar_init(wi_full, 1);
-            for (int i = 0; i < 4; ++i) mbar_init(&h_full[i], 1);
-            for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&tmem_full[i], 1); }
-            mbar_init(h_staged, 8);
+            for (int i = 0; i < 8; ++i) mbar_init(&h_full[i], 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&h_staged[i], 8 / NH); }
+            for (int i = 0; i < 4; ++i) mbar_init(&tmem_full[i], 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -145,11 +151,14 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     if (s > 0) {
                         const int t = dir ? T - 1 - s : s;
                         const int tprev = dir ? t + 1 : t - 1;
-                        wait_counter_x(counter, (published + (unsigned)s) * (unsigned)gsize);
-                        fence_proxy_async_global();
-                        for (int g = 0; g < nhb; ++g) {
-                            mbar_arrive_expect_tx(&h_full[g], (uint32_t)cpb * kHBox);
-                            tma_load_4d(h_s + (size_t)g * cpb * kHBox, &tmH, &h_full[g], 0, b0, dir * nkc + g * cpb, tprev);
+                        for (int hf = 0; hf < NH; ++hf) {
+                            wait_counter_x(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
+                            fence_proxy_async_global();
+                            for (int g = 0; g < nhb; ++g) {
+                                mbar_arrive_expect_tx(&h_full[hf * 4 + g], (uint32_t)cpb * kHalfBox);
+                                tma_load_4d(h_s + (size_t)(hf * nkc + g * cpb) * kHalfBox, &tmH, &h_full[hf * 4 + g], 0, b0 + hf * HS,
+                                            dir * nkc + g * cpb, tprev);
+                            }
                         }
                     }
                     if (s + 1 < T) load_x(s + 1);
@@ -158,14 +167,20 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer + publisher (one elected thread) ==========================================
+        // ===== MMA issuer (one elected thread) ======================================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(GR, NS);
+            constexpr uint32_t idesc = make_idesc_bf16(GR, NS), idesc_h = make_idesc_bf16(GR, HS);
             int cur_dir = -1;
-            unsigned int xn = 0, wn = 0;
-            uint32_t hphase = 0, sphase = 0;
+            unsigned int xn = 0, wn = 0, nst = 0;
+            uint32_t hphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1, b0 = (item >> 1) * NS;
+                const int dir = item & 1;
+                if (nst > 0) {
+                    // the cell warps have read the last accumulators of the previous item (they arrive on h_staged
+                    // after their tcgen05.ld): the x halves below may overwrite them
+                    for (int hf = 0; hf < NH; ++hf) mbar_wait(&h_staged[hf], (nst - 1) & 1);
+                    tc_fence_after();
+                }
                 if (dir != cur_dir) {
                     mbar_wait(wh_full, wn & 1);
                     tc_fence_after();
@@ -202,36 +217,49 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 x_part(0);
                 for (int s = 0; s < T; ++s) {
                     const int par = s & 1;
-                    if (s > 0) {
-                        const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS);
-                        for (int g = 0; g < nhb; ++g) {
-                            mbar_wait(&h_full[g], hphase);
-                            tc_fence_after();
-                            for (int j = 0; j < cpb; ++j) {
-                                const int kc = g * cpb + j;
-                                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)kc * kHBox), 16, 1024);
+                    for (int hf = 0; hf < NH; ++hf) {
+                        if (s > 0) {
+                            const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS + hf * HS);
+                            for (int g = 0; g < nhb; ++g) {
+                                mbar_wait(&h_full[hf * 4 + g], hphase);
+                                tc_fence_after();
+                                for (int j = 0; j < cpb; ++j) {
+                                    const int kc = g * cpb + j;
+                                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)(hf * nkc + kc) * kHalfBox), 16, 1024);
 #pragma unroll
-                                for (int k = 0; k < LK / 16; ++k)
-                                    umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), bdesc + (uint64_t)(2 * k),
-                                                 idesc, 1u);
+                                    for (int k = 0; k < LK / 16; ++k)
+                                        umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), bdesc + (uint64_t)(2 * k),
+                                                     idesc_h, 1u);
+                                }
                             }
                         }
-                        hphase ^= 1;
+                        umma_commit(&tmem_full[hf * 2 + par]);
                     }
-                    umma_commit(&tmem_full[par]);
+                    if (s > 0) hphase ^= 1;
+                    ++nst;
                     if (s + 1 < T) x_part(par ^ 1);   // runs while step s is in its cell / publish / counter phases
-                    // publish h_t: the cell warps stored it to hcat themselves and arrived on h_staged; ONE gpu-scope
-                    // release (cumulative over what the barrier ordered before it) makes it visible to the group
-                    mbar_wait(h_staged, sphase);
-                    sphase ^= 1;
-                    red_release_gpu_inc_x(counter);
                 }
             }
+        }
+    } else if (warp == 10) {
+        // ===== publisher (one elected thread): h_t of a half was stored to hcat by its cell warps, which arrived on
+        // h_staged; ONE gpu-scope release (cumulative over what the barrier ordered before it) makes it visible
+        if (elect_one()) {
+            uint32_t sphase = 0;
+            for (int item = group; item < p.nitems; item += p.ngroups)
+                for (int s = 0; s < T; ++s) {
+                    for (int hf = 0; hf < NH; ++hf) {
+                        mbar_wait(&h_staged[hf], sphase);
+                        red_release_gpu_inc_x(counter + hf);
+                    }
+                    sphase ^= 1;
+                }
         }
     } else {
         // ===== cell update ==========================================================================
         const int qd = warp & 3;
         const int ch = (warp - 2) >> 2;
+        const int hf = NH == 2 ? ch : 0;          // the half this warp's 32 sequences belong to
         const int r = qd * 32 + lane;
         const CellLane CL(lane);
         unsigned int use[2] = {0u, 0u};           // completions of tmem_full[parity] consumed so far
@@ -245,7 +273,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             for (int s = 0; s < T; ++s) {
                 const int par = s & 1;
                 uint32_t acc[32];
-                mbar_wait(&tmem_full[par], use[par] & 1);
+                mbar_wait(&tmem_full[hf * 2 + par], use[par] & 1);
                 ++use[par];
                 tc_fence_after();
                 tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(par * NS + ch * 32), acc);
@@ -271,7 +299,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(h_staged);
+                if (lane == 0) mbar_arrive(&h_staged[hf]);
                 if (SAVE) {
                     // gates_save [2, T, B, 4H]: this thread holds gate row r for 32 sequences; a lane pair swaps halves so
                     // that the even lane writes rows (r, r+1) of sequence 2i and the odd lane those of sequence 2i+1.
@@ -327,11 +355,12 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     if (rc) return rc;
     rc = make_tmap_2d(&twi, wih_p, 2, 8ull * H, (uint64_t)I, (uint64_t)I * 2, GR, LK, 1);
     if (rc) return rc;
-    {   // hcat [B, T, 2H] as (k in chunk, b, chunk, t): box = cpb chunks of [64 seq x 64 k]
-        const int nkc = H / LK, cpb = nkc >= 4 ? nkc / 4 : 1;
+    static const int halves = getenv("RCNN_FWD_HALVES") ? (atoi(getenv("RCNN_FWD_HALVES")) == 1 ? 1 : 2) : 2;
+    {   // hcat [B, T, 2H] as (k in chunk, b, chunk, t): box = cpb chunks of [64 / halves seq x 64 k]
+        const int nkc = H / LK, cpb = halves == 1 ? (nkc >= 4 ? nkc / 4 : 1) : (nkc >= 2 ? nkc / 2 : 1);
         const uint64_t dims[4] = {(uint64_t)LK, (uint64_t)B, 2ull * nkc, (uint64_t)T};
         const uint64_t strides[3] = {(uint64_t)T * 2 * H * 2, (uint64_t)LK * 2, 2ull * H * 2};
-        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)NS, (uint32_t)cpb, 1u};
+        const uint32_t box[4] = {(uint32_t)LK, (uint32_t)(NS / halves), (uint32_t)cpb, 1u};
         rc = make_tmap_4d(&th, hcat, 2, dims, strides, box, 1);
         if (rc) return rc;
     }
@@ -356,11 +385,12 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
     if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;
     cudaStream_t s = (cudaStream_t)stream;
-    p.sync = group_counters(p.ngroups, s);
+    p.sync = group_counters(p.ngroups * halves, s);
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
     const size_t smem = fwdx_smem_bytes(H, I, save);
-    if (save) RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else RCNN_CUDA(cudaFuncSetAttribute(lstm_fwdx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = save ? (halves == 2 ? lstm_fwdx_kernel<true, 2> : lstm_fwdx_kernel<true, 1>)
+                     : (halves == 2 ? lstm_fwdx_kernel<false, 2> : lstm_fwdx_kernel<false, 1>);
+    RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
     cfg.blockDim = dim3(kThreads);
@@ -372,8 +402,7 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_FWD, s);
-    if (save) RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<true>, twh, twi, th, tx, p));
-    else RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwdx_kernel<false>, twh, twi, th, tx, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, twh, twi, th, tx, p));
     count_launch();
     return RCNN_OK;
 }
