@@ -46,7 +46,7 @@ constexpr int LU = 32;     // hidden units per CTA
 constexpr int LK = 64;
 constexpr uint32_t kWTile = 128 * LK * 2;   // [128 output units x 64 k] bf16, SW128 = 16 KB
 constexpr uint32_t kBChunk = NS * LK * 2;   // [64 seq x 64 k] bf16, SW128 = 8 KB
-constexpr int kThreads = 320;   // warp 0 poll/TMA, warp 1 MMA, warps 2-9 cell update
+constexpr int kThreads = 384;   // warp 0 poll/TMA loads, warp 1 MMA, warps 2-9 cell update, warps 10-11 publishers (one per half)
 
 struct BwdParams {
     int B, T, H;
@@ -57,7 +57,7 @@ struct BwdParams {
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
     float *db;                 // [2*4H] out or nullptr: column sums of dG (bias gradient), zeroed before the launch
     __nv_bfloat16 *xbuf;       // exchange buffer [2][ngroups][src CTA][dst CTA][8 warps][32 units][8 seq]
-    unsigned int *sync;        // [ngroups] zeroed before the launch
+    unsigned int *sync;        // [ngroups * NH] zeroed before the launch
     long long *tl;             // debug timeline or nullptr
 };
 #define TL_MARK(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
@@ -106,6 +106,11 @@ __device__ __forceinline__ uint2 ld_ro_v2(const void *p) {
     return r;
 }
 
+// NH = 2: the item's 64 sequences are two HALVES of 32 with independent dependency chains (the cell warps are split
+// that way already: warps 0-3 / 4-7 own and drain sequences 0-31 / 32-63): own half of every 4 KB exchange block, own
+// accumulator columns, barriers, counter and publisher thread.  The halves run half a step apart, so the exchange
+// latency of one (TMA stores, release, counter propagation, TMA load) hides behind the MMAs and cell phase of the other.
+template <int NH>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXin,
                 const __grid_constant__ CUtensorMap tmXout, const BwdParams p) {
@@ -118,24 +123,26 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     unsigned char *b_s = w_s + (size_t)nmb * 2 * kWTile;        // 2 chunks [64 seq x 64 k] bf16, SW128: this CTA's dG_t
     unsigned char *x_s = b_s + 2 * kBChunk;                     // gsize x 4 KB: partials in (by source) / out (by destination)
     uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + (size_t)gsize * 4096);
-    uint64_t *w_full = bars, *b_ready = bars + 1, *x_ready = bars + 2;
-    uint64_t *d_full = bars + 3;     // [4] accumulator block mb complete
-    uint64_t *staged = bars + 7;     // [4] block mb drained into x_s (8 warps)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+    uint64_t *w_full = bars, *b_ready = bars + 1, *x_ready = bars + 3;   // b_ready, x_ready: [2 halves]
+    uint64_t *d_full = bars + 5;     // [2 halves][4] accumulator block mb complete
+    uint64_t *staged = bars + 13;    // [2 halves][4] block mb drained into x_s (the half's cell warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+    constexpr int HS = NS / NH;                 // sequences per half
+    constexpr uint32_t XB = 4096 / NH;          // bytes of a half's share of one (source, destination) exchange block
+    constexpr int XR = 4 / NH;                  // ... in 1 KB rows of the exchange tensor map
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
-    unsigned int *counter = p.sync + group;
+    unsigned int *counter = p.sync + group * NH;   // one per half
     // exchange buffer: [parity][group][src CTA][dst CTA][warp 8][unit 32][seq 8] bf16 (4 KB per (src, dst))
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            mbar_init(b_ready, 8);
-            mbar_init(x_ready, 1);
-            for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&staged[i], 8); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&b_ready[i], 8 / NH); mbar_init(&x_ready[i], 1); }
+            for (int i = 0; i < 8; ++i) { mbar_init(&d_full[i], 1); mbar_init(&staged[i], 8 / NH); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -166,39 +173,54 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 }
                 for (int s = 0; s < T; ++s) {
                     if (s > 0) {
-                        wait_counter_b(counter, (published + (unsigned)s) * (unsigned)gsize);
-                        TL_MARK(0);
-                        fence_proxy_async_global();
-                        // the 16 partials of this CTA's units, published by the group in the previous step
-                        mbar_arrive_expect_tx(x_ready, (uint32_t)gsize * 4096u);
-                        tma_load_5d(x_s, &tmXin, x_ready, 0, 0, c, 0, (int)((npub - 1) & 1) * p.ngroups + group);
-                    }
-                    if (s + 1 < T) {
-                        // block by block as the cell warps drain the accumulators: the partials for destination
-                        // CTAs 4mb .. 4mb+3 (16 KB, contiguous in shared and global memory)
-                        for (int mb = 0; mb < nmb; ++mb) {
-                            mbar_wait(&staged[mb], npub & 1);
-                            if (mb == nmb - 1) TL_MARK(7);
-                            tma_store_5d(&tmXout, x_s + (size_t)mb * 16384, 0, 0, 4 * mb, c, (int)(npub & 1) * p.ngroups + group);
-                            tma_store_commit();
+                        // the partials of this CTA's units (all sources), published by the group in the previous step.
+                        // (The counter includes this CTA's own increment, which followed the completion of its stores
+                        // out of the same shared-memory area.)
+                        for (int hf = 0; hf < NH; ++hf) {
+                            wait_counter_b(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
+                            if (hf == 0) TL_MARK(0);
+                            fence_proxy_async_global();
+                            mbar_arrive_expect_tx(&x_ready[hf], (uint32_t)gsize * XB);
+                            tma_load_5d(x_s + (size_t)hf * gsize * XB, &tmXin, &x_ready[hf], 0, XR * hf, c, 0,
+                                        (int)((npub - 1) & 1) * p.ngroups + group);
                         }
-                        tma_store_wait<0>();                      // written, not merely read out of shared memory
-                        TL_MARK(1);
-                        // the partials are complete for this thread; the release increment makes them visible to the
-                        // group (readers poll with acquire loads and fetch with TMA)
-                        fence_proxy_async_global();
-                        red_release_gpu_inc_b(counter);
-                        TL_MARK(6);
-                        ++npub;
                     }
+                    if (s + 1 < T) ++npub;
                 }
                 published += (unsigned)(T - 1);
             }
         }
+    } else if (warp >= 10) {
+        // ===== publisher of half (warp - 10): partial sums -> exchange buffer -> release =================
+        const int hf = warp - 10;
+        if (hf < NH && elect_one()) {
+            tma_prefetch_desc(&tmXout);
+            unsigned int npub = 0;
+            unsigned char *xs = x_s + (size_t)hf * gsize * XB;
+            for (int item = group; item < p.nitems; item += p.ngroups)
+                for (int s = 0; s + 1 < T; ++s) {
+                    // block by block as the cell warps drain the accumulators: the partials for destination
+                    // CTAs 4mb .. 4mb+3 (contiguous in shared and global memory)
+                    for (int mb = 0; mb < nmb; ++mb) {
+                        mbar_wait(&staged[hf * 4 + mb], npub & 1);
+                        if (hf == 0 && mb == nmb - 1) TL_MARK(7);
+                        tma_store_5d(&tmXout, xs + (size_t)mb * 4 * XB, 0, XR * hf, 4 * mb, c, (int)(npub & 1) * p.ngroups + group);
+                        tma_store_commit();
+                    }
+                    tma_store_wait<0>();                      // written, not merely read out of shared memory
+                    if (hf == 0) TL_MARK(1);
+                    // the partials are complete for this thread; the release increment makes them visible to the
+                    // group (readers poll with acquire loads and fetch with TMA)
+                    fence_proxy_async_global();
+                    red_release_gpu_inc_b(counter + hf);
+                    if (hf == 0) TL_MARK(6);
+                    ++npub;
+                }
+        }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) ===================================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NS);
+            constexpr uint32_t idesc = make_idesc_bf16(128, HS);
             int cur_dir = -1;
             uint32_t wphase = 0, bphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups) {
@@ -217,23 +239,26 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                 }
                 for (int s = 0; s + 1 < T; ++s) {
-                    mbar_wait(b_ready, bphase);
-                    bphase ^= 1;
-                    TL_MARK(2);
-                    tc_fence_after();
-                    for (int mb = 0; mb < nmb; ++mb) {
+                    for (int hf = 0; hf < NH; ++hf) {
+                        mbar_wait(&b_ready[hf], bphase);
+                        if (hf == 0) TL_MARK(2);
+                        tc_fence_after();
+                        for (int mb = 0; mb < nmb; ++mb) {
 #pragma unroll
-                        for (int kc = 0; kc < 2; ++kc) {
-                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_s + kc * kBChunk), 16, 1024);
+                            for (int kc = 0; kc < 2; ++kc) {
+                                // rows (sequences) [HS hf, +HS) of the dG chunk
+                                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_s + kc * kBChunk + hf * HS * 128), 16, 1024);
 #pragma unroll
-                            for (int k = 0; k < LK / 16; ++k)
-                                umma_bf16_ts(tmem_base + 256u + (uint32_t)(mb * NS),
-                                             tmem_base + (uint32_t)(8 * ((mb * 2 + kc) * (LK / 16) + k)),
-                                             bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                                for (int k = 0; k < LK / 16; ++k)
+                                    umma_bf16_ts(tmem_base + 256u + (uint32_t)(mb * NS + hf * HS),
+                                                 tmem_base + (uint32_t)(8 * ((mb * 2 + kc) * (LK / 16) + k)),
+                                                 bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                            }
+                            umma_commit(&d_full[hf * 4 + mb]);    // the cell warps drain block mb while the next one is multiplied
                         }
-                        umma_commit(&d_full[mb]);    // the cell warps drain block mb while the next one is multiplied
+                        if (hf == NH - 1) TL_MARK(3);
                     }
-                    TL_MARK(3);
+                    bphase ^= 1;
                 }
             }
         }
@@ -242,6 +267,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const int w = warp - 2;               // sequences 8w .. 8w+7 of the tile; lane = hidden unit 32c + lane
         const int qd = warp & 3;              // TMEM lane quadrant (drain phase)
         const int hq = (warp - 2) >> 2;       // which 32 of the 64 sequence columns this warp drains
+        const int hf = NH == 2 ? hq : 0;      // the half this warp belongs to (owns AND drains the same 32 sequences)
+        unsigned char *xs = x_s + (size_t)hf * gsize * XB;   // the half's exchange area: partials in / out
         unsigned int npub = 0, nwait = 0, nmma = 0;   // publishes so far, x_ready / d_full phases
         for (int item = group; item < p.nitems; item += p.ngroups) {
             const int dir = item & 1, b0 = (item >> 1) * NS;
@@ -274,14 +301,14 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) rec[i] = 0.f;
                 if (s > 0) {
-                    mbar_wait(x_ready, nwait & 1);
+                    mbar_wait(&x_ready[hf], nwait & 1);
                     ++nwait;
-                    const unsigned char *src = x_s + ((size_t)w * 256 + (size_t)lane * 8) * 2;
+                    const unsigned char *src = xs + ((size_t)(w % (8 / NH)) * 256 + (size_t)lane * 8) * 2;
                     for (int sc = 0; sc < gsize; sc += 8) {     // 8 shared-memory loads in flight per round
                         uint4 v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
-                            v[u] = sc + u < gsize ? *reinterpret_cast<const uint4 *>(src + (size_t)(sc + u) * 4096) : make_uint4(0u, 0u, 0u, 0u);
+                            v[u] = sc + u < gsize ? *reinterpret_cast<const uint4 *>(src + (size_t)(sc + u) * XB) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -325,7 +352,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(b_ready);
+                    if (lane == 0) mbar_arrive(&b_ready[hf]);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -337,7 +364,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (more) {
                     // ---- drain the accumulators: partial^T [unit, seq] -> exchange buffer (bf16) ---------
                     for (int mb = 0; mb < nmb; ++mb) {
-                        mbar_wait(&d_full[mb], nmma & 1);
+                        mbar_wait(&d_full[hf * 4 + mb], nmma & 1);
                         if (threadIdx.x == 64 && mb == nmb - 1) TL_MARK(4);
                         tc_fence_after();
                         uint32_t acc[32];
@@ -355,12 +382,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                                                                                      __uint_as_float(acc[8 * g4 + 2 * k + 1]));
                                     vw[k] = *reinterpret_cast<const uint32_t *>(&h2);
                                 }
-                                *reinterpret_cast<uint4 *>(x_s + (size_t)dstc * 4096 + ((size_t)(hq * 4 + g4) * 256 + (size_t)lane * 8) * 2) = v;
+                                *reinterpret_cast<uint4 *>(xs + (size_t)dstc * XB + ((size_t)((NH == 2 ? 0 : hq) * 4 + g4) * 256 + (size_t)lane * 8) * 2) = v;
                             }
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&staged[mb]);
+                        if (lane == 0) mbar_arrive(&staged[hf * 4 + mb]);
                     }
                     tc_fence_before();
                     ++nmma;
@@ -532,13 +559,15 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     // (H = 64: the box reads 64 rows past the direction's block or zero fill; those accumulator lanes are unused)
     int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, 128, LK, 1);
     if (rc) return rc;
+    static const int halves = getenv("RCNN_BWD_HALVES") ? (atoi(getenv("RCNN_BWD_HALVES")) == 1 ? 1 : 2) : 2;
     const int gsz = H / 32, ngr = bwd_groups(B, H);
     CUtensorMap txin, txout;
     {   // exchange buffer as float32 [2*ngroups][src][dst][4][256]: load box = all sources of one destination,
         // store box = all destinations of one source
         const uint64_t dims[5] = {256, 4, (uint64_t)gsz, (uint64_t)gsz, 2ull * ngr};
         const uint64_t strides[4] = {1024, 4096, (uint64_t)gsz * 4096, (uint64_t)gsz * gsz * 4096};
-        const uint32_t box_in[5] = {256, 4, 1, (uint32_t)gsz, 1}, box_out[5] = {256, 4, (uint32_t)(gsz < 4 ? gsz : 4), 1, 1};
+        const uint32_t xr = 4u / (uint32_t)halves;
+        const uint32_t box_in[5] = {256, xr, 1, (uint32_t)gsz, 1}, box_out[5] = {256, xr, (uint32_t)(gsz < 4 ? gsz : 4), 1, 1};
         rc = make_tmap_nd(&txin, workspace, 4, 5, dims, strides, box_in, 0);
         if (rc) return rc;
         rc = make_tmap_nd(&txout, workspace, 4, 5, dims, strides, box_out, 0);
@@ -556,10 +585,11 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     const int gsize = H / 32;
     const size_t smem = bwd_smem_bytes(H);
     cudaStream_t s = (cudaStream_t)stream;
-    RCNN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = halves == 2 ? lstm_bwd_kernel<2> : lstm_bwd_kernel<1>;
+    RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.nitems = 2 * ((B + NS - 1) / NS);
     p.ngroups = bwd_groups(B, H);
-    p.sync = group_counters(p.ngroups, s);
+    p.sync = group_counters(p.ngroups * halves, s);
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
@@ -572,7 +602,7 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope prof(RCNN_K_LSTM_BWD, s);
-    RCNN_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_kernel, tw, txin, txout, p));
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, tw, txin, txout, p));
     count_launch();
     return RCNN_OK;
 }
