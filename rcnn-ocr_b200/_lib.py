@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "librcnn_ocr_b200.so")
+# RCNN_OCR_B200_LIB: load a differently built copy of the library (A/B experiments)
+_LIB_PATH = os.path.abspath(os.environ.get("RCNN_OCR_B200_LIB") or os.path.join(_HERE, "librcnn_ocr_b200.so"))
 _lib = None
 
 
