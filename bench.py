@@ -160,7 +160,7 @@ def run_reference(args, rank):
         "e2e": {"value": round(val, 2), "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, B, world):
@@ -236,7 +236,6 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=device)
     _lib.check(_lib.lib().rcnn_device_check(), "rcnn_device_check")
     peaks = load_peaks()
@@ -483,7 +482,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
             "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)] if losses else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Captured graphs hold NCCL work: drop them before the process group; a watchdog ends the process
         # if the teardown still blocks (the result line is already out).
@@ -497,7 +496,23 @@ def run_ours(args, rank, world, local_rank):
         os._exit(0)
 
 
+_RESULT_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the result line only: file descriptor 1 is pointed at stderr for everything else that
+    # prints from native code (NCCL's "NCCL version ..." banner under NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE)
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -519,7 +534,7 @@ def main():
         run_reference(args, rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
-        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"}))
+        emit({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"})
         sys.exit(2)
     args.warmup = max(args.warmup, 3)
     run_ours(args, rank, world, local_rank)
