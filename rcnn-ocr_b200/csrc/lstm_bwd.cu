@@ -23,14 +23,17 @@
 // on a 5-D tensor map of the exchange buffer [parity x group][src CTA][dst CTA][4][1 KB]: the drained
 // accumulators are staged in shared memory and stored, the 16 partials of the CTA's own 32 units are
 // loaded back into the same shared-memory area the next step and summed by the cell warps.
-//   warp 0      loads W once; per step: polls the group counter (acquire gpu-scope loads), TMA-loads the
-//               partials, later TMA-stores this CTA's partials, waits for their completion and
-//               releases the counter (the only gpu-scope fence of the step is this one thread's)
+// With NH = 2 (default) the 64 sequences are two halves of 32 with independent chains (own half of every
+// exchange block, accumulator columns, barriers, counter, publisher), see the kernel's comment.
+//   warp 0      loads W once; per step and half: polls the group counter (acquire gpu-scope loads) and
+//               TMA-loads the partials
 //   warp 1      MMA issuer (one elected thread)
 //   warps 2-9   cell update: warp w owns sequences 8w..8w+7 of the tile, lane = hidden unit of the
 //               CTA, so every global access of a warp is one contiguous 128/256-byte row; dc and the
 //               bias-gradient sums stay in registers for the whole sequence; after the MMA the same
-//               warps drain TMEM (lane = output unit) to the exchange buffer.
+//               warps drain TMEM (lane = output unit) to the exchange area.
+//   warps 10-11 publisher of half 0 / 1 (one elected thread each): TMA-stores this CTA's partials, waits
+//               for their completion and RELEASES the counter (the only gpu-scope fence of the step)
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"

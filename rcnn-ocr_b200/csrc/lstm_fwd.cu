@@ -1,4 +1,7 @@
-// K2 (forward): persistent recurrent LSTM kernel, both directions of a BidirectionalLSTM block.
+// K2 (forward), UNFUSED variant: persistent recurrent LSTM kernel, both directions of a BidirectionalLSTM block,
+// on a precomputed input projection.  The default path is lstm_fwdx.cu (input projection fused, two half-items
+// per group, dedicated publisher warp); this kernel serves the input sizes that one does not take (I not a
+// multiple of 64, or > 512).
 //
 // Replaces the T dependent timesteps inside nn.LSTM(bidirectional=True, batch_first=True) at
 // model/model.py:154-156,161 (cuDNN RNN in the reference): gates = xp_t + h_{t-1} W_hh^T,

@@ -1,4 +1,4 @@
-// K2 (forward, inference): recurrent LSTM kernel with the INPUT PROJECTION fused in.
+// K2 (forward, inference and training): recurrent LSTM kernel with the INPUT PROJECTION fused in.
 //
 // Same decomposition, exchange and cell arithmetic as lstm_fwd.cu (groups of H/32 CTAs, 64-sequence work
 // items, transposed product with the weights as the M = 128 operand, W_hh in tensor memory).  In addition the
@@ -11,7 +11,9 @@
 // group counter of step t are in flight -- the tensor pipe idles ~75 % of a step otherwise.  The separate xp
 // GEMM (nn.LSTM's `W_ih x_t + b` for all t, model/model.py:154-156,161), its 134 MB fp16 output and the
 // re-read of that output disappear from the inference path; the bias is a per-thread constant (a thread owns
-// one gate row).  SAVE (training): the activated gates (fp16, lane pairs exchange halves so that every store is 32
+// one gate row).  Threads: warp 0 TMA producer + counter poller, warp 1 MMA issuer, warps 2-9 cell update (they
+// store h_t to hcat themselves), warp 10 publisher (one release per half and step: a MEMBAR issued by the MMA
+// thread would wait behind its queued MMAs).  SAVE (training): the activated gates (fp16, lane pairs exchange halves so that every store is 32
 // bits) and c_t leave by plain global stores after the step is published -- off the dependent chain, and shared
 // memory has no room left for a staging tile.
 #include <cuda_fp16.h>
