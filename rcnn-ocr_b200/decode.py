@@ -8,6 +8,8 @@ layout explicit.  Only ids[B,T] int32 and len[B] cross back to the host.
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 import torch
 
@@ -47,30 +49,69 @@ def ctc_greedy_ids(logits: torch.Tensor, blank: int = 0, batch_first: bool = Tru
     return (ids, lens, conf) if return_confidence else (ids, lens)
 
 
+_PINNED = {}     # (B, T, device) -> (pinned ids buffer, pinned lens buffer); a handful of batch shapes per process
+
+
 def _to_host(ids: torch.Tensor, lens: torch.Tensor):
-    """One packed device->host copy of ids and lens."""
+    """Device->host copy of ids and lens through cached pinned buffers (two async copies, one sync);
+    returns numpy arrays the caller owns."""
     B, T = ids.shape
-    packed = torch.empty((B, T + 1), dtype=torch.int32, device=ids.device)
-    packed[:, :T] = ids
-    packed[:, T] = lens
-    host = torch.empty((B, T + 1), dtype=torch.int32, pin_memory=True)
-    host.copy_(packed, non_blocking=True)
+    key = (B, T, ids.device.index)
+    if key not in _PINNED:
+        if len(_PINNED) >= 16:
+            _PINNED.clear()
+        _PINNED[key] = (torch.empty((B, T), dtype=torch.int32, pin_memory=True),
+                        torch.empty((B,), dtype=torch.int32, pin_memory=True))
+    h_ids, h_lens = _PINNED[key]
+    h_ids.copy_(ids if ids.is_contiguous() else ids.contiguous(), non_blocking=True)
+    h_lens.copy_(lens, non_blocking=True)
     torch.cuda.current_stream(ids.device).synchronize()
-    arr = host.numpy()
-    return arr[:, :T], arr[:, T]
+    return h_ids.numpy().copy(), h_lens.numpy().copy()
+
+
+@functools.lru_cache(maxsize=8)
+def _alphabet_tables(alphabet: tuple):
+    """(code points as uint32 if every class is a single character else None, object table)."""
+    single = all(isinstance(a, str) and len(a) == 1 for a in alphabet)
+    cps = np.array([ord(a) for a in alphabet], dtype=np.uint32) if single and alphabet else None
+    return cps, np.asarray(list(alphabet), dtype=object)
+
+
+def ids_to_text_host(ids_h: np.ndarray, lens_h: np.ndarray, alphabet):
+    """Host half of the decode: ids [B,T] int32 (left-packed) / lens [B] -> (texts, seqs) with
+    ``alphabet[p - 1]`` per emitted class as at training/utils.py:146.  The whole batch is gathered and mapped at
+    once (single-character alphabets: one code-point gather + one utf-32 decode), then cut per line."""
+    B, T = ids_h.shape
+    lens_l = lens_h.tolist()
+    if B == 0 or T == 0:
+        return ["" for _ in lens_l], [[] for _ in lens_l]
+    mask = np.arange(T, dtype=np.int64)[None, :] < lens_h.astype(np.int64)[:, None]
+    flat = ids_h[mask]
+    # (indexing as in the reference: class 0, possible only with blank != 0, wraps to alphabet[-1]; ids beyond
+    # the alphabet raise IndexError)
+    fl = flat.tolist()
+    cps, table = _alphabet_tables(tuple(alphabet))
+    seqs, texts, o = [], [], 0
+    if cps is not None:
+        allc = cps[flat - 1].tobytes().decode("utf-32-le")
+        for n in lens_l:
+            seqs.append(fl[o:o + n])
+            texts.append(allc[o:o + n])
+            o += n
+    else:
+        toks = table[flat - 1].tolist() if flat.size else []
+        for n in lens_l:
+            seqs.append(fl[o:o + n])
+            texts.append("".join(toks[o:o + n]))
+            o += n
+    return texts, seqs
 
 
 def ids_to_text(ids: torch.Tensor, lens: torch.Tensor, alphabet):
-    """Device ids [B,T] / lens [B] (as returned by ctc_greedy_ids) -> (texts, seqs): one packed D2H
-    copy, then ``alphabet[p - 1]`` per emitted class as at training/utils.py:146."""
+    """Device ids [B,T] / lens [B] (as returned by ctc_greedy_ids) -> (texts, seqs): D2H of ids and lens,
+    then the charset mapping on the host (``ids_to_text_host``)."""
     ids_h, lens_h = _to_host(ids, lens)
-    table = np.asarray(list(alphabet), dtype=object)
-    seqs, texts = [], []
-    for b in range(ids_h.shape[0]):
-        row = ids_h[b, : lens_h[b]]
-        seqs.append(row.tolist())
-        texts.append("".join(table[row - 1]) if len(row) else "")
-    return texts, seqs
+    return ids_to_text_host(ids_h, lens_h, alphabet)
 
 
 def ctc_greedy_decoder(logits: torch.Tensor, alphabet, blank: int = 0, batch_first=None):

@@ -13,7 +13,7 @@ from typing import List, Union
 import torch
 
 from .charset import ctc_alphabet, decode_tokens, load_charset
-from .decode import _to_host, ctc_greedy_ids
+from .decode import _to_host, ctc_greedy_ids, ids_to_text_host
 from .model import RCNN
 
 
@@ -78,7 +78,7 @@ class OCRInference:
             out = ctc_greedy_ids(logits, blank=self.blank, return_confidence=return_confidence)
             ids_h, lens_h = _to_host(out[0], out[1])
             conf_h = out[2].cpu().tolist() if return_confidence else None
-            for j in range(ids_h.shape[0]):
-                text = "".join(self.alphabet[k - 1] for k in ids_h[j, : lens_h[j]])
+            texts, _ = ids_to_text_host(ids_h, lens_h, self.alphabet)
+            for j, text in enumerate(texts):
                 results.append((text, conf_h[j]) if return_confidence else text)
         return results[0] if is_single else results

@@ -79,3 +79,26 @@ def test_charset_matches_reference_semantics(tmp_path):
     from rcnn_ocr_b200.charset import encode_ctc_targets
     flat, lens = encode_ctc_targets(["ab", "", "c a"], stoi)
     assert flat == [5, 6, 7, 4, 5] and lens == [2, 0, 3]
+
+
+def test_host_half_of_the_decode_matches_the_per_line_mapping():
+    """ids_to_text_host (batch-wide gather + one utf-32 decode for single-character alphabets, object table
+    otherwise) against the reference's per-line ``''.join(alphabet[p - 1] ...)`` (training/utils.py:146): ragged
+    and empty lines, an empty batch, multi-character tokens, non-BMP characters, out-of-range ids."""
+    import numpy as np
+    from rcnn_ocr_b200.decode import ids_to_text_host
+    rng = np.random.default_rng(0)
+    for alphabet in ([chr(0x430 + i) for i in range(60)], [chr(0x4E00 + i) for i in range(194)],
+                     ["a", "<PAD>", "bc", "\U0001F600", " "], ["x"]):
+        C = len(alphabet)
+        for B, T in ((0, 7), (1, 1), (5, 0), (37, 64), (256, 64)):
+            lens = rng.integers(0, T + 1, B).astype(np.int32)
+            ids = np.full((B, T), -1, np.int32)
+            for b in range(B):
+                ids[b, :lens[b]] = rng.integers(1, C + 1, lens[b])
+            texts, seqs = ids_to_text_host(ids, lens, alphabet)
+            want_seqs = [ids[b, :lens[b]].tolist() for b in range(B)]
+            want_texts = ["".join(alphabet[k - 1] for k in row) for row in want_seqs]
+            assert seqs == want_seqs and texts == want_texts
+    with pytest.raises(IndexError):
+        ids_to_text_host(np.array([[3, -1]], np.int32), np.array([1], np.int32), ["a", "b"])
