@@ -42,7 +42,9 @@ struct FxParams {
     __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
     __nv_bfloat16 *hcat;  // [B, T, 2H]
     unsigned int *sync;   // [ngroups * NH] zeroed before the launch
+    long long *tl;        // debug timeline (CTA 0, half 0) or nullptr
 };
+#define TLX(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
 
 // release / acquire at gpu scope around the TMA-stored h_t: see lstm_fwd.cu
 __device__ __forceinline__ void red_release_gpu_inc_x(unsigned int *p) {
@@ -100,6 +102,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
     unsigned int *counter = p.sync + group * NH;          // one per half
+    long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
 
     if (warp == 1) {
         if (lane == 0) {
@@ -155,6 +158,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                         const int tprev = dir ? t + 1 : t - 1;
                         for (int hf = 0; hf < NH; ++hf) {
                             wait_counter_x(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
+                            if (hf == 0) TLX(0);                     // P0: half 0's counter seen
                             fence_proxy_async_global();
                             for (int g = 0; g < nhb; ++g) {
                                 mbar_arrive_expect_tx(&h_full[hf * 4 + g], (uint32_t)cpb * kHalfBox);
@@ -224,6 +228,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                             const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS + hf * HS);
                             for (int g = 0; g < nhb; ++g) {
                                 mbar_wait(&h_full[hf * 4 + g], hphase);
+                                if (hf == 0 && g == 0) TLX(1);       // M0: first h box of half 0 landed
                                 tc_fence_after();
                                 for (int j = 0; j < cpb; ++j) {
                                     const int kc = g * cpb + j;
@@ -236,6 +241,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                             }
                         }
                         umma_commit(&tmem_full[hf * 2 + par]);
+                        if (hf == 0) TLX(2);                         // M1: half 0's MMAs issued
+                        if (hf == NH - 1) TLX(3);                    // M2: last half's MMAs issued
                     }
                     if (s > 0) hphase ^= 1;
                     ++nst;
@@ -252,7 +259,9 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 for (int s = 0; s < T; ++s) {
                     for (int hf = 0; hf < NH; ++hf) {
                         mbar_wait(&h_staged[hf], sphase);
+                        if (hf == 0) TLX(6);                         // R0: half 0 stored by its cell warps
                         red_release_gpu_inc_x(counter + hf);
+                        if (hf == 0) TLX(7);                         // R1: half 0 released
                     }
                     sphase ^= 1;
                 }
@@ -277,6 +286,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 uint32_t acc[32];
                 mbar_wait(&tmem_full[hf * 2 + par], use[par] & 1);
                 ++use[par];
+                if (threadIdx.x == 64) TLX(4);                       // E0: half 0's accumulator complete
                 tc_fence_after();
                 tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(par * NS + ch * 32), acc);
                 tmem_ld_wait();
@@ -302,6 +312,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_staged[hf]);
+                if (threadIdx.x == 64) TLX(5);                       // E1: cell phase done, h_t stored
                 if (SAVE) {
                     // gates_save [2, T, B, 4H]: this thread holds gate row r for 32 sequences; a lane pair swaps halves so
                     // that the even lane writes rows (r, r+1) of sequence 2i and the odd lane those of sequence 2i+1.
@@ -380,6 +391,7 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     p.bias = bias_p;
     p.csave = c_save;
     p.hcat = (__nv_bfloat16 *)hcat;
+    p.tl = debug_timeline();
     p.gsave = (__half *)gates_save;
     const int gsize = H / 32;
     p.nitems = 2 * ((B + NS - 1) / NS);
