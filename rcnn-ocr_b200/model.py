@@ -179,24 +179,24 @@ class BidirectionalLSTM(nn.Module):
                 self._prepared = (key, _Prepared(ops.lstm_pack(*self.rnn.ordered()), _cast2d(self.linear.weight)))
         return self._prepared[1]
 
-    def prefetch_weights(self, first: bool) -> "_Prepared":
+    def prefetch_weights(self) -> "_Prepared":
         """Training: convert this block's parameters for the kernels on the prefetch stream, concurrently with
-        whatever the current stream runs next (the recurrent kernels leave 20 SMs idle).  ``first``: the block
-        whose recurrence starts right away -- its forward views are converted on the current stream."""
+        whatever the current stream runs next (the input cast; the recurrent kernels leave 20 SMs idle).  The
+        forward views come first and have their own event."""
         main = torch.cuda.current_stream()
         side = _side_stream(self.linear.weight.device)
         with torch.no_grad():
-            packed = ops.lstm_pack(*self.rnn.ordered(), parts=1) if first else None
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                packed = ops.lstm_pack(*self.rnn.ordered(), parts=2 if first else 3, into=packed)
+                packed = ops.lstm_pack(*self.rnn.ordered(), parts=1)
+                ev_rows = side.record_event()
+                ops.lstm_pack(*self.rnn.ordered(), parts=2, into=packed)
                 lin_wb = _cast2d(self.linear.weight)
                 lin_wt = ops.transpose_bf16(lin_wb)
                 ev = side.record_event()
-            packed.blob.record_stream(side if first else main)
-            lin_wb.record_stream(main)
-            lin_wt.record_stream(main)
-        return _Prepared(packed, lin_wb, lin_wt, rows_event=None if first else ev, rest_event=ev)
+            for t in (packed.blob, lin_wb, lin_wt):
+                t.record_stream(main)
+        return _Prepared(packed, lin_wb, lin_wt, rows_event=ev_rows, rest_event=ev)
 
     def train(self, mode: bool = True):
         if mode:
@@ -215,12 +215,12 @@ class BidirectionalLSTM(nn.Module):
 
 class EncRNN(nn.Sequential):
     """nn.Sequential of BidirectionalLSTM blocks (same state-dict keys); in training the parameter conversions of
-    all blocks but the first block's forward views run on a second stream, under the first recurrence."""
+    all blocks run on a second stream, under the input cast and the first recurrence."""
 
     def forward(self, x):
         if _PREFETCH and self.training and x.is_cuda and torch.is_grad_enabled():
-            for i, blk in enumerate(self):
-                blk._prefetched = blk.prefetch_weights(first=(i == 0))
+            for blk in self:
+                blk._prefetched = blk.prefetch_weights()
         return super().forward(x)
 
 
