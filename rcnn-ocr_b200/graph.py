@@ -36,6 +36,12 @@ class GraphedStep:
             self.static_out = fn(*self.static_in)
         torch.cuda.synchronize()
 
+    def replay(self):
+        """Replay on whatever the static input tensors (``self.static_in``) hold -- for callers that stage the
+        next inputs straight into them (e.g. H2D copies on a copy stream, two GraphedSteps used in turn)."""
+        self.graph.replay()
+        return self.static_out
+
     def __call__(self, *inputs):
         """Copy ``inputs`` (device, or pinned host) into the static tensors and replay.  The result
         tensors are overwritten by the next call: clone what must outlive it."""
