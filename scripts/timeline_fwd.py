@@ -1,9 +1,11 @@
+"""Per-timestep timeline of the UNFUSED forward kernel (lstm_fwd_kernel, xp precomputed by K1); the default path is
+lstm_fwdx_kernel (scripts/timeline_fwdx.py).  An input width above 512 selects the unfused kernel."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import rcnn_ocr_b200 as R
 from rcnn_ocr_b200 import _lib
-B, T, I, H = 256, 64, 512, 512
+B, T, I, H = 256, 64, 576, 512
 torch.manual_seed(0)
 blk = R.BidirectionalLSTM(I, H, H).cuda()
 x = torch.randn(B, T, I, device="cuda")
