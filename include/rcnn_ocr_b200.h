@@ -152,7 +152,8 @@ int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcols, const vo
  *                               direction; also the buffer h_{t-1} is re-read from
  *   gates_save f16 [2, T, B, 4H] activated gates in P order, c_save f32 [2, T, B, H]: both NULL
  *                               for inference, both set when a backward pass will follow
- *   H must be 64, 128, 256 or 512 (cluster of H/32 CTAs per direction and 128 sequences).
+ *   H must be 64, 128, 256 or 512 (a group of H/32 CTAs owns one (direction, 64-sequence tile) work item at a
+ *   time; cooperative launch, the groups synchronise per step through release / acquire counters).
  * ------------------------------------------------------------------------------------- */
 size_t rcnn_lstm_packed_bytes(int I, int H);
 int rcnn_lstm_pack_weights(const float *w_ih_f, const float *w_hh_f, const float *b_ih_f, const float *b_hh_f,
