@@ -102,3 +102,26 @@ def test_host_half_of_the_decode_matches_the_per_line_mapping():
             assert seqs == want_seqs and texts == want_texts
     with pytest.raises(IndexError):
         ids_to_text_host(np.array([[3, -1]], np.int32), np.array([1], np.int32), ["a", "b"])
+
+
+def test_encoder_container_keeps_the_reference_state_dict_keys():
+    """make_enc_rnn returns an nn.Sequential subclass (EncRNN: weight-conversion prefetch in training) whose
+    state-dict keys and shapes are those of the reference's enc_rnn (model/model.py:195-198); the hand-off
+    format to the CTC head is a constructor choice, not a parameter."""
+    import torch.nn as nn
+    enc = R.make_enc_rnn(512, 64)
+    assert isinstance(enc, nn.Sequential) and len(enc) == 2
+    want = []
+    for i, isz in ((0, 512), (1, 64)):
+        for sfx in ("", "_reverse"):
+            want += [(f"{i}.rnn.weight_ih_l0{sfx}", (256, isz)), (f"{i}.rnn.weight_hh_l0{sfx}", (256, 64)),
+                     (f"{i}.rnn.bias_ih_l0{sfx}", (256,)), (f"{i}.rnn.bias_hh_l0{sfx}", (256,))]
+        want += [(f"{i}.linear.weight", (64, 128)), (f"{i}.linear.bias", (64,))]
+    got = [(k, tuple(v.shape)) for k, v in enc.state_dict().items()]
+    assert got == want
+    assert enc[0].out_dtype == torch.bfloat16 and enc[1].out_dtype == torch.float32
+    assert R.make_enc_rnn(512, 64, out_dtype=torch.bfloat16)[1].out_dtype == torch.bfloat16
+    from rcnn_ocr_b200 import ops
+    assert ops.weight_grads_supported(512, 512, 64) and ops.weight_grads_supported(256, 256, 128)
+    assert not ops.weight_grads_supported(512, 512, 16) and not ops.weight_grads_supported(64, 64, 64)
+    assert ops.fused_forward_supported(512, 512) and not ops.fused_forward_supported(576, 512)
