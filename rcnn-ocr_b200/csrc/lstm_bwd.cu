@@ -45,7 +45,6 @@ namespace {
 using namespace sm100;
 
 constexpr int NS = 64;     // sequences per work item (UMMA N)
-constexpr int LU = 32;     // hidden units per CTA
 constexpr int LK = 64;
 constexpr uint32_t kWTile = 128 * LK * 2;   // [128 output units x 64 k] bf16, SW128 = 16 KB
 constexpr uint32_t kBChunk = NS * LK * 2;   // [64 seq x 64 k] bf16, SW128 = 8 KB
@@ -93,15 +92,6 @@ __device__ __forceinline__ void wait_counter_b(const unsigned int *p, unsigned i
             __trap();
         }
     }
-}
-// L2-only loads / stores of the exchange buffer (it is rewritten every other step: never through L1)
-__device__ __forceinline__ uint4 ld_cg_v4(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-__device__ __forceinline__ void st_cg_v4(void *p, const uint4 &v) {
-    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint2 ld_ro_v2(const void *p) {
     uint2 r;
