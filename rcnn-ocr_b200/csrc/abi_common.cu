@@ -1,5 +1,7 @@
 // Error plumbing and device probing behind the C ABI (include/rcnn_ocr_b200.h).
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include "common.cuh"
 
 namespace rcnn {
@@ -19,7 +21,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 int num_sms() {
-    static thread_local int cached_dev = -1, cached = 0;
+    static thread_local int cached_dev = -1, cached = 0;   // keyed by the device id: re-read when the thread switches device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (dev != cached_dev) {
@@ -37,9 +39,14 @@ static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
 // ---- group-barrier counters for the recurrent kernels -------------------------------------------
-static const int kCounterRegion = 256, kCounterRegions = 64, kMaxDevices = 32;
+// Regions [0, kEagerRegions) are a ring for eager launches (a region is reused after kEagerRegions later calls,
+// in stream order behind its memset); a launch that is being CAPTURED into a CUDA graph keeps its region for
+// every replay, so it takes one of the remaining regions for good (never handed out again): an eager launch on
+// another stream can no longer memset a region a graph replay is spinning on.  The indices are atomic.
+static const int kCounterRegion = 256, kEagerRegions = 64, kCaptureRegions = 448, kMaxDevices = 32;
 static unsigned int *g_counters[kMaxDevices] = {};
-static unsigned int g_counter_next[kMaxDevices] = {};
+static std::atomic<unsigned int> g_counter_next[kMaxDevices], g_capture_next[kMaxDevices];
+static std::mutex g_counter_mutex;
 
 unsigned int *group_counters(int n, cudaStream_t s) {
     int dev = 0;
@@ -47,13 +54,35 @@ unsigned int *group_counters(int n, cudaStream_t s) {
         set_error("group_counters: n=%d device=%d unsupported", n, dev);
         return nullptr;
     }
-    if (!g_counters[dev]) {   // one-time 64 KB per device (like a library handle's workspace)
-        if (cudaMalloc(&g_counters[dev], sizeof(unsigned int) * kCounterRegion * kCounterRegions) != cudaSuccess) {
-            set_error("group_counters: cudaMalloc failed");
-            return nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (!g_counters[dev]) {   // one-time 512 KB per device (like a library handle's workspace)
+        std::lock_guard<std::mutex> lock(g_counter_mutex);
+        if (!g_counters[dev]) {
+            if (cap != cudaStreamCaptureStatusNone) {
+                set_error("group_counters: first use inside a stream capture (run one eager step first)");
+                return nullptr;
+            }
+            unsigned int *q = nullptr;
+            if (cudaMalloc(&q, sizeof(unsigned int) * kCounterRegion * (kEagerRegions + kCaptureRegions)) != cudaSuccess) {
+                set_error("group_counters: cudaMalloc failed");
+                return nullptr;
+            }
+            g_counters[dev] = q;
         }
     }
-    unsigned int *p = g_counters[dev] + (size_t)(g_counter_next[dev]++ % kCounterRegions) * kCounterRegion;
+    unsigned int region;
+    if (cap != cudaStreamCaptureStatusNone) {
+        region = g_capture_next[dev].fetch_add(1u);
+        if (region >= (unsigned)kCaptureRegions) {
+            set_error("group_counters: more than %d captured recurrent launches on device %d", kCaptureRegions, dev);
+            return nullptr;
+        }
+        region += kEagerRegions;
+    } else {
+        region = g_counter_next[dev].fetch_add(1u) % kEagerRegions;
+    }
+    unsigned int *p = g_counters[dev] + (size_t)region * kCounterRegion;
     if (cudaMemsetAsync(p, 0, sizeof(unsigned int) * kCounterRegion, s) != cudaSuccess) {
         set_error("group_counters: cudaMemsetAsync failed");
         return nullptr;

@@ -384,8 +384,10 @@ int launch_fwd(const CUtensorMap &tw, const CUtensorMap &th, const CUtensorMap &
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    static thread_local int max_clusters[2][4] = {};   // [SAVE][log2 H/64], per calling thread (device assumed fixed per thread)
-    int &mc = max_clusters[SAVE ? 1 : 0][p.H == 64 ? 0 : p.H == 128 ? 1 : p.H == 256 ? 2 : 3];
+    static thread_local int max_clusters[32][2][4] = {};   // [device][SAVE][log2 H/64]
+    int dev_id = 0;
+    RCNN_CUDA(cudaGetDevice(&dev_id));
+    int &mc = max_clusters[dev_id & 31][SAVE ? 1 : 0][p.H == 64 ? 0 : p.H == 128 ? 1 : p.H == 256 ? 2 : 3];
     if (mc == 0) {
         cfg.gridDim = dim3((unsigned)(p.csize * 1024));
         RCNN_CUDA(cudaOccupancyMaxActiveClusters(&mc, lstm_fwd_kernel<SAVE>, &cfg));

@@ -37,11 +37,26 @@ def _lengths(v, n: int, device, name: str):
     return torch.tensor(vals, dtype=torch.int64, device=device), (max(vals) if vals else 0)
 
 
+def sum_check(target_lengths, tg_numel: int) -> bool:
+    """Concatenated targets with host-resident lengths: True when the lengths overrun the target vector
+    (torch raises for this; device-resident lengths are checked by the kernel, which flags the row as bad)."""
+    if isinstance(target_lengths, torch.Tensor):
+        if target_lengths.is_cuda:
+            return False
+        total = int(target_lengths.sum())
+    else:
+        total = sum(int(a) for a in target_lengths)
+    return total > tg_numel
+
+
 class _CTCFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, targets, input_lengths, target_lengths, blank, reduction, zero_infinity,
                 from_logits, max_target_length):
         _lib.require_cuda(x, "log_probs/logits")
+        # decided BEFORE any conversion: autograd is off inside forward(), so x.float() / x.contiguous() below
+        # return tensors with requires_grad == False (bf16 / fp16 log-probs under autocast, strided classes)
+        need_grad = ctx.needs_input_grad[0]
         if x.dim() != 3:
             raise RuntimeError(f"expected [T,N,C] input, got {tuple(x.shape)}")
         if x.dtype != torch.float32:
@@ -66,6 +81,7 @@ class _CTCFunction(torch.autograd.Function):
         elif tg.dim() == 1:
             tg = tg.contiguous()
             tgt_stride, bound = 0, None
+            tg_numel = tg.numel()
             if tg.numel() == 0:
                 tg = torch.zeros((1,), dtype=torch.int64, device=dev)
         else:
@@ -75,10 +91,16 @@ class _CTCFunction(torch.autograd.Function):
                 max_target_length = tl_max if bound is None else min(tl_max, bound)
             elif bound is not None:
                 max_target_length = bound
-            else:  # concatenated targets with device-resident lengths: one host sync
-                max_target_length = int(tl.max()) if N > 0 else 0
+            else:  # concatenated targets with device-resident lengths: one host sync (maximum and sum together)
+                mx_sum = torch.stack([tl.max(), tl.sum()]).tolist() if N > 0 else [0, 0]
+                max_target_length = int(mx_sum[0])
+                if mx_sum[1] > tg_numel:
+                    raise RuntimeError("sum(target_lengths) exceeds the number of concatenated targets")
         max_target_length = max(int(max_target_length), 0)
-        need_grad = x.requires_grad
+        if bound is not None:
+            max_target_length = min(max_target_length, bound)   # never read past a padded row
+        elif tl_max is not None and sum_check(target_lengths, tg_numel):
+            raise RuntimeError("sum(target_lengths) exceeds the number of concatenated targets")
         L = _lib.lib()
         with torch.cuda.device(dev):
             nll = torch.empty((N,), dtype=torch.float32, device=dev)

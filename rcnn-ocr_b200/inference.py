@@ -19,7 +19,8 @@ from .model import RCNN
 
 class OCRInference:
     def __init__(self, model_path=None, charset_path=None, device: str = "auto", img_h: int = 64,
-                 img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256, decoder: str = "ctc"):
+                 img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256,
+                 decoder: str | None = None):
         if device == "auto":
             device = "cuda"
         self.device = torch.device(device)
@@ -30,20 +31,37 @@ class OCRInference:
         self.alphabet, self.num_ctc_classes, self.blank = ctc_alphabet(self.itos)
         self.pad_id, self.eos_id = self.stoi.get("<PAD>", 0), self.stoi.get("<EOS>", 2)
         self.blank_id = self.stoi.get("<BLANK>")
+        self.unused_checkpoint_keys: List[str] = []
         if model is None:
-            model = RCNN(num_classes=len(self.itos), hidden_size=hidden_size,
-                         sos_id=self.stoi.get("<SOS>", 1), eos_id=self.eos_id,
-                         pad_id=self.pad_id, blank_id=self.blank_id, decoder=decoder)
+            state = None
             if model_path is not None:
                 state = torch.load(model_path, map_location="cpu")
                 if isinstance(state, dict) and "model_state" in state:
                     state = state["model_state"]
                 elif isinstance(state, dict) and "model_state_dict" in state:
                     state = state["model_state_dict"]
-                if any(k.startswith("ctc_head.") for k in state):
+                has_ctc = any(k.startswith("ctc_head.") for k in state)
+                has_attn = any(k.startswith("attn.") for k in state)
+                if decoder is None:
+                    # a reference checkpoint carries attn.* and no CTC head: decode it the reference's way
+                    decoder = "ctc" if has_ctc or not has_attn else "attention"
+                elif decoder == "ctc" and not has_ctc:
+                    raise ValueError(f"{model_path} has no ctc_head.* weights: its predictions through a randomly "
+                                     "initialised CTC head would be garbage; pass decoder='attention' (or None) "
+                                     "to decode a reference checkpoint with its own attention decoder")
+            decoder = decoder or "ctc"
+            model = RCNN(num_classes=len(self.itos), hidden_size=hidden_size,
+                         sos_id=self.stoi.get("<SOS>", 1), eos_id=self.eos_id,
+                         pad_id=self.pad_id, blank_id=self.blank_id, decoder=decoder)
+            if state is not None:
+                if decoder == "ctc":
                     model.load_state_dict(state, strict=True)
                 else:
-                    model.load_reference_state_dict(state)
+                    self.unused_checkpoint_keys = model.load_reference_state_dict(state)
+                    if self.unused_checkpoint_keys:
+                        import warnings
+                        warnings.warn(f"{len(self.unused_checkpoint_keys)} checkpoint keys were not used: "
+                                      f"{self.unused_checkpoint_keys[:5]}")
         self.model = model.to(self.device).eval()
 
     @torch.no_grad()

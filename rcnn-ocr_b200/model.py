@@ -374,10 +374,11 @@ class RCNN(nn.Module):
         self.enc_rnn = make_enc_rnn(self.cnn.out_channels, hidden_size,
                                     out_dtype=torch.bfloat16 if decoder == "ctc" else torch.float32)
         self.enc_dropout = nn.Dropout(enc_dropout_p)
-        self.ctc_head = CTCHead(hidden_size, self.num_ctc_classes)
-        # decoder="attention": the reference's own decoder (model/model.py:204-214), inference path on the device;
-        # forward() then returns what the reference's forward returns and attn.* of a checkpoint is loaded too
+        # decoder="attention": the reference's own decoder (model/model.py:204-214); forward() then returns what the
+        # reference's forward returns, attn.* of a checkpoint is loaded too, and there is NO ctc_head, so that the
+        # state dict has exactly the reference's keys (its strict=True loaders accept checkpoints saved from here)
         self.attn = None
+        self.ctc_head = CTCHead(hidden_size, self.num_ctc_classes) if decoder == "ctc" else None
         if decoder == "attention":
             from .attention import Attention
             self.attn = Attention(input_size=hidden_size, hidden_size=hidden_size, num_classes=num_classes, sos_id=sos_id,

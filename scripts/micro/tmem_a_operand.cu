@@ -7,15 +7,7 @@
 #include "sm100.cuh"
 using namespace rcnn::sm100;
 
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
+// (tmem_cp_128x256b / umma_bf16_ts moved into sm100.cuh after this probe)
 
 __global__ void __launch_bounds__(128) probe(float *out) {
     __shared__ __align__(1024) unsigned char a_s[16384];   // [128 x 64] bf16 SW128
