@@ -4,6 +4,7 @@ Run in the build container only (it reads /root/reference, which does not exist 
 the GPU box):   python tests/make_golden.py
 
   decode_*.npz   training/utils.py:122-150  ctc_greedy_decoder  (reference code, imported)
+  decodefn_*.npz training/utils.py:153-162  decode              (reference code, imported)
   bilstm_*.npz   model/model.py:151-163     BidirectionalLSTM   (reference code, imported)
   encrnn_*.npz   model/model.py:195-198     Sequential of two blocks, outputs + all grads
   attn_*.npz     model/model.py:50-148      Attention (reference code, imported), eval mode
@@ -21,7 +22,7 @@ import torch.nn.functional as F
 REF = "/root/reference"
 sys.path.insert(0, REF)
 from model.model import BidirectionalLSTM  # noqa: E402
-from training.utils import ctc_greedy_decoder  # noqa: E402
+from training.utils import ctc_greedy_decoder, decode as ref_decode  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -73,6 +74,24 @@ def gen_decode():
     texts, seqs = ctc_greedy_decoder(logits, list("abcdef"), blank=3)
     np.savez_compressed(os.path.join(OUT, "decode_blank3.npz"), logits=logits.numpy(), blank=3,
                         alphabet=json.dumps(list("abcdef")), texts=json.dumps(texts), seqs=json.dumps(seqs))
+
+
+def gen_decode_fn():
+    """decodefn_*.npz: the reference's ``decode(ctc_out, alphabet, method)`` (training/utils.py:153-162) --
+    tuple unwrap, log_softmax, greedy -- called exactly as a validation loop would call it."""
+    itos = charset()
+    g = torch.Generator().manual_seed(4321)
+    cases = {
+        "tuple_b12_t9": ((torch.randn(12, 9, len(itos) + 1, generator=g) * 3, torch.zeros(1)), itos),   # tuple input
+        "plain_b6_t20": (torch.randn(6, 20, 11, generator=g), list("abcdefghij")),                     # B < T: heuristic
+        "cfga_b32_t16": ((torch.randn(32, 16, len(itos) + 1, generator=g),), itos),                    # config.json geometry
+    }
+    for name, (out, alpha) in cases.items():
+        texts, seqs = ref_decode(out, alpha, method="greedy")
+        logits = out[0] if isinstance(out, tuple) else out
+        np.savez_compressed(os.path.join(OUT, f"decodefn_{name}.npz"), logits=logits.numpy(),
+                            is_tuple=np.array(int(isinstance(out, tuple))), alphabet=json.dumps(alpha),
+                            texts=json.dumps(texts), seqs=json.dumps(seqs))
 
 
 def gen_bilstm():
@@ -194,6 +213,7 @@ def gen_attention():
 
 if __name__ == "__main__":
     gen_decode()
+    gen_decode_fn()
     gen_bilstm()
     gen_ctc()
     gen_attention()

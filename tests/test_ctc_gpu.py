@@ -177,3 +177,55 @@ def test_full_size_properties():
                                                tl[sl].cpu().numpy(), 0, True, True)
     np.testing.assert_allclose(nll[sl].detach().cpu().numpy(), want_nll, rtol=RTOL)
     _assert_grad(x.grad[:, sl].cpu().numpy(), want_g)
+
+
+def test_low_precision_and_strided_inputs_still_get_gradients():
+    """bf16 / fp16 log-probs (autocast) and inputs with a non-unit class stride are converted inside
+    forward(); the gradient must still come back (in the input's dtype and shape) and equal the fp32 result."""
+    g = torch.Generator().manual_seed(21)
+    T, N, C, L = 12, 5, 9, 4
+    base = torch.randn(T, N, C, generator=g).cuda()
+    tg = torch.randint(1, C, (N, L), generator=g).cuda()
+    il, tl = torch.full((N,), T), torch.randint(1, L + 1, (N,), generator=g)
+
+    def run(x):
+        x = x.detach().clone().requires_grad_(True)
+        loss = R.ctc_loss(x.log_softmax(-1) if x.dtype == torch.float32 else x, tg, il, tl, 0, "sum", True)
+        loss.backward()
+        return loss.item(), x.grad
+
+    # bf16 log-probs: compare against the fp32 path fed the same (bf16-rounded) values
+    lp16 = base.log_softmax(-1).to(torch.bfloat16)
+    x16 = lp16.detach().clone().requires_grad_(True)
+    loss16 = R.ctc_loss(x16, tg, il, tl, 0, "sum", True)
+    loss16.backward()
+    assert x16.grad is not None and x16.grad.dtype == torch.bfloat16 and x16.grad.shape == x16.shape
+    x32 = lp16.float().detach().clone().requires_grad_(True)
+    loss32 = R.ctc_loss(x32, tg, il, tl, 0, "sum", True)
+    loss32.backward()
+    np.testing.assert_allclose(loss16.item(), loss32.item(), rtol=1e-6)
+    np.testing.assert_allclose(x16.grad.float().cpu().numpy(), x32.grad.cpu().numpy(), rtol=1e-2, atol=1e-2)
+    assert x16.grad.float().abs().max().item() > 0
+
+    # class stride 2 (a slice of a wider tensor): converted with .contiguous() inside forward()
+    wide = torch.zeros(T, N, 2 * C, device="cuda")
+    wide[:, :, ::2] = base.log_softmax(-1)
+    xs = wide.detach().clone().requires_grad_(True)
+    loss_s = R.ctc_loss(xs[:, :, ::2], tg, il, tl, 0, "sum", True)
+    loss_s.backward()
+    xd = base.log_softmax(-1).detach().clone().requires_grad_(True)
+    loss_d = R.ctc_loss(xd, tg, il, tl, 0, "sum", True)
+    loss_d.backward()
+    np.testing.assert_allclose(loss_s.item(), loss_d.item(), rtol=1e-6)
+    np.testing.assert_allclose(xs.grad[:, :, ::2].cpu().numpy(), xd.grad.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert (xs.grad[:, :, 1::2] == 0).all()
+
+
+def test_target_overrun_raises_like_torch():
+    x = torch.randn(6, 2, 5, device="cuda").log_softmax(-1)
+    with pytest.raises(RuntimeError):      # concatenated targets shorter than sum(target_lengths)
+        R.ctc_loss(x, torch.tensor([1, 2, 3]), torch.tensor([6, 6]), torch.tensor([2, 2]))
+    # padded targets: a length beyond the row width is a bad row (inf / NaN-free zero with zero_infinity), never an OOB read
+    out = R.ctc_loss(x, torch.tensor([[1, 2], [3, 4]]).cuda(), torch.tensor([6, 6]), torch.tensor([2, 5]), 0, "none", True,
+                     max_target_length=5)
+    assert torch.isfinite(out).all()

@@ -33,6 +33,23 @@ def test_golden_reference_outputs(name):
     assert seqs_h == seqs and texts_h == texts
 
 
+@pytest.mark.parametrize("name", _names("decodefn_"))
+def test_decode_function_matches_the_reference(name):
+    """``decode(ctc_out, alphabet, method)`` against the reference's own ``decode`` (training/utils.py:153-162:
+    tuple unwrap, log_softmax, greedy with the shape heuristic), bit-exact strings and index lists."""
+    d = golden(name)
+    alphabet = json.loads(str(d["alphabet"]))
+    logits = torch.from_numpy(d["logits"]).cuda()
+    out = (logits, torch.zeros(1, device="cuda")) if int(d["is_tuple"]) else logits
+    texts, seqs = R.decode(out, alphabet, method="greedy")
+    assert seqs == json.loads(str(d["seqs"]))
+    assert texts == json.loads(str(d["texts"]))
+    texts2, seqs2 = R.decode(out, alphabet)          # default method
+    assert (texts2, seqs2) == (texts, seqs)
+    with pytest.raises(ValueError):
+        R.decode(out, alphabet, method="beam")
+
+
 def _check(logits, blank=0, **kw):
     ids, lens = R.ctc_greedy_ids(logits, blank=blank, **kw)
     x = logits.float().cpu().numpy()

@@ -17,6 +17,16 @@ def _names(prefix):
     return sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
 
 
+@pytest.mark.parametrize("name", _names("decodefn_"))
+def test_decode_function_goldens(name):
+    """The reference's decode() = log_softmax + greedy; the oracle's greedy on the raw scores gives the same
+    strings (log_softmax is argmax-invariant on these inputs)."""
+    d = golden(name)
+    alphabet = json.loads(str(d["alphabet"]))
+    texts, seqs = oracle.ctc_greedy_decoder(d["logits"], alphabet, blank=0)
+    assert seqs == json.loads(str(d["seqs"])) and texts == json.loads(str(d["texts"]))
+
+
 @pytest.mark.parametrize("name", _names("decode_"))
 def test_decode_matches_reference(name):
     d = golden(name)
