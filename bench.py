@@ -188,6 +188,9 @@ class TrainStep:
 
     def __call__(self, feats, tg, il, tl):
         self.opt.zero_grad(set_to_none=True)
+        # the feature columns come from a trainable backbone (model/model.py:216-219): they need their gradient,
+        # so block 1's dX GEMM is part of the step (backward = 2 x forward FLOPs)
+        feats = feats.detach().requires_grad_(True)
         logits = self.head(self.enc(feats))                                  # [B,T,C] fp32
         loss = self.R.ctc_loss_from_logits(logits.permute(1, 0, 2), tg, il, tl, 0, "mean", True,
                                            max_target_length=CFG["LMAX"])
@@ -213,6 +216,200 @@ class InferStep:
         feats = feats.to(self.t.params[0].device, non_blocking=True)   # pinned host -> device
         logits = self.t.head(self.t.enc(feats))
         return self.t.R.ctc_greedy_decoder(logits, self.alphabet, batch_first=True)
+
+
+
+# ----------------------------------------------------------------------------- vendor bar (torch on the same B200)
+class _VendorBlock(torch.nn.Module):
+    """model/model.py:151-163 as the reference writes it: nn.LSTM (cuDNN on CUDA) + nn.Linear (cuBLAS)."""
+
+    def __init__(self, n_in, n_hidden, n_out):
+        super().__init__()
+        self.rnn = torch.nn.LSTM(n_in, n_hidden, bidirectional=True, batch_first=True)
+        self.linear = torch.nn.Linear(2 * n_hidden, n_out)
+
+    def forward(self, x):
+        self.rnn.flatten_parameters()
+        y, _ = self.rnn(x)
+        return self.linear(y)
+
+
+class VendorStep:
+    """The same cfg-B train step through torch's own CUDA kernels (cuDNN LSTM, cuBLAS, ATen log_softmax + CTC,
+    fused Adam) under bf16 autocast, as training/train.py:499-508 runs its model -- the bar to beat on this box."""
+
+    def __init__(self, device):
+        torch.manual_seed(0)
+        self.enc = torch.nn.Sequential(_VendorBlock(CFG["IN"], CFG["H"], CFG["H"]),
+                                       _VendorBlock(CFG["H"], CFG["H"], CFG["H"])).to(device)
+        self.head = torch.nn.Linear(CFG["H"], CFG["C"]).to(device)
+        self.params = list(self.enc.parameters()) + list(self.head.parameters())
+        self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True, capturable=True)
+        self.il = [CFG["T"]] * CFG["B"]
+
+    def __call__(self, feats, tg, il, tl):
+        import torch.nn.functional as F
+        self.opt.zero_grad(set_to_none=True)
+        feats = feats.detach().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = self.head(self.enc(feats))
+        lp = F.log_softmax(logits.float(), dim=2).permute(1, 0, 2)
+        loss = F.ctc_loss(lp, tg, il, tl, blank=0, reduction="mean", zero_infinity=True)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    @torch.no_grad()
+    def infer(self, feats):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = self.head(self.enc(feats))
+        return logits.argmax(dim=2)     # (the reference then loops over B*T .item() calls on the host; not timed here)
+
+
+def run_vendor(args, dev, B, timed_fn):
+    """Returns the `vendor` object: torch-CUDA train step and encoder+argmax inference at cfg B, device-resident,
+    CUDA-graph replay when torch's ops allow the capture (else eager, stated)."""
+    import rcnn_ocr_b200 as R
+    v = VendorStep(dev[0][0].device)
+    # F.ctc_loss takes the lengths from the host (IntArrayRef): CPU tensors avoid a sync per step
+    # (a captured graph bakes them in, so the ring rotates the features and keeps batch 0's targets / lengths)
+    il0, tl0 = dev[0][2].cpu(), dev[0][3].cpu()
+    batches = [[b[0], dev[0][1], il0, tl0] for b in dev]
+    mode = "eager"
+    fn = lambda i: v(*batches[i % len(batches)])
+    if args.graph:
+        try:
+            g = R.GraphedStep(lambda f, t: v(f, t, il0, tl0), batches[0][:2])
+            fn = lambda i: g(*batches[i % len(batches)][:2])
+            mode = "cuda-graph replay"
+        except Exception as e:  # noqa: BLE001 -- ATen's CTC stages its offsets through pageable host memory
+            torch.cuda.synchronize()
+            mode = f"eager (capture failed: {type(e).__name__})"
+    ms = timed_fn(fn)
+    v.enc.eval()
+    ms_inf = timed_fn(lambda i: v.infer(batches[i % len(batches)][0]))
+    return {"value": round(B / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms, 4), "launch_mode": mode,
+            "infer": {"value": round(B / (ms_inf * 1e-3), 1), "ms_per_step": round(ms_inf, 4),
+                      "note": "encoder + head + argmax only (no collapse / strings)"},
+            "what": "torch 2.11 CUDA: nn.LSTM (cuDNN, bidirectional, batch_first) + nn.Linear x2 + head under bf16 autocast, "
+                    "F.log_softmax + F.ctc_loss (ATen CUDA), backward, fused Adam -- model/model.py:154-162, "
+                    "training/train.py:499-508 on the same GPU, same inputs, device-resident"}
+
+
+# ----------------------------------------------------------------------------- cfg 1: minimal_inference
+def run_cfg1(args, device, timed_fn, cpu: bool):
+    """BASELINE configs[0] (minimal_inference.py:13-15 -> inference.py:155-180): RCNN(194, hidden 256), 32 synthetic
+    lines of 32x128, eval, greedy decode -> strings."""
+    import rcnn_ocr_b200 as R
+    torch.manual_seed(0)
+    model = R.RCNN(194, hidden_size=256).to(device).eval().to(memory_format=torch.channels_last)
+    alphabet = [chr(0x4E00 + i) for i in range(194)]
+    g = torch.Generator().manual_seed(1234)
+    host = [(torch.rand(32, 3, 32, 128, generator=g) * 2 - 1).pin_memory() for _ in range(4)]
+    dev = [h.to(device).contiguous(memory_format=torch.channels_last) for h in host]
+
+    @torch.no_grad()
+    def fwd(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feats = model._features(x)
+        return R.ctc_greedy_ids(model.ctc_head(model._encode_features(feats)))
+
+    gfwd, mode = fwd, "eager"
+    if args.graph:
+        try:
+            gfwd = R.GraphedStep(fwd, [dev[0]])
+            mode = "cuda-graph replay"
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            mode = f"eager (capture failed: {type(e).__name__})"
+    ms = timed_fn(lambda i: gfwd(dev[i % 4]))
+
+    def e2e(i):
+        x = host[i % 4].to(device, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        ids, lens = gfwd(x)
+        return R.ids_to_text(ids, lens, alphabet)[0]
+
+    ms_e2e = timed_fn(e2e)
+    T = int(model._features(dev[0]).shape[1])
+    out = {"value": round(32 / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms, 4), "launch_mode": mode,
+           "e2e": {"value": round(32 / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 4),
+                   "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 32 * (T + 1) * 4},
+           "config": {"workload": "cfg1 minimal_inference: RCNN(194, hidden 256) eval, x[32,3,32,128] in [-1,1], greedy "
+                                  "CTC decode -> strings", "T": T, "backbone": "torch/cuDNN, channels_last + bf16 autocast"}}
+    if cpu:
+        from oracle import ref_port
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = ref_port.RefRCNN(194, 256).eval()
+        x = host[0].clone()
+        ref.infer(x[:4], alphabet)
+        t0 = time.perf_counter()
+        ref.infer(x, alphabet)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": round(32 / dt, 1), "unit": "lines/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "one batch of 32 lines after a 4-line warm-up, oracle/ref_port.RefRCNN (SE-ResNet31 + "
+                                         "nn.LSTM encoder + head on torch CPU, the reference's per-frame .item() decode loop)"}
+    return out
+
+
+# ----------------------------------------------------------------------------- cfg 4: full train step, strong scaling
+class FullTrainStep:
+    """BASELINE configs[3] (training/train.py:493-508 with configs/config.json:20-29): images -> SE-ResNet31 (torch/cuDNN,
+    channels_last, bf16 autocast) -> enc_rnn (K1/K2) -> CTC head -> fused CTC loss (K3) -> backward -> gradient
+    all-reduce of ALL parameters -> Adam.  GLOBAL batch 512, sharded over the ranks (strong scaling)."""
+    GLOBAL_B = 512
+
+    def __init__(self, device, world, hidden):
+        import rcnn_ocr_b200 as R
+        from rcnn_ocr_b200.dist import GradAllReducer
+        self.R = R
+        torch.manual_seed(0)
+        self.model = R.RCNN(194, hidden_size=hidden).to(device).to(memory_format=torch.channels_last)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True, capturable=True)
+        self.reducer = GradAllReducer(self.params) if world > 1 else None
+
+    def __call__(self, x, tg, il, tl):
+        self.opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feats = self.model._features(x)
+        logits = self.model.ctc_head(self.model._encode_features(feats))
+        loss = self.R.ctc_loss_from_logits(logits.permute(1, 0, 2), tg, il, tl, 0, "mean", True,
+                                           max_target_length=tg.shape[1])
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        return loss
+
+
+def run_cfg4(args, device, world, rank, timed_fn, hidden=256):
+    from rcnn_ocr_b200.dist import shard_range
+    import rcnn_ocr_b200 as R
+    lo, hi = shard_range(FullTrainStep.GLOBAL_B, rank, world)
+    Bl = hi - lo
+    step = FullTrainStep(device, world, hidden)
+    with torch.no_grad():
+        T = int(step.model._features(torch.zeros(1, 3, 32, 128, device=device)).shape[1])
+    lmax = max(1, min(32, T // 2))            # labels U{1..lmax}: a CTC alignment must fit T frames
+    batches = []
+    for i in range(4):
+        g = torch.Generator().manual_seed(4321 + 31 * rank + i)
+        x = (torch.rand(Bl, 3, 32, 128, generator=g) * 2 - 1).to(device).contiguous(memory_format=torch.channels_last)
+        tl = torch.randint(1, lmax + 1, (Bl,), generator=g).to(device)
+        tg = torch.randint(4, 195, (Bl, lmax), generator=g).to(device)      # itos[3:] -> CTC classes 4..194
+        batches.append([x, tg, torch.full((Bl,), T, dtype=torch.long, device=device), tl])
+    fn, mode = step, "eager"
+    if args.graph and (world == 1 or args.graph_dp):
+        try:
+            fn = R.GraphedStep(step, batches[0])
+            mode = "cuda-graph replay"
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            fn, mode = step, f"eager (capture failed: {type(e).__name__})"
+    ms = timed_fn(lambda i: fn(*batches[i % 4]))
+    # share of the step that is this repo's kernels: the same step without the backbone (features as inputs)
+    return {"ms": ms, "mode": mode, "T": T, "lmax": lmax, "per_gpu_batch": Bl, "hidden": hidden, "keep": (step, fn)}
+
 
 
 def timed(fn, steps, warmup, sync, barrier):
@@ -375,7 +572,39 @@ def run_ours(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             attn_res["cpu_baseline"] = {"value": round(32 / dt, 1), "unit": "lines/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "32 lines x 26 steps, oracle/ref_port.RefAttention (the reference's op sequence)"}
+    # ---- cfg 5: inference sweep over the batch size (global batch B5, sharded over the ranks, no collective) ----
+    from rcnn_ocr_b200.dist import shard_range
+    tf = lambda fn: max_over_ranks(timed(fn, args.steps, args.warmup, sync, barrier))
+    sweep = []
+    for B5 in ([] if args.no_extras else [1, 32, 256, 4096]):
+        lo5, hi5 = shard_range(B5, rank, world)
+        if B5 < world:
+            continue
+        g5 = torch.Generator().manual_seed(99 + rank)
+        f5 = [torch.randn(hi5 - lo5, CFG["T"], CFG["IN"], generator=g5).to(device) for _ in range(2 if B5 >= 4096 else 4)]
+        fn5 = step.R.GraphedStep(infer.device, [f5[0]]) if use_graph else infer.device
+        ms5 = tf(lambda i: fn5(f5[i % len(f5)]))
+        sweep.append({"global_batch": B5, "per_gpu_batch": hi5 - lo5, "ms_per_batch": round(ms5, 4),
+                      "value": round(B5 / (ms5 * 1e-3), 1), "unit": "lines/s"})
+        del fn5, f5
     step.enc.train(); step.head.train()
+
+    # ---- vendor bar, cfg 1, cfg 4 (strong scaling) ------------------------------------------------------------
+    vendor = cfg1 = cfg4 = None
+    if not args.no_extras:
+        if world == 1:
+            vendor = run_vendor(args, dev, B, tf)
+            cfg1 = run_cfg1(args, device, tf, cpu=(rank == 0 and not args.no_cpu_baseline))
+        r4 = run_cfg4(args, device, world, rank, tf, hidden=256)
+        gb = FullTrainStep.GLOBAL_B
+        cfg4 = {"value": round(gb / (r4["ms"] * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(r4["ms"], 4),
+                "scaling": "strong", "global_batch": gb, "per_gpu_batch": r4["per_gpu_batch"], "launch_mode": r4["mode"],
+                "config": {"workload": "cfg4 full train step (training/train.py:493-508, configs/config.json:20-29): images "
+                                       "[B,3,32,128] -> SE-ResNet31 (torch/cuDNN, channels_last, bf16 autocast) -> enc_rnn "
+                                       f"(hidden {r4['hidden']}) -> CTC head -> fused CTC loss -> backward -> all-reduce of all "
+                                       "gradients -> Adam", "T": r4["T"], "label_len": f"U{{1..{r4['lmax']}}}",
+                           "parallelism": f"dp{world}"}}
+        del r4
 
     # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
     _lib.prof_enable(True)
@@ -485,6 +714,10 @@ def run_ours(args, rank, world, local_rank):
             "launch_mode": "cuda-graph replay (one graph = the whole step)" if use_graph else "eager",
             "gpu_launches": round(launches * args.steps),
             "gpu_launches_per_step": round(launches, 1),
+            "vendor": vendor,
+            "vs_vendor": ({"train": round(total_B / (ms_train * 1e-3) / vendor["value"], 3),
+                           "infer": round(total_B / (ms_inf * 1e-3) / vendor["infer"]["value"], 3)} if vendor else None),
+            "cfg1_minimal_inference": cfg1, "cfg4_strong": cfg4, "cfg5_infer_sweep": sweep or None,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
             "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)] if losses else None,
         }
@@ -528,6 +761,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=64, help="lines per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-attention", action="store_true", help="skip the attention-decoder (section 8f-1) measurement")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the vendor bar, cfg 1 (minimal_inference), cfg 4 (strong-scaled full step) and the cfg 5 sweep")
     ap.add_argument("--no-graph-dp", dest="graph_dp", action="store_false",
                     help="N>1: launch eagerly (default: the NCCL bucket all-reduces on the side stream join the capture)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",

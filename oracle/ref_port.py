@@ -108,3 +108,22 @@ class RefAttention(nn.Module):
             probs[:, t] = logits
             y = logits.argmax(1)
         return probs
+
+
+class RefRCNN(nn.Module):
+    """cfg 1 (minimal_inference.py:13-15 -> inference.py:155-180) on the CPU: SE-ResNet31 (the state-dict compatible
+    restatement of model/seresnet31.py:70-187, pinned to the reference module in tests/test_oracle_golden.py) ->
+    mean over height -> the reference's encoder blocks -> a CTC head (the north_star's decoder) -> the reference's
+    greedy loop.  Timed as bench.py's cfg-1 CPU baseline."""
+
+    def __init__(self, num_classes: int, hidden: int):
+        super().__init__()
+        import rcnn_ocr_b200 as R          # only the pure-torch backbone restatement; no kernels on this path
+        self.cnn = R.SEResNet31(3, 512)
+        self.enc_rnn = make_encoder(512, hidden)
+        self.head = nn.Linear(hidden, num_classes + 1)
+
+    @torch.no_grad()
+    def infer(self, x, alphabet):
+        feats = self.cnn(x).mean(dim=2).permute(0, 2, 1)
+        return greedy_decode_loop(self.head(self.enc_rnn(feats)), alphabet, 0)

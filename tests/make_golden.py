@@ -5,6 +5,7 @@ the GPU box):   python tests/make_golden.py
 
   decode_*.npz   training/utils.py:122-150  ctc_greedy_decoder  (reference code, imported)
   decodefn_*.npz training/utils.py:153-162  decode              (reference code, imported)
+  cnn_*.npz      model/seresnet31.py:70-187 SEResNet31          (reference code, imported)
   bilstm_*.npz   model/model.py:151-163     BidirectionalLSTM   (reference code, imported)
   encrnn_*.npz   model/model.py:195-198     Sequential of two blocks, outputs + all grads
   attn_*.npz     model/model.py:50-148      Attention (reference code, imported), eval mode
@@ -92,6 +93,29 @@ def gen_decode_fn():
         np.savez_compressed(os.path.join(OUT, f"decodefn_{name}.npz"), logits=logits.numpy(),
                             is_tuple=np.array(int(isinstance(out, tuple))), alphabet=json.dumps(alpha),
                             texts=json.dumps(texts), seqs=json.dumps(seqs))
+
+
+def gen_cnn():
+    """cnn_*.npz: the reference's SEResNet31 (model/seresnet31.py:70-187, imported) in eval mode on recipe weights
+    (conftest.recipe_state_dict: a function of the state-dict keys only), input and output stored."""
+    from model.seresnet31 import SEResNet31
+    from conftest import recipe_state_dict
+    ref = SEResNet31(3, 512).eval()
+    ref.load_state_dict(recipe_state_dict(ref, 77), strict=True)
+    g = torch.Generator().manual_seed(78)
+    x = torch.rand(2, 3, 32, 64, generator=g) * 2 - 1
+    with torch.no_grad():
+        y = ref(x)
+    np.savez_compressed(os.path.join(OUT, "cnn_eval_2x32x64.npz"), x=x.numpy(), y=y.numpy(), seed=np.array(77),
+                        keys=json.dumps(sorted(ref.state_dict().keys())))
+    # training mode (batch statistics), one forward + backward: output, input gradient, one weight gradient
+    ref.train()
+    ref.load_state_dict(recipe_state_dict(ref, 79), strict=True)
+    xt = (torch.rand(4, 3, 32, 64, generator=g) * 2 - 1).requires_grad_(True)
+    yt = ref(xt)
+    yt.square().mean().backward()
+    np.savez_compressed(os.path.join(OUT, "cnn_train_4x32x64.npz"), x=xt.detach().numpy(), y=yt.detach().numpy(),
+                        dx=xt.grad.numpy(), dw0=ref.conv0[0].weight.grad.numpy(), seed=np.array(79))
 
 
 def gen_bilstm():
@@ -214,6 +238,7 @@ def gen_attention():
 if __name__ == "__main__":
     gen_decode()
     gen_decode_fn()
+    gen_cnn()
     gen_bilstm()
     gen_ctc()
     gen_attention()

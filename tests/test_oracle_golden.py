@@ -170,3 +170,27 @@ def test_attention_port_matches_reference_module_outputs():
         np.testing.assert_allclose(got, d["probs"], rtol=1e-5, atol=1e-5)
         n += 1
     assert n >= 2
+
+
+def test_cnn_adapter_matches_the_reference_backbone():
+    """rcnn_ocr_b200.SEResNet31 (the state-dict compatible restatement that RCNN keeps so that it stays a drop-in,
+    and that oracle/ref_port.RefRCNN times on the CPU) against the reference's own module (model/seresnet31.py:70-187,
+    imported by tests/make_golden.py): same keys, same eval-mode output, same training-mode output and gradients."""
+    import rcnn_ocr_b200 as R
+    from conftest import recipe_state_dict
+    d = golden("cnn_eval_2x32x64.npz")
+    ours = R.SEResNet31(3, 512).eval()
+    assert sorted(ours.state_dict().keys()) == json.loads(str(d["keys"]))
+    ours.load_state_dict(recipe_state_dict(ours, int(d["seed"])), strict=True)
+    with torch.no_grad():
+        y = ours(torch.from_numpy(d["x"]))
+    np.testing.assert_allclose(y.numpy(), d["y"], rtol=1e-5, atol=1e-5 * np.abs(d["y"]).max())
+    t = golden("cnn_train_4x32x64.npz")
+    ours.train()
+    ours.load_state_dict(recipe_state_dict(ours, int(t["seed"])), strict=True)
+    x = torch.from_numpy(t["x"]).requires_grad_(True)
+    yt = ours(x)
+    yt.square().mean().backward()
+    np.testing.assert_allclose(yt.detach().numpy(), t["y"], rtol=1e-4, atol=1e-5 * np.abs(t["y"]).max())
+    np.testing.assert_allclose(x.grad.numpy(), t["dx"], rtol=1e-3, atol=1e-4 * np.abs(t["dx"]).max())
+    np.testing.assert_allclose(ours.conv0[0].weight.grad.numpy(), t["dw0"], rtol=1e-3, atol=1e-4 * np.abs(t["dw0"]).max())
