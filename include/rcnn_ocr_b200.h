@@ -278,6 +278,9 @@ int rcnn_attn_argmax(const float *logits, int B, int V, int blank, float *probs,
 /* Debug aid: when buf != NULL the recurrent kernels record clock64() marks of cluster 0 / CTA 0 per
  * timestep into buf[step*8 + k] (int64); NULL switches it off. */
 int rcnn_debug_timeline(void *buf);
+/* Debug aid: device pointer to one uint32 that the recurrent kernels increment whenever a validating warp had to
+ * re-fetch exchange packets that the optimistic TMA fetch overtook (flag-in-data exchange); NULL switches it off. */
+int rcnn_debug_refetch_counter(void *counter);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long rcnn_launch_count(void);
 int rcnn_prof_enable(int on);

@@ -63,6 +63,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_launch_count.restype = ctypes.c_ulonglong
     L.rcnn_debug_timeline.restype = i
     L.rcnn_debug_timeline.argtypes = [vp]
+    L.rcnn_debug_refetch_counter.restype = i
+    L.rcnn_debug_refetch_counter.argtypes = [vp]
     L.rcnn_lstm_hprev.restype = i
     L.rcnn_lstm_hprev.argtypes = [vp, vp, i, i, i, vp]
     L.rcnn_lstm_unpack_grads.restype = i

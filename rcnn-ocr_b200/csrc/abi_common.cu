@@ -35,6 +35,8 @@ int num_sms() {
 
 static long long *g_timeline = nullptr;
 long long *debug_timeline() { return g_timeline; }
+static unsigned int *g_refetch = nullptr;
+unsigned int *debug_refetch() { return g_refetch; }
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 
@@ -114,6 +116,7 @@ void prof_end(int slot, cudaStream_t s) {
 extern "C" {
 
 int rcnn_debug_timeline(void *buf) { rcnn::g_timeline = (long long *)buf; return RCNN_OK; }
+int rcnn_debug_refetch_counter(void *counter) { rcnn::g_refetch = (unsigned int *)counter; return RCNN_OK; }
 
 unsigned long long rcnn_launch_count(void) { return rcnn::g_launches; }
 

@@ -35,6 +35,8 @@ int cuda_fail(cudaError_t e, const char *what);
 int num_sms();
 // optional per-step clock64 timeline of cluster 0 / CTA 0 of the recurrent kernels (debug aid)
 long long *debug_timeline();
+// optional device counter of exchange packets re-fetched after the optimistic TMA fetch (debug aid)
+unsigned int *debug_refetch();
 void count_launch();
 // `n` zeroed 32-bit counters (zeroed on `s`, in stream order) for the recurrent kernels' group barriers.
 // The storage is a per-device ring of regions allocated once; a region is reused only after 64 later calls.

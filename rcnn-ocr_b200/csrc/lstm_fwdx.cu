@@ -16,8 +16,26 @@
 // thread would wait behind its queued MMAs).  SAVE (training): the activated gates (fp16, lane pairs exchange halves so that every store is 32
 // bits) and c_t leave by plain global stores after the step is published -- off the dependent chain, and shared
 // memory has no room left for a staging tile.
+//
+// EXCHANGE, experimental variant (LL = true, RCNN_EXCHANGE=ll; measured SLOWER than the counter protocol, which stays
+// the default -- profiles/ll_exchange_r02.txt): FLAG-IN-DATA, fetched optimistically by TMA and VALIDATED element by element.
+// hcat is filled with the bf16 pattern 0xFFFF before the launch (a NaN encoding the cell arithmetic never produces:
+// cvt.rn.bf16 returns the canonical NaN 0x7FFF), so "this element has been written" can be read off the element.
+//   * the cell warps store h_t with relaxed gpu-scope 16-byte stores -- no fence, no counter;
+//   * the loader warp (warp 10) polls one CANARY word per source CTA and half with relaxed gpu-scope loads (L2 is
+//     the point of coherence); when the canaries of a half are all in, it TMA-loads the half's h tile (as before);
+//   * the canaries prove nothing about the other packets, so the half's cell warps SCAN the tile in shared memory
+//     and re-fetch any packet that still holds a sentinel element straight from global memory (relaxed gpu-scope
+//     loads, polled until valid) before they release the tile to the MMA thread (generic -> async proxy fence).
+// Every element the MMA consumes has therefore been seen with a written value: the protocol makes no assumption
+// about store atomicity or ordering (each location of hcat is written exactly once per launch).  The step's exchange is
+// store trip + canary poll + TMA round trip + scan, without the MEMBAR.ALL.GPU of a release (1,300 cycles) and the
+// counter's own round trip.  Pure LSU polling of the whole tile was measured first and is 2x SLOWER than the
+// counter protocol (17 B/clk per SM against TMA's 125: profiles/timeline_fwdx_r02_ll_lsu.txt).
+// LL = false (default) is the release / acquire counter protocol.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "sm100.cuh"
 #include "lstm_cell.cuh"
@@ -42,6 +60,8 @@ struct FxParams {
     __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
     __nv_bfloat16 *hcat;  // [B, T, 2H]
     unsigned int *sync;   // [ngroups * NH] zeroed before the launch
+    int ll_delay;           // (LL) cycles between the last canary and the TMA fetch (RCNN_LL_DELAY, default 0)
+    unsigned int *refetch;  // (LL, optional) counts warp-level re-fetches of packets the TMA fetch overtook
     long long *tl;        // debug timeline (CTA 0, half 0) or nullptr
 };
 #define TLX(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
@@ -66,11 +86,26 @@ __device__ __forceinline__ void wait_counter_x(const unsigned int *p, unsigned i
     }
 }
 
+// flag-in-data exchange: relaxed gpu-scope 16-byte accesses (L1 is bypassed; L2 is the point of coherence)
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(void *p, const uint4 &v) {
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// true when none of the eight bf16 elements of the packet is the sentinel 0xFFFF
+__device__ __forceinline__ bool packet_valid(const uint4 &v) {
+    return (__vcmpeq2(v.x, 0xffffffffu) | __vcmpeq2(v.y, 0xffffffffu) | __vcmpeq2(v.z, 0xffffffffu) | __vcmpeq2(v.w, 0xffffffffu)) == 0u;
+}
+
 // NH = 2: the item's 64 sequences are two HALVES of 32 with independent dependency chains -- own h tile, own
 // accumulator columns, own counter; the cell warps were split that way already (4 warps per 32 sequences).  The
 // halves fall half a step apart, so the exchange latency of one (release, counter propagation, TMA load of h) hides
 // behind the MMAs and the cell phase of the other.  The x half of a step is still one N = 64 product.
-template <bool SAVE, int NH>
+// HL = log2(H / 64): compile-time tile geometry for the LL validation pass (ignored when !LL)
+template <bool SAVE, int NH, bool LL, int HL>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
@@ -96,7 +131,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     uint64_t *x_full = h_full + 8, *x_empty = x_full + 2; // [2] each
     uint64_t *tmem_full = x_empty + 2;                    // [2 halves][2]: accumulator columns of (half, step parity)
     uint64_t *h_staged = tmem_full + 4;                   // [2 halves]: h_t of the half is in hcat (its cell warps)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_staged + 2);
+    uint64_t *h_land = h_staged + 2;                      // [2 halves][4] (LL): the TMA-fetched tile landed, not yet validated
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_land + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
@@ -107,7 +143,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(wh_full, 1); mbar_init(wcp_done, 1); mbar_init(wi_full, 1);
-            for (int i = 0; i < 8; ++i) mbar_init(&h_full[i], 1);
+            for (int i = 0; i < 8; ++i) { mbar_init(&h_full[i], LL ? 8 / NH : 1); mbar_init(&h_land[i], 1); }   // LL: h_full = one arrival per validating warp
             for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&h_staged[i], 8 / NH); }
             for (int i = 0; i < 4; ++i) mbar_init(&tmem_full[i], 1);
             fence_barrier_init();
@@ -153,7 +189,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 };
                 load_x(0);
                 for (int s = 0; s < T; ++s) {
-                    if (s > 0) {
+                    if (!LL && s > 0) {   // (LL: the cell warps ingest h_{t-1} themselves)
                         const int t = dir ? T - 1 - s : s;
                         const int tprev = dir ? t + 1 : t - 1;
                         for (int hf = 0; hf < NH; ++hf) {
@@ -251,9 +287,70 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             }
         }
     } else if (warp == 10) {
+        if (LL) {
+            // ===== h loader (whole warp): canary poll -> optimistic TMA load of the half's tile ==================
+            // lane l watches source CTA l % gsize of half l / gsize: the first word (units 32 src, 32 src + 1) of the
+            // half's first sequence, stored by lane 0 of that CTA's first cell warp of the half
+            const int src = lane % gsize, hfl = lane / gsize;
+            if (elect_one()) tma_prefetch_desc(&tmH);
+            for (int item = group; item < p.nitems; item += p.ngroups) {
+                const int dir = item & 1, b0 = (item >> 1) * NS;
+                const bool watch = hfl < NH && b0 + hfl * HS < p.B;
+                for (int s = 1; s < T; ++s) {
+                    const int t = dir ? T - 1 - s : s;
+                    const int tprev = dir ? t + 1 : t - 1;
+                    const unsigned int *canary = reinterpret_cast<const unsigned int *>(
+                        p.hcat + ((size_t)(b0 + hfl * HS) * T + tprev) * 2 * H + (size_t)dir * H + 32 * src);
+                    // four canary words per (source, half): word 0 of the packet each of the source's four cell warps
+                    // of that half stores for the half's first sequence
+                    unsigned need = watch ? 0xfu : 0u;
+                    long long seen_at = 0;
+                    // a half without a single live sequence is never fetched (its cell warps zero the tile once)
+                    bool issued[2] = {false, NH == 1 || b0 + HS >= p.B};
+                    long long t0 = 0;
+                    for (unsigned spins = 0; !(issued[0] && issued[1]); ++spins) {
+                        if (need) {
+                            unsigned int v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if ((need >> q) & 1u)
+                                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[q]) : "l"(canary + 4 * q) : "memory");
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (((need >> q) & 1u) && __vcmpeq2(v[q], 0xffffffffu) == 0u) need &= ~(1u << q);
+                            if (tl && !need) seen_at = clock64();
+                        }
+                        const unsigned waiting = __ballot_sync(FULL, need != 0u);
+#pragma unroll
+                        for (int hf = 0; hf < NH; ++hf) {
+                            const unsigned hmask = ((gsize >= 32 ? 0u : (1u << gsize)) - 1u) << (hf * gsize);
+                            if (!issued[hf] && (waiting & hmask) == 0u) {
+                                if (p.ll_delay > 0) { const long long d0 = clock64(); while (clock64() - d0 < p.ll_delay) {} }
+                                if (elect_one()) {
+                                    if (hf == 0) TLX(0);             // P0: half 0's canaries seen
+                                    for (int g = 0; g < nhb; ++g) {
+                                        mbar_arrive_expect_tx(&h_land[hf * 4 + g], (uint32_t)cpb * kHalfBox);
+                                        tma_load_4d(h_s + (size_t)(hf * nkc + g * cpb) * kHalfBox, &tmH, &h_land[hf * 4 + g], 0,
+                                                    b0 + hf * HS, dir * nkc + g * cpb, tprev);
+                                    }
+                                }
+                                __syncwarp();
+                                issued[hf] = true;
+                            }
+                        }
+                        if (spins == 4096u) t0 = clock64();
+                        if (spins > 4096u && clock64() - t0 > 4000000000LL) {
+                            if (lane == 0) printf("rcnn-ocr_b200: lstm_fwdx h exchange timed out (block %d, step %d)\n", blockIdx.x, s);
+                            __trap();
+                        }
+                    }
+                    if (tl) tl[(size_t)T * 8 + (size_t)s * 32 + lane] = seen_at;   // per-source arrival times (debug timeline)
+                }
+            }
+        }
         // ===== publisher (one elected thread): h_t of a half was stored to hcat by its cell warps, which arrived on
         // h_staged; ONE gpu-scope release (cumulative over what the barrier ordered before it) makes it visible
-        if (elect_one()) {
+        if (!LL && elect_one()) {
             uint32_t sphase = 0;
             for (int item = group; item < p.nitems; item += p.ngroups)
                 for (int s = 0; s < T; ++s) {
@@ -274,6 +371,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         const int r = qd * 32 + lane;
         const CellLane CL(lane);
         unsigned int use[2] = {0u, 0u};           // completions of tmem_full[parity] consumed so far
+        uint32_t lphase = 0;                      // (LL) phase of h_land
         const int g = lane & 3, ul = lane >> 2;
         for (int item = group; item < p.nitems; item += p.ngroups) {
             const int dir = item & 1, b0 = (item >> 1) * NS;
@@ -306,8 +404,10 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 {   // h_t: 8 units (16 bytes) of sequence 32ch + lane, straight to hcat[b, t, dir*H + 32c + 8qd ..]
                     const int t = dir ? T - 1 - s : s;
                     const int b = b0 + 32 * ch + lane;
-                    if (b < p.B)
-                        *reinterpret_cast<uint4 *>(p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + 8 * qd) = hq;
+                    if (b < p.B) {
+                        __nv_bfloat16 *dst = p.hcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + 8 * qd;
+                        if (LL) st_relaxed_gpu_v4(dst, hq); else *reinterpret_cast<uint4 *>(dst) = hq;
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -332,6 +432,75 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                         const int bc = b0 + 32 * ch + 4 * k + g;
                         if (bc < p.B) crow[(size_t)bc * H] = cst[k];
                     }
+                }
+                if (LL && s + 1 < T) {
+                    // ---- validate the TMA-fetched h_t tile of this half for step s+1 (see the header comment) ----------
+                    // warp qd of the half checks sequences 8qd .. 8qd+7.  Per barrier group (CPB chunks of 64 units) a lane
+                    // reads piece lane%8 (16 bytes) of rows lane/8 and lane/8 + 4 of every chunk: 2*CPB packets, all at
+                    // compile-time offsets from two swizzled base addresses
+                    constexpr int NKC = 1 << HL, CPB = NKC >= 2 ? NKC / 2 : 1, NHB = NKC / CPB;
+                    const int t = dir ? T - 1 - s : s;
+                    const int piece = lane & 7, rsub = lane >> 3;
+                    unsigned char *hs = h_s + (size_t)(hf * NKC) * kHalfBox + (size_t)(8 * qd + rsub) * 128;
+                    const uint32_t sbase[2] = {smem_u32(hs) + (uint32_t)((piece ^ rsub) << 4),
+                                               smem_u32(hs) + 4u * 128u + (uint32_t)((piece ^ (rsub + 4)) << 4)};
+                    const bool half_live = b0 + 32 * hf < p.B;
+                    if (!half_live && s == 0) {      // no live sequence in this half: zero operand rows, once per item
+#pragma unroll
+                        for (int i = 0; i < 2 * NKC; ++i)
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sbase[i & 1] + (uint32_t)(i >> 1) * kHalfBox), "r"(0u) : "memory");
+                        fence_proxy_async_smem();
+                    }
+#pragma unroll
+                    for (int g2 = 0; g2 < NHB; ++g2) {
+                        if (!half_live) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&h_full[hf * 4 + g2]);
+                            continue;
+                        }
+                        mbar_wait(&h_land[hf * 4 + g2], lphase);
+                        if (threadIdx.x == 64 && g2 == 0) TLX(6);    // R0: half 0's first TMA box landed
+                        uint4 v[2 * CPB];
+#pragma unroll
+                        for (int i = 0; i < 2 * CPB; ++i)
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                         : "r"(sbase[i & 1] + (uint32_t)(g2 * CPB + (i >> 1)) * kHalfBox) : "memory");
+                        unsigned pend = 0u;
+#pragma unroll
+                        for (int i = 0; i < 2 * CPB; ++i)
+                            if (!packet_valid(v[i])) pend |= 1u << i;
+                        if (__any_sync(FULL, pend != 0u)) {
+                            // rare: packets the fetch overtook -- poll them from global memory until they are there
+                            const unsigned char *grow = reinterpret_cast<const unsigned char *>(p.hcat + (size_t)t * 2 * H + (size_t)dir * H)
+                                                        + (size_t)(b0 + 32 * hf + 8 * qd + rsub) * ((size_t)T * 2 * H * 2) + (size_t)piece * 16;
+                            long long t0 = 0;
+                            for (unsigned spins = 0;; ++spins) {
+#pragma unroll
+                                for (int i = 0; i < 2 * CPB; ++i)
+                                    if ((pend >> i) & 1u) {
+                                        const uint4 w = ld_relaxed_gpu_v4(grow + (size_t)(4 * (i & 1)) * ((size_t)T * 2 * H * 2)
+                                                                          + (size_t)(g2 * CPB + (i >> 1)) * 128);
+                                        if (packet_valid(w)) {
+                                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase[i & 1] + (uint32_t)(g2 * CPB + (i >> 1)) * kHalfBox),
+                                                         "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+                                            pend &= ~(1u << i);
+                                        }
+                                    }
+                                if (!__any_sync(FULL, pend != 0u)) break;
+                                if (spins == 1024u) t0 = clock64();
+                                if (spins > 1024u && clock64() - t0 > 4000000000LL) {
+                                    printf("rcnn-ocr_b200: lstm_fwdx h packet never arrived (block %d, step %d)\n", blockIdx.x, s);
+                                    __trap();
+                                }
+                            }
+                            fence_proxy_async_smem();
+                            if (p.refetch && lane == 0) atomicAdd(p.refetch, 1u);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&h_full[hf * 4 + g2]);
+                        if (threadIdx.x == 64 && g2 == 0) TLX(7);    // R1: warp 2's share of half 0's first box validated
+                    }
+                    if (half_live) lphase ^= 1;
                 }
             }
         }
@@ -392,6 +561,9 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     p.csave = c_save;
     p.hcat = (__nv_bfloat16 *)hcat;
     p.tl = debug_timeline();
+    p.refetch = debug_refetch();
+    static const int ll_delay = getenv("RCNN_LL_DELAY") ? atoi(getenv("RCNN_LL_DELAY")) : 0;
+    p.ll_delay = ll_delay;
     p.gsave = (__half *)gates_save;
     const int gsize = H / 32;
     p.nitems = 2 * ((B + NS - 1) / NS);
@@ -399,11 +571,30 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
     if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;
     cudaStream_t s = (cudaStream_t)stream;
-    p.sync = group_counters(p.ngroups * halves, s);
-    if (!p.sync) return RCNN_ERR_CUDA_BASE;
+    // exchange protocol: flag-in-data (default; needs the two-halves layout) or the release / acquire counter
+    // (measured: the counter protocol is faster -- profiles/ll_exchange_r02.txt; "ll" is kept as a tested experiment)
+    static const bool ll_env = getenv("RCNN_EXCHANGE") && strcmp(getenv("RCNN_EXCHANGE"), "ll") == 0;
+    const bool ll = ll_env && halves == 2;
+    if (ll) {
+        // every element of hcat that the kernel will poll starts as the sentinel (bf16 0xFFFF)
+        RCNN_CUDA(cudaMemsetAsync(hcat, 0xFF, (size_t)B * T * 2 * H * sizeof(__nv_bfloat16), s));
+        p.sync = nullptr;
+    } else {
+        p.sync = group_counters(p.ngroups * halves, s);
+        if (!p.sync) return RCNN_ERR_CUDA_BASE;
+    }
     const size_t smem = fwdx_smem_bytes(H, I, save);
-    auto kern = save ? (halves == 2 ? lstm_fwdx_kernel<true, 2> : lstm_fwdx_kernel<true, 1>)
-                     : (halves == 2 ? lstm_fwdx_kernel<false, 2> : lstm_fwdx_kernel<false, 1>);
+    using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FxParams);
+    KernT kern;
+    if (ll) {
+        static const KernT tab[2][4] = {
+            {lstm_fwdx_kernel<false, 2, true, 0>, lstm_fwdx_kernel<false, 2, true, 1>, lstm_fwdx_kernel<false, 2, true, 2>, lstm_fwdx_kernel<false, 2, true, 3>},
+            {lstm_fwdx_kernel<true, 2, true, 0>, lstm_fwdx_kernel<true, 2, true, 1>, lstm_fwdx_kernel<true, 2, true, 2>, lstm_fwdx_kernel<true, 2, true, 3>}};
+        kern = tab[save ? 1 : 0][H == 64 ? 0 : H == 128 ? 1 : H == 256 ? 2 : 3];
+    } else {
+        kern = save ? (halves == 2 ? lstm_fwdx_kernel<true, 2, false, 0> : lstm_fwdx_kernel<true, 1, false, 0>)
+                    : (halves == 2 ? lstm_fwdx_kernel<false, 2, false, 0> : lstm_fwdx_kernel<false, 1, false, 0>);
+    }
     RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));

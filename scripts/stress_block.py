@@ -23,6 +23,9 @@ for _ in range(2):
 packed = ops.lstm_pack(*ws)
 x = torch.randn(B, T, I, device="cuda", generator=g).bfloat16()
 dh = torch.randn(B, T, 2 * H, device="cuda", generator=g) / (B * T) ** 0.5
+from rcnn_ocr_b200 import _lib
+refetch = torch.zeros(1, dtype=torch.int32, device="cuda")
+_lib.lib().rcnn_debug_refetch_counter(refetch.data_ptr())
 ref = None
 bad = 0
 for it in range(iters):
@@ -56,4 +59,6 @@ for _ in range(20):
     dG, db = ops.lstm_backward(packed, gates, cs, dh, B, T)
 e1.record()
 torch.cuda.synchronize()
+print(f"warp-level packet re-fetches after the optimistic TMA fetch: {int(refetch.item())} in {iters} forward+backward passes")
+_lib.lib().rcnn_debug_refetch_counter(None)
 print(f"B={B} T={T} I={I} H={H}: {bad} of {iters - 1} repeats differ; backward {e0.elapsed_time(e1) / 20 * 1e3:.1f} us")

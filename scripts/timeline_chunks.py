@@ -9,7 +9,7 @@ blk = R.BidirectionalLSTM(I, H, H).cuda()
 x = torch.randn(B, T, I, device="cuda")
 for it in range(3):
     y = blk(x); y.sum().backward()
-tl = torch.zeros(T * 8 + 256, dtype=torch.int64, device="cuda")
+tl = torch.zeros(T * 8 + T * 32 + 256, dtype=torch.int64, device="cuda")
 _lib.lib().rcnn_debug_timeline(tl.data_ptr())
 y = blk(x); y.sum().backward()
 torch.cuda.synchronize()

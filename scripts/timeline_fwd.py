@@ -16,7 +16,7 @@ for mode in ("train", "infer"):
             y = blk(x.requires_grad_(True))
         else:
             with torch.no_grad(): y = blk(x)
-    tl = torch.zeros(T * 8, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(T * 8 + T * 32, dtype=torch.int64, device="cuda")   # + per-source arrival slots (fwdx)
     _lib.lib().rcnn_debug_timeline(tl.data_ptr())
     if mode == "train":
         y = blk(x.requires_grad_(True))

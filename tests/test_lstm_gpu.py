@@ -236,3 +236,17 @@ def test_step_exchange_is_ordered_under_poisoned_buffers():
                     assert torch.equal(a, b), f"repeat {it}: {name} differs from the first run"
     finally:
         ops._POISON = old
+
+
+def test_flag_in_data_exchange_variant_matches_oracle():
+    """RCNN_EXCHANGE=ll selects the experimental flag-in-data exchange of the fused forward kernel (sentinel-filled
+    hcat, canary poll, optimistic TMA fetch, element-wise validation; slower than the default counter protocol --
+    profiles/ll_exchange_r02.txt).  The switch is read once per process, so the forward parity cases run again in a
+    child process with the variant selected."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RCNN_EXCHANGE="ll", RCNN_POISON="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k",
+                        "test_fused_input_projection_forward_matches_oracle"], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
