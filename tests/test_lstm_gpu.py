@@ -1,6 +1,8 @@
 """GPU parity: BidirectionalLSTM block (K1 GEMMs + K2 recurrent kernels) vs the float64
 explicit-equation oracle (oracle/lstm_ref.py, pinned to the reference module in
 tests/golden).  Tolerance (north_star): 1e-2 absolute on outputs with bf16 operands."""
+import os
+
 import numpy as np
 import pytest
 import torch
