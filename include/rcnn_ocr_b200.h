@@ -194,6 +194,12 @@ size_t rcnn_lstm_backward_workspace_bytes(int B, int T, int H);
 int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
                        int B, int T, int H, void *dG, float *db_p, void *workspace, size_t workspace_bytes,
                        rcnn_stream_t stream);
+/* rcnn_lstm_plan: how the recurrent kernels lay a batch over the GPU -- `*ngroups` groups of H/32 CTAs, each working
+ * on `*nslot` work items (direction, 64 sequences) at a time: 1 while every item gets a group of its own, 2 (two
+ * interleaved dependency chains per half, one item's step inside the other's exchange latency) once items would queue
+ * behind each other (the backward kernel; the forward kernel only with RCNN_FWD_SLOTS=2, it measures no gain there).
+ * which: 0 = rcnn_lstm_forward_fused, 1 = rcnn_lstm_backward.  Reporting / tests only. */
+int rcnn_lstm_plan(int which, int B, int H, int *nslot, int *ngroups);
 /* out[col] = sum over rows of src[row*ld + col]  (bf16 [rows, cols] -> f32 [cols]) */
 int rcnn_colsum_bf16(const void *src, int64_t ld, int64_t rows, int cols, float *out, rcnn_stream_t stream);
 /* out bf16 [B, T, 2H]: out[b, t, dir*H+u] = hcat[b, t-1 (dir 0) / t+1 (dir 1), dir*H+u], 0 at the

@@ -45,7 +45,7 @@ void count_launch() { ++g_launches; }
 // in stream order behind its memset); a launch that is being CAPTURED into a CUDA graph keeps its region for
 // every replay, so it takes one of the remaining regions for good (never handed out again): an eager launch on
 // another stream can no longer memset a region a graph replay is spinning on.  The indices are atomic.
-static const int kCounterRegion = 256, kEagerRegions = 64, kCaptureRegions = 448, kMaxDevices = 32;
+static const int kCounterRegion = 512, kEagerRegions = 64, kCaptureRegions = 448, kMaxDevices = 32;
 static unsigned int *g_counters[kMaxDevices] = {};
 static std::atomic<unsigned int> g_counter_next[kMaxDevices], g_capture_next[kMaxDevices];
 static std::mutex g_counter_mutex;

@@ -48,7 +48,9 @@ constexpr int NS = 64;     // sequences per work item (UMMA N)
 constexpr int LK = 64;
 constexpr uint32_t kWTile = 128 * LK * 2;   // [128 output units x 64 k] bf16, SW128 = 16 KB
 constexpr uint32_t kBChunk = NS * LK * 2;   // [64 seq x 64 k] bf16, SW128 = 8 KB
-constexpr int kThreads = 384;   // warp 0 poll/TMA loads, warp 1 MMA, warps 2-9 cell update, warps 10-11 publishers (one per half)
+constexpr uint32_t kStageWarp = 3 * 8 * 32 * 4;   // bytes of activation staging per cell warp (two-slot kernel)
+constexpr int kThreads = 384;
+constexpr int kThreads2 = 640;  // two slots: warps 2-9 cell update of slot 0, 10-17 of slot 1, 18-19 publishers   // warp 0 poll/TMA loads, warp 1 MMA, warps 2-9 cell update, warps 10-11 publishers (one per half)
 
 struct BwdParams {
     int B, T, H;
@@ -59,7 +61,7 @@ struct BwdParams {
     __nv_bfloat16 *dG;         // [B, T, 2*4H] out: pre-activation gate gradients, packed order
     float *db;                 // [2*4H] out or nullptr: column sums of dG (bias gradient), zeroed before the launch
     __nv_bfloat16 *xbuf;       // exchange buffer [2][ngroups][src CTA][dst CTA][8 warps][32 units][8 seq]
-    unsigned int *sync;        // [ngroups * NH] zeroed before the launch
+    unsigned int *sync;        // [ngroups][slot][2 halves] zeroed before the launch
     long long *tl;             // debug timeline or nullptr
 };
 #define TL_MARK(k) do { if (tl) tl[(s) * 8 + (k)] = clock64(); } while (0)
@@ -80,6 +82,12 @@ __device__ __forceinline__ void red_release_gpu_inc_b(unsigned int *p) {
 __device__ __forceinline__ unsigned int ld_acquire_gpu_b(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// the four chain counters of a two-slot group ([slot][half], 16 bytes) in ONE acquire load: one round trip polls them all
+__device__ __forceinline__ uint4 ld_acquire_gpu_v4_b(const unsigned int *p) {
+    uint4 v;
+    asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 // Bounded spin on the group counter: a protocol bug traps instead of hanging the GPU.
@@ -103,8 +111,20 @@ __device__ __forceinline__ uint2 ld_ro_v2(const void *p) {
 // that way already: warps 0-3 / 4-7 own and drain sequences 0-31 / 32-63): own half of every 4 KB exchange block, own
 // accumulator columns, barriers, counter and publisher thread.  The halves run half a step apart, so the exchange
 // latency of one (TMA stores, release, counter propagation, TMA load) hides behind the MMAs and cell phase of the other.
-template <int NH>
-__global__ void __launch_bounds__(kThreads, 1)
+//
+// NSLOT = 2: the group works on TWO ITEMS at once (slot 0: item i, slot 1: item i + ngroups; same direction, so the
+// same W_hh slice in tensor memory) -- four independent chains q = 2 slot + half per CTA.  Chosen by the host when a
+// batch has more items than the GPU has groups (B > 256 at H = 512): the items of a group used to run back to back,
+// each of them 55 % exchange latency (profiles/timeline_bwd_r01_final3.txt); now a step of one item runs inside the
+// exchange of the other.  Per slot: own dG tile, own exchange area in shared and in global memory, own barriers and
+// counters.  Shared between the slots: the cell warps (they alternate: step s of slot 0, step s of slot 1), the
+// publisher threads, and the ACCUMULATOR columns (tensor memory is full: 256 columns of W_hh, 256 of accumulators) --
+// a warp drains slot 0's accumulators before it hands slot 1's dG tile to the MMA thread, and the other way round in
+// the next step, so a chain's b_ready barrier already orders the reuse.  Shared memory: the W_hh staging tiles
+// (needed only until tcgen05.cp has copied them, once per launch: groups keep their direction) and the two exchange
+// areas occupy the same bytes.
+template <int NH, int NSLOT>
+__global__ void __launch_bounds__(NSLOT == 2 ? kThreads2 : kThreads, 1)
 lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmXin,
                 const __grid_constant__ CUtensorMap tmXout, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -112,30 +132,47 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int H = p.H, T = p.T, B = p.B;
     const int nmb = (H + 127) / 128;           // accumulators: blocks of 128 output units (H = 64: one, half used)
     const int gsize = H / 32;
+    const size_t wbytes = (size_t)nmb * 2 * kWTile, xslot = (size_t)gsize * 4096;
+    // NSLOT = 1: [W tiles][dG tile][exchange area];  NSLOT = 2: [W tiles | 2 exchange areas][2 dG tiles]
     unsigned char *w_s = smem;                                  // nmb x 2 tiles [128 units x 64 k] bf16, SW128
-    unsigned char *b_s = w_s + (size_t)nmb * 2 * kWTile;        // 2 chunks [64 seq x 64 k] bf16, SW128: this CTA's dG_t
-    unsigned char *x_s = b_s + 2 * kBChunk;                     // gsize x 4 KB: partials in (by source) / out (by destination)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(x_s + (size_t)gsize * 4096);
-    uint64_t *w_full = bars, *b_ready = bars + 1, *x_ready = bars + 3;   // b_ready, x_ready: [2 halves]
-    uint64_t *d_full = bars + 5;     // [2 halves][4] accumulator block mb complete
-    uint64_t *staged = bars + 13;    // [2 halves][4] block mb drained into x_s (the half's cell warps)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+    unsigned char *b_s = NSLOT == 1 ? w_s + wbytes : smem + (wbytes > NSLOT * xslot ? wbytes : NSLOT * xslot);
+                                                                // per slot 2 chunks [64 seq x 64 k] bf16, SW128: this CTA's dG_t
+    unsigned char *x_s = NSLOT == 1 ? b_s + 2 * kBChunk : smem; // per slot gsize x 4 KB: partials in (by source) / out (by destination)
+    // (two slots) per cell warp 3 KB: c_t, c_{t-1} and dh of the warp's 8 sequences x 32 units, fetched a step ahead with
+    // cp.async instead of into registers (the sixteen cell warps have 112 registers each)
+    unsigned char *stage_s = b_s + (size_t)NSLOT * 2 * kBChunk;
+    uint64_t *bars = reinterpret_cast<uint64_t *>((NSLOT == 1 ? x_s + xslot : stage_s + 16 * kStageWarp));
+    // barriers of chain q = 2 slot + half
+    uint64_t *w_full = bars, *b_ready = bars + 1, *x_ready = bars + 5;
+    uint64_t *d_full = bars + 9;     // [4 chains][4] accumulator block mb complete
+    uint64_t *staged = bars + 25;    // [4 chains][4] block mb drained into x_s (the chain's cell warps)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 41);
     constexpr int HS = NS / NH;                 // sequences per half
     constexpr uint32_t XB = 4096 / NH;          // bytes of a half's share of one (source, destination) exchange block
     constexpr int XR = 4 / NH;                  // ... in 1 KB rows of the exchange tensor map
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles.  One slot: 0 poller, 1 MMA, 2-9 cell update, 10-11 publishers.  Two slots: warps 0-3 are the four
+    // single-thread roles (poller, MMA, two publishers) and give most of their registers to the sixteen cell warps
+    // (setmaxnreg: 640 threads leave 96 registers each, the cell code wants ~150 -- spilled, with the poller's acquire
+    // loads invalidating L1 all the time, its phases ran 5-10x slower)
+    constexpr int kPubWarp = NSLOT == 2 ? 2 : 10;    // first publisher warp
+    constexpr int kCell0 = NSLOT == 2 ? 4 : 2;       // first cell warp
+    constexpr bool kIsCellFirst = true;
+    (void)kIsCellFirst;
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
-    unsigned int *counter = p.sync + group * NH;   // one per half
-    // exchange buffer: [parity][group][src CTA][dst CTA][warp 8][unit 32][seq 8] bf16 (4 KB per (src, dst))
+    unsigned int *counter = p.sync + (size_t)group * NSLOT * 2;   // [slot][half]
+    const int xgroups = p.ngroups * NSLOT;        // exchange areas per parity in global memory
+    const int rstride = NSLOT * p.ngroups;        // items a group advances by per round
+    // exchange buffer: [parity][group][slot][src CTA][dst CTA][warp 8][unit 32][seq 8] bf16 (4 KB per (src, dst))
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(w_full, 1);
-            for (int i = 0; i < 2; ++i) { mbar_init(&b_ready[i], 8 / NH); mbar_init(&x_ready[i], 1); }
-            for (int i = 0; i < 8; ++i) { mbar_init(&d_full[i], 1); mbar_init(&staged[i], 8 / NH); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&b_ready[i], 8 / NH); mbar_init(&x_ready[i], 1); }
+            for (int i = 0; i < 16; ++i) { mbar_init(&d_full[i], 1); mbar_init(&staged[i], 8 / NH); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -148,15 +185,22 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
     // processing order: the forward direction is back-propagated from t = T-1 down to 0, the
     // reverse direction from t = 0 up to T-1.  Every step but an item's last publishes partial sums.
+    const bool single_thread_role = NSLOT == 2 ? warp < 4 : (warp < 2 || warp >= kPubWarp);
+    if (single_thread_role) {
     if (warp == 0) {
         // ===== W loader + counter poller (one elected thread) ====================================
         if (elect_one()) {
             tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmXin); tma_prefetch_desc(&tmXout);
             int cur_dir = -1;
             unsigned int published = 0, npub = 0;
-            for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1;
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int dir = it0 & 1;
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
                 if (dir != cur_dir) {
+                    if (NSLOT == 2 && cur_dir != -1) {   // the staging tiles share their bytes with the exchange areas
+                        printf("rcnn-ocr_b200: lstm_bwd two-slot groups must keep their direction (block %d)\n", blockIdx.x);
+                        __trap();
+                    }
                     // rows = output units j of this direction, columns = the 128 packed gate indices of CTA c
                     mbar_arrive_expect_tx(w_full, (uint32_t)nmb * 2 * kWTile);
                     for (int mb = 0; mb < nmb; ++mb)
@@ -164,51 +208,110 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                             tma_load_2d(w_s + (size_t)(mb * 2 + kc) * kWTile, &tmW, w_full, c * 128 + kc * LK, dir * H + mb * 128);
                     cur_dir = dir;
                 }
-                for (int s = 0; s < T; ++s) {
-                    if (s > 0) {
-                        // the partials of this CTA's units (all sources), published by the group in the previous step.
-                        // (The counter includes this CTA's own increment, which followed the completion of its stores
-                        // out of the same shared-memory area.)
-                        for (int hf = 0; hf < NH; ++hf) {
-                            wait_counter_b(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
-                            if (hf == 0) TL_MARK(0);
+                if (NSLOT == 2) {
+                    // four chains, each at its own step: whichever counter has reached its target gets its partials fetched
+                    unsigned int sq[4] = {1u, 1u, 1u, 1u};     // next step (1 .. T-1) whose partials chain q needs
+                    int remaining = nsl * NH * (T - 1);
+                    long long t0 = 0;
+                    for (unsigned spins = 0; remaining > 0; ++spins) {
+                        const uint4 v = ld_acquire_gpu_v4_b(counter);
+                        const unsigned int val[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int slot = q >> 1, hf = q & 1;
+                            if (hf >= NH || slot >= nsl || sq[q] >= (unsigned)T) continue;
+                            if (val[q] < (published + sq[q]) * (unsigned)gsize) continue;
+                            const int s = (int)sq[q];
+                            if (q == 0) TL_MARK(0);
                             fence_proxy_async_global();
-                            mbar_arrive_expect_tx(&x_ready[hf], (uint32_t)gsize * XB);
-                            tma_load_5d(x_s + (size_t)hf * gsize * XB, &tmXin, &x_ready[hf], 0, XR * hf, c, 0,
-                                        (int)((npub - 1) & 1) * p.ngroups + group);
+                            mbar_arrive_expect_tx(&x_ready[q], (uint32_t)gsize * XB);
+                            tma_load_5d(x_s + (size_t)slot * xslot + (size_t)hf * gsize * XB, &tmXin, &x_ready[q], 0, XR * hf, c, 0,
+                                        (int)((npub + sq[q] - 1u) & 1u) * xgroups + group * NSLOT + slot);
+                            ++sq[q];
+                            --remaining;
+                            spins = 0;
+                        }
+                        if (spins == 4096u) t0 = clock64();
+                        if (spins > 4096u && clock64() - t0 > 4000000000LL) {
+                            printf("rcnn-ocr_b200: lstm_bwd group counters timed out (block %d)\n", blockIdx.x);
+                            __trap();
                         }
                     }
-                    if (s + 1 < T) ++npub;
+                    npub += (unsigned)(T - 1);
+                } else {
+                    for (int s = 0; s < T; ++s) {
+                        if (s > 0) {
+                            // the partials of this CTA's units (all sources), published by the group in the previous step.
+                            // (The counter includes this CTA's own increment, which followed the completion of its stores
+                            // out of the same shared-memory area.)
+                            for (int hf = 0; hf < NH; ++hf) {
+                                wait_counter_b(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
+                                if (hf == 0) TL_MARK(0);
+                                fence_proxy_async_global();
+                                mbar_arrive_expect_tx(&x_ready[hf], (uint32_t)gsize * XB);
+                                tma_load_5d(x_s + (size_t)hf * gsize * XB, &tmXin, &x_ready[hf], 0, XR * hf, c, 0,
+                                            (int)((npub - 1) & 1) * xgroups + group);
+                            }
+                        }
+                        if (s + 1 < T) ++npub;
+                    }
                 }
                 published += (unsigned)(T - 1);
             }
         }
-    } else if (warp >= 10) {
-        // ===== publisher of half (warp - 10): partial sums -> exchange buffer -> release =================
-        const int hf = warp - 10;
+    } else if (warp >= kPubWarp && warp < kPubWarp + 2) {
+        // ===== publisher of half (warp - kPubWarp), both slots: partial sums -> exchange buffer -> release ====
+        const int hf = warp - kPubWarp;
         if (hf < NH && elect_one()) {
             tma_prefetch_desc(&tmXout);
-            unsigned int npub = 0;
-            unsigned char *xs = x_s + (size_t)hf * gsize * XB;
-            for (int item = group; item < p.nitems; item += p.ngroups)
-                for (int s = 0; s + 1 < T; ++s) {
-                    // block by block as the cell warps drain the accumulators: the partials for destination
-                    // CTAs 4mb .. 4mb+3 (contiguous in shared and global memory)
-                    for (int mb = 0; mb < nmb; ++mb) {
-                        mbar_wait(&staged[hf * 4 + mb], npub & 1);
-                        if (hf == 0 && mb == nmb - 1) TL_MARK(7);
-                        tma_store_5d(&tmXout, xs + (size_t)mb * 4 * XB, 0, XR * hf, 4 * mb, c, (int)(npub & 1) * p.ngroups + group);
-                        tma_store_commit();
-                    }
-                    tma_store_wait<0>();                      // written, not merely read out of shared memory
-                    if (hf == 0) TL_MARK(1);
-                    // the partials are complete for this thread; the release increment makes them visible to the
-                    // group (readers poll with acquire loads and fetch with TMA)
-                    fence_proxy_async_global();
-                    red_release_gpu_inc_b(counter + hf);
-                    if (hf == 0) TL_MARK(6);
-                    ++npub;
+            unsigned int npubs[2] = {0u, 0u};     // publishes so far, per slot
+            auto publish = [&](const int slot, const int s) {
+                const int q = slot * 2 + hf;
+                unsigned char *xs = x_s + (size_t)slot * xslot + (size_t)hf * gsize * XB;
+                const unsigned int np = npubs[slot];
+                // block by block as the cell warps drain the accumulators: the partials for destination
+                // CTAs 4mb .. 4mb+3 (contiguous in shared and global memory)
+                for (int mb = 0; mb < nmb; ++mb) {
+                    mbar_wait(&staged[q * 4 + mb], np & 1u);
+                    if (q == 0 && mb == nmb - 1) TL_MARK(7);
+                    tma_store_5d(&tmXout, xs + (size_t)mb * 4 * XB, 0, XR * hf, 4 * mb, c,
+                                 (int)(np & 1u) * xgroups + group * NSLOT + slot);
+                    tma_store_commit();
                 }
+                tma_store_wait<0>();                      // written, not merely read out of shared memory
+                if (q == 0) TL_MARK(1);
+                // the partials are complete for this thread; the release increment makes them visible to the
+                // group (readers poll with acquire loads and fetch with TMA)
+                fence_proxy_async_global();
+                red_release_gpu_inc_b(counter + q);
+                if (q == 0) TL_MARK(6);
+                ++npubs[slot];
+            };
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
+                if (NSLOT == 2) {
+                    // whichever slot's first block has been drained
+                    int sp[2] = {0, 0};
+                    int remaining = nsl * (T - 1);
+                    long long t0 = 0;
+                    for (unsigned spins = 0; remaining > 0; ++spins) {
+#pragma unroll
+                        for (int slot = 0; slot < 2; ++slot) {
+                            if (slot >= nsl || sp[slot] >= T - 1) continue;
+                            if (!mbar_test(&staged[(slot * 2 + hf) * 4], npubs[slot] & 1u)) continue;
+                            publish(slot, sp[slot]);
+                            ++sp[slot]; --remaining; spins = 0;
+                        }
+                        if (spins == 65536u) t0 = clock64();
+                        if (spins > 65536u && clock64() - t0 > 4000000000LL) {
+                            printf("rcnn-ocr_b200: lstm_bwd publisher timed out (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    }
+                } else {
+                    for (int s = 0; s + 1 < T; ++s) publish(0, s);
+                }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) ===================================================
@@ -216,8 +319,10 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             constexpr uint32_t idesc = make_idesc_bf16(128, HS);
             int cur_dir = -1;
             uint32_t wphase = 0, bphase = 0;
-            for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1;
+            unsigned int ni[4] = {0u, 0u, 0u, 0u};   // (two slots) products issued per chain since the launch
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int dir = it0 & 1;
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
                 if (dir != cur_dir) {
                     // weights: shared memory -> tensor memory, one K = 16 slice per copy (in issue order with the MMAs)
                     mbar_wait(w_full, wphase);
@@ -231,79 +336,167 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                             tmem_cp_128x256b(tmem_base + (uint32_t)(8 * (t2 * (LK / 16) + k)), wdesc + (uint64_t)(2 * k));
                     }
                 }
-                for (int s = 0; s + 1 < T; ++s) {
-                    for (int hf = 0; hf < NH; ++hf) {
-                        mbar_wait(&b_ready[hf], bphase);
-                        if (hf == 0) TL_MARK(2);
-                        tc_fence_after();
-                        for (int mb = 0; mb < nmb; ++mb) {
+                auto product = [&](int slot, int hf) {   // partial^T blocks of chain (slot, hf): nmb x 8 MMAs
+                    const int q = slot * 2 + hf;
+                    tc_fence_after();
+                    for (int mb = 0; mb < nmb; ++mb) {
 #pragma unroll
-                            for (int kc = 0; kc < 2; ++kc) {
-                                // rows (sequences) [HS hf, +HS) of the dG chunk
-                                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(b_s + kc * kBChunk + hf * HS * 128), 16, 1024);
+                        for (int kc = 0; kc < 2; ++kc) {
+                            // rows (sequences) [HS hf, +HS) of the slot's dG chunk
+                            const uint64_t bdesc = make_smem_desc_sw128(
+                                smem_u32(b_s + (size_t)slot * 2 * kBChunk + kc * kBChunk + hf * HS * 128), 16, 1024);
 #pragma unroll
-                                for (int k = 0; k < LK / 16; ++k)
-                                    umma_bf16_ts(tmem_base + 256u + (uint32_t)(mb * NS + hf * HS),
-                                                 tmem_base + (uint32_t)(8 * ((mb * 2 + kc) * (LK / 16) + k)),
-                                                 bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
-                            }
-                            umma_commit(&d_full[hf * 4 + mb]);    // the cell warps drain block mb while the next one is multiplied
+                            for (int k = 0; k < LK / 16; ++k)
+                                umma_bf16_ts(tmem_base + 256u + (uint32_t)(mb * NS + hf * HS),
+                                             tmem_base + (uint32_t)(8 * ((mb * 2 + kc) * (LK / 16) + k)),
+                                             bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
                         }
-                        if (hf == NH - 1) TL_MARK(3);
+                        umma_commit(&d_full[q * 4 + mb]);    // the cell warps drain block mb while the next one is multiplied
                     }
-                    bphase ^= 1;
+                };
+                if (NSLOT == 2) {
+                    // four chains in whatever order their dG tiles arrive.  The two slots of a half share the accumulator
+                    // columns: a product is issued only when the other slot's previous one has been drained.
+                    unsigned int rs[4] = {0u, 0u, 0u, 0u};     // products issued this round
+                    int remaining = nsl * NH * (T - 1);
+                    long long t0 = 0;
+                    for (unsigned spins = 0; remaining > 0; ++spins) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int slot = q >> 1, hf = q & 1, o = q ^ 2;
+                            if (hf >= NH || slot >= nsl || rs[q] >= (unsigned)(T - 1)) continue;
+                            if (!mbar_test(&b_ready[q], ni[q] & 1u)) continue;
+                            if (ni[o] > 0u && !mbar_test(&staged[o * 4 + nmb - 1], (ni[o] - 1u) & 1u)) continue;
+                            const int s = (int)rs[q];
+                            if (q == 0) TL_MARK(2);
+                            product(slot, hf);
+                            if (q == NH - 1) TL_MARK(3);
+                            ++ni[q];
+                            ++rs[q];
+                            --remaining;
+                            spins = 0;
+                        }
+                        if (spins == 65536u) t0 = clock64();
+                        if (spins > 65536u && clock64() - t0 > 4000000000LL) {
+                            printf("rcnn-ocr_b200: lstm_bwd MMA thread timed out (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    }
+                } else {
+                    for (int s = 0; s + 1 < T; ++s) {
+                        for (int hf = 0; hf < NH; ++hf) {
+                            mbar_wait(&b_ready[hf], bphase);
+                            if (hf == 0) TL_MARK(2);
+                            product(0, hf);
+                            if (hf == NH - 1) TL_MARK(3);
+                        }
+                        bphase ^= 1;
+                    }
                 }
             }
         }
+    }
     } else {
         // ===== cell update + exchange ============================================================
-        const int w = warp - 2;               // sequences 8w .. 8w+7 of the tile; lane = hidden unit 32c + lane
+        const int myslot = (warp - kCell0) >> 3;   // (two slots) warps 4-11 serve slot 0, warps 12-19 slot 1
+        const int w = (warp - kCell0) & 7;    // sequences 8w .. 8w+7 of the tile; lane = hidden unit 32c + lane
         const int qd = warp & 3;              // TMEM lane quadrant (drain phase)
-        const int hq = (warp - 2) >> 2;       // which 32 of the 64 sequence columns this warp drains
+        const int hq = w >> 2;                // which 32 of the 64 sequence columns this warp drains
         const int hf = NH == 2 ? hq : 0;      // the half this warp belongs to (owns AND drains the same 32 sequences)
-        unsigned char *xs = x_s + (size_t)hf * gsize * XB;   // the half's exchange area: partials in / out
-        unsigned int npub = 0, nwait = 0, nmma = 0;   // publishes so far, x_ready / d_full phases
-        for (int item = group; item < p.nitems; item += p.ngroups) {
-            const int dir = item & 1, b0 = (item >> 1) * NS;
-            float dc[8], dbacc[4];
+        // saved activations of one (slot, step): issued before anything of the phase is waited for.  (Not earlier: the
+        // proxy fences of the dG store and of the drain wait for the thread's outstanding loads -- with the loads of the
+        // next step in flight across them the step grew from 9,000 to 10,500 cycles.)
+        uint2 gq[8];
+        float cc[8], cp[8], dhu[8];
+        const uint32_t stg = smem_u32(stage_s) + (uint32_t)((warp - kCell0) & 15) * kStageWarp + (uint32_t)lane * 4u;   // + (array * 8 + i) * 128
+        auto issue_loads = [&](int dir, int b0, int s) {
+            const int t = dir ? s : T - 1 - s;
+            const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
+            // (two slots: the base pointers pass through an empty asm so that the compiler cannot keep the 32 per-sequence
+            // addresses of a step alive across the whole time loop)
+            const __half *gates_p = p.gates;
+            const float *csave_p = p.csave, *dhcat_p = p.dhcat;
+            if (NSLOT == 2) asm volatile("" : "+l"(gates_p), "+l"(csave_p), "+l"(dhcat_p));
+            const bool has_prev = tfp >= 0 && tfp < T;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dbacc[i] = 0.f;
-            for (int s = 0; s < T; ++s) {
-                const int t = dir ? s : T - 1 - s;
-                const int tfp = dir ? t + 1 : t - 1;   // forward-time predecessor: where c_{prev} lives
-                // ---- saved activations of this step (issued before anything is waited for) ----------
-                uint2 gq[8];
-                float cc[8], cp[8], dhu[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = b0 + 8 * w + i;
-                    if (b < B) {
-                        const size_t rtb = ((size_t)dir * T + t) * B + b;
-                        gq[i] = ld_ro_v2(p.gates + rtb * 4 * H + (size_t)c * 128 + 4 * lane);
-                        cc[i] = ld_nc_f32(p.csave + rtb * H + 32 * c + lane);
-                        cp[i] = (tfp >= 0 && tfp < T) ? ld_nc_f32(p.csave + (((size_t)dir * T + tfp) * B + b) * H + 32 * c + lane) : 0.f;
-                        dhu[i] = ld_nc_f32(p.dhcat + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + lane);
+            for (int i = 0; i < 8; ++i) {
+                const int b = b0 + 8 * w + i;
+                if (b < B) {
+                    const size_t rtb = ((size_t)dir * T + t) * B + b;
+                    gq[i] = ld_ro_v2(gates_p + rtb * 4 * H + (size_t)c * 128 + 4 * lane);
+                    const float *pc = csave_p + rtb * H + 32 * c + lane;
+                    const float *pp = csave_p + (((size_t)dir * T + (has_prev ? tfp : t)) * B + b) * H + 32 * c + lane;
+                    const float *pd = dhcat_p + ((size_t)b * T + t) * 2 * H + (size_t)dir * H + 32 * c + lane;
+                    if (NSLOT == 2) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stg + (uint32_t)(0 * 8 + i) * 128u), "l"(pc) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stg + (uint32_t)(1 * 8 + i) * 128u), "l"(pp) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stg + (uint32_t)(2 * 8 + i) * 128u), "l"(pd) : "memory");
                     } else {
-                        gq[i] = make_uint2(0u, 0u); cc[i] = 0.f; cp[i] = 0.f; dhu[i] = 0.f;
+                        cc[i] = ld_nc_f32(pc);
+                        cp[i] = has_prev ? ld_nc_f32(pp) : 0.f;
+                        dhu[i] = ld_nc_f32(pd);
+                    }
+                } else {
+                    gq[i] = make_uint2(0u, 0u);
+                    if (NSLOT == 2) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + (uint32_t)(a * 8 + i) * 128u), "f"(0.f) : "memory");
+                    } else {
+                        cc[i] = 0.f; cp[i] = 0.f; dhu[i] = 0.f;
                     }
                 }
-                // ---- recurrent term: sum of the partials every CTA of the group published last step ---
+            }
+            if (NSLOT == 2) asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // (two slots) the staged activations of this phase -> registers; c_{t-1} of a direction's first step is zero
+        auto fetch_staged = [&](int dir, int s) {
+            const int t = dir ? s : T - 1 - s;
+            const int tfp = dir ? t + 1 : t - 1;
+            const bool has_prev = tfp >= 0 && tfp < T;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[i]) : "r"(stg + (uint32_t)(0 * 8 + i) * 128u) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cp[i]) : "r"(stg + (uint32_t)(1 * 8 + i) * 128u) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dhu[i]) : "r"(stg + (uint32_t)(2 * 8 + i) * 128u) : "memory");
+                if (!has_prev) cp[i] = 0.f;
+            }
+        };
+        unsigned int xph = 0u, dph = 0u;       // x_ready / d_full phases consumed by the warp's chain
+        for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+            const int dir = it0 & 1;
+            const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
+            float dc[NSLOT][8], dbacc[4];   // (only dc[0] / dc[NSLOT-1] of the warp's own slot is live)
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; ++sl)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dc[sl][i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dbacc[i] = 0.f;
+            // ---- cell phase of (slot, step s): partial sums in -> dh -> gate gradients -> dG tile for the MMA thread
+            auto cell_phase = [&](const int slot, float (&dcs)[8], const int s) {
+                const int t = dir ? s : T - 1 - s;
+                const bool more = s + 1 < T;
+                const int q = slot * 2 + hf;
+                const int b0 = ((it0 + slot * p.ngroups) >> 1) * NS;
+                unsigned char *xs = x_s + (size_t)slot * xslot + (size_t)hf * gsize * XB;   // the chain's exchange area: partials in / out
+                unsigned char *bs = b_s + (size_t)slot * 2 * kBChunk;
+                issue_loads(dir, b0, s);
+                // recurrent term: sum of the partials every CTA of the group published last step
                 float rec[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) rec[i] = 0.f;
                 if (s > 0) {
-                    mbar_wait(&x_ready[hf], nwait & 1);
-                    ++nwait;
+                    mbar_wait(&x_ready[q], xph & 1u);
                     const unsigned char *src = xs + ((size_t)(w % (8 / NH)) * 256 + (size_t)lane * 8) * 2;
-                    for (int sc = 0; sc < gsize; sc += 8) {     // 8 shared-memory loads in flight per round
-                        uint4 v[8];
+                    constexpr int NV = NSLOT == 2 ? 4 : 8;      // shared-memory loads in flight per round (registers)
+                    for (int sc = 0; sc < gsize; sc += NV) {
+                        uint4 v[NV];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
+                        for (int u = 0; u < NV; ++u)
                             v[u] = sc + u < gsize ? *reinterpret_cast<const uint4 *>(src + (size_t)(sc + u) * XB) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < NV; ++u) {
                             const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -312,8 +505,9 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                             }
                         }
                     }
+                    ++xph;
                 }
-                // ---- cell backward -----------------------------------------------------------------
+                if (NSLOT == 2) fetch_staged(dir, s);
                 uint2 dgq[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -323,8 +517,8 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     const float dh = dhu[i] + rec[i];
                     const float tc = tanh_fast_b(cc[i]);
                     const float d_o = dh * tc;
-                    const float dct = fmaf(dh * og, 1.f - tc * tc, dc[i]);
-                    dc[i] = dct * fg;
+                    const float dct = fmaf(dh * og, 1.f - tc * tc, dcs[i]);
+                    dcs[i] = dct * fg;
                     const float o0 = dct * gg * ig * (1.f - ig);
                     const float o1 = dct * cp[i] * fg * (1.f - fg);
                     const float o2 = dct * ig * (1.f - gg * gg);
@@ -334,60 +528,76 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     dgq[i].x = *reinterpret_cast<const uint32_t *>(&lo);
                     dgq[i].y = *reinterpret_cast<const uint32_t *>(&hi);
                 }
-                const bool more = s + 1 < T;
                 if (more) {
                     // dG_t of this CTA as the K-major SW128 B operand: row = sequence, k = 4*lane + gate
                     const int chunk = lane >> 4, piece = (lane & 15) >> 1, sub = (lane & 1) * 8;
+                    // (32-bit shared addresses formed from one base: eight generic pointers kept across the time loop cost
+                    // the two-slot kernel's 96-register budget six spilled pairs)
+                    const uint32_t bs0 = smem_u32(bs) + (uint32_t)(chunk * kBChunk + 8 * w * 128 + sub);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = 8 * w + i;
-                        *reinterpret_cast<uint2 *>(b_s + chunk * kBChunk + row * 128 + ((piece ^ (row & 7)) << 4) + sub) = dgq[i];
-                    }
+                    for (int i = 0; i < 8; ++i)   // row = 8 w + i, so row & 7 = i
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bs0 + (uint32_t)(i * 128) + (uint32_t)((piece ^ i) << 4)),
+                                     "r"(dgq[i].x), "r"(dgq[i].y) : "memory");
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&b_ready[hf]);
+                    if (lane == 0) mbar_arrive(&b_ready[q]);
                 }
+                __nv_bfloat16 *dG_p = p.dG;
+                int tt = t;
+                if (NSLOT == 2) asm volatile("" : "+l"(dG_p), "+r"(tt));   // addresses formed here, not carried through the phase
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int b = b0 + 8 * w + i;
                     if (b < B)
-                        *reinterpret_cast<uint2 *>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128 + 4 * lane) = dgq[i];
+                        *reinterpret_cast<uint2 *>(dG_p + ((size_t)b * T + tt) * 8 * H + (size_t)dir * 4 * H + (size_t)c * 128 + 4 * lane) = dgq[i];
                 }
-                if (threadIdx.x == 64) TL_MARK(5);
-                if (more) {
-                    // ---- drain the accumulators: partial^T [unit, seq] -> exchange buffer (bf16) ---------
-                    for (int mb = 0; mb < nmb; ++mb) {
-                        mbar_wait(&d_full[hf * 4 + mb], nmma & 1);
-                        if (threadIdx.x == 64 && mb == nmb - 1) TL_MARK(4);
-                        tc_fence_after();
-                        uint32_t acc[32];
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(mb * NS + hq * 32), acc);
-                        tmem_ld_wait();
-                        const int dstc = mb * 4 + qd;                 // CTA that owns output units [128mb + 32qd, +32)
-                        if (dstc < gsize) {
+                if (warp == kCell0 && lane == 0) TL_MARK(5);
+            };
+            // ---- drain of (slot, step s): accumulators partial^T [unit, seq] -> exchange area (bf16), block by block
+            auto drain_phase = [&](const int slot, const int s) {
+                const int q = slot * 2 + hf;
+                unsigned char *xs = x_s + (size_t)slot * xslot + (size_t)hf * gsize * XB;
+                for (int mb = 0; mb < nmb; ++mb) {
+                    mbar_wait(&d_full[q * 4 + mb], dph & 1u);
+                    if (warp == kCell0 && lane == 0 && mb == nmb - 1) TL_MARK(4);
+                    tc_fence_after();
+                    uint32_t acc[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(mb * NS + hq * 32), acc);
+                    tmem_ld_wait();
+                    const int dstc = mb * 4 + qd;                 // CTA that owns output units [128mb + 32qd, +32)
+                    if (dstc < gsize) {
 #pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {          // 8 sequences = one reader warp's slice
-                                uint4 v;
-                                uint32_t *vw = reinterpret_cast<uint32_t *>(&v);
+                        for (int g4 = 0; g4 < 4; ++g4) {          // 8 sequences = one reader warp's slice
+                            uint4 v;
+                            uint32_t *vw = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * g4 + 2 * k]),
-                                                                                     __uint_as_float(acc[8 * g4 + 2 * k + 1]));
-                                    vw[k] = *reinterpret_cast<const uint32_t *>(&h2);
-                                }
-                                *reinterpret_cast<uint4 *>(xs + (size_t)dstc * XB + ((size_t)((NH == 2 ? 0 : hq) * 4 + g4) * 256 + (size_t)lane * 8) * 2) = v;
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * g4 + 2 * k]),
+                                                                                 __uint_as_float(acc[8 * g4 + 2 * k + 1]));
+                                vw[k] = *reinterpret_cast<const uint32_t *>(&h2);
                             }
+                            *reinterpret_cast<uint4 *>(xs + (size_t)dstc * XB + ((size_t)((NH == 2 ? 0 : hq) * 4 + g4) * 256 + (size_t)lane * 8) * 2) = v;
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&staged[hf * 4 + mb]);
                     }
-                    tc_fence_before();
-                    ++nmma;
-                    ++npub;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&staged[q * 4 + mb]);
+                }
+                tc_fence_before();
+                ++dph;
+            };
+            // every slot has its own eight warps (their own registers for the activations loaded a step ahead), so the
+            // chains of the two slots depend on each other only through the tensor pipe and the accumulator columns.
+            // (Measured first: ONE set of warps serving both slots, in a fixed order A0 B0 A1 B1 / A0 A1 B0 B1 -- one
+            // chain's wait holds the other's publish back, 14,100 - 15,200 cycles per step pair -- and event driven, which
+            // needs the activation loads issued on demand: 20,600.  Back to back the pair costs 2 x 9,150.)
+            if (myslot < nsl) {
+                for (int s = 0; s < T; ++s) {
+                    if (myslot == 0) cell_phase(0, dc[0], s); else cell_phase(NSLOT - 1, dc[NSLOT - 1], s);
+                    if (s + 1 < T) drain_phase(myslot, s);
                 }
             }
-            if (p.db != nullptr) {
+            if (p.db != nullptr && myslot < nsl) {
                 float *dst = p.db + (size_t)dir * 4 * H + (size_t)c * 128 + 4 * lane;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) atomicAdd(dst + i, dbacc[i]);
@@ -401,14 +611,34 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
 }
 
-size_t bwd_smem_bytes(int H) { return 1024 + (size_t)((H + 127) / 128) * 2 * kWTile + 2 * kBChunk + (size_t)(H / 32) * 4096 + 256; }
+size_t bwd_smem_bytes(int H, int nslot) {
+    const size_t wbytes = (size_t)((H + 127) / 128) * 2 * kWTile, xslot = (size_t)(H / 32) * 4096;
+    if (nslot == 1) return 1024 + wbytes + 2 * kBChunk + xslot + 512;
+    return 1024 + (wbytes > nslot * xslot ? wbytes : nslot * xslot) + (size_t)nslot * 2 * kBChunk + 16 * kStageWarp + 512;
+}
 
-int bwd_groups(int B, int H) {
+// How a batch is laid over the GPU: groups of H/32 CTAs (one CTA per SM: shared memory), each working on `nslot`
+// items (64 sequences of one direction) at a time.  One slot while every item gets a group of its own; two slots
+// once items would queue behind each other (RCNN_BWD_SLOTS=1 keeps the one-slot kernel for A/B measurements).
+struct BwdCfg { int nslot, ngroups; };
+BwdCfg bwd_config(int B, int H) {
+    static const int force = getenv("RCNN_BWD_SLOTS") ? atoi(getenv("RCNN_BWD_SLOTS")) : 0;
     const int gsize = H / 32, nitems = 2 * ((B + NS - 1) / NS);
-    const int max_groups = num_sms() / gsize;    // one CTA per SM (shared memory)
+    const int max_groups = num_sms() / gsize;
+    BwdCfg cfg;
+    if (force != 1 && nitems > max_groups && max_groups >= 2) {
+        const int even_max = max_groups & ~1;
+        int need = (nitems + 1) / 2;
+        need += need & 1;                            // even: slot 1 = item + ngroups has the direction of slot 0
+        cfg.nslot = 2;
+        cfg.ngroups = need < even_max ? need : even_max;
+        return cfg;
+    }
     int ng = nitems < max_groups ? nitems : max_groups;
     if (ng > 1 && (ng & 1) && nitems > ng) --ng;   // even: a group keeps its direction (and W slice)
-    return ng;
+    cfg.nslot = 1;
+    cfg.ngroups = ng;
+    return cfg;
 }
 
 // column sums of dG: db[col] = sum_rows dG[row, col]   (rows = B*T, cols = 8H)
@@ -525,11 +755,29 @@ __global__ void lstm_unpack_grads_kernel(const UnpackArgs a) {
 }  // namespace
 }  // namespace rcnn
 
+namespace rcnn { void fwdx_plan(int B, int H, int *nslot, int *ngroups); }
+
+extern "C" int rcnn_lstm_plan(int which, int B, int H, int *nslot, int *ngroups) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(nslot && ngroups, "lstm_plan: null pointer");
+    RCNN_CHECK_ARG(B > 0 && (H == 64 || H == 128 || H == 256 || H == 512), "lstm_plan: bad shape B=%d H=%d", B, H);
+    RCNN_CHECK_ARG(which == 0 || which == 1, "lstm_plan: which = %d (0 forward, 1 backward)", which);
+    if (which == 1) {
+        const BwdCfg cfg = bwd_config(B, H);
+        *nslot = cfg.nslot;
+        *ngroups = cfg.ngroups;
+    } else {
+        fwdx_plan(B, H, nslot, ngroups);
+    }
+    return RCNN_OK;
+}
+
 extern "C" size_t rcnn_lstm_backward_workspace_bytes(int B, int T, int H) {
     using namespace rcnn;
     if (B <= 0 || T <= 0 || !(H == 64 || H == 128 || H == 256 || H == 512)) return 0;
     const size_t gsize = H / 32;
-    return 2 * (size_t)bwd_groups(B, H) * gsize * gsize * 8 * 32 * 8 * sizeof(__nv_bfloat16);
+    const BwdCfg cfg = bwd_config(B, H);
+    return 2 * (size_t)cfg.ngroups * cfg.nslot * gsize * gsize * 8 * 32 * 8 * sizeof(__nv_bfloat16);
 }
 
 extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, const float *c_save, const float *dhcat,
@@ -553,7 +801,8 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     int rc = make_tmap_2d(&tw, whh_pt, 2, 2ull * H, 4ull * H, 4ull * H * 2, 128, LK, 1);
     if (rc) return rc;
     static const int halves = getenv("RCNN_BWD_HALVES") ? (atoi(getenv("RCNN_BWD_HALVES")) == 1 ? 1 : 2) : 2;
-    const int gsz = H / 32, ngr = bwd_groups(B, H);
+    const BwdCfg bcfg = bwd_config(B, H);
+    const int gsz = H / 32, ngr = bcfg.ngroups * bcfg.nslot;   // exchange areas per parity
     CUtensorMap txin, txout;
     {   // exchange buffer as float32 [2*ngroups][src][dst][4][256]: load box = all sources of one destination,
         // store box = all destinations of one source
@@ -576,17 +825,18 @@ extern "C" int rcnn_lstm_backward(const void *whh_pt, const void *gates_save, co
     p.xbuf = (__nv_bfloat16 *)workspace;
     p.tl = debug_timeline();
     const int gsize = H / 32;
-    const size_t smem = bwd_smem_bytes(H);
+    const size_t smem = bwd_smem_bytes(H, bcfg.nslot);
     cudaStream_t s = (cudaStream_t)stream;
-    auto kern = halves == 2 ? lstm_bwd_kernel<2> : lstm_bwd_kernel<1>;
+    auto kern = bcfg.nslot == 2 ? (halves == 2 ? lstm_bwd_kernel<2, 2> : lstm_bwd_kernel<1, 2>)
+                                : (halves == 2 ? lstm_bwd_kernel<2, 1> : lstm_bwd_kernel<1, 1>);
     RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.nitems = 2 * ((B + NS - 1) / NS);
-    p.ngroups = bwd_groups(B, H);
-    p.sync = group_counters(p.ngroups * halves, s);
+    p.ngroups = bcfg.ngroups;
+    p.sync = group_counters(p.ngroups * bcfg.nslot * 2, s);
     if (!p.sync) return RCNN_ERR_CUDA_BASE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(bcfg.nslot == 2 ? kThreads2 : kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -59,7 +59,7 @@ struct FxParams {
     float *csave;         // [2, T, B, H] (training only)
     __half *gsave;        // [2, T, B, 4H] activated gates, packed order (training only)
     __nv_bfloat16 *hcat;  // [B, T, 2H]
-    unsigned int *sync;   // [ngroups * NH] zeroed before the launch
+    unsigned int *sync;   // [ngroups][slot][NH] zeroed before the launch
     int ll_delay;           // (LL) cycles between the last canary and the TMA fetch (RCNN_LL_DELAY, default 0)
     unsigned int *refetch;  // (LL, optional) counts warp-level re-fetches of packets the TMA fetch overtook
     long long *tl;        // debug timeline (CTA 0, half 0) or nullptr
@@ -105,8 +105,18 @@ __device__ __forceinline__ bool packet_valid(const uint4 &v) {
 // halves fall half a step apart, so the exchange latency of one (release, counter propagation, TMA load of h) hides
 // behind the MMAs and the cell phase of the other.  The x half of a step is still one N = 64 product.
 // HL = log2(H / 64): compile-time tile geometry for the LL validation pass (ignored when !LL)
-template <bool SAVE, int NH, bool LL, int HL>
-__global__ void __launch_bounds__(kThreads, 1)
+//
+// NSLOT = 2 (needs NH = 2, counter protocol): the group works on TWO ITEMS at once (slot 0: item i, slot 1: item
+// i + ngroups -- same direction, same weights), four independent chains q = 2 slot + half per CTA.  Chosen by the
+// host when a batch has more items than the GPU has groups (B > 256 at H = 512): a group's items used to run back
+// to back, each waiting two thirds of a step for its exchange; now one slot's MMAs and cell phase run inside the
+// other's exchange.  Per slot: own accumulator columns ([256 + 128 slot, +128): tensor memory is exactly full), own
+// counters and barriers, own c state in the cell warps' registers.  Shared: W_hh / W_ih, the cell warps (step s of
+// slot 0, then step s of slot 1), the x ring, and the h tile of a half -- shared memory has no room for a second
+// one, so the TMA load of slot 1's h_{t-1} waits until the MMAs that read slot 0's have completed (h_free), and the
+// other way round.  One publisher warp per half (a release blocks its thread for ~1,300 cycles).
+template <bool SAVE, int NH, bool LL, int HL, int NSLOT>
+__global__ void __launch_bounds__(NSLOT == 2 ? kThreads + 32 : kThreads, 1)
 lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWi,
                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
                  const FxParams p) {
@@ -132,24 +142,33 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
     uint64_t *tmem_full = x_empty + 2;                    // [2 halves][2]: accumulator columns of (half, step parity)
     uint64_t *h_staged = tmem_full + 4;                   // [2 halves]: h_t of the half is in hcat (its cell warps)
     uint64_t *h_land = h_staged + 2;                      // [2 halves][4] (LL): the TMA-fetched tile landed, not yet validated
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_land + 8);
+    // two-slot extras: the barriers of slot 1's chains and the "h tile of half hf may be overwritten" barriers
+    uint64_t *tmem_full1 = h_land + 8;                    // [2 halves][2]
+    uint64_t *h_staged1 = tmem_full1 + 4;                 // [2 halves]
+    uint64_t *h_free = h_staged1 + 2;                     // [2 halves]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_free + 2);
+    static_assert(NSLOT == 1 || (NSLOT == 2 && NH == 2 && !LL), "two slots: two halves each, counter protocol");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x / gsize;
     const int c = blockIdx.x % gsize;
-    unsigned int *counter = p.sync + group * NH;          // one per half
+    unsigned int *counter = p.sync + (size_t)group * NSLOT * NH;   // [slot][half]
     long long *tl = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
+    const int rstride = NSLOT * p.ngroups;                // items a group advances by per round
+    auto tfull = [&](int slot, int i) { return slot ? &tmem_full1[i] : &tmem_full[i]; };     // i = half * 2 + parity
+    auto hstaged = [&](int slot, int hf) { return slot ? &h_staged1[hf] : &h_staged[hf]; };
 
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(wh_full, 1); mbar_init(wcp_done, 1); mbar_init(wi_full, 1);
             for (int i = 0; i < 8; ++i) { mbar_init(&h_full[i], LL ? 8 / NH : 1); mbar_init(&h_land[i], 1); }   // LL: h_full = one arrival per validating warp
             for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&h_staged[i], 8 / NH); }
-            for (int i = 0; i < 4; ++i) mbar_init(&tmem_full[i], 1);
+            for (int i = 0; i < 4; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_full1[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&h_staged1[i], 8 / NH); mbar_init(&h_free[i], 1); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_slot);   // [0, 256): W_hh slice (A operand); [256, 320), [320, 384): the two accumulators
+        tmem_alloc<512>(tmem_slot);   // [0, 256): W_hh slice (A operand); [256 + 128 slot + 64 parity, +64): the accumulators
     }
     tc_fence_before();
     __syncthreads();
@@ -162,9 +181,15 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWi); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
             int cur_dir = -1;
             unsigned int xn = 0, wn = 0, published = 0;
-            for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1, b0 = (item >> 1) * NS;
+            unsigned int nload[2] = {0u, 0u};            // (two slots) loads issued into the h tile of half hf
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int dir = it0 & 1;
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
                 if (dir != cur_dir) {
+                    if (NSLOT == 2 && cur_dir != -1) {
+                        printf("rcnn-ocr_b200: lstm_fwdx two-slot groups must keep their direction (block %d)\n", blockIdx.x);
+                        __trap();
+                    }
                     // W_hh slice -> weight area -> (MMA thread) tensor memory; then W_ih takes the area for good.
                     // (On a direction change the previous item's last x-half MMAs must have read the old W_ih.)
                     if (xn > 0) mbar_wait(&x_empty[(xn - 1) & 1], ((xn - 1) >> 1) & 1);
@@ -178,32 +203,42 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     ++wn;
                     cur_dir = dir;
                 }
-                auto load_x = [&](int xs) {       // x_t of step xs: nxs ring operations of xcs K-chunks each
+                auto load_x = [&](int slot, int xs) {       // x_t of step xs: nxs ring operations of xcs K-chunks each
                     const int t = dir ? T - 1 - xs : xs;
+                    const int b0 = ((it0 + slot * p.ngroups) >> 1) * NS;
                     for (int j = 0; j < nxs; ++j, ++xn) {
-                        const int slot = xn & 1;
-                        mbar_wait(&x_empty[slot], ((xn >> 1) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)xcs * kHBox);
-                        tma_load_4d(x_s + (size_t)slot * xcs * kHBox, &tmX, &x_full[slot], 0, b0, j * xcs, t);
+                        const int rs = xn & 1;
+                        mbar_wait(&x_empty[rs], ((xn >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&x_full[rs], (uint32_t)xcs * kHBox);
+                        tma_load_4d(x_s + (size_t)rs * xcs * kHBox, &tmX, &x_full[rs], 0, b0, j * xcs, t);
                     }
                 };
-                load_x(0);
+                for (int slot = 0; slot < nsl; ++slot) load_x(slot, 0);
                 for (int s = 0; s < T; ++s) {
-                    if (!LL && s > 0) {   // (LL: the cell warps ingest h_{t-1} themselves)
-                        const int t = dir ? T - 1 - s : s;
-                        const int tprev = dir ? t + 1 : t - 1;
-                        for (int hf = 0; hf < NH; ++hf) {
-                            wait_counter_x(counter + hf, (published + (unsigned)s) * (unsigned)gsize);
-                            if (hf == 0) TLX(0);                     // P0: half 0's counter seen
-                            fence_proxy_async_global();
-                            for (int g = 0; g < nhb; ++g) {
-                                mbar_arrive_expect_tx(&h_full[hf * 4 + g], (uint32_t)cpb * kHalfBox);
-                                tma_load_4d(h_s + (size_t)(hf * nkc + g * cpb) * kHalfBox, &tmH, &h_full[hf * 4 + g], 0, b0 + hf * HS,
-                                            dir * nkc + g * cpb, tprev);
+                    for (int slot = 0; slot < nsl; ++slot) {
+                        if (!LL && s > 0) {   // (LL: the cell warps ingest h_{t-1} themselves)
+                            const int t = dir ? T - 1 - s : s;
+                            const int tprev = dir ? t + 1 : t - 1;
+                            const int b0 = ((it0 + slot * p.ngroups) >> 1) * NS;
+#pragma unroll
+                            for (int hf = 0; hf < NH; ++hf) {
+                                wait_counter_x(counter + slot * NH + hf, (published + (unsigned)s) * (unsigned)gsize);
+                                if (slot == 0 && hf == 0) TLX(0);                     // P0: half 0's counter seen
+                                if (NSLOT == 2) {
+                                    // the half's tile is shared by the slots: the MMAs that read its previous contents are done
+                                    if (nload[hf] > 0) mbar_wait(&h_free[hf], (nload[hf] - 1) & 1);
+                                    ++nload[hf];
+                                }
+                                fence_proxy_async_global();
+                                for (int g = 0; g < nhb; ++g) {
+                                    mbar_arrive_expect_tx(&h_full[hf * 4 + g], (uint32_t)cpb * kHalfBox);
+                                    tma_load_4d(h_s + (size_t)(hf * nkc + g * cpb) * kHalfBox, &tmH, &h_full[hf * 4 + g], 0, b0 + hf * HS,
+                                                dir * nkc + g * cpb, tprev);
+                                }
                             }
                         }
+                        if (s + 1 < T) load_x(slot, s + 1);
                     }
-                    if (s + 1 < T) load_x(s + 1);
                 }
                 published += (unsigned)T;
             }
@@ -214,15 +249,19 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             constexpr uint32_t idesc = make_idesc_bf16(GR, NS), idesc_h = make_idesc_bf16(GR, HS);
             int cur_dir = -1;
             unsigned int xn = 0, wn = 0, nst = 0;
-            uint32_t hphase = 0;
-            for (int item = group; item < p.nitems; item += p.ngroups) {
-                const int dir = item & 1;
+            uint32_t hph[2] = {0u, 0u};                  // phase of h_full[half][*] (two slots: two loads per step)
+            int prev_nsl = 0;
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int dir = it0 & 1;
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
                 if (nst > 0) {
                     // the cell warps have read the last accumulators of the previous item (they arrive on h_staged
                     // after their tcgen05.ld): the x halves below may overwrite them
-                    for (int hf = 0; hf < NH; ++hf) mbar_wait(&h_staged[hf], (nst - 1) & 1);
+                    for (int slot = 0; slot < prev_nsl; ++slot)
+                        for (int hf = 0; hf < NH; ++hf) mbar_wait(hstaged(slot, hf), (nst - 1) & 1);
                     tc_fence_after();
                 }
+                prev_nsl = nsl;
                 if (dir != cur_dir) {
                     mbar_wait(wh_full, wn & 1);
                     tc_fence_after();
@@ -238,55 +277,59 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     ++wn;
                     cur_dir = dir;
                 }
-                // x half of a step: acc[par] = W_ih_slice x_t^T  (first MMA overwrites)
-                auto x_part = [&](int par) {
-                    const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS);
+                // x half of a step: acc[slot][par] = W_ih_slice x_t^T  (first MMA overwrites)
+                auto x_part = [&](int slot, int par) {
+                    const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(slot * 2 * NS + par * NS);
                     for (int j = 0; j < nxs; ++j, ++xn) {
-                        const int slot = xn & 1;
-                        mbar_wait(&x_full[slot], (xn >> 1) & 1);
+                        const int rs = xn & 1;
+                        mbar_wait(&x_full[rs], (xn >> 1) & 1);
                         tc_fence_after();
                         for (int jj = 0; jj < xcs; ++jj) {
                             const int kc = j * xcs + jj;
                             const uint64_t adesc = make_smem_desc_sw128(smem_u32(w_s + (size_t)kc * kWTile), 16, 1024);
-                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(x_s + (size_t)(slot * xcs + jj) * kHBox), 16, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(x_s + (size_t)(rs * xcs + jj) * kHBox), 16, 1024);
 #pragma unroll
                             for (int k = 0; k < LK / 16; ++k)
                                 umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j | jj | k) != 0);
                         }
-                        umma_commit(&x_empty[slot]);
+                        umma_commit(&x_empty[rs]);
                     }
                 };
-                x_part(0);
+                for (int slot = 0; slot < nsl; ++slot) x_part(slot, 0);
                 for (int s = 0; s < T; ++s) {
                     const int par = s & 1;
-                    for (int hf = 0; hf < NH; ++hf) {
-                        if (s > 0) {
-                            const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(par * NS + hf * HS);
-                            for (int g = 0; g < nhb; ++g) {
-                                mbar_wait(&h_full[hf * 4 + g], hphase);
-                                if (hf == 0 && g == 0) TLX(1);       // M0: first h box of half 0 landed
-                                tc_fence_after();
-                                for (int j = 0; j < cpb; ++j) {
-                                    const int kc = g * cpb + j;
-                                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)(hf * nkc + kc) * kHalfBox), 16, 1024);
+                    for (int slot = 0; slot < nsl; ++slot) {
 #pragma unroll
-                                    for (int k = 0; k < LK / 16; ++k)
-                                        umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), bdesc + (uint64_t)(2 * k),
-                                                     idesc_h, 1u);
+                        for (int hf = 0; hf < NH; ++hf) {
+                            if (s > 0) {
+                                const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(slot * 2 * NS + par * NS + hf * HS);
+                                for (int g = 0; g < nhb; ++g) {
+                                    mbar_wait(&h_full[hf * 4 + g], hph[hf]);
+                                    if (slot == 0 && hf == 0 && g == 0) TLX(1);       // M0: first h box of half 0 landed
+                                    tc_fence_after();
+                                    for (int j = 0; j < cpb; ++j) {
+                                        const int kc = g * cpb + j;
+                                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(h_s + (size_t)(hf * nkc + kc) * kHalfBox), 16, 1024);
+#pragma unroll
+                                        for (int k = 0; k < LK / 16; ++k)
+                                            umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(8 * (kc * (LK / 16) + k)), bdesc + (uint64_t)(2 * k),
+                                                         idesc_h, 1u);
+                                    }
                                 }
+                                hph[hf] ^= 1u;
+                                if (NSLOT == 2) umma_commit(&h_free[hf]);   // the half's tile may take the other slot's h
                             }
+                            umma_commit(tfull(slot, hf * 2 + par));
+                            if (slot == 0 && hf == 0) TLX(2);                         // M1: half 0's MMAs issued
+                            if (slot == 0 && hf == NH - 1) TLX(3);                    // M2: last half's MMAs issued
                         }
-                        umma_commit(&tmem_full[hf * 2 + par]);
-                        if (hf == 0) TLX(2);                         // M1: half 0's MMAs issued
-                        if (hf == NH - 1) TLX(3);                    // M2: last half's MMAs issued
+                        if (s + 1 < T) x_part(slot, par ^ 1);   // runs while step s is in its cell / publish / counter phases
                     }
-                    if (s > 0) hphase ^= 1;
                     ++nst;
-                    if (s + 1 < T) x_part(par ^ 1);   // runs while step s is in its cell / publish / counter phases
                 }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp >= 10) {
         if (LL) {
             // ===== h loader (whole warp): canary poll -> optimistic TMA load of the half's tile ==================
             // lane l watches source CTA l % gsize of half l / gsize: the first word (units 32 src, 32 src + 1) of the
@@ -349,19 +392,24 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
             }
         }
         // ===== publisher (one elected thread): h_t of a half was stored to hcat by its cell warps, which arrived on
-        // h_staged; ONE gpu-scope release (cumulative over what the barrier ordered before it) makes it visible
+        // h_staged; ONE gpu-scope release (cumulative over what the barrier ordered before it) makes it visible.
+        // One slot: warp 10 serves both halves.  Two slots: warp 10 + hf serves half hf of both slots in turn.
         if (!LL && elect_one()) {
             uint32_t sphase = 0;
-            for (int item = group; item < p.nitems; item += p.ngroups)
+            const int hf_lo = NSLOT == 2 ? warp - 10 : 0, hf_hi = NSLOT == 2 ? warp - 9 : NH;
+            for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+                const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
                 for (int s = 0; s < T; ++s) {
-                    for (int hf = 0; hf < NH; ++hf) {
-                        mbar_wait(&h_staged[hf], sphase);
-                        if (hf == 0) TLX(6);                         // R0: half 0 stored by its cell warps
-                        red_release_gpu_inc_x(counter + hf);
-                        if (hf == 0) TLX(7);                         // R1: half 0 released
-                    }
+                    for (int slot = 0; slot < nsl; ++slot)
+                        for (int hf = hf_lo; hf < hf_hi; ++hf) {
+                            mbar_wait(hstaged(slot, hf), sphase);
+                            if (slot == 0 && hf == 0) TLX(6);                         // R0: half 0 stored by its cell warps
+                            red_release_gpu_inc_x(counter + slot * NH + hf);
+                            if (slot == 0 && hf == 0) TLX(7);                         // R1: half 0 released
+                        }
                     sphase ^= 1;
                 }
+            }
         }
     } else {
         // ===== cell update ==========================================================================
@@ -373,20 +421,27 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         unsigned int use[2] = {0u, 0u};           // completions of tmem_full[parity] consumed so far
         uint32_t lphase = 0;                      // (LL) phase of h_land
         const int g = lane & 3, ul = lane >> 2;
-        for (int item = group; item < p.nitems; item += p.ngroups) {
-            const int dir = item & 1, b0 = (item >> 1) * NS;
+        for (int it0 = group; it0 < p.nitems; it0 += rstride) {
+            const int dir = it0 & 1;
+            const int nsl = (NSLOT == 2 && it0 + p.ngroups < p.nitems) ? 2 : 1;
             const float bias = p.bias[(size_t)dir * 4 * H + (size_t)c * GR + r];
-            float cst[8];
+            float cstate[NSLOT][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cst[k] = 0.f;
+            for (int sl = 0; sl < NSLOT; ++sl)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cstate[sl][k] = 0.f;
             for (int s = 0; s < T; ++s) {
                 const int par = s & 1;
+#pragma unroll
+              for (int slot = 0; slot < NSLOT; ++slot) {
+                if (slot >= nsl) continue;
+                const int b0 = ((it0 + slot * p.ngroups) >> 1) * NS;
+                float (&cst)[8] = cstate[slot];
                 uint32_t acc[32];
-                mbar_wait(&tmem_full[hf * 2 + par], use[par] & 1);
-                ++use[par];
-                if (threadIdx.x == 64) TLX(4);                       // E0: half 0's accumulator complete
+                mbar_wait(tfull(slot, hf * 2 + par), use[par] & 1);
+                if (threadIdx.x == 64 && slot == 0) TLX(4);          // E0: half 0's accumulator complete
                 tc_fence_after();
-                tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(par * NS + ch * 32), acc);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + 256u + (uint32_t)(slot * 2 * NS + par * NS + ch * 32), acc);
                 tmem_ld_wait();
                 float pre[32];
 #pragma unroll
@@ -411,8 +466,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&h_staged[hf]);
-                if (threadIdx.x == 64) TLX(5);                       // E1: cell phase done, h_t stored
+                if (lane == 0) mbar_arrive(hstaged(slot, hf));
+                if (threadIdx.x == 64 && slot == 0) TLX(5);          // E1: cell phase done, h_t stored
                 if (SAVE) {
                     // gates_save [2, T, B, 4H]: this thread holds gate row r for 32 sequences; a lane pair swaps halves so
                     // that the even lane writes rows (r, r+1) of sequence 2i and the odd lane those of sequence 2i+1.
@@ -502,6 +557,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                     }
                     if (half_live) lphase ^= 1;
                 }
+              }
+                ++use[par];
             }
         }
     }
@@ -515,10 +572,36 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
 size_t fwdx_smem_bytes(int H, int I, bool save) {
     (void)save;
     const int nkc = H / LK, nki = I / LK, nkw = nkc > nki ? nkc : nki, xcs = nki >= 2 ? 2 : 1;
-    return 1024 + (size_t)nkw * kWTile + (size_t)nkc * kHBox + 2 * (size_t)xcs * kHBox + 256;
+    return 1024 + (size_t)nkw * kWTile + (size_t)nkc * kHBox + 2 * (size_t)xcs * kHBox + 512;
 }
 
 }  // namespace
+
+// Groups of H/32 CTAs and work items per group at a time.  The forward kernel stays with ONE item per group: the
+// two-slot variant (RCNN_FWD_SLOTS=2; parity-tested) measures 432 us per launch at B = 512 against 439 us for two items
+// back to back -- the tensor pipe is the shared resource here (128 small MMAs per item and step, 4,100 of a 5,450-cycle
+// step) and the strictly ordered producer / MMA threads serialise the two slots' chains; rec-before-x ordering made it
+// 452 us.  The backward kernel (11 % tensor pipe) is where two slots pay: lstm_bwd.cu.
+void fwdx_plan(int B, int H, int *nslot, int *ngroups) {
+    static const int force_slots = getenv("RCNN_FWD_SLOTS") ? atoi(getenv("RCNN_FWD_SLOTS")) : 1;
+    static const bool one_chain = getenv("RCNN_FWD_HALVES") && atoi(getenv("RCNN_FWD_HALVES")) == 1;
+    static const bool ll_env = getenv("RCNN_EXCHANGE") && strcmp(getenv("RCNN_EXCHANGE"), "ll") == 0;
+    const int gsize = H / 32, nitems = 2 * ((B + NS - 1) / NS);
+    const int max_groups = num_sms() / gsize;
+    if (force_slots != 1 && !ll_env && !one_chain && nitems > max_groups && max_groups >= 2) {
+        const int even_max = max_groups & ~1;
+        int need = (nitems + 1) / 2;
+        need += need & 1;                            // even: slot 1 = item + ngroups has the direction of slot 0
+        *nslot = 2;
+        *ngroups = need < even_max ? need : even_max;
+        return;
+    }
+    int ng = nitems < max_groups ? nitems : max_groups;
+    if (ng > 1 && (ng & 1) && nitems > ng) --ng;
+    *nslot = 1;
+    *ngroups = ng;
+}
+
 }  // namespace rcnn
 
 extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const float *bias_p, const void *whh_p, int B, int T,
@@ -567,20 +650,19 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     p.gsave = (__half *)gates_save;
     const int gsize = H / 32;
     p.nitems = 2 * ((B + NS - 1) / NS);
-    const int max_groups = num_sms() / gsize;
-    p.ngroups = p.nitems < max_groups ? p.nitems : max_groups;
-    if (p.ngroups > 1 && (p.ngroups & 1) && p.nitems > p.ngroups) --p.ngroups;
+    static const bool ll_env = getenv("RCNN_EXCHANGE") && strcmp(getenv("RCNN_EXCHANGE"), "ll") == 0;
+    const bool ll = ll_env && halves == 2;
+    int nslot = 1;
+    fwdx_plan(B, H, &nslot, &p.ngroups);
     cudaStream_t s = (cudaStream_t)stream;
     // exchange protocol: flag-in-data (default; needs the two-halves layout) or the release / acquire counter
     // (measured: the counter protocol is faster -- profiles/ll_exchange_r02.txt; "ll" is kept as a tested experiment)
-    static const bool ll_env = getenv("RCNN_EXCHANGE") && strcmp(getenv("RCNN_EXCHANGE"), "ll") == 0;
-    const bool ll = ll_env && halves == 2;
     if (ll) {
         // every element of hcat that the kernel will poll starts as the sentinel (bf16 0xFFFF)
         RCNN_CUDA(cudaMemsetAsync(hcat, 0xFF, (size_t)B * T * 2 * H * sizeof(__nv_bfloat16), s));
         p.sync = nullptr;
     } else {
-        p.sync = group_counters(p.ngroups * halves, s);
+        p.sync = group_counters(p.ngroups * nslot * halves, s);
         if (!p.sync) return RCNN_ERR_CUDA_BASE;
     }
     const size_t smem = fwdx_smem_bytes(H, I, save);
@@ -588,17 +670,18 @@ extern "C" int rcnn_lstm_forward_fused(const void *x, const void *wih_p, const f
     KernT kern;
     if (ll) {
         static const KernT tab[2][4] = {
-            {lstm_fwdx_kernel<false, 2, true, 0>, lstm_fwdx_kernel<false, 2, true, 1>, lstm_fwdx_kernel<false, 2, true, 2>, lstm_fwdx_kernel<false, 2, true, 3>},
-            {lstm_fwdx_kernel<true, 2, true, 0>, lstm_fwdx_kernel<true, 2, true, 1>, lstm_fwdx_kernel<true, 2, true, 2>, lstm_fwdx_kernel<true, 2, true, 3>}};
+            {lstm_fwdx_kernel<false, 2, true, 0, 1>, lstm_fwdx_kernel<false, 2, true, 1, 1>, lstm_fwdx_kernel<false, 2, true, 2, 1>, lstm_fwdx_kernel<false, 2, true, 3, 1>},
+            {lstm_fwdx_kernel<true, 2, true, 0, 1>, lstm_fwdx_kernel<true, 2, true, 1, 1>, lstm_fwdx_kernel<true, 2, true, 2, 1>, lstm_fwdx_kernel<true, 2, true, 3, 1>}};
         kern = tab[save ? 1 : 0][H == 64 ? 0 : H == 128 ? 1 : H == 256 ? 2 : 3];
     } else {
-        kern = save ? (halves == 2 ? lstm_fwdx_kernel<true, 2, false, 0> : lstm_fwdx_kernel<true, 1, false, 0>)
-                    : (halves == 2 ? lstm_fwdx_kernel<false, 2, false, 0> : lstm_fwdx_kernel<false, 1, false, 0>);
+        kern = nslot == 2 ? (save ? lstm_fwdx_kernel<true, 2, false, 0, 2> : lstm_fwdx_kernel<false, 2, false, 0, 2>)
+               : save     ? (halves == 2 ? lstm_fwdx_kernel<true, 2, false, 0, 1> : lstm_fwdx_kernel<true, 1, false, 0, 1>)
+                          : (halves == 2 ? lstm_fwdx_kernel<false, 2, false, 0, 1> : lstm_fwdx_kernel<false, 1, false, 0, 1>);
     }
     RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(gsize * p.ngroups));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(nslot == 2 ? kThreads + 32 : kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -228,6 +228,16 @@ def lstm_backward(packed: PackedLSTMWeights, gates, csave, dhcat, B: int, T: int
     return dG, db
 
 
+def lstm_plan(B: int, H: int, backward: bool = False):
+    """(work items a CTA group works on at a time, CTA groups) of the recurrent kernels for a batch of B sequences:
+    two interleaved items per group once items would otherwise queue behind each other (rcnn_lstm_plan)."""
+    import ctypes
+    nslot, ngroups = ctypes.c_int(0), ctypes.c_int(0)
+    rc = _lib.lib().rcnn_lstm_plan(int(backward), B, H, ctypes.byref(nslot), ctypes.byref(ngroups))
+    _lib.check(rc, "rcnn_lstm_plan")
+    return nslot.value, ngroups.value
+
+
 def cast_bf16_2d(x: torch.Tensor) -> torch.Tensor:
     """float32 [R,C] (rows contiguous) -> bf16 [R,C] view whose row pitch is padded to a multiple of
     8 elements (pad columns zero), ready to be a GEMM operand for any C."""
