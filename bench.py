@@ -238,8 +238,9 @@ class VendorStep:
     """The same cfg-B train step through torch's own CUDA kernels (cuDNN LSTM, cuBLAS, ATen log_softmax + CTC,
     fused Adam) under bf16 autocast, as training/train.py:499-508 runs its model -- the bar to beat on this box."""
 
-    def __init__(self, device):
+    def __init__(self, device, dtype=torch.bfloat16):
         torch.manual_seed(0)
+        self.dtype = dtype
         self.enc = torch.nn.Sequential(_VendorBlock(CFG["IN"], CFG["H"], CFG["H"]),
                                        _VendorBlock(CFG["H"], CFG["H"], CFG["H"])).to(device)
         self.head = torch.nn.Linear(CFG["H"], CFG["C"]).to(device)
@@ -251,7 +252,7 @@ class VendorStep:
         import torch.nn.functional as F
         self.opt.zero_grad(set_to_none=True)
         feats = feats.detach().requires_grad_(True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=self.dtype):
             logits = self.head(self.enc(feats))
         lp = F.log_softmax(logits.float(), dim=2).permute(1, 0, 2)
         loss = F.ctc_loss(lp, tg, il, tl, blank=0, reduction="mean", zero_infinity=True)
@@ -259,39 +260,95 @@ class VendorStep:
         self.opt.step()
         return loss
 
+    def no_ctc(self, feats, w):
+        """The same step with the CTC loss replaced by a weighted sum of the logits: everything but ATen's CTC, which
+        cannot be captured into a CUDA graph (it stages its offsets through pageable host memory)."""
+        self.opt.zero_grad(set_to_none=True)
+        feats = feats.detach().requires_grad_(True)
+        with torch.autocast("cuda", dtype=self.dtype):
+            logits = self.head(self.enc(feats))
+        loss = (logits.float() * w).sum()
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def ctc_only(self, logits, tg, il, tl):
+        import torch.nn.functional as F
+        logits.grad = None
+        lp = F.log_softmax(logits, dim=2).permute(1, 0, 2)
+        loss = F.ctc_loss(lp, tg, il, tl, blank=0, reduction="mean", zero_infinity=True)
+        loss.backward()
+        return loss
+
     @torch.no_grad()
     def infer(self, feats):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=self.dtype):
             logits = self.head(self.enc(feats))
         return logits.argmax(dim=2)     # (the reference then loops over B*T .item() calls on the host; not timed here)
 
 
 def run_vendor(args, dev, B, timed_fn):
     """Returns the `vendor` object: torch-CUDA train step and encoder+argmax inference at cfg B, device-resident,
-    CUDA-graph replay when torch's ops allow the capture (else eager, stated)."""
+    CUDA-graph replay when torch's ops allow the capture (else eager, stated).  Measured under bf16 autocast (this
+    build's arithmetic) and under fp16 autocast (what the reference's torch.cuda.amp.autocast() picks,
+    training/train.py:499); `value` is the faster of the two -- the bar to beat."""
     import rcnn_ocr_b200 as R
-    v = VendorStep(dev[0][0].device)
     # F.ctc_loss takes the lengths from the host (IntArrayRef): CPU tensors avoid a sync per step
     # (a captured graph bakes them in, so the ring rotates the features and keeps batch 0's targets / lengths)
     il0, tl0 = dev[0][2].cpu(), dev[0][3].cpu()
     batches = [[b[0], dev[0][1], il0, tl0] for b in dev]
-    mode = "eager"
-    fn = lambda i: v(*batches[i % len(batches)])
-    if args.graph:
-        try:
-            g = R.GraphedStep(lambda f, t: v(f, t, il0, tl0), batches[0][:2])
-            fn = lambda i: g(*batches[i % len(batches)][:2])
-            mode = "cuda-graph replay"
-        except Exception as e:  # noqa: BLE001 -- ATen's CTC stages its offsets through pageable host memory
-            torch.cuda.synchronize()
-            mode = f"eager (capture failed: {type(e).__name__})"
-    ms = timed_fn(fn)
-    v.enc.eval()
-    ms_inf = timed_fn(lambda i: v.infer(batches[i % len(batches)][0]))
-    return {"value": round(B / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms, 4), "launch_mode": mode,
-            "infer": {"value": round(B / (ms_inf * 1e-3), 1), "ms_per_step": round(ms_inf, 4),
+    runs = {}
+    for name, dtype in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        v = VendorStep(dev[0][0].device, dtype)
+        mode = "eager"
+        fn = lambda i: v(*batches[i % len(batches)])
+        if args.graph:
+            try:
+                g = R.GraphedStep(lambda f, t: v(f, t, il0, tl0), batches[0][:2])
+                fn = lambda i: g(*batches[i % len(batches)][:2])
+                mode = "cuda-graph replay"
+            except Exception as e:  # noqa: BLE001 -- ATen's CTC stages its offsets through pageable host memory
+                torch.cuda.synchronize()
+                mode = f"eager (capture failed: {type(e).__name__})"
+        ms = timed_fn(fn)
+        # launch-overhead-free estimate of the same step: (everything but the CTC) as one graph replay + the CTC part alone
+        est = None
+        if args.graph and mode != "cuda-graph replay":
+            try:
+                wsum = torch.randn(B, CFG["T"], CFG["C"], device=dev[0][0].device) / (B * CFG["T"])
+                g2 = R.GraphedStep(lambda f: v.no_ctc(f, wsum), [batches[0][0]])
+                ms_g = timed_fn(lambda i: g2(batches[i % len(batches)][0]))
+                lg = torch.randn(B, CFG["T"], CFG["C"], device=dev[0][0].device, requires_grad=True)
+                ms_c = timed_fn(lambda i: v.ctc_only(lg, dev[0][1], il0, tl0))
+                est = {"ms_per_step": round(ms_g + ms_c, 4), "graph_without_ctc_ms": round(ms_g, 4), "ctc_alone_eager_ms": round(ms_c, 4),
+                       "value": round(B / ((ms_g + ms_c) * 1e-3), 1)}
+                del g2
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.synchronize()
+                est = {"error": type(e).__name__}
+        v.enc.eval()
+        ginf, mode_inf = v.infer, "eager"
+        if args.graph:
+            try:
+                ginf = R.GraphedStep(v.infer, [batches[0][0]])
+                mode_inf = "cuda-graph replay"
+            except Exception:  # noqa: BLE001
+                torch.cuda.synchronize()
+        ms_inf = timed_fn(lambda i: ginf(batches[i % len(batches)][0]))
+        if est and "value" in est and est["value"] > B / (ms * 1e-3):
+            ms, mode = est["ms_per_step"], "cuda-graph replay of everything but the CTC + ATen CTC eager (sum of the two)"
+        runs[name] = {"value": round(B / (ms * 1e-3), 1), "ms_per_step": round(ms, 4), "launch_mode": mode, "split": est,
+                      "infer": {"value": round(B / (ms_inf * 1e-3), 1), "ms_per_step": round(ms_inf, 4), "launch_mode": mode_inf}}
+        del v, ginf
+    best = max(runs, key=lambda k: runs[k]["value"])
+    best_inf = max(runs, key=lambda k: runs[k]["infer"]["value"])
+    return {"value": runs[best]["value"], "unit": "lines/s", "ms_per_step": runs[best]["ms_per_step"],
+            "launch_mode": runs[best]["launch_mode"], "autocast": best,
+            "infer": {"value": runs[best_inf]["infer"]["value"], "ms_per_step": runs[best_inf]["infer"]["ms_per_step"],
+                      "autocast": best_inf, "launch_mode": runs[best_inf]["infer"]["launch_mode"],
                       "note": "encoder + head + argmax only (no collapse / strings)"},
-            "what": "torch 2.11 CUDA: nn.LSTM (cuDNN, bidirectional, batch_first) + nn.Linear x2 + head under bf16 autocast, "
+            "by_autocast_dtype": runs,
+            "what": "torch 2.11 CUDA: nn.LSTM (cuDNN, bidirectional, batch_first) + nn.Linear x2 + head under autocast, "
                     "F.log_softmax + F.ctc_loss (ATen CUDA), backward, fused Adam -- model/model.py:154-162, "
                     "training/train.py:499-508 on the same GPU, same inputs, device-resident"}
 
@@ -410,6 +467,46 @@ def run_cfg4(args, device, world, rank, timed_fn, hidden=256):
     # share of the step that is this repo's kernels: the same step without the backbone (features as inputs)
     return {"ms": ms, "mode": mode, "T": T, "lmax": lmax, "per_gpu_batch": Bl, "hidden": hidden, "keep": (step, fn)}
 
+
+
+def run_b512(args, step, infer, device, timed_fn, sync, peaks, use_graph):
+    """cfg B at 512 lines per GPU (BASELINE configs[3] names a batch of 512): 16 (direction, 64-sequence) work items for
+    8 CTA groups.  The backward recurrent kernel then works on two items per group at a time (rcnn_lstm_plan)."""
+    from rcnn_ocr_b200 import _lib, ops
+    B2, T, H = 2 * CFG["B"], CFG["T"], CFG["H"]
+    ring = [[t.to(device) for t in make_batch(B2, 4321 + i)] for i in range(4)]
+    ring = [[b[0].to(torch.bfloat16)] + b[1:] for b in ring]
+    step(*ring[0])
+    sync()
+    g = step.R.GraphedStep(step, ring[0]) if use_graph else step
+    ms = timed_fn(lambda i: g(*ring[i % 4]))
+    step.enc.eval(); step.head.eval()
+    gi = step.R.GraphedStep(infer.device, [ring[0][0]]) if use_graph else infer.device
+    ms_inf = timed_fn(lambda i: gi(ring[i % 4][0]))
+    step.enc.train(); step.head.train()
+    _lib.prof_enable(True)
+    for i in range(args.steps):
+        step(*ring[i % 4])
+    sync()
+    kern = {}
+    rec_flops = 2.0 * B2 * T * H * 4 * H * 2
+    for kid, name in {3: "lstm_fwd", 4: "lstm_bwd"}.items():
+        kms, n = _lib.prof_read(kid)
+        if n:
+            per = kms / n
+            fl = rec_flops * (2 if name == "lstm_fwd" else 1)     # the forward also multiplies W_ih x_t
+            kern[name] = {"ms_per_launch": round(per, 4), "us_per_timestep": round(per * 1e3 / T, 3),
+                          "tensor_frac": round(fl / (per * 1e-3) / 1e12 / peaks["tf_sus"], 4)}
+    _lib.prof_enable(False)
+    _lib.lib().rcnn_prof_reset()
+    del g, gi
+    pf, pb = ops.lstm_plan(B2, H), ops.lstm_plan(B2, H, backward=True)
+    return {"value": round(B2 / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms, 4), "per_gpu_batch": B2,
+            "infer": {"value": round(B2 / (ms_inf * 1e-3), 1), "ms_per_step": round(ms_inf, 4)},
+            "kernels": kern,
+            "plan": {"forward": {"items_per_group": pf[0], "groups": pf[1]}, "backward": {"items_per_group": pb[0], "groups": pb[1]}},
+            "note": "same train / inference step as the headline at 512 lines per GPU, device-resident, "
+                    + ("CUDA-graph replay" if use_graph else "eager")}
 
 
 def timed(fn, steps, warmup, sync, barrier):
@@ -596,9 +693,10 @@ def run_ours(args, rank, world, local_rank):
     step.enc.train(); step.head.train()
 
     # ---- vendor bar, cfg 1, cfg 4 (strong scaling) ------------------------------------------------------------
-    vendor = cfg1 = cfg4 = None
+    vendor = cfg1 = cfg4 = b512 = None
     if not args.no_extras:
         if world == 1:
+            b512 = run_b512(args, step, infer, device, tf, sync, peaks, use_graph)
             vendor = run_vendor(args, dev, B, tf)
             cfg1 = run_cfg1(args, device, tf, cpu=(rank == 0 and not args.no_cpu_baseline))
         r4 = run_cfg4(args, device, world, rank, tf, hidden=256)
@@ -723,6 +821,7 @@ def run_ours(args, rank, world, local_rank):
             "vendor": vendor,
             "vs_vendor": ({"train": round(total_B / (ms_train * 1e-3) / vendor["value"], 3),
                            "infer": round(total_B / (ms_inf * 1e-3) / vendor["infer"]["value"], 3)} if vendor else None),
+            "cfgB_batch512": b512,
             "cfg1_minimal_inference": cfg1, "cfg4_strong": cfg4, "cfg5_infer_sweep": sweep or None,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
             "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)] if losses else None,

@@ -13,6 +13,8 @@ from rcnn_ocr_b200 import ops
 pytestmark = pytest.mark.gpu
 
 ATOL = 1e-2
+# gradients: bf16 operands and bf16 dG; measured worst case over the shapes below 6.5e-3 (profiles/parity_errors_r02.txt)
+GRAD_RTOL = 1e-2
 
 
 def _params(I, H, O, seed, scale=None):
@@ -107,7 +109,7 @@ def _block_and_oracle(I, H, O, seed):
 def test_block_forward_backward_matches_oracle(B, T, I, H, O):
     """Whole block (cast, K1 GEMMs, K2 fwd/bwd, linear) against float64 autograd of the
     explicit-equation oracle.  Outputs: 1e-2 absolute (north_star).  Gradients: bf16 operands and
-    bf16 dG give ~1e-2 relative error, asserted as max|diff| <= 3e-2 * max|grad| per tensor."""
+    bf16 dG: measured <= 6.5e-3 of max|grad| per tensor (profiles/parity_errors_r02.txt), asserted at 1e-2."""
     blk, params = _block_and_oracle(I, H, O, seed=B + H)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(B, T, I, generator=g)
@@ -122,15 +124,23 @@ def test_block_forward_backward_matches_oracle(B, T, I, H, O):
     assert (out.detach().cpu().double() - want.detach()).abs().max().item() < ATOL
     (out * w.cuda()).sum().backward()
 
+    worst = {}
+
     def close(got, ref, name):
         ref = ref.double()
         err = (got.detach().cpu().double() - ref).abs().max().item()
         scale = ref.abs().max().item()
-        assert err <= 3e-2 * scale + 1e-6, f"{name}: max|diff| {err:.3e} vs max|grad| {scale:.3e}"
+        worst[name] = err / max(scale, 1e-30)
+        assert err <= GRAD_RTOL * scale + 1e-6, f"{name}: max|diff| {err:.3e} vs max|grad| {scale:.3e}"
 
     close(xg.grad, xd.grad, "dx")
     for k, p in blk.named_parameters():
         close(p.grad, params[k].grad, k)
+    fwd_err = (out.detach().cpu().double() - want.detach()).abs().max().item()
+    k = max(worst, key=worst.get)
+    # measured errors, for the record (pytest -s; profiles/parity_errors_r02.txt)
+    print(f"\nparity B={B} T={T} I={I} H={H}: forward max|diff| {fwd_err:.2e} (bar {ATOL:.0e}); "
+          f"gradients max|diff|/max|grad| worst {worst[k]:.2e} ({k}), dx {worst['dx']:.2e} (bar {GRAD_RTOL:.0e})")
 
 
 def test_state_dict_contract_and_init():
