@@ -293,6 +293,20 @@ int rcnn_prof_enable(int on);
 int rcnn_prof_reset(void);
 int rcnn_prof_read(int kernel, double *total_ms, int *launches);
 
+/* ---------------------------------------------------------------------------------------
+ * K7  host -> device input step: ResizeAndPadA + Normalize(0.5, 0.5) + HWC -> CHW + batch
+ *     (data/transforms.py:62-120,179; inference.py:93-124,159-164; data/dataset.py:147-156)
+ *   pixels   u8, the decoded images of the batch packed into one buffer (any sizes, row pitch per image)
+ *   desc     i64 [N, 6] per image: byte offset, height, width, row pitch in bytes, channels (1 grey, 3, 4 = alpha
+ *            dropped), bgr (1: channel order B,G,R as cv2.imread returns it)
+ *   out      f32 (out_dtype 0) or bf16 (1) [N, 3, img_h, img_w]: each image resized with its aspect ratio kept
+ *            (scale = min(img_h / h, img_w / w), OpenCV INTER_AREA arithmetic when shrinking, INTER_LINEAR when
+ *            enlarging), placed on a white canvas (align_h / align_v: 0 left / top, 1 center, 2 right / bottom; the
+ *            reference uses left / center), then (v - 127.5) / 127.5.
+ * ------------------------------------------------------------------------------------- */
+int rcnn_preprocess_lines(const void *pixels, const int64_t *desc, int N, int img_h, int img_w, int align_h,
+                          int align_v, void *out, int out_dtype, rcnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

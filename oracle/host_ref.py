@@ -70,3 +70,67 @@ def word_error_rate(reference: str, hypothesis: str) -> float:
     if len(ref_words) == 0:
         return float("inf") if len(hyp_words) > 0 else 0.0
     return levenshtein(ref_words, hyp_words) / len(ref_words)
+
+
+# ---- input step (restated; cv2 and numpy are the reference's own dependencies and are present) -------------------
+#   resize_and_pad        data/transforms.py:91-120  (ResizeAndPadA.apply)
+#   normalize_chw         data/transforms.py:179 + ToTensorV2: albumentations' normalize is float32
+#                         (img - mean * 255) * reciprocal(std * 255), then HWC -> CHW
+#   pack_attention_targets data/transforms.py:123-157
+# Pinned by tests/golden/preproc_*.npz and pack_attn_*.npz, which tests/make_golden.py wrote by calling the reference's
+# own ResizeAndPadA.apply / pack_attention_targets (albumentations stubbed for the import).
+
+def resize_and_pad(img, img_h: int, img_w: int, align_h: str = "left", align_v: str = "center"):
+    import cv2
+    import numpy as np
+    if img.ndim == 2:
+        img = cv2.cvtColor(img, cv2.COLOR_GRAY2RGB)
+    elif img.shape[2] == 4:
+        img = cv2.cvtColor(img, cv2.COLOR_RGBA2RGB)
+    elif img.shape[2] == 1:
+        img = cv2.cvtColor(img[:, :, 0], cv2.COLOR_GRAY2RGB)
+    h, w = img.shape[:2]
+    scale = min(img_h / max(h, 1), img_w / max(w, 1))
+    new_w = max(1, int(round(w * scale)))
+    new_h = max(1, int(round(h * scale)))
+    interp = cv2.INTER_AREA if (new_h < h or new_w < w) else cv2.INTER_LINEAR
+    resized = cv2.resize(img, (new_w, new_h), interpolation=interp)
+    canvas = np.full((img_h, img_w, 3), 255, dtype=img.dtype)
+    x0 = 0 if align_h == "left" else (img_w - new_w if align_h == "right" else (img_w - new_w) // 2)
+    y0 = 0 if align_v == "top" else (img_h - new_h if align_v == "bottom" else (img_h - new_h) // 2)
+    x0 = max(0, min(x0, img_w - new_w))
+    y0 = max(0, min(y0, img_h - new_h))
+    canvas[y0:y0 + new_h, x0:x0 + new_w] = resized
+    return canvas
+
+
+def normalize_chw(canvas):
+    import numpy as np
+    out = (canvas.astype(np.float32) - np.float32(127.5)) * np.reciprocal(np.float32(127.5))
+    return np.ascontiguousarray(out.transpose(2, 0, 1))
+
+
+def pack_attention_targets(texts, stoi, max_len, drop_blank=True):
+    import numpy as np
+    PAD, SOS, EOS = stoi["<PAD>"], stoi["<SOS>"], stoi["<EOS>"]
+    BLANK = stoi.get("<BLANK>")
+    n, t = len(texts), max_len + 1
+    text_in = np.full((n, t), PAD, dtype=np.int64)
+    text_in[:, 0] = SOS
+    target_y = np.full((n, t), PAD, dtype=np.int64)
+    lengths = np.zeros(n, dtype=np.int64)
+    for i, s in enumerate(texts):
+        ids = []
+        for ch in s:
+            if ch not in stoi:
+                continue
+            k = stoi[ch]
+            if drop_blank and BLANK is not None and k == BLANK:
+                continue
+            ids.append(k)
+        m = min(len(ids), max_len)
+        text_in[i, 1:1 + m] = ids[:m]
+        target_y[i, :m] = ids[:m]
+        target_y[i, m] = EOS
+        lengths[i] = m + 1
+    return text_in, target_y, lengths

@@ -12,6 +12,7 @@ Surface (mirrors the reference; citations are path:line under the reference tree
   ctc_greedy_decoder, decode     training/utils.py:122-162
   load_charset, decode_tokens    data/transforms.py:39-59, 196-206
   validation_metrics, ...        training/metrics.py:5-32 as used at training/train.py:582-598
+  LinePreprocessor, pack_*       data/transforms.py:62-157,179 (ResizeAndPadA + Normalize + ToTensorV2, target packing)
 """
 from ._lib import lib, library_path, LibraryMissing  # noqa: F401
 from .charset import load_charset, decode_tokens, ctc_alphabet  # noqa: F401
@@ -21,6 +22,7 @@ from .model import BidirectionalLSTM, CTCHead, RCNN, SEResNet31, make_enc_rnn  #
 from .inference import OCRInference  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from .attention import Attention, AttentionCell  # noqa: F401
+from .preprocess import LinePreprocessor, pack_ctc_targets, pack_attention_targets  # noqa: F401
 from .metrics import CharsetTable, edit_stats, character_error_rates, word_error_rates, validation_metrics  # noqa: F401
 
 __version__ = "0.1.0"

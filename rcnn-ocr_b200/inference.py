@@ -3,9 +3,10 @@ batch loop -> model -> decode -> strings.  decoder="ctc" (default): greedy CTC d
 decoder="attention": the reference's own path -- greedy attention decoding on the device (K6), argmax,
 ``decode_tokens`` (inference.py:166-180), so existing reference checkpoints predict unchanged.
 
-Image file / PIL preprocessing (cv2 + albumentations, inference.py:93-124) is host-side I/O
-outside the hot path; ``predict`` takes preprocessed tensors
-[3, img_h, img_w] in [-1, 1] (or an already batched [B, 3, H, W] tensor)."""
+``predict`` takes what the reference's takes (inference.py:93-124): file paths, PIL images, uint8 numpy arrays
+([H,W], [H,W,3] RGB, [H,W,4] RGBA) or a list of them -- resized, padded, normalised and batched on the device by ONE
+launch per batch (preprocess.LinePreprocessor, kernel K7, instead of cv2 + albumentations + a copy per image) -- and,
+in addition, preprocessed tensors [3, img_h, img_w] in [-1, 1] (or an already batched [B, 3, H, W] tensor)."""
 from __future__ import annotations
 
 from typing import List, Union
@@ -15,6 +16,7 @@ import torch
 from .charset import ctc_alphabet, decode_tokens, load_charset
 from .decode import _to_host, ctc_greedy_ids, ids_to_text_host
 from .model import RCNN
+from .preprocess import LinePreprocessor
 
 
 class OCRInference:
@@ -63,24 +65,29 @@ class OCRInference:
                         warnings.warn(f"{len(self.unused_checkpoint_keys)} checkpoint keys were not used: "
                                       f"{self.unused_checkpoint_keys[:5]}")
         self.model = model.to(self.device).eval()
+        self.transform = LinePreprocessor(img_h, img_w, self.device)      # get_val_transform(img_h, img_w), on the device
 
     @torch.no_grad()
-    def predict(self, images: Union[torch.Tensor, List[torch.Tensor]], max_length: int = 25,
-                batch_size: int = 32, return_confidence: bool = False):
-        is_single = isinstance(images, torch.Tensor) and images.dim() == 3
+    def predict(self, images, max_length: int = 25, batch_size: int = 32, return_confidence: bool = False):
+        """inference.py:126-194: one item (path / PIL image / numpy array / [3,H,W] tensor) -> ``str`` (or
+        ``(str, confidence)``); a list (or a batched [B,3,H,W] tensor) -> a list."""
         if isinstance(images, torch.Tensor):
-            items = [images] if images.dim() == 3 else list(images)
+            is_single = images.dim() == 3
+            items = [images] if is_single else list(images)
         else:
-            items = list(images)
-        for it in items:
-            if not isinstance(it, torch.Tensor):
-                raise TypeError("predict() takes preprocessed tensors; file/PIL preprocessing is outside "
-                                "the hot path (see module docstring)")
+            is_single = not isinstance(images, list)
+            items = [images] if is_single else list(images)
         results = []
         for i in range(0, len(items), batch_size):
-            chunk = torch.stack([t.float() for t in items[i:i + batch_size]])
-            if not chunk.is_cuda:
-                chunk = chunk.pin_memory().to(self.device, non_blocking=True)
+            part = items[i:i + batch_size]
+            if all(isinstance(t, torch.Tensor) for t in part):
+                chunk = torch.stack([t.float() for t in part])
+                if not chunk.is_cuda:
+                    chunk = chunk.pin_memory().to(self.device, non_blocking=True)
+            elif any(isinstance(t, torch.Tensor) for t in part):
+                raise ValueError("a batch mixes preprocessed tensors with raw images")
+            else:
+                chunk = self.transform(part)          # decode on the host, everything else in one launch
             logits = self.model(chunk, is_train=False, batch_max_length=max_length)
             if getattr(self.model, "attn", None) is not None:     # the reference's decode step, inference.py:167-189
                 pred = logits.argmax(dim=-1)

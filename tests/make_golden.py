@@ -235,6 +235,66 @@ def gen_attention():
     case("noblank", 5, 7, 64, 128, 30, 4, seed=13, blank=None, scale=3.0)
 
 
+def _import_reference_transforms():
+    """data/transforms.py imports albumentations (absent here) for the augmentation pipeline; ResizeAndPadA.apply and
+    pack_attention_targets need only cv2 / numpy / torch, so the package is stubbed for the import."""
+    import types
+    if "albumentations" not in sys.modules:
+        A = types.ModuleType("albumentations")
+
+        class ImageOnlyTransform:
+            def __init__(self, always_apply=True, p=1.0):
+                pass
+
+        A.ImageOnlyTransform = ImageOnlyTransform
+        for name in ("Compose", "Normalize", "ShiftScaleRotate", "RandomBrightnessContrast", "InvertImg"):
+            setattr(A, name, lambda *a, **k: None)
+        pt = types.ModuleType("albumentations.pytorch")
+        pt.ToTensorV2 = lambda *a, **k: None
+        sys.modules["albumentations"] = A
+        sys.modules["albumentations.pytorch"] = pt
+    import data.transforms as T
+    return T
+
+
+def gen_preprocess():
+    """Input step goldens from the reference's own ResizeAndPadA.apply (data/transforms.py:91-120) on seeded images of
+    assorted sizes / channel counts, followed by A.Normalize(0.5, 0.5)'s arithmetic (albumentations' normalize:
+    float32 (img - 127.5) * reciprocal(127.5)) and ToTensorV2's HWC -> CHW; and target packing goldens from
+    pack_attention_targets (data/transforms.py:123-157)."""
+    T = _import_reference_transforms()
+    rng = np.random.default_rng(2024)
+    for name, (ih, iw) in (("preproc_32x128", (32, 128)), ("preproc_64x256", (64, 256))):
+        shapes = [(20, 57, 3), (11, 40, 3), (64, 200, 3), (50, 173, 3), (96, 300, 3), (32, 128, 3), (31, 90, 1), (70, 41, 4),
+                  (ih, iw, 3), (2 * ih, 2 * iw, 3), (3 * ih, iw * 3, 3), (9, 900, 3), (200, 30, 3), (1, 1, 3), (ih // 2, iw // 2, 3)]
+        if ih == 64:
+            shapes = [(40, 150, 3), (130, 500, 3), (64, 256, 1), (20, 300, 4), (128, 512, 3)]
+        tf = T.ResizeAndPadA(img_h=ih, img_w=iw)
+        arrs, outs = {}, []
+        for i, (h, w, c) in enumerate(shapes):
+            # smooth + noise content (pure noise hides coordinate errors behind rounding)
+            yy, xx = np.mgrid[0:h, 0:w]
+            base = 127 + 90 * np.sin(xx / 5.0 + i) * np.cos(yy / 3.0) + rng.normal(0, 25, (h, w))
+            img = np.clip(np.stack([base + 10 * k for k in range(c)], -1), 0, 255).astype(np.uint8)
+            if c == 1:
+                img = img[:, :, 0]
+            arrs[f"img{i}"] = img
+            canvas = tf.apply(img.copy())
+            assert canvas.shape == (ih, iw, 3) and canvas.dtype == np.uint8
+            outs.append(canvas)
+        # the padded canvases as the reference produced them (uint8 HWC); Normalize + ToTensorV2 are applied by the test:
+        # float32 (v - 127.5) * reciprocal(127.5), HWC -> CHW (albumentations' normalize, ToTensorV2's transpose)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), n=len(shapes), img_h=ih, img_w=iw, canvas=np.stack(outs), **arrs)
+    itos = charset()
+    stoi = {s: i for i, s in enumerate(itos)}
+    texts = ["", "a", "привет мир", "Hello, World!", "x" * 40, "№42 «тест»", "\u4e2d\u6587 not in charset", " ", "a<b>c"]
+    for ml in (25, 5):
+        ti, ty, ln = T.pack_attention_targets(texts, stoi, ml)
+        np.savez_compressed(os.path.join(OUT, f"pack_attn_ml{ml}.npz"), texts=np.array(texts, dtype=object), max_len=ml,
+                            itos=np.array(itos, dtype=object),
+                            text_in=ti.numpy(), target_y=ty.numpy(), lengths=ln.numpy())
+
+
 if __name__ == "__main__":
     gen_decode()
     gen_decode_fn()
@@ -242,5 +302,6 @@ if __name__ == "__main__":
     gen_bilstm()
     gen_ctc()
     gen_attention()
+    gen_preprocess()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")

@@ -86,8 +86,8 @@ def test_inference_api_shapes(tmp_path):
     one = ocr.predict(imgs[0], return_confidence=True)
     assert isinstance(one, tuple) and isinstance(one[0], str) and 0.0 <= one[1] <= 1.0
     assert one[0] == out[0]
-    with pytest.raises(TypeError):
-        ocr.predict(["/not/a/tensor.png"])
+    with pytest.raises(FileNotFoundError):           # paths are read like the reference does (inference.py:104-107)
+        ocr.predict(["/not/a/file.png"])
 
 
 def test_rcnn_with_the_reference_attention_decoder(tmp_path):

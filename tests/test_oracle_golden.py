@@ -194,3 +194,34 @@ def test_cnn_adapter_matches_the_reference_backbone():
     np.testing.assert_allclose(yt.detach().numpy(), t["y"], rtol=1e-4, atol=1e-5 * np.abs(t["y"]).max())
     np.testing.assert_allclose(x.grad.numpy(), t["dx"], rtol=1e-3, atol=1e-4 * np.abs(t["dx"]).max())
     np.testing.assert_allclose(ours.conv0[0].weight.grad.numpy(), t["dw0"], rtol=1e-3, atol=1e-4 * np.abs(t["dw0"]).max())
+
+
+@pytest.mark.parametrize("name", ["preproc_32x128", "preproc_64x256"])
+def test_input_step_oracle_matches_the_reference_transform(name):
+    """oracle/host_ref.resize_and_pad against canvases produced by the reference's own ResizeAndPadA.apply."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ih, iw = int(d["img_h"]), int(d["img_w"])
+    for i in range(int(d["n"])):
+        got = host_ref.resize_and_pad(d[f"img{i}"], ih, iw)
+        np.testing.assert_array_equal(got, d["canvas"][i], err_msg=f"image {i} {d[f'img{i}'].shape}")
+    chw = host_ref.normalize_chw(d["canvas"][0])
+    assert chw.shape == (3, ih, iw) and chw.dtype == np.float32 and chw.max() <= 1.0 and chw.min() >= -1.0
+
+
+@pytest.mark.parametrize("name", ["pack_attn_ml25", "pack_attn_ml5"])
+def test_target_packing_matches_the_reference(name):
+    """The vectorised packers (product host code, no kernel involved) and the oracle restatement against the reference's
+    pack_attention_targets; the CTC packer is the same character walk shifted by one class (class k = itos[k-1])."""
+    from rcnn_ocr_b200 import preprocess
+    d = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    texts, ml = [str(t) for t in d["texts"]], int(d["max_len"])
+    stoi = {str(t): i for i, t in enumerate(d["itos"])}      # configs/charset.txt as the generator read it
+    for impl in (host_ref.pack_attention_targets, preprocess.pack_attention_targets):
+        ti, ty, ln = [np.asarray(a) for a in impl(texts, stoi, ml)]
+        np.testing.assert_array_equal(ti, d["text_in"])
+        np.testing.assert_array_equal(ty, d["target_y"])
+        np.testing.assert_array_equal(ln, d["lengths"])
+    tg, tl = preprocess.pack_ctc_targets(texts, stoi, max_len=ml)
+    np.testing.assert_array_equal(tl.numpy(), d["lengths"] - 1)
+    want = np.concatenate([d["target_y"][i, :d["lengths"][i] - 1] + 1 for i in range(len(texts))])
+    np.testing.assert_array_equal(tg.numpy(), want)
