@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 CFG = dict(T=64, IN=512, H=512, C=195, LMAX=32, B=256)
@@ -387,10 +388,38 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
         return R.ids_to_text(ids, lens, alphabet)[0]
 
     ms_e2e = timed_fn(e2e)
+    # from decoded pixels: uint8 line images of assorted sizes -> K7 (resize + pad + normalise + batch, one launch) ->
+    # model -> strings, against the reference's host-side input step (cv2 + numpy per image, inference.py:93-124,159-164)
+    rng = np.random.default_rng(7)
+    raw = [[rng.integers(0, 256, (int(rng.integers(24, 80)), int(rng.integers(90, 400)), 3), dtype=np.uint8) for _ in range(32)]
+           for _ in range(4)]
+    pre = R.LinePreprocessor(32, 128, device)
+
+    def e2e_pixels(i):
+        x = pre(raw[i % 4]).contiguous(memory_format=torch.channels_last)
+        ids, lens = gfwd(x)
+        return R.ids_to_text(ids, lens, alphabet)[0]
+
+    ms_pix = timed_fn(e2e_pixels)
+    ms_k7 = timed_fn(lambda i: pre(raw[i % 4]))
+    host_prep_ms = None
+    if cpu:
+        from oracle import host_ref
+        t0 = time.perf_counter()
+        for k in range(3):
+            torch.stack([torch.from_numpy(host_ref.normalize_chw(host_ref.resize_and_pad(im, 32, 128))) for im in raw[k]]).to(device)
+        torch.cuda.synchronize()
+        host_prep_ms = (time.perf_counter() - t0) / 3 * 1e3
     T = int(model._features(dev[0]).shape[1])
     out = {"value": round(32 / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms, 4), "launch_mode": mode,
            "e2e": {"value": round(32 / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 4),
                    "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 32 * (T + 1) * 4},
+           "e2e_from_pixels": {"value": round(32 / (ms_pix * 1e-3), 1), "ms_per_batch": round(ms_pix, 4),
+                               "input_step_ms": round(ms_k7, 4), "host_input_step_ms": None if host_prep_ms is None else round(host_prep_ms, 3),
+                               "h2d_bytes_per_step": int(sum(im.size for im in raw[0])),
+                               "note": "32 uint8 line images (24-80 x 90-400 px) -> K7 on the device (one pinned copy + one launch) -> "
+                                       "model -> strings; host_input_step_ms = the reference's per-image cv2 resize + pad + "
+                                       "normalise + stack + copy on this host (oracle/host_ref, wall clock)"},
            "config": {"workload": "cfg1 minimal_inference: RCNN(194, hidden 256) eval, x[32,3,32,128] in [-1,1], greedy "
                                   "CTC decode -> strings", "T": T, "backbone": "torch/cuDNN, channels_last + bf16 autocast"}}
     if cpu:

@@ -6,9 +6,16 @@ loads with ``load_state_dict(strict=True)``.  ``forward(batch_H, text=None, is_t
 batch_max_length=25)`` returns what the reference returns: greedy-decoded ``probs [B, steps, V]``
 for ``is_train=False`` (model/model.py:89-108), teacher-forced logits for ``is_train=True``
 (:110-148).  The step loop runs on the tcgen05 GEMM (K1) plus three small kernels (K6, csrc/attn.cu);
-``i2h(batch_H)`` is hoisted out of the loop.  Not covered in this round: the backward pass and
-dropout (training of the attention decoder): the module must be in ``eval()`` mode or have
-``dropout_p == 0``, and it does not record an autograd graph.
+``i2h(batch_H)`` is hoisted out of the loop.
+
+Training (``is_train=True`` with autograd enabled): ``_train_forward`` records an autograd graph -- every product
+(i2h, h2h, the LSTMCell gates over [context | h], the generator) runs on the tcgen05 GEMM through
+``model._LinearFn`` (bf16 operands, fp32 accumulate, its backward on the K1 kernels as well), the one-hot half of
+the LSTMCell input is a row gather of ``W_ih[:, C + y]``, the score / softmax / context and the cell update are fp32
+elementwise torch ops.  Dropout (``dropout_p`` on alpha and on the generator input, model/model.py:41,136) and
+scheduled sampling (``sampling_prob``: one ``torch.rand(1)`` per step on the CPU generator as at :139, the fed-back
+token is the argmax of that step's logits) follow the reference; gradients are pinned to the reference module's own
+(tests/golden/attn_train_*.npz).  With autograd disabled the fused inference kernels (K6) run.
 """
 from __future__ import annotations
 
@@ -78,8 +85,8 @@ class Attention(nn.Module):
         if batch_H.dim() != 3 or batch_H.shape[2] != self.input_size:
             raise RuntimeError(f"Attention expects [B, T, {self.input_size}], got {tuple(batch_H.shape)}")
         if self.training and self.dropout_p > 0:
-            raise NotImplementedError("the attention decoder runs in eval() mode only (dropout / training are "
-                                      "outside this round's scope)")
+            raise NotImplementedError("dropout belongs to the autograd path (_train_forward); the fused kernels run "
+                                      "in eval() mode or with dropout_p == 0")
         B, T, C = batch_H.shape
         H, V = self.hidden_size, self.num_classes
         dev = batch_H.device
@@ -131,13 +138,62 @@ class Attention(nn.Module):
                 out[:, :, blank] = -1e4
             return out
 
+    def _train_forward(self, batch_H, text, steps):
+        """model/model.py:110-148 with an autograd graph (see the module docstring)."""
+        import torch.nn.functional as F
+        from .model import _LinearFn
+        _lib.require_cuda(batch_H, "batch_H")
+        if batch_H.dim() != 3 or batch_H.shape[2] != self.input_size:
+            raise RuntimeError(f"Attention expects [B, T, {self.input_size}], got {tuple(batch_H.shape)}")
+        cell = self.attention_cell
+        B, T, C = batch_H.shape
+        H = self.hidden_size
+        dev = batch_H.device
+        text = text.to(device=dev, dtype=torch.int64)
+        enc = batch_H.float()
+        drop = self.dropout_p if self.training else 0.0
+        projH = _LinearFn.apply(enc, cell.i2h.weight, None, True)                       # hoisted i2h(batch_H) [B,T,H]
+        wcat = torch.cat([cell.rnn.weight_ih[:, :C], cell.rnn.weight_hh], 1)            # [4H, C+H]
+        bcat = cell.rnn.bias_ih + cell.rnn.bias_hh
+        embT = cell.rnn.weight_ih[:, C:].t()                                            # [V, 4H]: one-hot input = row gather
+        v = cell.score.weight.reshape(1, 1, H)
+        h = torch.zeros((B, H), dtype=torch.float32, device=dev)
+        c = torch.zeros((B, H), dtype=torch.float32, device=dev)
+        targets = text[:, 0]
+        hids = []
+        for t in range(steps):
+            proj_h = _LinearFn.apply(h, cell.h2h.weight, cell.h2h.bias, True)
+            e = (torch.tanh(projH + proj_h.unsqueeze(1)) * v).sum(-1)                   # [B,T]
+            alpha = F.dropout(torch.softmax(e, dim=1), p=drop, training=drop > 0)
+            context = (alpha.unsqueeze(2) * enc).sum(1)                                 # [B,C]
+            gates = _LinearFn.apply(torch.cat([context, h], 1), wcat, bcat, True) + embT.index_select(0, targets)
+            gi, gf, gg, go = gates.chunk(4, 1)
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h = torch.sigmoid(go) * torch.tanh(c)
+            hids.append(h)
+            if t < steps - 1:
+                if self.sampling_prob > 0 and torch.rand(1).item() < self.sampling_prob:
+                    with torch.no_grad():                                               # (no gradient through the argmax)
+                        out = F.dropout(h, p=drop, training=drop > 0)
+                        targets = _LinearFn.apply(out, self.generator.weight, self.generator.bias, False).argmax(1)
+                else:
+                    targets = text[:, t + 1]
+        out_hid = torch.stack(hids, 1)                                                  # [B,steps,H]
+        logits = _LinearFn.apply(out_hid, self.generator.weight, self.generator.bias, True)
+        if self.blank_id is not None:
+            mask = torch.zeros(self.num_classes, dtype=torch.bool, device=dev)
+            mask[int(self.blank_id)] = True
+            logits = logits.masked_fill(mask, -1e4)
+        return logits
+
     def forward(self, batch_H, text=None, is_train=True, batch_max_length=25):
         steps = batch_max_length + 1
         if not is_train:
             return self._decode(batch_H, steps, None)
         assert text is not None, "For training, `text` with <SOS> at text[:,0] is required"
-        if self.sampling_prob > 0 and self.training:
-            raise NotImplementedError("scheduled sampling belongs to the training path (out of scope)")
         if text.shape[1] < steps:
             raise RuntimeError(f"text has {text.shape[1]} columns, {steps} steps need text[:, :{steps}]")
+        needs_graph = torch.is_grad_enabled() and (batch_H.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_graph or (self.training and (self.dropout_p > 0 or self.sampling_prob > 0)):
+            return self._train_forward(batch_H, text, steps)
         return self._decode(batch_H, steps, text)

@@ -235,6 +235,49 @@ def gen_attention():
     case("noblank", 5, 7, 64, 128, 30, 4, seed=13, blank=None, scale=3.0)
 
 
+def gen_attention_train():
+    """model/model.py:110-148 in train() mode (reference code, imported): teacher-forced logits and the gradients of every
+    parameter and of batch_H for loss = sum(logits * w).  dropout_p = 0 (dropout draws cannot be reproduced across
+    implementations); sampling_prob 0, 1 (every step feeds back its own argmax) and 0.5 (the reference draws
+    torch.rand(1) on the CPU generator once per step: same seed, same decisions)."""
+    from model.model import Attention
+
+    def case(name, B, T, C, H, V, steps, seed, sampling, blank=3, scale=2.0):
+        torch.manual_seed(seed)
+        m = Attention(input_size=C, hidden_size=H, num_classes=V, sos_id=1, eos_id=2, pad_id=0, blank_id=blank,
+                      dropout_p=0.0, sampling_prob=sampling).train()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.mul_(scale)
+        g = torch.Generator().manual_seed(seed + 1)
+        batch_H = torch.randn(B, T, C, generator=g).requires_grad_(True)
+        text = torch.randint(4, V, (B, steps), generator=g)
+        text[:, 0] = 1
+        w = torch.randn(B, steps, V, generator=g) / (B * steps) ** 0.5
+        torch.manual_seed(seed + 2)               # the scheduled-sampling draws start here
+        logits = m(batch_H, text=text, is_train=True, batch_max_length=steps - 1)
+        (logits * w).sum().backward()
+        out = {"batch_H": batch_H.detach().numpy(), "text": text.numpy(), "w": w.numpy(), "logits": logits.detach().numpy(),
+               "g.batch_H": batch_H.grad.numpy(), "seed": seed, "sampling": sampling,
+               "dims": np.array([B, T, C, H, V, steps, -1 if blank is None else blank])}
+        # the weights are re-created from the seed by the build's own module (same registration order, hence the same
+        # default init as the reference's: asserted here), times `scale`
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+        import rcnn_ocr_b200 as R
+        torch.manual_seed(seed)
+        ours = R.Attention(C, H, V, 1, 2, 0, blank, dropout_p=0.0)
+        for k, v in m.state_dict().items():
+            assert torch.equal(ours.state_dict()[k] * scale, v), k
+        out["scale"] = scale
+        for k, p in m.named_parameters():
+            out["g." + k] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"attn_train_{name}.npz"), **out)
+
+    case("tf", 6, 9, 64, 64, 24, 7, seed=21, sampling=0.0)
+    case("sampled", 5, 8, 32, 32, 24, 6, seed=22, sampling=1.0)
+    case("mixed", 7, 6, 32, 64, 30, 8, seed=23, sampling=0.5, blank=None)
+
+
 def _import_reference_transforms():
     """data/transforms.py imports albumentations (absent here) for the augmentation pipeline; ResizeAndPadA.apply and
     pack_attention_targets need only cv2 / numpy / torch, so the package is stubbed for the import."""
@@ -302,6 +345,7 @@ if __name__ == "__main__":
     gen_bilstm()
     gen_ctc()
     gen_attention()
+    gen_attention_train()
     gen_preprocess()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")

@@ -160,6 +160,8 @@ def test_attention_port_matches_reference_module_outputs():
     from oracle.ref_port import RefAttention
     n = 0
     for path in sorted(glob.glob(os.path.join(GOLDEN, "attn_*.npz"))):
+        if os.path.basename(path).startswith("attn_train_"):
+            continue                       # gradients of the training path: tests/test_attention_gpu.py
         d = np.load(path)
         if "seed_scale" in d.files:
             continue
