@@ -184,7 +184,8 @@ class TrainStep:
         self.head = R.CTCHead(CFG["H"], CFG["C"]).to(device)
         self.params = list(self.enc.parameters()) + list(self.head.parameters())
         self.opt = torch.optim.Adam(self.params, lr=5.1e-4, weight_decay=1.95e-5, fused=True, capturable=True)
-        self.reducer = GradAllReducer(self.params) if world > 1 else None
+        self.reducer = GradAllReducer(self.params, producers=[list(m.parameters()) for m in self.enc.children()]
+                                      + [list(self.head.parameters())]) if world > 1 else None
         self.world = world
 
     def __call__(self, feats, tg, il, tl):
@@ -559,6 +560,9 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        # NCCL's all-reduce kernels run beside this library's kernels on the SMs those leave free (the recurrent kernels
+        # 20, the GEMMs 16 under data parallelism: dist.GradAllReducer): cap their CTA count accordingly
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=device)
     _lib.check(_lib.lib().rcnn_device_check(), "rcnn_device_check")
     peaks = load_peaks()

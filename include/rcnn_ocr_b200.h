@@ -287,6 +287,10 @@ int rcnn_debug_timeline(void *buf);
 /* Debug aid: device pointer to one uint32 that the recurrent kernels increment whenever a validating warp had to
  * re-fetch exchange packets that the optimistic TMA fetch overtook (flag-in-data exchange); NULL switches it off. */
 int rcnn_debug_refetch_counter(void *counter);
+/* The persistent GEMM kernels (K1) size their grids to the SM count minus `n` (default 0; 0 <= n <= 64).  The data-parallel
+ * reducer reserves 16: NCCL's all-reduce kernels then run beside a weight-gradient or input-gradient GEMM instead of waiting
+ * for the one CTA per SM it would hold until its last tile (rcnn-ocr_b200/dist.py). */
+int rcnn_reserve_sms(int n);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long rcnn_launch_count(void);
 int rcnn_prof_enable(int on);

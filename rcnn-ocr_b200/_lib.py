@@ -58,6 +58,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_lstm_forward_fused.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
     L.rcnn_preprocess_lines.restype = i
     L.rcnn_preprocess_lines.argtypes = [vp, vp, i, i, i, i, i, vp, i, vp]
+    L.rcnn_reserve_sms.restype = i
+    L.rcnn_reserve_sms.argtypes = [i]
     L.rcnn_lstm_plan.restype = i
     L.rcnn_lstm_plan.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.rcnn_lstm_weight_grads.restype = i

@@ -20,6 +20,14 @@ int cuda_fail(cudaError_t e, const char *what) {
     return RCNN_ERR_CUDA_BASE + (int)e;
 }
 
+// SMs the persistent GEMM kernels leave free (rcnn_reserve_sms): under data parallelism NCCL's all-reduce kernels need
+// a few SMs of their own to run beside a GEMM that would otherwise hold one CTA on every SM until it ends
+static int g_reserved_sms = 0;
+int gemm_sms() {
+    const int n = num_sms() - g_reserved_sms;
+    return n < 2 ? 2 : n;
+}
+
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;   // keyed by the device id: re-read when the thread switches device
     int dev = 0;
@@ -114,6 +122,15 @@ void prof_end(int slot, cudaStream_t s) {
 }  // namespace rcnn
 
 extern "C" {
+
+int rcnn_reserve_sms(int n) {
+    if (n < 0 || n > 64) {
+        rcnn::set_error("reserve_sms: %d out of range (0 .. 64)", n);
+        return RCNN_ERR_ARG;
+    }
+    rcnn::g_reserved_sms = n;
+    return RCNN_OK;
+}
 
 int rcnn_debug_timeline(void *buf) { rcnn::g_timeline = (long long *)buf; return RCNN_OK; }
 int rcnn_debug_refetch_counter(void *counter) { rcnn::g_refetch = (unsigned int *)counter; return RCNN_OK; }

@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int num_sms();
+int gemm_sms();   // num_sms() minus the SMs reserved for concurrent collectives (rcnn_reserve_sms)
 // optional per-step clock64 timeline of cluster 0 / CTA 0 of the recurrent kernels (debug aid)
 long long *debug_timeline();
 // optional device counter of exchange packets re-fetched after the optimistic TMA fetch (debug aid)

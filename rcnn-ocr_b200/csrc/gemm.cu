@@ -815,7 +815,7 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long
     constexpr size_t smem = PCfg<TN>::kSmem;
     RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<OutT, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ((N + TN - 1) / TN) * ((M + BM - 1) / BM);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
     ProfScope prof(RCNN_K_GEMM, s);
     gemm_tn_kernel<OutT, TN><<<grid, kPThreads, smem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
     RCNN_LAUNCH_CHECK("gemm_tn_kernel");
@@ -827,7 +827,7 @@ int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long
                      int N, int K, cudaStream_t s) {
     RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_pair_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmem));
     const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
-    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    const int pairs = tiles < gemm_sms() / 2 ? tiles : gemm_sms() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(kPThreads);
@@ -862,7 +862,7 @@ int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long
 int launch_atb_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &td, int M, int N, int tkb, int groups,
                     int a_gcols, int b_gcols, const AtbSeq &seq, cudaStream_t s) {
     const int ptiles = ((M + 255) / 256) * ((N + 255) / 256) * groups;
-    int sp = (num_sms() / 2) / ptiles;                      // fill the 74 CTA pairs once
+    int sp = (gemm_sms() / 2) / ptiles;                      // fill the 74 CTA pairs once
     sp = sp < 1 ? 1 : (sp > tkb ? tkb : sp);
     const int kbs = (tkb + sp - 1) / sp;
     sp = (tkb + kbs - 1) / kbs;
@@ -967,7 +967,7 @@ extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcol
     if (rc) return rc;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
     const int total_kb = (K + BK - 1) / BK;
-    int splits = (2 * num_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
+    int splits = (2 * gemm_sms() + tiles - 1) / tiles;          // aim at ~2 CTAs per SM
     splits = splits < 1 ? 1 : (splits > total_kb ? total_kb : splits);
     const int kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per_split - 1) / kb_per_split;

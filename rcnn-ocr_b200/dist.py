@@ -8,17 +8,35 @@ each finished gradient into its bucket and, when a bucket is complete, launches 
 all-reduce on the communication stream so it overlaps the rest of backward.  ``finish()`` waits
 for the outstanding collectives and averages.  Inference is batch-sharded with no collective.
 
-Bucket size: 8 MB.  The encoder's gradients arrive block by block (head, block 2: 19 MB, block 1: 19 MB at
-H = 512); round 1 used 32 MB buckets, so that the first bucket spanned the head, block 2 and part of block 1 and
-NOTHING was reduced before the very last weight-gradient GEMM (0.2 - 0.28 ms of exposed all-reduce per step,
-VERDICT r1).  With 8 MB buckets block 2's gradients reduce under block 1's recurrent backward kernel (which leaves
-20 SMs idle) and only block 1's own LSTM weight gradients (two buckets, produced together by its last GEMMs) are
-exposed.
+Buckets: one per producer (``producers``: head, block 2: 19 MB, block 1: 19 MB at H = 512), up to 24 MB.  Round 1 used
+32 MB buckets in plain reverse order: the first bucket spanned the head, block 2 and part of block 1 and NOTHING was
+reduced before the very last weight-gradient GEMM.  Now block 2's gradients reduce under block 1's
+recurrent backward kernel (which leaves 20 SMs idle) and only block 1's own bucket is exposed -- as one call (8 MB
+buckets made it three LL-protocol calls of 43 us each on 2 GPUs), started at the event its backward records after the
+weight-gradient GEMMs (``mark_grads_ready``) so that it runs beside the block's input-gradient GEMM, which leaves it
+16 SMs (``rcnn_reserve_sms``: a persistent GEMM otherwise holds one CTA on every SM and NCCL's kernel waits for it).
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+
+# Events recorded by a backward function right after the kernels that produced a parameter's gradient (keyed by
+# id(param)): a bucket whose gradients all carry one waits for those events instead of for everything the compute
+# stream has been given so far -- block 1's input-gradient GEMM, enqueued after its weight-gradient GEMMs but before
+# autograd runs the hooks, then overlaps the all-reduce of block 1's buckets (model._BiLSTMBlockFn.backward).
+GRAD_READY = {}
+
+
+def mark_grads_ready(params):
+    """Called from a backward pass: the gradients of ``params`` are complete at this point of the current stream."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    ev = torch.cuda.Event()
+    ev.record()
+    for p in params:
+        GRAD_READY[id(p)] = ev
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -29,7 +47,9 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class GradAllReducer:
-    def __init__(self, params, bucket_bytes: int = 8 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 24 << 20, group=None, reserve_sms: int = 16, producers=None):
+        """params: the parameters to reduce, in registration (forward) order.  producers: optional list of parameter
+        lists in forward order (e.g. [block 1, block 2, head]) -- buckets never span two of them."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -38,18 +58,38 @@ class GradAllReducer:
         self._pending = {}
         self._works = []
         self._handles = []
+        self._needs_compute = {}     # bucket -> some gradient was copied on the compute stream: wait for that stream
         if self.world == 1 or not self.params:
             return
-        cur, cur_bytes = [], 0
-        for p in reversed(self.params):
-            nbytes = p.numel() * 4
-            if cur and cur_bytes + nbytes > bucket_bytes:
+        # one bucket per producer: the gradients of a BidirectionalLSTM block (19 MB at H = 512) are final together, at
+        # the end of that block's backward, so they travel as ONE all-reduce (three 8 MB calls cost 3 x 43 us with the
+        # LL protocol, measured on 2 GPUs; one call of 19 MB is shorter and is launched once).  Parameters are taken in
+        # reverse registration order (the order backward produces them); a bucket closes when the next parameter
+        # belongs to another producer (`owner`: the module path up to the block) or would push it past bucket_bytes.
+        if producers is None:
+            producers = [self.params]
+        else:
+            producers = [[p for p in g if p.requires_grad] for g in producers]
+            covered = {id(p) for g in producers for p in g}
+            rest = [p for p in self.params if id(p) not in covered]
+            if rest:
+                producers = [rest] + producers
+        for plist in reversed(producers):
+            cur, cur_bytes = [], 0
+            for p in reversed(plist):
+                nbytes = p.numel() * 4
+                if cur and cur_bytes + nbytes > bucket_bytes:
+                    self._close(cur)
+                    cur, cur_bytes = [], 0
+                cur.append(p)
+                cur_bytes += nbytes
+            if cur:
                 self._close(cur)
-                cur, cur_bytes = [], 0
-            cur.append(p)
-            cur_bytes += nbytes
-        if cur:
-            self._close(cur)
+        import os
+        reserve_sms = int(os.environ.get("RCNN_RESERVE_SMS", reserve_sms))
+        if reserve_sms and self.params[0].is_cuda:
+            from . import _lib
+            _lib.check(_lib.lib().rcnn_reserve_sms(int(reserve_sms)), "rcnn_reserve_sms")
         self._avg = dist.get_backend(group) == "nccl"
         self._stream = torch.cuda.Stream() if self.params[0].is_cuda else None
         for p in self.params:
@@ -68,6 +108,8 @@ class GradAllReducer:
     def _on_grad(self, p):
         bi = self._bucket_of[p]
         flat, layout = self.buckets[bi]
+        ev = GRAD_READY.pop(id(p), None) if self._stream is not None else None
+        self._needs_compute.setdefault(bi, False)
         for q, off, n in layout:
             if q is p:
                 # same strides as the parameter (channels_last conv weights stay channels_last: the fused optimizers
@@ -75,7 +117,17 @@ class GradAllReducer:
                 dense = p.is_contiguous() or p.numel() == 0 or \
                     sum((sz - 1) * st for sz, st in zip(p.shape, p.stride())) + 1 == p.numel()
                 view = flat[off:off + n].as_strided(p.shape, p.stride()) if dense else flat[off:off + n].view_as(p)
-                view.copy_(p.grad)
+                if ev is not None:
+                    # the gradient was complete at `ev`: copy it on the communication stream, behind that event only
+                    # (not behind what the compute stream was given since, e.g. the block's input-gradient GEMM)
+                    g = p.grad
+                    self._stream.wait_event(ev)
+                    with torch.cuda.stream(self._stream):
+                        view.copy_(g)
+                    g.record_stream(self._stream)
+                else:
+                    view.copy_(p.grad)
+                    self._needs_compute[bi] = True
                 p.grad = view          # the optimizer reads the reduced values in place
                 break
         left = self._pending.get(bi, len(layout)) - 1
@@ -87,7 +139,8 @@ class GradAllReducer:
         flat, _ = self.buckets[bi]
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         if self._stream is not None:
-            self._stream.wait_stream(torch.cuda.current_stream())
+            if self._needs_compute.pop(bi, True):
+                self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
                 self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
         else:
@@ -108,6 +161,8 @@ class GradAllReducer:
             torch.cuda.current_stream().wait_stream(self._stream)
         self._works.clear()
         self._pending.clear()
+        self._needs_compute.clear()
+        GRAD_READY.clear()
 
     def remove(self):
         for h in self._handles:

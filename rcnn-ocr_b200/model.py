@@ -94,6 +94,9 @@ class _BiLSTMBlockFn(torch.autograd.Function):
             ctx.lin_wt = prepared.lin_wt
             ctx.dims = (B, T, I, H, O)
             ctx.x_dtype = x.dtype
+            # the parameter objects whose gradients this function returns (for dist.mark_grads_ready)
+            ctx.params = [t for t in (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r, lin_w, lin_b)
+                          if isinstance(t, torch.nn.Parameter)] or None
         return out.view(B, T, O)
 
     @staticmethod
@@ -112,10 +115,8 @@ class _BiLSTMBlockFn(torch.autograd.Function):
         # ---- recurrence ---------------------------------------------------------------------
         dG, db_p = ops.lstm_backward(packed, gates, csave, dhcat, B, T)   # [B,T,8H] bf16, [8H] f32
         dG2 = dG.view(BT, 8 * H)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx_dtype = torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32
-            dx = ops.gemm_bf16(dG2, packed.wih_pt, None, dx_dtype).view(B, T, I).to(ctx.x_dtype)
+        # weight gradients first: under data parallelism their all-reduce starts at the event recorded here and runs
+        # while the input-gradient GEMM below (and whatever backward work precedes this block in the model) executes
         if ops.weight_grads_supported(I, H, T):
             g = ops.lstm_weight_grads(dG, xb, hcat, db_p, B, T, I, H)  # torch layout, no h_prev copy / unpack pass
         else:
@@ -123,6 +124,13 @@ class _BiLSTMBlockFn(torch.autograd.Function):
             hprev = ops.lstm_hprev(hcat).view(BT, 2 * H)
             dwhh_p = ops.gemm_bf16_atb_grouped(dG2, hprev, 2, 4 * H, H)   # per direction: [4H, H] = dG_d^T h_prev_d
             g = ops.lstm_unpack_grads(dwih_p, dwhh_p, db_p, I, H)
+        if ctx.params is not None:
+            from .dist import mark_grads_ready
+            mark_grads_ready(ctx.params)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx_dtype = torch.bfloat16 if ctx.x_dtype == torch.bfloat16 else torch.float32
+            dx = ops.gemm_bf16(dG2, packed.wih_pt, None, dx_dtype).view(B, T, I).to(ctx.x_dtype)
         return (dx, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], d_lin_w, d_lin_b, None, None, None)
 
 

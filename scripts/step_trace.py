@@ -12,10 +12,17 @@ from torch.profiler import ProfilerActivity, profile
 
 import bench
 
-dev = torch.device("cuda", 0)
+# under torchrun (WORLD_SIZE > 1) the data-parallel step is traced on rank 0
+world, rank, lrank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda", lrank)
 torch.cuda.set_device(dev)
-step = bench.TrainStep(dev, 1, 0)
-batch = [t.to(dev) for t in bench.make_batch(256, 1234)]
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+step = bench.TrainStep(dev, world, rank)
+batch = [t.to(dev) for t in bench.make_batch(256, 1234 + rank)]
+step(*batch)
+torch.cuda.synchronize()
 gstep = step.R.GraphedStep(step, batch)
 for _ in range(5):
     gstep(*batch)
@@ -23,6 +30,9 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     gstep(*batch)
     torch.cuda.synchronize()
+if rank != 0:
+    dist.barrier()
+    os._exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
 evs.sort(key=lambda e: e.time_range.start)
 t0, t1 = evs[0].time_range.start, evs[-1].time_range.end
@@ -48,3 +58,8 @@ for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 if os.environ.get("TRACE_ORDER"):
     for st, dur, name in order:
         print(f"{st:9.1f} {dur:8.1f}  {name}")
+
+if world > 1:
+    sys.stdout.flush()
+    dist.barrier()
+    os._exit(0)
