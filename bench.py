@@ -36,7 +36,7 @@ L2_BYTES = 126 * 1024 * 1024
 
 def load_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (None if absent)."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     try:
         with open(path) as fh:
             return json.load(fh).get(kernel)
@@ -499,6 +499,65 @@ def run_cfg4(args, device, world, rank, timed_fn, hidden=256):
 
 
 
+def run_cfg2(args, device, timed_fn, peaks, cpu: bool):
+    """BASELINE configs[1]: CTC loss fwd+bwd microbench, T=64, C=195, labels U{1..32}, batch 256, against torch's CTCLoss
+    (SURVEY 8d cfg 2).  Ours: ONE launch from the logits (log_softmax + loss + gradient at the logits); torch: log_softmax,
+    ctc_loss, ctc_loss_backward, log_softmax_backward (ATen CUDA on the same GPU; torch CPU on the host cores)."""
+    import torch.nn.functional as F
+    import rcnn_ocr_b200 as R
+    from rcnn_ocr_b200 import _lib
+    T, C, N = CFG["T"], CFG["C"], CFG["B"]
+    g = torch.Generator().manual_seed(1234)
+    xs = [torch.randn(N, T, C, generator=g).to(device).requires_grad_(True) for _ in range(16)]   # 16 x 12.8 MB x (x + grad) > L2
+    tl = torch.randint(1, 33, (N,), generator=g)
+    tg = torch.randint(1, C, (N, 32), generator=g)
+    il = torch.full((N,), T)
+    tgd, ild, tld = tg.to(device), il.to(device), tl.to(device)
+
+    def ours(i):
+        x = xs[i % 16]
+        x.grad = None
+        R.ctc_loss_from_logits(x.permute(1, 0, 2), tgd, ild, tld, 0, "mean", True, max_target_length=32).backward()
+
+    def aten(i):
+        x = xs[i % 16]
+        x.grad = None
+        F.ctc_loss(F.log_softmax(x, 2).permute(1, 0, 2), tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+
+    ms_api = timed_fn(ours)
+    _lib.prof_enable(True)
+    for i in range(args.steps):
+        ours(i)
+    torch.cuda.synchronize()
+    kms, n = _lib.prof_read(1)
+    _lib.prof_enable(False)
+    _lib.lib().rcnn_prof_reset()
+    ms_k = kms / max(n, 1)
+    ms_aten = timed_fn(aten)
+    alg = 2.0 * T * C * 4 * N
+    out = {"ours": {"kernel_us": round(ms_k * 1e3, 2), "api_fwd_bwd_us": round(ms_api * 1e3, 2),
+                    "GBps": round(alg / (ms_k * 1e-3) / 1e9, 1), "hbm_frac": round(alg / (ms_k * 1e-3) / 1e9 / peaks["hbm"], 4),
+                    "seq_per_s": round(N / (ms_k * 1e-3))},
+           "torch_cuda": {"api_fwd_bwd_us": round(ms_aten * 1e3, 2), "seq_per_s": round(N / (ms_aten * 1e-3)),
+                          "what": "F.log_softmax + F.ctc_loss + backward, ATen CUDA, eager, same GPU and inputs"},
+           "speedup_vs_torch_cuda": round(ms_aten / ms_api, 2),
+           "config": {"T": T, "N": N, "C": C, "label_len": "U{1..32}", "reduction": "mean", "zero_infinity": True,
+                      "algorithmic_bytes_per_seq": 2 * T * C * 4}}
+    if cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        xc = xs[0].detach().cpu().requires_grad_(True)
+        best = None
+        for _ in range(4):
+            xc.grad = None
+            t0 = time.perf_counter()
+            F.ctc_loss(F.log_softmax(xc, 2).permute(1, 0, 2), tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["torch_cpu"] = {"fwd_bwd_ms": round(best * 1e3, 2), "seq_per_s": round(N / best), "cores": os.cpu_count(),
+                            "what": "the same torch ops on the host cores (min of 3 after a warm-up)"}
+    return out
+
+
 def run_b512(args, step, infer, device, timed_fn, sync, peaks, use_graph):
     """cfg B at 512 lines per GPU (BASELINE configs[3] names a batch of 512): 16 (direction, 64-sequence) work items for
     8 CTA groups.  The backward recurrent kernel then works on two items per group at a time (rcnn_lstm_plan)."""
@@ -726,10 +785,11 @@ def run_ours(args, rank, world, local_rank):
     step.enc.train(); step.head.train()
 
     # ---- vendor bar, cfg 1, cfg 4 (strong scaling) ------------------------------------------------------------
-    vendor = cfg1 = cfg4 = b512 = None
+    vendor = cfg1 = cfg2 = cfg4 = b512 = None
     if not args.no_extras:
         if world == 1:
             b512 = run_b512(args, step, infer, device, tf, sync, peaks, use_graph)
+            cfg2 = run_cfg2(args, device, tf, peaks, cpu=(rank == 0 and not args.no_cpu_baseline))
             vendor = run_vendor(args, dev, B, tf)
             cfg1 = run_cfg1(args, device, tf, cpu=(rank == 0 and not args.no_cpu_baseline))
         r4 = run_cfg4(args, device, world, rank, tf, hidden=256)
@@ -783,7 +843,7 @@ def run_ours(args, rank, world, local_rank):
             ach = launch_flops / (per_launch_ms * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf_sus"],
                     "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sus"], 4), "traffic": load_traffic(dom),
-                    "traffic_note": "DRAM bytes per launch, ncu --set full capture at this config (profiles/ncu_traffic_r01.json)",
+                    "traffic_note": "DRAM bytes per launch, ncu --set full capture at this config (profiles/ncu_traffic_r02.json)",
                     "algorithmic": f"2*B*T*H*4H*2dirs = {rec_flops / 1e9:.1f} GFLOP of recurrent matmuls per launch (one block)"
                                    + (f" + {(launch_flops - rec_flops) / 1e9:.1f} GFLOP of fused input projection" if dom == "lstm_fwd" else ""),
                     "us_per_timestep": round(per_launch_ms * 1e3 / T, 3), "peak_source": peaks["src"]}
@@ -854,7 +914,7 @@ def run_ours(args, rank, world, local_rank):
             "vendor": vendor,
             "vs_vendor": ({"train": round(total_B / (ms_train * 1e-3) / vendor["value"], 3),
                            "infer": round(total_B / (ms_inf * 1e-3) / vendor["infer"]["value"], 3)} if vendor else None),
-            "cfgB_batch512": b512,
+            "cfgB_batch512": b512, "cfg2_ctc_microbench": cfg2,
             "cfg1_minimal_inference": cfg1, "cfg4_strong": cfg4, "cfg5_infer_sweep": sweep or None,
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "clocks": clk,
             "loss_first_last": [round(losses[0], 4), round(losses[-1], 4)] if losses else None,
