@@ -389,6 +389,17 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
         return R.ids_to_text(ids, lens, alphabet)[0]
 
     ms_e2e = timed_fn(e2e)
+    # the same model the way the reference runs it on a GPU (inference.py:155-166): fp32, NCHW, eager launches -- what the
+    # channels_last + bf16 autocast + graph replay of the backbone (section 8f-2) is measured against
+    model_ref = R.RCNN(194, hidden_size=256).to(device).eval()
+    xs_ref = [h.to(device) for h in host]
+
+    @torch.no_grad()
+    def fwd_ref(i):
+        return R.ctc_greedy_ids(model_ref(xs_ref[i % 4], is_train=False))
+
+    ms_fp32 = timed_fn(fwd_ref)
+    del model_ref, xs_ref
     # from decoded pixels: uint8 line images of assorted sizes -> K7 (resize + pad + normalise + batch, one launch) ->
     # model -> strings, against the reference's host-side input step (cv2 + numpy per image, inference.py:93-124,159-164)
     rng = np.random.default_rng(7)
@@ -421,6 +432,9 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
                                "note": "32 uint8 line images (24-80 x 90-400 px) -> K7 on the device (one pinned copy + one launch) -> "
                                        "model -> strings; host_input_step_ms = the reference's per-image cv2 resize + pad + "
                                        "normalise + stack + copy on this host (oracle/host_ref, wall clock)"},
+           "backbone_fp32_nchw_eager": {"value": round(32 / (ms_fp32 * 1e-3), 1), "ms_per_batch": round(ms_fp32, 4),
+                                        "note": "same RCNN, backbone in fp32 / NCHW / eager launches (the reference's GPU settings), "
+                                                "device-resident; `value` above uses channels_last + bf16 autocast + graph replay"},
            "config": {"workload": "cfg1 minimal_inference: RCNN(194, hidden 256) eval, x[32,3,32,128] in [-1,1], greedy "
                                   "CTC decode -> strings", "T": T, "backbone": "torch/cuDNN, channels_last + bf16 autocast"}}
     if cpu:

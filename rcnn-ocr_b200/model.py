@@ -241,6 +241,9 @@ def make_enc_rnn(enc_dim: int, hidden_size: int, out_dtype: torch.dtype = torch.
                   BidirectionalLSTM(hidden_size, hidden_size, hidden_size, out_dtype=out_dtype))
 
 
+_PAD_CACHE = {}   # (weight pointer, N, K, device) -> (zero-padded bf16 weight buffer, zero-padded bias buffer), see _LinearFn
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (bf16 operands, fp32 accumulate), any N."""
 
@@ -251,13 +254,31 @@ class _LinearFn(torch.autograd.Function):
         K = x.shape[-1]
         x2 = x.reshape(-1, K)
         xb = x2 if x2.dtype == torch.bfloat16 and x2.is_contiguous() else ops.cast_bf16_2d(x2)
-        wb = ops.cast_bf16_2d(weight.detach())
-        out = ops.gemm_bf16(xb, wb, bias.detach().float().contiguous() if bias is not None else None, torch.float32)
+        N, M = weight.shape[0], x2.shape[0]
+        if N % 32 and N > 128 and M >= 512:
+            # An odd class count (C = 195: rows of 780 bytes) keeps the GEMM off its CTA-pair kernel and off the TMA-store
+            # epilogue (27 us for 3.3 GFLOP).  The weight is cast into the first N rows of a zero-padded [256k, K] buffer
+            # (kept per weight tensor: the pad rows are written once), the product is computed N-padded with 16-byte
+            # aligned output rows and the caller gets the [.., :N] view -- the CTC and decode kernels take a row pitch.
+            Np = (N + 255) // 256 * 256
+            key = (weight.data_ptr(), N, K, str(weight.device))
+            pad = _PAD_CACHE.get(key)
+            if pad is None:
+                pad = (torch.zeros((Np, (K + 7) // 8 * 8), dtype=torch.bfloat16, device=weight.device),
+                       torch.zeros((Np,), dtype=torch.float32, device=weight.device))
+                _PAD_CACHE[key] = pad
+            wb = ops.cast_bf16_2d(weight.detach(), out=pad[0])
+            if bias is not None:
+                pad[1][:N].copy_(bias.detach())
+            out = ops.gemm_bf16(xb, pad[0][:, :K], pad[1] if bias is not None else None, torch.float32)[:, :N]
+        else:
+            wb = ops.cast_bf16_2d(weight.detach())
+            out = ops.gemm_bf16(xb, wb, bias.detach().float().contiguous() if bias is not None else None, torch.float32)
         if save:
             ctx.save_for_backward(xb, wb)
             ctx.x_dtype = x.dtype
             ctx.has_bias = bias is not None
-        return out.view(*lead, weight.shape[0])
+        return out.view(*lead, N) if out.is_contiguous() else out.unflatten(0, lead)
 
     @staticmethod
     def backward(ctx, dout):

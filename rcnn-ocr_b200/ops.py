@@ -238,9 +238,10 @@ def lstm_plan(B: int, H: int, backward: bool = False):
     return nslot.value, ngroups.value
 
 
-def cast_bf16_2d(x: torch.Tensor) -> torch.Tensor:
+def cast_bf16_2d(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """float32 [R,C] (rows contiguous) -> bf16 [R,C] view whose row pitch is padded to a multiple of
-    8 elements (pad columns zero), ready to be a GEMM operand for any C."""
+    8 elements (pad columns zero), ready to be a GEMM operand for any C.  ``out``: an existing bf16 buffer
+    [>= R, pad8(C)] whose first R rows are written."""
     _lib.require_cuda(x, "x")
     assert x.dim() == 2
     if x.dtype != torch.float32:
@@ -250,10 +251,13 @@ def cast_bf16_2d(x: torch.Tensor) -> torch.Tensor:
     R, C = x.shape
     ldd = _pad8(C)
     with torch.cuda.device(x.device):
-        out = torch.empty((R, ldd), dtype=torch.bfloat16, device=x.device)
+        if out is None:
+            out = torch.empty((R, ldd), dtype=torch.bfloat16, device=x.device)
+        else:
+            assert out.dtype == torch.bfloat16 and out.shape[0] >= R and out.shape[1] == ldd and out.is_contiguous()
         rc = _lib.lib().rcnn_cast_bf16_2d(x.data_ptr(), x.stride(0), out.data_ptr(), ldd, R, C, _lib.stream_ptr())
         _lib.check(rc, "rcnn_cast_bf16_2d")
-    return out[:, :C]
+    return out[:R, :C]
 
 
 def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
