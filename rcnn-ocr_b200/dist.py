@@ -142,21 +142,34 @@ class GradAllReducer:
             if self._needs_compute.pop(bi, True):
                 self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
-                self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
+                self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, bi))
         else:
-            self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat))
+            self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, bi))
 
-    def finish(self):
-        """Call after backward(): waits for every bucket and leaves averaged gradients in p.grad."""
+    def finish(self, params=None):
+        """Call after backward(): waits for the outstanding all-reduces and leaves averaged gradients in p.grad.
+        ``params``: wait only for the buckets that hold these parameters (their optimizer step can then run while the
+        later buckets -- the first block's, produced last -- are still being reduced); a final ``finish()`` waits for the rest."""
         if self.world == 1:
             return
+        only = None if params is None else {self._bucket_of[p] for p in params if p in self._bucket_of}
         for bi, (flat, layout) in enumerate(self.buckets):   # buckets whose params got no grad this step
+            if only is not None and bi not in only:
+                continue
             if self._pending.get(bi, len(layout)) != 0 and any(p.grad is not None for p, _, _ in layout):
                 self._launch(bi)
-        for work, flat in self._works:
+                self._pending[bi] = 0
+        rest = []
+        for work, flat, bi in self._works:
+            if only is not None and bi not in only:
+                rest.append((work, flat, bi))
+                continue
             work.wait()
             if not self._avg:
                 flat.div_(self.world)
+        self._works = rest
+        if only is not None:
+            return
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
         self._works.clear()

@@ -23,8 +23,13 @@ def _worker(rank, world, port, out_dir):
     torch.manual_seed(0)                                  # identical replicas
     model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 8),
                                 torch.nn.Tanh(), torch.nn.Linear(8, 4))
-    reducer = GradAllReducer(model.parameters(), bucket_bytes=600)      # forces several buckets
+    layers = [list(m.parameters()) for m in model if isinstance(m, torch.nn.Linear)]
+    # one bucket per producer (layer), split further by the byte cap: buckets never span two producers
+    reducer = GradAllReducer(list(model.parameters()), bucket_bytes=600, producers=layers)
     assert len(reducer.buckets) >= 3
+    for flat, layout in reducer.buckets:
+        owners = {next(i for i, ps in enumerate(layers) if any(q is p for q in ps)) for p, _, _ in layout}
+        assert len(owners) == 1
     g = torch.Generator().manual_seed(100)
     x_all = torch.randn(12, 16, generator=g)
     y_all = torch.randn(12, 4, generator=g)
@@ -34,7 +39,12 @@ def _worker(rank, world, port, out_dir):
             p.grad = None
         loss = ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean()
         loss.backward()
+        if it == 1:
+            # staged finish: the last layers' buckets first (their optimizer step could run now), then the rest
+            reducer.finish(layers[2] + layers[1])
+            assert all(bi in {reducer._bucket_of[p] for p in layers[0]} for _, _, bi in reducer._works)
         reducer.finish()
+        assert not reducer._works
     torch.save([p.grad.clone() for p in model.parameters()], os.path.join(out_dir, f"g{rank}.pt"))
     dist.destroy_process_group()
 
