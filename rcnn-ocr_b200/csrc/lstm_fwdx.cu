@@ -51,6 +51,14 @@ constexpr int LK = 64;
 constexpr uint32_t kWTile = GR * LK * 2;   // 16 KB
 constexpr uint32_t kHBox = NS * LK * 2;    //  8 KB
 constexpr int kThreads = 352;              // warp 0 TMA, warp 1 MMA, warps 2-9 cell update, warp 10 publisher
+#ifndef RCNN_FWD_WARP_RELEASE
+#define RCNN_FWD_WARP_RELEASE 0
+#endif
+// Experiment (compile with -DRCNN_FWD_WARP_RELEASE=1): every cell warp releases the group counter itself after its h stores
+// instead of handing off to the publisher thread (whose mbarrier wake-up is ~190 cycles of every step).  Measured SLOWER:
+// 248 against 219 us per inference launch at B = 256 (step 6,400 against 5,450 cycles) -- four MEMBAR.ALL.GPU per half
+// and step instead of one, each ~1,400 cycles in which the warp cannot start on the next accumulator.
+constexpr bool kWarpRelease = RCNN_FWD_WARP_RELEASE != 0;
 
 struct FxParams {
     int B, T, H, I;
@@ -222,7 +230,8 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                             const int b0 = ((it0 + slot * p.ngroups) >> 1) * NS;
 #pragma unroll
                             for (int hf = 0; hf < NH; ++hf) {
-                                wait_counter_x(counter + slot * NH + hf, (published + (unsigned)s) * (unsigned)gsize);
+                                wait_counter_x(counter + slot * NH + hf,
+                                               (published + (unsigned)s) * (unsigned)gsize * (kWarpRelease && !LL ? (unsigned)(8 / NH) : 1u));
                                 if (slot == 0 && hf == 0) TLX(0);                     // P0: half 0's counter seen
                                 if (NSLOT == 2) {
                                     // the half's tile is shared by the slots: the MMAs that read its previous contents are done
@@ -394,7 +403,7 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
         // ===== publisher (one elected thread): h_t of a half was stored to hcat by its cell warps, which arrived on
         // h_staged; ONE gpu-scope release (cumulative over what the barrier ordered before it) makes it visible.
         // One slot: warp 10 serves both halves.  Two slots: warp 10 + hf serves half hf of both slots in turn.
-        if (!LL && elect_one()) {
+        if (!LL && !kWarpRelease && elect_one()) {
             uint32_t sphase = 0;
             const int hf_lo = NSLOT == 2 ? warp - 10 : 0, hf_hi = NSLOT == 2 ? warp - 9 : NH;
             for (int it0 = group; it0 < p.nitems; it0 += rstride) {
@@ -466,7 +475,14 @@ lstm_fwdx_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(hstaged(slot, hf));
+                if (lane == 0) {
+                    mbar_arrive(hstaged(slot, hf));                  // (the MMA thread: the accumulators have been read)
+                    if (kWarpRelease && !LL) {
+                        if (threadIdx.x == 64 && slot == 0) TLX(6);
+                        red_release_gpu_inc_x(counter + slot * NH + hf);   // cumulative over the warp's h stores (__syncwarp)
+                        if (threadIdx.x == 64 && slot == 0) TLX(7);
+                    }
+                }
                 if (threadIdx.x == 64 && slot == 0) TLX(5);          // E1: cell phase done, h_t stored
                 if (SAVE) {
                     // gates_save [2, T, B, 4H]: this thread holds gate row r for 32 sequences; a lane pair swaps halves so
