@@ -92,8 +92,12 @@ for B in (1, 8, 32, 64, 128, 256, 512, 1024, 2048, 4096):
                              "lines_per_s_graph": round(B / (ms_graph * 1e-3), 1)})
     del gi, feats
 step.enc.train(); step.head.train()
+_warm = [t.to(dev) for t in bench.make_batch(256, 5)]
+for _ in range(5):            # one-time costs (library workspaces, attribute calls, allocator growth) stay out of the first row
+    step(*_warm)
+torch.cuda.synchronize()
 for B in (64, 128, 256, 512, 1024):
     batches = [[t.to(dev) for t in bench.make_batch(B, 77 + i)] for i in range(3)]
-    ms = time_ms(lambda i: step(*batches[i]), 3, reps=10, warm=3)
+    ms = time_ms(lambda i: step(*batches[i]), 3, reps=20, warm=5)
     out["train"].append({"B": B, "ms_eager": round(ms, 4), "lines_per_s": round(B / (ms * 1e-3), 1)})
 print(json.dumps(out, indent=1))
