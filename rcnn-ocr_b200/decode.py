@@ -114,6 +114,39 @@ def ids_to_text(ids: torch.Tensor, lens: torch.Tensor, alphabet):
     return ids_to_text_host(ids_h, lens_h, alphabet)
 
 
+class PendingTexts:
+    """The host half of a decode, deferred: the device->host copies of ids / lens are enqueued (own pinned buffers, own
+    event) when the object is made, ``result()`` waits for that event only and maps through the charset.  A serving
+    loop launches batch i+1 before it asks for batch i's strings, so the copy and the Python work of one batch run
+    under the kernels of the next (``ids_to_text`` = the same with an immediate ``result()``)."""
+
+    _pool = {}
+
+    def __init__(self, ids: torch.Tensor, lens: torch.Tensor, alphabet):
+        B, T = ids.shape
+        key = (B, T, ids.device.index)
+        ring = PendingTexts._pool.setdefault(key, {"next": 0, "bufs": []})
+        if len(ring["bufs"]) < 4:
+            ring["bufs"].append((torch.empty((B, T), dtype=torch.int32, pin_memory=True),
+                                 torch.empty((B,), dtype=torch.int32, pin_memory=True), torch.cuda.Event()))
+        self.h_ids, self.h_lens, self.event = ring["bufs"][ring["next"] % len(ring["bufs"])]
+        ring["next"] += 1
+        self.alphabet = alphabet
+        self.h_ids.copy_(ids if ids.is_contiguous() else ids.contiguous(), non_blocking=True)
+        self.h_lens.copy_(lens, non_blocking=True)
+        self.event.record(torch.cuda.current_stream(ids.device))
+
+    def result(self):
+        self.event.synchronize()
+        return ids_to_text_host(self.h_ids.numpy(), self.h_lens.numpy(), self.alphabet)
+
+
+def ids_to_text_async(ids: torch.Tensor, lens: torch.Tensor, alphabet) -> PendingTexts:
+    """Enqueue the D2H of a decoded batch and return a handle; ``.result()`` gives ``(texts, seqs)``.  At most four
+    handles per batch shape may be outstanding (their pinned buffers rotate)."""
+    return PendingTexts(ids, lens, alphabet)
+
+
 def ctc_greedy_decoder(logits: torch.Tensor, alphabet, blank: int = 0, batch_first=None):
     """Drop-in for training/utils.py:122-150.  Returns (texts, seqs)."""
     if batch_first is None:  # the reference's heuristic, utils.py:132-133

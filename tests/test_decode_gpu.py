@@ -135,3 +135,18 @@ def test_full_size_sweep_properties():
     assert int(ids.max()) < 195 and not bool(((ids == 0)).any())
     pad = torch.arange(64, device="cuda")[None, :] >= lens[:, None]
     assert bool((ids[pad] == -1).all()) and bool((ids[~pad] > 0).all())
+
+
+def test_deferred_host_half_equals_the_immediate_one():
+    """ids_to_text_async: three batches in flight (own pinned buffers and events), results asked for in order and out of
+    order, equal to ids_to_text of the same ids."""
+    import rcnn_ocr_b200 as R
+    g = torch.Generator(device="cuda").manual_seed(3)
+    alphabet = [chr(0x430 + i) for i in range(40)]
+    batches = [torch.randn(17, 23, 41, device="cuda", generator=g) for _ in range(3)]
+    outs = [R.ctc_greedy_ids(b) for b in batches]
+    outs = [(i.clone(), l.clone()) for i, l in outs]
+    want = [R.ids_to_text(i, l, alphabet) for i, l in outs]
+    pend = [R.ids_to_text_async(i, l, alphabet) for i, l in outs]
+    for k in (1, 0, 2):
+        assert pend[k].result() == want[k]
