@@ -46,10 +46,26 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _Done:
+    """Stand-in for a collective whose completion is already ordered on the communication stream."""
+
+    def wait(self):
+        return True
+
+
 class GradAllReducer:
-    def __init__(self, params, bucket_bytes: int = 24 << 20, group=None, reserve_sms: int = 16, producers=None):
+    def __init__(self, params, bucket_bytes: int = 24 << 20, group=None, reserve_sms: int = 16, producers=None,
+                 wire_dtype: torch.dtype | None = None):
         """params: the parameters to reduce, in registration (forward) order.  producers: optional list of parameter
-        lists in forward order (e.g. [block 1, block 2, head]) -- buckets never span two of them."""
+        lists in forward order (e.g. [block 1, block 2, head]) -- buckets never span two of them.  wire_dtype:
+        ``torch.bfloat16`` sends the gradients as bf16 (half the bytes of the exposed all-reduce; the sum is still formed
+        by NCCL in bf16, so the averaged gradients carry bf16 rounding) -- off by default (RCNN_DP_WIRE=bf16 turns it on for
+        measurements): the default keeps the fp32 sums that make the N-GPU step equal the 1-GPU step on the whole batch."""
+        import os as _os
+        if wire_dtype is None and _os.environ.get("RCNN_DP_WIRE", "") == "bf16":
+            wire_dtype = torch.bfloat16
+        self.wire_dtype = wire_dtype
+        self._wire = {}
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -142,7 +158,17 @@ class GradAllReducer:
             if self._needs_compute.pop(bi, True):
                 self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
-                self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, bi))
+                if self.wire_dtype is not None:
+                    wire = self._wire.get(bi)
+                    if wire is None:
+                        wire = self._wire[bi] = torch.empty_like(flat, dtype=self.wire_dtype)
+                    wire.copy_(flat)
+                    work = dist.all_reduce(wire, op=op, group=self.group, async_op=True)
+                    work.wait()                      # (the communication stream waits; the host does not)
+                    flat.copy_(wire)
+                    self._works.append((_Done(), flat, bi))
+                else:
+                    self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, bi))
         else:
             self._works.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, bi))
 
