@@ -264,8 +264,11 @@ ctc_kernel(const CtcParams p) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     const int s = lane + 32 * j;
-                    g[j] = (s < S) ? __ldg(row + ext[s]) * kLog2e - z : -INFINITY;   // (L1 hit: the row was just read)
-                    u = fmaxf(u, g[j]);
+                    g[j] = -INFINITY;
+                    if (32 * j < S) {      // (uniform over the CTA: slots beyond this sequence's lattice cost no issue slots)
+                        g[j] = (s < S) ? __ldg(row + ext[s]) * kLog2e - z : -INFINITY;   // (L1 hit: the row was just read)
+                        u = fmaxf(u, g[j]);
+                    }
                 }
                 u = warp_max(u);
                 if (u == -INFINITY) u = 0.f;
@@ -294,8 +297,11 @@ ctc_kernel(const CtcParams p) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int s = lane + 32 * j;
-            g[j] = (s < S) ? __ldg(row + ext[s]) * kLog2e - z : -INFINITY;
-            u = fmaxf(u, g[j]);
+            g[j] = -INFINITY;
+            if (32 * j < S) {
+                g[j] = (s < S) ? __ldg(row + ext[s]) * kLog2e - z : -INFINITY;
+                u = fmaxf(u, g[j]);
+            }
         }
         u = warp_max(u);
         if (u == -INFINITY) u = 0.f;
@@ -313,7 +319,12 @@ ctc_kernel(const CtcParams p) {
     const bool want_grad = p.grad != nullptr;
     if (Tn > 0 && !any_bad) {
         if (warp == 0) {
-            alpha_pass<K>(lpe, alpha, ext, S, SP, Tn, lane);
+            // states per lane chosen per SEQUENCE (S = 2 L + 1 <= 32: one; <= 64: two; ...): a short label sequence pays for
+            // one logsumexp per lane and step instead of the K the longest label of the batch needs
+            if (K >= 3 && S <= 32) alpha_pass<1>(lpe, alpha, ext, S, SP, Tn, lane);
+            else if (K >= 3 && S <= 64) alpha_pass<2>(lpe, alpha, ext, S, SP, Tn, lane);
+            else if (K == 2 && S <= 32) alpha_pass<1>(lpe, alpha, ext, S, SP, Tn, lane);
+            else alpha_pass<K>(lpe, alpha, ext, S, SP, Tn, lane);
             __syncwarp();
             // log-likelihood: the two terminal states, plus the exact sum of the row shifts
             double us = 0.0;
@@ -326,7 +337,10 @@ ctc_kernel(const CtcParams p) {
                 misc[0] = (float)(-((double)ll2 + us) * (double)kLn2);
             }
         } else if (warp == 1 && want_grad) {
-            beta_pass<K>(lpe, beta, ext, S, SP, Tn, lane);
+            if (K >= 3 && S <= 32) beta_pass<1>(lpe, beta, ext, S, SP, Tn, lane);
+            else if (K >= 3 && S <= 64) beta_pass<2>(lpe, beta, ext, S, SP, Tn, lane);
+            else if (K == 2 && S <= 32) beta_pass<1>(lpe, beta, ext, S, SP, Tn, lane);
+            else beta_pass<K>(lpe, beta, ext, S, SP, Tn, lane);
         }
     } else if (tid == 0) {
         misc[0] = any_bad ? NAN : (L == 0 ? 0.f : INFINITY);
@@ -380,29 +394,37 @@ ctc_kernel(const CtcParams p) {
             for (int j = 0; j < K; ++j) {
                 const int s = lane + 32 * j;
                 float w = -INFINITY;
-                if (s < S) {
-                    const float lp = lpe[(size_t)t * SP + s];
-                    if (lp != -INFINITY) w = alpha[(size_t)t * SP + s] + beta[(size_t)t * SP + s] - lp;
+                if (32 * j < S) {          // (uniform over the CTA)
+                    if (s < S) {
+                        const float lp = lpe[(size_t)t * SP + s];
+                        if (lp != -INFINITY) w = alpha[(size_t)t * SP + s] + beta[(size_t)t * SP + s] - lp;
+                    }
+                    mx = fmaxf(mx, w);
                 }
                 v[j] = w;
-                mx = fmaxf(mx, w);
             }
             mx = warp_max(mx);
             float zsum = 0.f, blank_sum = 0.f;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                v[j] = (v[j] == -INFINITY) ? 0.f : ex2(v[j] - mx);
-                zsum += v[j];
+                if (32 * j < S) {
+                    v[j] = (v[j] == -INFINITY) ? 0.f : ex2(v[j] - mx);
+                    zsum += v[j];
+                } else {
+                    v[j] = 0.f;
+                }
             }
             zsum = warp_sum(zsum);
             const float inv = 1.f / zsum;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int s = lane + 32 * j;
-                v[j] *= inv;
-                if (s < S) {
-                    if (s & 1) wocc[s] = v[j];
-                    else blank_sum += v[j];
+                if (32 * j < S) {
+                    v[j] *= inv;
+                    if (s < S) {
+                        if (s & 1) wocc[s] = v[j];
+                        else blank_sum += v[j];
+                    }
                 }
             }
             blank_sum = warp_sum(blank_sum);
@@ -410,7 +432,7 @@ ctc_kernel(const CtcParams p) {
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const int s = lane + 32 * j;
-                if (s < S && (s & 1)) {
+                if (32 * j < S && s < S && (s & 1)) {
                     const int lk = link[s];
                     if (lk >= 0) {                       // first occurrence of its label: sum the chain
                         float tot = v[j];
