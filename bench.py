@@ -675,16 +675,10 @@ def run_ours(args, rank, world, local_rank):
     step(*dev[0])                                        # one eager step: counts this library's launches per step
     sync()
     launches = ops.launch_count() - l0                   # (a graph replay runs exactly the kernels captured from it)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms_train = timed(lambda i: gstep(*dev[i % RING]), args.steps, args.warmup, sync, barrier)
-    clk = clocks.stop()
-    ms_train = max_over_ranks(ms_train)
-
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------
+    # two captured graphs used in turn; the next step's inputs are copied into the idle graph's static tensors on a copy
+    # stream while the other graph runs (device-resident loop: from the ring in HBM; end-to-end loop: from pinned host
+    # memory).  At N > 1 both graphs hold the NCCL bucket all-reduces and every rank replays them in the same order.
     copy_stream = torch.cuda.Stream()
-    # two captured graphs used in turn, the H2D copies land straight in their static inputs (no device-to-device
-    # copy); at N > 1 both graphs hold the NCCL bucket all-reduces and every rank replays them in the same order
     pingpong = use_graph
     gsteps = [gstep, step.R.GraphedStep(step, dev[0])] if pingpong else None
     slots = [g.static_in for g in gsteps] if pingpong else \
@@ -692,13 +686,39 @@ def run_ours(args, rank, world, local_rank):
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
-    def stage(i):
+    def stage(i, source=None):
         s = i % 2
+        src = (source or host)[i % RING]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[s])
-            for d, h in zip(slots[s], host[i % RING]):
+            for d, h in zip(slots[s], src):
                 d.copy_(h, non_blocking=True)
             ready[s].record(copy_stream)
+
+    def dev_train(i):                                   # inputs resident in HBM (ring of 8 sets > L2)
+        if not pingpong:
+            return gstep(*dev[i % RING])
+        s = i % 2
+        if dev_train.primed is False:
+            stage(i, dev)
+            dev_train.primed = True
+        stage(i + 1, dev)
+        torch.cuda.current_stream().wait_event(ready[s])
+        out = gsteps[s].replay()
+        freed[s].record()
+        return out
+
+    dev_train.primed = False
+    for f in freed:
+        f.record()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_train = timed(dev_train, args.steps, args.warmup, sync, barrier)
+    clk = clocks.stop()
+    ms_train = max_over_ranks(ms_train)
+    sync()
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------
 
     losses = []
 
@@ -926,7 +946,8 @@ def run_ours(args, rank, world, local_rank):
                                       "note": "CER/WER/accuracy of one decoded batch on the device (K5 edit distance), "
                                               "wall clock incl. the D2H of the per-pair integers"},
                       "attention_decoder": attn_res},
-            "launch_mode": "cuda-graph replay (one graph = the whole step)" if use_graph else "eager",
+            "launch_mode": ("cuda-graph replay (one graph = the whole step; two graphs used in turn, the next step's inputs are "
+                            "copied from the ring in HBM into the idle graph's static tensors on a copy stream)") if use_graph else "eager",
             "gpu_launches": round(launches * args.steps),
             "gpu_launches_per_step": round(launches, 1),
             "vendor": vendor,
