@@ -268,6 +268,13 @@ int rcnn_attn_cell(const float *gates, const float *embT, const int64_t *y, int 
                    void *xcat, int64_t ldx, int C, float *hid_out, int64_t hid_ld, rcnn_stream_t stream);
 int rcnn_attn_argmax(const float *logits, int B, int V, int blank, float *probs, int64_t probs_ld,
                      int64_t *y, rcnn_stream_t stream);
+/* the same two with explicit row pitches of proj_h / logits (elements): the greedy decode forms h2h(h_t) for the next step and
+ * generator(h_t) for this one in ONE product over concatenated weights and hands each kernel its column block */
+int rcnn_attn_score_context_ld(const float *projH, const float *projh, int64_t projh_ld, const float *v, const float *enc,
+                               int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                               float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream);
+int rcnn_attn_argmax_ld(const float *logits, int64_t logits_ld, int B, int V, int blank, float *probs, int64_t probs_ld,
+                        int64_t *y, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch

@@ -54,6 +54,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_attn_cell.argtypes = [vp, vp, vp, i, i, i, vp, vp, i64, i, vp, i64, vp]
     L.rcnn_attn_argmax.restype = i
     L.rcnn_attn_argmax.argtypes = [vp, i, i, i, vp, i64, vp, vp]
+    L.rcnn_attn_score_context_ld.restype = i
+    L.rcnn_attn_score_context_ld.argtypes = [vp, vp, i64, vp, vp, i64, i64, i, i, i, i, vp, vp, i64, vp]
+    L.rcnn_attn_argmax_ld.restype = i
+    L.rcnn_attn_argmax_ld.argtypes = [vp, i64, i, i, i, vp, i64, vp, vp]
     L.rcnn_lstm_forward_fused.restype = i
     L.rcnn_lstm_forward_fused.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp]
     L.rcnn_preprocess_lines.restype = i

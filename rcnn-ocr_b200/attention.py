@@ -74,6 +74,16 @@ class Attention(nn.Module):
                     "gen": ops.cast_bf16_2d(self.generator.weight.detach()),                              # [V, H]
                     "gen_b": self.generator.bias.detach().float().contiguous(),
                 }
+                # greedy decode: h2h(h_t) (for step t+1) and generator(h_t) (for step t) in ONE product, N padded to 32 k
+                H, V = self.hidden_size, self.num_classes
+                Np = (H + V + 31) // 32 * 32
+                comb = torch.zeros((Np, H), dtype=torch.float32, device=cell.h2h.weight.device)
+                comb[:H] = cell.h2h.weight.detach()
+                comb[H:H + V] = self.generator.weight.detach()
+                comb_b = torch.zeros((Np,), dtype=torch.float32, device=comb.device)
+                comb_b[:H] = cell.h2h.bias.detach()
+                comb_b[H:H + V] = self.generator.bias.detach()
+                w["comb"], w["comb_b"] = ops.cast_bf16_2d(comb), comb_b
             self._prepared = (key, w)
         return self._prepared[1]
 
@@ -112,25 +122,35 @@ class Attention(nn.Module):
             if not greedy:
                 text = text.to(device=dev, dtype=torch.int64).contiguous()
             s = _lib.stream_ptr()
+            if greedy:
+                # step: score / context (proj_h of h_{t-1}) -> gates GEMM -> cell (h_t) -> ONE GEMM over [h2h | generator]:
+                # columns [0, H) = proj_h for the next step, [H, H + V) = this step's logits -> mask + argmax.  5 launches.
+                Np = w["comb"].shape[0]
+                hg = torch.empty((B, Np), dtype=torch.float32, device=dev)
+                hg[:, :H] = w["h2h_b"]                                             # h2h(h_0 = 0) = its bias
+                for t in range(steps):
+                    _lib.check(L.rcnn_attn_score_context_ld(projH.data_ptr(), hg.data_ptr(), hg.stride(0), w["v"].data_ptr(),
+                                                            enc.data_ptr(), enc.stride(0), enc.stride(1), B, T, H, C, None,
+                                                            xcat.data_ptr(), xcat.stride(0), s), "rcnn_attn_score_context")
+                    ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
+                    _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), y.data_ptr(), B, H, V, c.data_ptr(),
+                                                xcat.data_ptr(), xcat.stride(0), C, None, 0, s), "rcnn_attn_cell")
+                    ops.gemm_bf16(hview, w["comb"], w["comb_b"], torch.float32, out=hg)
+                    pt = probs[:, t]
+                    _lib.check(L.rcnn_attn_argmax_ld(hg[:, H:].data_ptr(), hg.stride(0), B, V, blank, pt.data_ptr(),
+                                                     probs.stride(0), y.data_ptr(), s), "rcnn_attn_argmax")
+                return probs
             for t in range(steps):
-                yt = y if greedy else text[:, t].contiguous()
+                yt = text[:, t].contiguous()
                 ops.gemm_bf16(hview, w["h2h"], w["h2h_b"], torch.float32, out=projh)
                 _lib.check(L.rcnn_attn_score_context(projH.data_ptr(), projh.data_ptr(), w["v"].data_ptr(), enc.data_ptr(),
                                                      enc.stride(0), enc.stride(1), B, T, H, C, None, xcat.data_ptr(),
                                                      xcat.stride(0), s), "rcnn_attn_score_context")
                 ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
-                hid = out_hid[:, t] if out_hid is not None else None
+                hid = out_hid[:, t]
                 _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), yt.data_ptr(), B, H, V, c.data_ptr(),
-                                            xcat.data_ptr(), xcat.stride(0), C,
-                                            hid.data_ptr() if hid is not None else None,
-                                            out_hid.stride(0) if out_hid is not None else 0, s), "rcnn_attn_cell")
-                if greedy:
-                    ops.gemm_bf16(hview, w["gen"], w["gen_b"], torch.float32, out=logits)
-                    pt = probs[:, t]
-                    _lib.check(L.rcnn_attn_argmax(logits.data_ptr(), B, V, blank, pt.data_ptr(), probs.stride(0),
-                                                  y.data_ptr(), s), "rcnn_attn_argmax")
-            if greedy:
-                return probs
+                                            xcat.data_ptr(), xcat.stride(0), C, hid.data_ptr(), out_hid.stride(0), s),
+                           "rcnn_attn_cell")
             # teacher forcing: logits = generator(out_hid) in one GEMM, then the blank mask (model/model.py:146-148)
             out = ops.gemm_bf16(ops.cast_bf16_2d(out_hid.view(B * steps, H)), w["gen"], w["gen_b"], torch.float32)
             out = out.view(B, steps, V)

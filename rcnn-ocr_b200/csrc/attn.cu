@@ -27,19 +27,38 @@ __device__ __forceinline__ float sigmoid_fast_a(float x) { return fmaf(tanh_fast
 __global__ void __launch_bounds__(256) attn_score_context_kernel(
     const float *__restrict__ projH, const float *__restrict__ projh, const float *__restrict__ v,
     const float *__restrict__ enc, long long enc_sb, long long enc_st, int T, int H, int C,
-    float *__restrict__ alpha_out, __nv_bfloat16 *__restrict__ xcat, long long ldx) {
-    extern __shared__ float sm[];
+    float *__restrict__ alpha_out, __nv_bfloat16 *__restrict__ xcat, long long ldx, long long projh_ld) {
+    extern __shared__ __align__(16) float sm[];
     float *ph = sm, *vs = sm + H, *e = sm + 2 * H;          // [H], [H], [T]
     __shared__ float red[2];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int j = threadIdx.x; j < H; j += blockDim.x) { ph[j] = projh[(size_t)b * H + j]; vs[j] = v[j]; }
+    for (int j = threadIdx.x; j < H; j += blockDim.x) { ph[j] = projh[(size_t)b * projh_ld + j]; vs[j] = v[j]; }
     __syncthreads();
-    for (int t = warp; t < T; t += nw) {
-        const float *row = projH + ((size_t)b * T + t) * H;
-        float s = 0.f;
-        for (int j = lane; j < H; j += 32) s = fmaf(vs[j], tanh_fast_a(row[j] + ph[j]), s);
-        s = warp_sum(s);
-        if (lane == 0) e[t] = s;
+    const bool vec4 = (H & 3) == 0 && (C & 3) == 0 && (enc_st & 3) == 0 && (enc_sb & 3) == 0 &&
+                      ((uintptr_t)projH & 15) == 0 && ((uintptr_t)enc & 15) == 0;
+    for (int t0 = warp; t0 < T; t0 += 2 * nw) {                // two frames per warp pass: their rows are requested together
+        const int t1 = t0 + nw;
+        const float *row0 = projH + ((size_t)b * T + t0) * H;
+        const float *row1 = projH + ((size_t)b * T + (t1 < T ? t1 : t0)) * H;
+        float s0 = 0.f, s1 = 0.f;
+        if (vec4) {
+            for (int j = 4 * lane; j < H; j += 128) {              // 128-bit loads (the kernel was bound by load instructions)
+                const float4 a = *reinterpret_cast<const float4 *>(row0 + j), c4 = *reinterpret_cast<const float4 *>(row1 + j);
+                const float4 p4 = *reinterpret_cast<const float4 *>(ph + j), v4 = *reinterpret_cast<const float4 *>(vs + j);
+                s0 = fmaf(v4.x, tanh_fast_a(a.x + p4.x), s0); s0 = fmaf(v4.y, tanh_fast_a(a.y + p4.y), s0);
+                s0 = fmaf(v4.z, tanh_fast_a(a.z + p4.z), s0); s0 = fmaf(v4.w, tanh_fast_a(a.w + p4.w), s0);
+                s1 = fmaf(v4.x, tanh_fast_a(c4.x + p4.x), s1); s1 = fmaf(v4.y, tanh_fast_a(c4.y + p4.y), s1);
+                s1 = fmaf(v4.z, tanh_fast_a(c4.z + p4.z), s1); s1 = fmaf(v4.w, tanh_fast_a(c4.w + p4.w), s1);
+            }
+        } else {
+            for (int j = lane; j < H; j += 32) {
+                s0 = fmaf(vs[j], tanh_fast_a(row0[j] + ph[j]), s0);
+                s1 = fmaf(vs[j], tanh_fast_a(row1[j] + ph[j]), s1);
+            }
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) { e[t0] = s0; if (t1 < T) e[t1] = s1; }
     }
     __syncthreads();
     if (warp == 0) {                                          // softmax over the T encoder frames
@@ -60,10 +79,38 @@ __global__ void __launch_bounds__(256) attn_score_context_kernel(
     }
     __syncthreads();
     const float *eb = enc + (size_t)b * enc_sb;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc = fmaf(e[t], eb[(size_t)t * enc_st + c], acc);
-        xcat[(size_t)b * ldx + c] = __float2bfloat16_rn(acc);
+    if (vec4 && (ldx & 3) == 0 && ((uintptr_t)xcat & 7) == 0) {
+        for (int c = 4 * threadIdx.x; c < C; c += 4 * blockDim.x) {       // four columns per thread, four frames in flight
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int t = 0;
+            for (; t + 3 < T; t += 4) {
+                float4 r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r[k] = *reinterpret_cast<const float4 *>(eb + (size_t)(t + k) * enc_st + c);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = e[t + k];
+                    acc.x = fmaf(a, r[k].x, acc.x); acc.y = fmaf(a, r[k].y, acc.y);
+                    acc.z = fmaf(a, r[k].z, acc.z); acc.w = fmaf(a, r[k].w, acc.w);
+                }
+            }
+            for (; t < T; ++t) {
+                const float4 r = *reinterpret_cast<const float4 *>(eb + (size_t)t * enc_st + c);
+                const float a = e[t];
+                acc.x = fmaf(a, r.x, acc.x); acc.y = fmaf(a, r.y, acc.y); acc.z = fmaf(a, r.z, acc.z); acc.w = fmaf(a, r.w, acc.w);
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t *>(&lo);
+            o.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(xcat + (size_t)b * ldx + c) = o;
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc = fmaf(e[t], eb[(size_t)t * enc_st + c], acc);
+            xcat[(size_t)b * ldx + c] = __float2bfloat16_rn(acc);
+        }
     }
 }
 
@@ -94,11 +141,11 @@ __global__ void attn_cell_kernel(const float *__restrict__ gates, const float *_
 // NaN counts as maximal: torch.argmax)
 __global__ void __launch_bounds__(128) attn_argmax_kernel(const float *__restrict__ logits, int B, int V, int blank,
                                                           float *__restrict__ probs, long long probs_ld,
-                                                          long long *__restrict__ y) {
+                                                          long long *__restrict__ y, long long logits_ld) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
     if (b >= B) return;
-    const float *row = logits + (size_t)b * V;
+    const float *row = logits + (size_t)b * logits_ld;
     float best = -INFINITY;
     int arg = 0x7fffffff;
     bool nan = false;
@@ -126,11 +173,20 @@ __global__ void __launch_bounds__(128) attn_argmax_kernel(const float *__restric
 }  // namespace
 }  // namespace rcnn
 
+extern "C" int rcnn_attn_score_context_ld(const float *projH, const float *projh, int64_t projh_ld, const float *v, const float *enc,
+                                          int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                                          float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream);
 extern "C" int rcnn_attn_score_context(const float *projH, const float *projh, const float *v, const float *enc,
                                        int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
                                        float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream) {
+    return rcnn_attn_score_context_ld(projH, projh, H, v, enc, enc_stride_b, enc_stride_t, B, T, H, C, alpha_out, xcat, ldx, stream);
+}
+
+extern "C" int rcnn_attn_score_context_ld(const float *projH, const float *projh, int64_t projh_ld, const float *v, const float *enc,
+                                          int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                                          float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream) {
     using namespace rcnn;
-    RCNN_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && C >= 1 && ldx >= C, "attn_score_context: bad shape");
+    RCNN_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && C >= 1 && ldx >= C && projh_ld >= H, "attn_score_context: bad shape");
     if (B == 0) return RCNN_OK;
     RCNN_CHECK_ARG(projH && projh && v && enc && xcat, "attn_score_context: null pointer");
     const size_t smem = sizeof(float) * (2 * (size_t)H + T);
@@ -138,7 +194,7 @@ extern "C" int rcnn_attn_score_context(const float *projH, const float *projh, c
     if (smem > 48 * 1024)
         RCNN_CUDA(cudaFuncSetAttribute(attn_score_context_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_score_context_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(projH, projh, v, enc, enc_stride_b, enc_stride_t, T, H, C,
-                                                                    alpha_out, (__nv_bfloat16 *)xcat, ldx);
+                                                                    alpha_out, (__nv_bfloat16 *)xcat, ldx, projh_ld);
     RCNN_LAUNCH_CHECK("attn_score_context_kernel");
     return RCNN_OK;
 }
@@ -156,13 +212,20 @@ extern "C" int rcnn_attn_cell(const float *gates, const float *embT, const int64
     return RCNN_OK;
 }
 
+extern "C" int rcnn_attn_argmax_ld(const float *logits, int64_t logits_ld, int B, int V, int blank, float *probs, int64_t probs_ld,
+                                   int64_t *y, rcnn_stream_t stream);
 extern "C" int rcnn_attn_argmax(const float *logits, int B, int V, int blank, float *probs, int64_t probs_ld,
                                 int64_t *y, rcnn_stream_t stream) {
+    return rcnn_attn_argmax_ld(logits, V, B, V, blank, probs, probs_ld, y, stream);
+}
+
+extern "C" int rcnn_attn_argmax_ld(const float *logits, int64_t logits_ld, int B, int V, int blank, float *probs, int64_t probs_ld,
+                                   int64_t *y, rcnn_stream_t stream) {
     using namespace rcnn;
-    RCNN_CHECK_ARG(B >= 0 && V >= 1, "attn_argmax: bad shape");
+    RCNN_CHECK_ARG(B >= 0 && V >= 1 && logits_ld >= V, "attn_argmax: bad shape");
     if (B == 0) return RCNN_OK;
     RCNN_CHECK_ARG(logits, "attn_argmax: null pointer");
-    attn_argmax_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(logits, B, V, blank, probs, probs_ld, (long long *)y);
+    attn_argmax_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(logits, B, V, blank, probs, probs_ld, (long long *)y, logits_ld);
     RCNN_LAUNCH_CHECK("attn_argmax_kernel");
     return RCNN_OK;
 }
