@@ -837,7 +837,10 @@ def run_ours(args, rank, world, local_rank):
                                        "[B,3,32,128] -> SE-ResNet31 (torch/cuDNN, channels_last, bf16 autocast) -> enc_rnn "
                                        f"(hidden {r4['hidden']}) -> CTC head -> fused CTC loss -> backward -> all-reduce of all "
                                        "gradients -> Adam", "T": r4["T"], "label_len": f"U{{1..{r4['lmax']}}}",
-                           "parallelism": f"dp{world}"}}
+                           "parallelism": f"dp{world}"},
+                "limiter": "the cuDNN backbone (98 % of the step's FLOPs, SURVEY 8d): at 512 / N lines per GPU its convolutions on "
+                           "32 x 128 images stop filling the GPU (27 ms at 512 lines, 6.6 ms at 64), and 184 MB of fp32 gradients are "
+                           "all-reduced per step; the hand-written part (enc_rnn H = 256, T = 16 + CTC) is < 1 ms of it"}
         del r4
 
     # ---- per-kernel timing for the roofline (separate pass; CUDA events on the launching stream) -
