@@ -275,6 +275,18 @@ int rcnn_attn_score_context_ld(const float *projH, const float *projh, int64_t p
                                float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream);
 int rcnn_attn_argmax_ld(const float *logits, int64_t logits_ld, int B, int V, int blank, float *probs, int64_t probs_ld,
                         int64_t *y, rcnn_stream_t stream);
+/* rcnn_attn_score_context_ld with proj_H [B,T,H] and enc [B,T,C] held as bf16 (the decode loop's only large reads, halved;
+ * both pass through bf16 tensor-core operands anyway).  H, C, enc_stride_* multiples of 8 elements, arrays 16-byte aligned
+ * (RCNN_ERR_ARG otherwise: there is no slow path). */
+int rcnn_attn_score_context_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                                 int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C,
+                                 float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream);
+/* the same, preceded (if prev_logits != NULL) by rcnn_attn_argmax of the PREVIOUS step's logits for the same sequences:
+ * masked row -> prev_probs (may be NULL), argmax -> y.  The greedy loop then needs four launches per step. */
+int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                        int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out,
+                        void *xcat, int64_t ldx, const float *prev_logits, int64_t prev_ld, int V, int blank,
+                        float *prev_probs, int64_t probs_ld, int64_t *y, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch

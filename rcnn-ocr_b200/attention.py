@@ -19,6 +19,8 @@ token is the argmax of that step's logits) follow the reference; gradients are p
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -108,7 +110,25 @@ class Attention(nn.Module):
             enc = enc.contiguous()
         with torch.cuda.device(dev):
             encb = ops.cast_bf16_3d(enc)
-            projH = ops.gemm_bf16(encb.view(B * T, C), w["i2h"], None, torch.float32)          # hoisted i2h(batch_H)
+            # hoisted i2h(batch_H).  The step kernel reads proj_H and batch_H as bf16 when the shapes allow 16-byte loads
+            half = H % 8 == 0 and C % 8 == 0 and os.environ.get("RCNN_ATTN_F32", "0") != "1"
+            projH = ops.gemm_bf16(encb.view(B * T, C), w["i2h"], None, torch.bfloat16 if half else torch.float32)
+
+            def score_context(ph, ph_ld, prev=None):
+                """K6a for this step; prev = (logits, ld, probs row block, y): K6c of the previous step rides along (bf16 kernel)"""
+                if half:
+                    pl, pld, pp, py = prev if prev is not None else (None, 0, None, None)
+                    rc = L.rcnn_attn_step_bf16(projH.data_ptr(), ph.data_ptr(), ph_ld, w["v"].data_ptr(), encb.data_ptr(),
+                                               encb.stride(0), encb.stride(1), B, T, H, C, None, xcat.data_ptr(), xcat.stride(0),
+                                               pl, pld, V, blank, pp, probs.stride(0) if pp is not None else 0, py, s)
+                else:
+                    if prev is not None:
+                        _lib.check(L.rcnn_attn_argmax_ld(prev[0], prev[1], B, V, blank, prev[2], probs.stride(0), prev[3], s),
+                                   "rcnn_attn_argmax")
+                    rc = L.rcnn_attn_score_context_ld(projH.data_ptr(), ph.data_ptr(), ph_ld, w["v"].data_ptr(), enc.data_ptr(),
+                                                      enc.stride(0), enc.stride(1), B, T, H, C, None, xcat.data_ptr(),
+                                                      xcat.stride(0), s)
+                _lib.check(rc, "rcnn_attn_score_context")
             xcat = torch.zeros((B, C + H), dtype=torch.bfloat16, device=dev)                    # [context | h], h_0 = 0
             hview = xcat[:, C:]
             c = torch.zeros((B, H), dtype=torch.float32, device=dev)
@@ -123,29 +143,26 @@ class Attention(nn.Module):
                 text = text.to(device=dev, dtype=torch.int64).contiguous()
             s = _lib.stream_ptr()
             if greedy:
-                # step: score / context (proj_h of h_{t-1}) -> gates GEMM -> cell (h_t) -> ONE GEMM over [h2h | generator]:
-                # columns [0, H) = proj_h for the next step, [H, H + V) = this step's logits -> mask + argmax.  5 launches.
+                # step: [argmax of the previous step's logits +] score / context (proj_h of h_{t-1}) -> gates GEMM -> cell (h_t)
+                # -> ONE GEMM over [h2h | generator]: columns [0, H) = proj_h for the next step, [H, H + V) = this step's
+                # logits.  4 launches per step (5 with fp32 operands), one argmax launch after the last step.
                 Np = w["comb"].shape[0]
                 hg = torch.empty((B, Np), dtype=torch.float32, device=dev)
                 hg[:, :H] = w["h2h_b"]                                             # h2h(h_0 = 0) = its bias
+                lg = hg[:, H:].data_ptr()
                 for t in range(steps):
-                    _lib.check(L.rcnn_attn_score_context_ld(projH.data_ptr(), hg.data_ptr(), hg.stride(0), w["v"].data_ptr(),
-                                                            enc.data_ptr(), enc.stride(0), enc.stride(1), B, T, H, C, None,
-                                                            xcat.data_ptr(), xcat.stride(0), s), "rcnn_attn_score_context")
+                    score_context(hg, hg.stride(0), None if t == 0 else (lg, hg.stride(0), probs[:, t - 1].data_ptr(), y.data_ptr()))
                     ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
                     _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), y.data_ptr(), B, H, V, c.data_ptr(),
                                                 xcat.data_ptr(), xcat.stride(0), C, None, 0, s), "rcnn_attn_cell")
                     ops.gemm_bf16(hview, w["comb"], w["comb_b"], torch.float32, out=hg)
-                    pt = probs[:, t]
-                    _lib.check(L.rcnn_attn_argmax_ld(hg[:, H:].data_ptr(), hg.stride(0), B, V, blank, pt.data_ptr(),
-                                                     probs.stride(0), y.data_ptr(), s), "rcnn_attn_argmax")
+                _lib.check(L.rcnn_attn_argmax_ld(lg, hg.stride(0), B, V, blank, probs[:, steps - 1].data_ptr(), probs.stride(0),
+                                                 y.data_ptr(), s), "rcnn_attn_argmax")
                 return probs
             for t in range(steps):
                 yt = text[:, t].contiguous()
                 ops.gemm_bf16(hview, w["h2h"], w["h2h_b"], torch.float32, out=projh)
-                _lib.check(L.rcnn_attn_score_context(projH.data_ptr(), projh.data_ptr(), w["v"].data_ptr(), enc.data_ptr(),
-                                                     enc.stride(0), enc.stride(1), B, T, H, C, None, xcat.data_ptr(),
-                                                     xcat.stride(0), s), "rcnn_attn_score_context")
+                score_context(projh, projh.stride(0))
                 ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
                 hid = out_hid[:, t]
                 _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), yt.data_ptr(), B, H, V, c.data_ptr(),

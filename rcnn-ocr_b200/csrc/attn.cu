@@ -128,6 +128,155 @@ __global__ void __launch_bounds__(256) attn_score_context_kernel(
     }
 }
 
+// mask + copy + argmax of one logits row by one warp (K6c's body; also run by the bf16 step kernel for the previous step)
+__device__ __forceinline__ int warp_argmax_row(const float *__restrict__ row, int V, int blank, float *__restrict__ probs_row,
+                                               int lane) {
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    bool nan = false;
+    for (int k0 = lane; k0 < V; k0 += 256) {                 // eight loads requested before the first compare
+        float xs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xs[u] = k0 + 32 * u < V ? row[k0 + 32 * u] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + 32 * u;
+            if (k < V) {
+                float x = xs[u];
+                if (k == blank) x = -1e4f;
+                if (probs_row) probs_row[k] = x;
+                const bool xn = x != x;
+                if (!nan && (xn || x > best || arg == 0x7fffffff)) { best = x; arg = k; nan = xn; }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int oa = __shfl_xor_sync(FULL, arg, o);
+        const bool on = __shfl_xor_sync(FULL, (int)nan, o) != 0;
+        bool take;
+        if (nan != on) take = on;                                 // a NaN beats any number
+        else if (nan) take = oa < arg;                            // two NaNs: the first index
+        else take = ob > best || (ob == best && oa < arg);
+        if (take) { best = ob; arg = oa; nan = on; }
+    }
+    return arg == 0x7fffffff ? 0 : arg;
+}
+
+// K6a with bf16 operands: proj_H [B,T,H] and enc [B,T,C] as bf16 (half the bytes of the step's only large reads; both
+// were rounded to bf16 on their way through the tensor cores already: proj_H is a bf16-operand product, the context is
+// the bf16 A operand of the gates GEMM).  Eight warps; warp w owns the frames t = w (mod 8) in both passes, a lane reads 16
+// bytes (eight values) of up to eight frames before it uses the first.  The context pass leaves per-warp partial sums
+// in shared memory, added up in frame order 0..7 by the thread that owns the column (deterministic).
+__device__ __forceinline__ void unpack8(const uint4 &q, float (&f)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
+    const __nv_bfloat16 *__restrict__ projH, const float *__restrict__ projh, const float *__restrict__ v,
+    const __nv_bfloat16 *__restrict__ enc, long long enc_sb, long long enc_st, int T, int H, int C,
+    float *__restrict__ alpha_out, __nv_bfloat16 *__restrict__ xcat, long long ldx, long long projh_ld,
+    const float *__restrict__ prev_logits, long long prev_ld, int V, int blank, float *__restrict__ prev_probs,
+    long long probs_ld, long long *__restrict__ y) {
+    extern __shared__ __align__(16) float sm[];
+    float *ph = sm, *vs = sm + H, *e = sm + 2 * H, *part = e + ((T + 3) & ~3);      // [H], [H], [T], [8][C]
+    __shared__ float red[2];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (prev_logits != nullptr && warp == 7) {                // K6c of the previous step for this sequence (saves a launch)
+        const int arg = warp_argmax_row(prev_logits + (size_t)b * prev_ld, V, blank,
+                                        prev_probs ? prev_probs + (size_t)b * probs_ld : nullptr, lane);
+        if (lane == 0 && y) y[b] = arg;
+    }
+    for (int j = threadIdx.x; j < H; j += 256) { ph[j] = projh[(size_t)b * projh_ld + j]; vs[j] = v[j]; }
+    __syncthreads();
+    const __nv_bfloat16 *pb = projH + (size_t)b * T * H;
+    for (int t0 = warp; t0 < T; t0 += 64) {                   // frames t0, t0+8, ..., t0+56 together
+        float s[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = 0.f;
+        for (int j = 8 * lane; j < H; j += 256) {
+            uint4 q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t0 + 8 * k;
+                q[k] = t < T ? *reinterpret_cast<const uint4 *>(pb + (size_t)t * H + j) : make_uint4(0, 0, 0, 0);
+            }
+            float p8[8], v8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { p8[i] = ph[j + i]; v8[i] = vs[j + i]; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float f[8];
+                unpack8(q[k], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[k] = fmaf(v8[i], tanh_fast_a(f[i] + p8[i]), s[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float r = warp_sum(s[k]);
+            if (lane == 0 && t0 + 8 * k < T) e[t0 + 8 * k] = r;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                          // softmax over the T encoder frames
+        float m = -INFINITY;
+        for (int t = lane; t < T; t += 32) m = fmaxf(m, e[t]);
+        m = warp_max(m);
+        float z = 0.f;
+        for (int t = lane; t < T; t += 32) z += __expf(e[t] - m);
+        z = warp_sum(z);
+        if (lane == 0) { red[0] = m; red[1] = 1.f / z; }
+    }
+    __syncthreads();
+    const float m = red[0], iz = red[1];
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float a = __expf(e[t] - m) * iz;
+        e[t] = a;
+        if (alpha_out) alpha_out[(size_t)b * T + t] = a;
+    }
+    __syncthreads();
+    const __nv_bfloat16 *eb = enc + (size_t)b * enc_sb;
+    for (int c = 8 * lane; c < C; c += 256) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int t0 = warp; t0 < T; t0 += 64) {
+            uint4 q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t0 + 8 * k;
+                q[k] = t < T ? *reinterpret_cast<const uint4 *>(eb + (size_t)t * enc_st + c) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t0 + 8 * k;
+                const float a = t < T ? e[t] : 0.f;
+                float f[8];
+                unpack8(q[k], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, f[i], acc[i]);
+            }
+        }
+        float4 *dst = reinterpret_cast<float4 *>(part + (size_t)warp * C + c);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    for (int c = 2 * threadIdx.x; c < C; c += 512) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a0 += part[(size_t)w * C + c]; a1 += part[(size_t)w * C + c + 1]; }
+        *reinterpret_cast<__nv_bfloat162 *>(xcat + (size_t)b * ldx + c) = __floats2bfloat162_rn(a0, a1);
+    }
+}
+
 // K6b: LSTMCell pointwise.  gates [B,4H] f32 (torch order i,f,g,o), embT [V,4H] f32 (column C+v of W_ih),
 // y [B] int64 previous tokens; c [B,H] f32 in place; h -> bf16 xcat[b, C + j], f32 hid_out[b*hid_ld + j] (optional)
 __global__ void attn_cell_kernel(const float *__restrict__ gates, const float *__restrict__ embT,
@@ -159,29 +308,8 @@ __global__ void __launch_bounds__(128) attn_argmax_kernel(const float *__restric
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + warp;
     if (b >= B) return;
-    const float *row = logits + (size_t)b * logits_ld;
-    float best = -INFINITY;
-    int arg = 0x7fffffff;
-    bool nan = false;
-    for (int k = lane; k < V; k += 32) {
-        float x = row[k];
-        if (k == blank) x = -1e4f;
-        if (probs) probs[(size_t)b * probs_ld + k] = x;
-        const bool xn = x != x;
-        if (!nan && (xn || x > best || arg == 0x7fffffff)) { best = x; arg = k; nan = xn; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(FULL, best, o);
-        const int oa = __shfl_xor_sync(FULL, arg, o);
-        const bool on = __shfl_xor_sync(FULL, (int)nan, o) != 0;
-        bool take;
-        if (nan != on) take = on;                                 // a NaN beats any number
-        else if (nan) take = oa < arg;                            // two NaNs: the first index
-        else take = ob > best || (ob == best && oa < arg);
-        if (take) { best = ob; arg = oa; nan = on; }
-    }
-    if (lane == 0 && y) y[b] = arg == 0x7fffffff ? 0 : arg;
+    const int arg = warp_argmax_row(logits + (size_t)b * logits_ld, V, blank, probs ? probs + (size_t)b * probs_ld : nullptr, lane);
+    if (lane == 0 && y) y[b] = arg;
 }
 
 }  // namespace
@@ -211,6 +339,37 @@ extern "C" int rcnn_attn_score_context_ld(const float *projH, const float *projh
                                                                     alpha_out, (__nv_bfloat16 *)xcat, ldx, projh_ld);
     RCNN_LAUNCH_CHECK("attn_score_context_kernel");
     return RCNN_OK;
+}
+
+extern "C" int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                                   int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out,
+                                   void *xcat, int64_t ldx, const float *prev_logits, int64_t prev_ld, int V, int blank,
+                                   float *prev_probs, int64_t probs_ld, int64_t *y, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && C >= 1 && ldx >= C && projh_ld >= H, "attn_score_context_bf16: bad shape");
+    RCNN_CHECK_ARG(prev_logits == nullptr || (V >= 1 && prev_ld >= V && (prev_probs == nullptr || probs_ld >= V)),
+                   "attn_step_bf16: bad logits shape");
+    if (B == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(projH && projh && v && enc && xcat, "attn_score_context_bf16: null pointer");
+    RCNN_CHECK_ARG(H % 8 == 0 && C % 8 == 0 && enc_stride_b % 8 == 0 && enc_stride_t % 8 == 0 && ldx % 2 == 0 &&
+                       ((uintptr_t)projH & 15) == 0 && ((uintptr_t)enc & 15) == 0 && ((uintptr_t)xcat & 3) == 0,
+                   "attn_score_context_bf16: H, C and the enc strides must be multiples of 8, the bf16 arrays 16-byte aligned");
+    const size_t smem = sizeof(float) * (2 * (size_t)H + ((T + 3) & ~3) + 8 * (size_t)C);
+    RCNN_CHECK_ARG(smem <= 200 * 1024, "attn_score_context_bf16: T=%d, H=%d, C=%d exceed shared memory", T, H, C);
+    if (smem > 48 * 1024)
+        RCNN_CUDA(cudaFuncSetAttribute(attn_score_context_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_score_context_bf16_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)projH, projh, v, (const __nv_bfloat16 *)enc, enc_stride_b, enc_stride_t, T, H, C, alpha_out,
+        (__nv_bfloat16 *)xcat, ldx, projh_ld, prev_logits, prev_ld, V, blank, prev_probs, probs_ld, (long long *)y);
+    RCNN_LAUNCH_CHECK("attn_score_context_bf16_kernel");
+    return RCNN_OK;
+}
+
+extern "C" int rcnn_attn_score_context_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v,
+                                            const void *enc, int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H,
+                                            int C, float *alpha_out, void *xcat, int64_t ldx, rcnn_stream_t stream) {
+    return rcnn_attn_step_bf16(projH, projh, projh_ld, v, enc, enc_stride_b, enc_stride_t, B, T, H, C, alpha_out, xcat, ldx,
+                               nullptr, 0, 0, -1, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int rcnn_attn_cell(const float *gates, const float *embT, const int64_t *y, int B, int H, int V, float *c,

@@ -170,13 +170,16 @@ __device__ __forceinline__ void store_row_chunk(__half *dst, const float (&v)[32
 // round the issuing thread spent as long on wait/commit bookkeeping as the tensor pipe spent on
 // the four MMAs (profiles/timeline_r01.txt).  Two 128-column TMEM accumulators alternate between
 // tiles, so the epilogue warps drain tile i while the MMA warp is already on tile i+1.
-// Tile width TN: 128 (K = 128 per stage, 3 stages) or 256 (K = 64 per stage, 4 stages).  With 128 x 128 tiles
+// Tile width TN: 128 (K = 128 per stage, 3 stages) or 256 (K = 64 per stage, 4 stages); 64 and 32 (K = 128 per stage, 4
+// stages) exist for products with few rows (the attention decoder's per-step GEMMs, M = batch): there the time is what ONE SM
+// can pull through its L2 port (~85 GB/s: a CTA of a 16-tile launch reads 768 KB), so narrow tiles spread the B operand over
+// 4-8x as many SMs.  With 128 x 128 tiles
 // every tile re-reads (128 + 128) x K operand elements for 128 x 128 x K MACs = 64 FLOP per L2 byte, and the
 // large GEMMs of the step then sit exactly at the L2 -> SM bandwidth (~12.5 TB/s: 830 TFLOP/s); 128 x 256
 // tiles raise that to 85 FLOP per byte and need half as many tcgen05.mma instructions (N = 256 each).
 constexpr int kPThreads = 352;                               // warps: 0 A-TMA, 1 MMA, 2-5 and 7-10 epilogue, 6 B-TMA
 template <int TN> struct PCfg {
-    static constexpr int kBoxes = TN == 128 ? 2 : 1;                       // k-boxes of 64 per stage
+    static constexpr int kBoxes = TN <= 128 ? 2 : 1;                       // k-boxes of 64 per stage
     static constexpr int kStages = TN == 128 ? 3 : 4;
     static constexpr uint32_t kAOp = kBoxes * kABytes;                     // A bytes per stage
     static constexpr uint32_t kBBox = TN * BK * 2;                         // one B box [TN x 64] bf16
@@ -275,6 +278,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 32 MMAs (~2,000 cycles) and four warps took about as long to drain it. =====================
         const int q = warp & 3;
         const int chalf = warp >= 7 ? 1 : 0;
+        constexpr int kCHalf = TN >= 64 ? TN / 2 : TN;                        // (a 32-column tile is drained by four warps)
         const int etid = warp < 6 ? threadIdx.x - 64 : threadIdx.x - 96;    // 0..255 over the epilogue threads
         const bool vec_ok = (ldd % (32 / (long long)sizeof(OutT)) == 0) && ((reinterpret_cast<uintptr_t>(D) & 31) == 0);
         int it = 0;
@@ -290,7 +294,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const int row = tile_m * BM + q * 32 + lane;
 #pragma unroll 1
-            for (int c0 = chalf * (TN / 2); c0 < (chalf + 1) * (TN / 2); c0 += 32) {
+            for (int c0 = chalf * kCHalf; c0 < (chalf + 1) * kCHalf && c0 < TN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
                 tmem_ld_wait();
@@ -911,9 +915,24 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
         if (out_dtype == RCNN_F16) return launch_gemm_pair<__half>(ta, tb, D, ldd, bias, M, N, K, s);
         return launch_gemm_pair<__nv_bfloat16>(ta, tb, D, ldd, bias, M, N, K, s);
     }
-    const int tn = force_tn == 128 || force_tn == 256 ? force_tn : (N > 128 ? 256 : 128);
+    int tn = N > 128 ? 256 : 128;
+    {   // few row blocks: narrow the tiles until about half of the SMs have one (see the note above gemm_tn_kernel)
+        const int ntm = (M + BM - 1) / BM;
+        while (tn > 32 && ntm * ((N + tn - 1) / tn) < gemm_sms() / 2) tn >>= 1;
+    }
+    if (force_tn == 32 || force_tn == 64 || force_tn == 128 || force_tn == 256) tn = force_tn;
     rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, (uint32_t)tn, BK, 1);
     if (rc) return rc;
+    if (tn == 64) {
+        if (out_dtype == RCNN_F32) return launch_gemm<float, 64>(ta, tb, D, ldd, bias, M, N, K, s);
+        if (out_dtype == RCNN_F16) return launch_gemm<__half, 64>(ta, tb, D, ldd, bias, M, N, K, s);
+        return launch_gemm<__nv_bfloat16, 64>(ta, tb, D, ldd, bias, M, N, K, s);
+    }
+    if (tn == 32) {
+        if (out_dtype == RCNN_F32) return launch_gemm<float, 32>(ta, tb, D, ldd, bias, M, N, K, s);
+        if (out_dtype == RCNN_F16) return launch_gemm<__half, 32>(ta, tb, D, ldd, bias, M, N, K, s);
+        return launch_gemm<__nv_bfloat16, 32>(ta, tb, D, ldd, bias, M, N, K, s);
+    }
     if (tn == 256) {
         if (out_dtype == RCNN_F32) return launch_gemm<float, 256>(ta, tb, D, ldd, bias, M, N, K, s);
         if (out_dtype == RCNN_F16) return launch_gemm<__half, 256>(ta, tb, D, ldd, bias, M, N, K, s);

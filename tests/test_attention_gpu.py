@@ -105,6 +105,58 @@ def test_argmax_kernel_is_bit_exact():
         assert torch.equal(y, want.argmax(1))
 
 
+@pytest.mark.parametrize("B,T,H,C", [(5, 13, 64, 72), (3, 70, 264, 520), (256, 64, 256, 256), (2, 1, 8, 8)])
+def test_score_context_kernels_match_the_formula(B, T, H, C):
+    """K6a (both operand widths) against model/model.py:35-41 in float64 on the same (already rounded) inputs:
+    alpha to 2e-3 (tanh.approx / __expf), context to bf16 rounding of the float64 value."""
+    L = R.lib()
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    projH = torch.randn(B, T, H, device="cuda", generator=g).bfloat16()
+    enc = torch.randn(B, T, C, device="cuda", generator=g).bfloat16()
+    projh = torch.randn(B, H + 24, device="cuda", generator=g)[:, 8:8 + H]          # a column block of a wider row
+    v = torch.randn(H, device="cuda", generator=g) / H ** 0.5
+    e = (torch.tanh(projH.double() + projh.double().unsqueeze(1)) * v.double()).sum(-1)
+    alpha = torch.softmax(e, 1)
+    ctx = (alpha.unsqueeze(2) * enc.double()).sum(1)
+    s = torch.cuda.current_stream().cuda_stream
+    for half in (True, False):
+        a_out = torch.empty(B, T, device="cuda")
+        xcat = torch.zeros(B, C + H, dtype=torch.bfloat16, device="cuda")
+        if half:
+            rc = L.rcnn_attn_score_context_bf16(projH.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), enc.data_ptr(),
+                                                enc.stride(0), enc.stride(1), B, T, H, C, a_out.data_ptr(), xcat.data_ptr(),
+                                                xcat.stride(0), s)
+        else:
+            pf, ef = projH.float(), enc.float()
+            rc = L.rcnn_attn_score_context_ld(pf.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), ef.data_ptr(),
+                                              ef.stride(0), ef.stride(1), B, T, H, C, a_out.data_ptr(), xcat.data_ptr(),
+                                              xcat.stride(0), s)
+        assert rc == 0
+        assert (a_out.double() - alpha).abs().max().item() <= 2e-3, half
+        got = xcat[:, :C].double()
+        assert ((got - ctx).abs() <= 2e-3 + 2 ** -7 * ctx.abs()).all(), (half, (got - ctx).abs().max().item())
+        assert (xcat[:, C:] == 0).all()                               # the h half of the row is not touched
+    # the step entry: the same kernel with the previous step's mask + copy + argmax riding along (bit-exact, K6c's rule)
+    V, blank = 37, 3
+    lg = torch.randint(-3, 4, (B, V + 11), device="cuda", generator=g).float()[:, 5:5 + V]
+    probs = torch.empty(B, 4, V, device="cuda")
+    y = torch.full((B,), -1, dtype=torch.int64, device="cuda")
+    x2 = torch.zeros_like(xcat)
+    xh = torch.zeros_like(xcat)
+    assert L.rcnn_attn_score_context_bf16(projH.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), enc.data_ptr(),
+                                          enc.stride(0), enc.stride(1), B, T, H, C, None, xh.data_ptr(), xh.stride(0), s) == 0
+    assert L.rcnn_attn_step_bf16(projH.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), enc.data_ptr(), enc.stride(0),
+                                 enc.stride(1), B, T, H, C, None, x2.data_ptr(), x2.stride(0), lg.data_ptr(), lg.stride(0), V,
+                                 blank, probs[:, 2].data_ptr(), probs.stride(0), y.data_ptr(), s) == 0
+    masked = lg.clone()
+    masked[:, blank] = -1e4
+    assert torch.equal(probs[:, 2], masked) and torch.equal(y, masked.argmax(1)) and torch.equal(x2, xh)
+    # shapes without 16-byte rows are refused, not run slowly
+    bad = L.rcnn_attn_score_context_bf16(projH.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), enc.data_ptr(),
+                                         enc.stride(0), enc.stride(1), B, T, H - 1, C, None, xcat.data_ptr(), xcat.stride(0), s)
+    assert bad != 0
+
+
 def test_state_dict_contract_and_errors():
     m = R.Attention(64, 64, 20, 1, 2, 0, 3)
     want = {"attention_cell.i2h.weight": (64, 64), "attention_cell.h2h.weight": (64, 64), "attention_cell.h2h.bias": (64,),

@@ -16,7 +16,9 @@ def _ref(a, b, bias):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 128), (16384, 4096, 512),
                                    (16384, 512, 1024), (16384, 195, 512), (100, 72, 40), (1, 8, 8),
-                                   (257, 129, 72), (2048, 1024, 256), (300, 200, 1000)])
+                                   (257, 129, 72), (2048, 1024, 256), (300, 200, 1000),
+                                   # few row blocks: tile widths 64 / 32 / 64 / 128 / 256 of the persistent kernel
+                                   (256, 2048, 1024), (256, 736, 512), (256, 4100, 200), (384, 3200, 64), (384, 6400, 72)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 def test_gemm_matches_fp32_matmul(M, N, K, out_dtype):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
