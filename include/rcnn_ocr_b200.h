@@ -288,6 +288,14 @@ int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_t projh_ld,
                         void *xcat, int64_t ldx, const float *prev_logits, int64_t prev_ld, int V, int blank,
                         float *prev_probs, int64_t probs_ld, int64_t *y, rcnn_stream_t stream);
 
+/* The decoder's gate product and LSTMCell step in one launch (model/model.py:43-45: rnn(concat([context, onehot]), hidden)):
+ * [c, h_t] = LSTMCell pointwise of  xcat[B, K] @ wcat_il[4H, K]^T + bias_il + embT_il[y]  with c [B, H] updated in place and h_t
+ * written as bf16 to h_out (row pitch h_ld; must not alias xcat) and, if hid_out != NULL, as f32.  The "_il" arrays are
+ * gate-interleaved along 4H: row / element 4u + g is gate g (torch order i, f, g, o) of hidden unit u.  H % 8 == 0. */
+int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
+                         const float *embT_il, const int64_t *y, int B, int H, int K, int V, float *c, void *h_out,
+                         int64_t h_ld, float *hid_out, int64_t hid_ld, rcnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.

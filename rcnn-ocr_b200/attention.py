@@ -76,6 +76,12 @@ class Attention(nn.Module):
                     "gen": ops.cast_bf16_2d(self.generator.weight.detach()),                              # [V, H]
                     "gen_b": self.generator.bias.detach().float().contiguous(),
                 }
+                if self.hidden_size % 8 == 0:
+                    # gate-interleaved copies (row 4u + g = gate g of unit u) for the GEMM whose epilogue is the LSTMCell step
+                    Hh, K = self.hidden_size, w["wcat"].shape[1]
+                    w["wcat_il"] = w["wcat"].view(4, Hh, K).permute(1, 0, 2).reshape(4 * Hh, K).contiguous()
+                    w["bcat_il"] = w["bcat"].view(4, Hh).t().reshape(-1).contiguous()
+                    w["embT_il"] = w["embT"].view(-1, 4, Hh).permute(0, 2, 1).reshape(-1, 4 * Hh).contiguous()
                 # greedy decode: h2h(h_t) (for step t+1) and generator(h_t) (for step t) in ONE product, N padded to 32 k
                 H, V = self.hidden_size, self.num_classes
                 Np = (H + V + 31) // 32 * 32
@@ -114,7 +120,7 @@ class Attention(nn.Module):
             half = H % 8 == 0 and C % 8 == 0 and os.environ.get("RCNN_ATTN_F32", "0") != "1"
             projH = ops.gemm_bf16(encb.view(B * T, C), w["i2h"], None, torch.bfloat16 if half else torch.float32)
 
-            def score_context(ph, ph_ld, prev=None):
+            def score_context(xcat, ph, ph_ld, prev=None):
                 """K6a for this step; prev = (logits, ld, probs row block, y): K6c of the previous step rides along (bf16 kernel)"""
                 if half:
                     pl, pld, pp, py = prev if prev is not None else (None, 0, None, None)
@@ -129,12 +135,12 @@ class Attention(nn.Module):
                                                       enc.stride(0), enc.stride(1), B, T, H, C, None, xcat.data_ptr(),
                                                       xcat.stride(0), s)
                 _lib.check(rc, "rcnn_attn_score_context")
-            xcat = torch.zeros((B, C + H), dtype=torch.bfloat16, device=dev)                    # [context | h], h_0 = 0
-            hview = xcat[:, C:]
+            # [context | h] rows, h_0 = 0.  Two of them: the fused gate GEMM + cell writes h_t into the other one, because
+            # CTAs that are still in their K loop read h_{t-1} from this one
+            fused = half and os.environ.get("RCNN_ATTN_FUSED_CELL", "1") != "0"
+            xc = [torch.zeros((B, C + H), dtype=torch.bfloat16, device=dev) for _ in range(2 if fused else 1)]
             c = torch.zeros((B, H), dtype=torch.float32, device=dev)
-            projh = torch.empty((B, H), dtype=torch.float32, device=dev)
-            gates = torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
-            logits = torch.empty((B, V), dtype=torch.float32, device=dev)
+            gates = None if fused else torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
             greedy = text is None
             probs = torch.zeros((B, steps, V), dtype=torch.float32, device=dev) if greedy else None
             out_hid = None if greedy else torch.zeros((B, steps, H), dtype=torch.float32, device=dev)
@@ -142,32 +148,46 @@ class Attention(nn.Module):
             if not greedy:
                 text = text.to(device=dev, dtype=torch.int64).contiguous()
             s = _lib.stream_ptr()
+
+            def gates_cell(t, tokens, hid):
+                """LSTMCell step t: reads [context | h_{t-1}] from xc[t % n], returns the buffer whose h half holds h_t"""
+                cur = xc[t % len(xc)]
+                hid_ptr, hid_ld = (hid.data_ptr(), out_hid.stride(0)) if hid is not None else (None, 0)
+                if fused:
+                    nxt = xc[(t + 1) % 2]
+                    _lib.check(L.rcnn_attn_gates_cell(cur.data_ptr(), cur.stride(0), w["wcat_il"].data_ptr(), w["wcat_il"].stride(0),
+                                                      w["bcat_il"].data_ptr(), w["embT_il"].data_ptr(), tokens.data_ptr(), B, H,
+                                                      C + H, V, c.data_ptr(), nxt[:, C:].data_ptr(), nxt.stride(0), hid_ptr, hid_ld,
+                                                      s), "rcnn_attn_gates_cell")
+                    return nxt
+                ops.gemm_bf16(cur, w["wcat"], w["bcat"], torch.float32, out=gates)
+                _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), tokens.data_ptr(), B, H, V, c.data_ptr(),
+                                            cur.data_ptr(), cur.stride(0), C, hid_ptr, hid_ld, s), "rcnn_attn_cell")
+                return cur
+
             if greedy:
-                # step: [argmax of the previous step's logits +] score / context (proj_h of h_{t-1}) -> gates GEMM -> cell (h_t)
+                # step: [argmax of the previous step's logits +] score / context (proj_h of h_{t-1}) -> gates GEMM + cell (h_t)
                 # -> ONE GEMM over [h2h | generator]: columns [0, H) = proj_h for the next step, [H, H + V) = this step's
-                # logits.  4 launches per step (5 with fp32 operands), one argmax launch after the last step.
+                # logits.  3 launches per step (5 with fp32 operands), one argmax launch after the last step.
                 Np = w["comb"].shape[0]
                 hg = torch.empty((B, Np), dtype=torch.float32, device=dev)
                 hg[:, :H] = w["h2h_b"]                                             # h2h(h_0 = 0) = its bias
                 lg = hg[:, H:].data_ptr()
                 for t in range(steps):
-                    score_context(hg, hg.stride(0), None if t == 0 else (lg, hg.stride(0), probs[:, t - 1].data_ptr(), y.data_ptr()))
-                    ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
-                    _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), y.data_ptr(), B, H, V, c.data_ptr(),
-                                                xcat.data_ptr(), xcat.stride(0), C, None, 0, s), "rcnn_attn_cell")
-                    ops.gemm_bf16(hview, w["comb"], w["comb_b"], torch.float32, out=hg)
+                    score_context(xc[t % len(xc)], hg, hg.stride(0),
+                                  None if t == 0 else (lg, hg.stride(0), probs[:, t - 1].data_ptr(), y.data_ptr()))
+                    hbuf = gates_cell(t, y, None)
+                    ops.gemm_bf16(hbuf[:, C:], w["comb"], w["comb_b"], torch.float32, out=hg)
                 _lib.check(L.rcnn_attn_argmax_ld(lg, hg.stride(0), B, V, blank, probs[:, steps - 1].data_ptr(), probs.stride(0),
                                                  y.data_ptr(), s), "rcnn_attn_argmax")
                 return probs
+            projh = torch.empty((B, H), dtype=torch.float32, device=dev)
             for t in range(steps):
                 yt = text[:, t].contiguous()
-                ops.gemm_bf16(hview, w["h2h"], w["h2h_b"], torch.float32, out=projh)
-                score_context(projh, projh.stride(0))
-                ops.gemm_bf16(xcat, w["wcat"], w["bcat"], torch.float32, out=gates)
-                hid = out_hid[:, t]
-                _lib.check(L.rcnn_attn_cell(gates.data_ptr(), w["embT"].data_ptr(), yt.data_ptr(), B, H, V, c.data_ptr(),
-                                            xcat.data_ptr(), xcat.stride(0), C, hid.data_ptr(), out_hid.stride(0), s),
-                           "rcnn_attn_cell")
+                cur = xc[t % len(xc)]
+                ops.gemm_bf16(cur[:, C:], w["h2h"], w["h2h_b"], torch.float32, out=projh)
+                score_context(cur, projh, projh.stride(0))
+                gates_cell(t, yt, out_hid[:, t])
             # teacher forcing: logits = generator(out_hid) in one GEMM, then the blank mask (model/model.py:146-148)
             out = ops.gemm_bf16(ops.cast_bf16_2d(out_hid.view(B * steps, H)), w["gen"], w["gen_b"], torch.float32)
             out = out.view(B, steps, V)

@@ -11,9 +11,12 @@
 // proj_H = i2h(batch_H) does not depend on the step and is hoisted out of the loop (the reference
 // recomputes it every step, model/model.py:35).  Sequences are independent: no exchange between CTAs.
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace rcnn {
 namespace {
+
+using namespace sm100;
 
 __device__ __forceinline__ float tanh_fast_a(float x) {
     float r;
@@ -178,6 +181,33 @@ __device__ __forceinline__ void unpack8(const uint4 &q, float (&f)[8]) {
     }
 }
 
+// One work item of the score pass: eight frames (t0 + 8k) x eight hidden units (j ..) of proj_H, 16 bytes per frame
+__device__ __forceinline__ void score_item_load(const __nv_bfloat16 *__restrict__ pb, int T, int H, int t0, int j, uint4 (&q)[8]) {
+    if (j >= H) return;                                       // (score_item_fma skips the item as well)
+    const __nv_bfloat16 *p = pb + j;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int t = min(t0 + 8 * k, T - 1);                 // past the end: a duplicate row whose score is not stored
+        q[k] = *reinterpret_cast<const uint4 *>(p + (size_t)t * H);
+    }
+}
+__device__ __forceinline__ void score_item_fma(const float *ph, const float *vs, int H, int j, const uint4 (&q)[8], float (&s)[8]) {
+    if (j >= H) return;
+    float p8[8], v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { p8[i] = ph[j + i]; v8[i] = vs[j + i]; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float f[8];
+        unpack8(q[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[k] = fmaf(v8[i], tanh_fast_a(f[i] + p8[i]), s[k]);
+    }
+}
+
+// STAGE: the sequence's encoder rows [T, C] are copied to shared memory with cp.async.bulk while the score pass runs (they do
+// not depend on it), so that the context pass starts from on-chip data; the kernel is a chain of L2 latencies, not bytes.
+template <bool STAGE>
 __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
     const __nv_bfloat16 *__restrict__ projH, const float *__restrict__ projh, const float *__restrict__ v,
     const __nv_bfloat16 *__restrict__ enc, long long enc_sb, long long enc_st, int T, int H, int C,
@@ -186,42 +216,58 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
     long long probs_ld, long long *__restrict__ y) {
     extern __shared__ __align__(16) float sm[];
     float *ph = sm, *vs = sm + H, *e = sm + 2 * H, *part = e + ((T + 3) & ~3);      // [H], [H], [T], [8][C]
+    __nv_bfloat16 *enc_s = reinterpret_cast<__nv_bfloat16 *>(part + 8 * (size_t)C);  // [T][C] (STAGE)
     __shared__ float red[2];
+    __shared__ __align__(8) uint64_t stage_bar;
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16 *pb = projH + (size_t)b * T * H;
+    const __nv_bfloat16 *eb = enc + (size_t)b * enc_sb;
+
+    // score pass, work items (frame block, unit block) double-buffered: item i+1 is requested before item i is used
+    const int nJ = (H + 255) / 256, nTb = warp < T ? (T - warp + 63) / 64 : 0, nI = nTb * nJ;
+    uint4 qa[8], qb[8];
+    if (nI > 0) score_item_load(pb, T, H, warp, 8 * lane, qa);
+    if (STAGE && threadIdx.x == 0) {                          // bulk copies (one if the rows are contiguous), one barrier
+        mbar_init(&stage_bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&stage_bar, (uint32_t)T * (uint32_t)C * 2u);
+        const uint32_t dst0 = smem_u32(enc_s), bar = smem_u32(&stage_bar);
+        const int rows = enc_st == C ? 1 : T;
+        const uint32_t bytes = enc_st == C ? (uint32_t)T * (uint32_t)C * 2u : (uint32_t)C * 2u;
+        for (int t = 0; t < rows; ++t)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst0 + (uint32_t)t * bytes), "l"(eb + (size_t)t * enc_st), "r"(bytes), "r"(bar) : "memory");
+    }
+    for (int j = threadIdx.x; j < H; j += 256) { ph[j] = projh[(size_t)b * projh_ld + j]; vs[j] = v[j]; }
     if (prev_logits != nullptr && warp == 7) {                // K6c of the previous step for this sequence (saves a launch)
         const int arg = warp_argmax_row(prev_logits + (size_t)b * prev_ld, V, blank,
                                         prev_probs ? prev_probs + (size_t)b * probs_ld : nullptr, lane);
         if (lane == 0 && y) y[b] = arg;
     }
-    for (int j = threadIdx.x; j < H; j += 256) { ph[j] = projh[(size_t)b * projh_ld + j]; vs[j] = v[j]; }
     __syncthreads();
-    const __nv_bfloat16 *pb = projH + (size_t)b * T * H;
-    for (int t0 = warp; t0 < T; t0 += 64) {                   // frames t0, t0+8, ..., t0+56 together
+    {
         float s[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = 0.f;
-        for (int j = 8 * lane; j < H; j += 256) {
-            uint4 q[8];
+        auto finish = [&](int it) {                           // last unit block of a frame block: reduce, store, reset
+            if (it % nJ != nJ - 1) return;
+            const int t0 = warp + 64 * (it / nJ);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int t = t0 + 8 * k;
-                q[k] = t < T ? *reinterpret_cast<const uint4 *>(pb + (size_t)t * H + j) : make_uint4(0, 0, 0, 0);
+                const float r = warp_sum(s[k]);
+                if (lane == 0 && t0 + 8 * k < T) e[t0 + 8 * k] = r;
+                s[k] = 0.f;
             }
-            float p8[8], v8[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { p8[i] = ph[j + i]; v8[i] = vs[j + i]; }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float f[8];
-                unpack8(q[k], f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s[k] = fmaf(v8[i], tanh_fast_a(f[i] + p8[i]), s[k]);
+        };
+        for (int it = 0; it < nI; it += 2) {
+            if (it + 1 < nI) score_item_load(pb, T, H, warp + 64 * ((it + 1) / nJ), 8 * lane + 256 * ((it + 1) % nJ), qb);
+            score_item_fma(ph, vs, H, 8 * lane + 256 * (it % nJ), qa, s);
+            finish(it);
+            if (it + 2 < nI) score_item_load(pb, T, H, warp + 64 * ((it + 2) / nJ), 8 * lane + 256 * ((it + 2) % nJ), qa);
+            if (it + 1 < nI) {
+                score_item_fma(ph, vs, H, 8 * lane + 256 * ((it + 1) % nJ), qb, s);
+                finish(it + 1);
             }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float r = warp_sum(s[k]);
-            if (lane == 0 && t0 + 8 * k < T) e[t0 + 8 * k] = r;
         }
     }
     __syncthreads();
@@ -235,6 +281,7 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
         if (lane == 0) { red[0] = m; red[1] = 1.f / z; }
     }
     __syncthreads();
+    if (STAGE) mbar_wait(&stage_bar, 0);
     const float m = red[0], iz = red[1];
     for (int t = threadIdx.x; t < T; t += 256) {
         const float a = __expf(e[t] - m) * iz;
@@ -242,7 +289,6 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
         if (alpha_out) alpha_out[(size_t)b * T + t] = a;
     }
     __syncthreads();
-    const __nv_bfloat16 *eb = enc + (size_t)b * enc_sb;
     for (int c = 8 * lane; c < C; c += 256) {
         float acc[8];
 #pragma unroll
@@ -251,8 +297,9 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
             uint4 q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int t = t0 + 8 * k;
-                q[k] = t < T ? *reinterpret_cast<const uint4 *>(eb + (size_t)t * enc_st + c) : make_uint4(0, 0, 0, 0);
+                const int t = min(t0 + 8 * k, T - 1);         // past the end: a duplicate row with weight 0
+                if (STAGE) q[k] = *reinterpret_cast<const uint4 *>(enc_s + (size_t)t * C + c);
+                else q[k] = *reinterpret_cast<const uint4 *>(eb + (size_t)t * enc_st + c);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -354,11 +401,14 @@ extern "C" int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_
     RCNN_CHECK_ARG(H % 8 == 0 && C % 8 == 0 && enc_stride_b % 8 == 0 && enc_stride_t % 8 == 0 && ldx % 2 == 0 &&
                        ((uintptr_t)projH & 15) == 0 && ((uintptr_t)enc & 15) == 0 && ((uintptr_t)xcat & 3) == 0,
                    "attn_score_context_bf16: H, C and the enc strides must be multiples of 8, the bf16 arrays 16-byte aligned");
-    const size_t smem = sizeof(float) * (2 * (size_t)H + ((T + 3) & ~3) + 8 * (size_t)C);
+    const size_t base = sizeof(float) * (2 * (size_t)H + ((T + 3) & ~3) + 8 * (size_t)C);
+    const size_t stage_bytes = (size_t)T * C * 2;
+    const bool stage = base + stage_bytes <= 100 * 1024;      // two CTAs per SM stay resident
+    const size_t smem = base + (stage ? stage_bytes : 0);
     RCNN_CHECK_ARG(smem <= 200 * 1024, "attn_score_context_bf16: T=%d, H=%d, C=%d exceed shared memory", T, H, C);
-    if (smem > 48 * 1024)
-        RCNN_CUDA(cudaFuncSetAttribute(attn_score_context_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_score_context_bf16_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(
+    auto kern = stage ? attn_score_context_bf16_kernel<true> : attn_score_context_bf16_kernel<false>;
+    if (smem > 48 * 1024) RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 256, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16 *)projH, projh, v, (const __nv_bfloat16 *)enc, enc_stride_b, enc_stride_t, T, H, C, alpha_out,
         (__nv_bfloat16 *)xcat, ldx, projh_ld, prev_logits, prev_ld, V, blank, prev_probs, probs_ld, (long long *)y);
     RCNN_LAUNCH_CHECK("attn_score_context_bf16_kernel");

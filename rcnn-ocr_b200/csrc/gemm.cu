@@ -188,10 +188,41 @@ template <int TN> struct PCfg {
     static constexpr size_t kSmem = 1024 + kStages * kStage + 256 + 2 * TN * sizeof(float);
 };
 
-template <typename OutT, int TN>
+template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<float>(float a, float) { return __float_as_uint(a); }
+
+// CELL epilogue (TN = 32, the attention decoder's gate product, attn.cu): the B rows are gate-interleaved (row 4u + g = gate g
+// of hidden unit u, torch order i, f, g, o), so the 32 accumulator columns a thread holds are all four gates of eight units and
+// the LSTMCell pointwise step (K6b) runs on them in registers: nothing is written to D.
+struct CellEpi {
+    const float *embT;           // [V, 4H] gate-interleaved: the one-hot half of the LSTMCell input, one row per token
+    const long long *y;          // [M] previous tokens
+    float *c;                    // [M, H] cell state, in place
+    __nv_bfloat16 *h_out;        // h_t as bf16, row pitch h_ld (NOT the A operand's buffer: other CTAs still read that)
+    float *hid_out;              // optional f32 copy, row pitch hid_ld
+    long long h_ld, hid_ld;
+    int V, H;
+};
+__device__ __forceinline__ float tanh_fast_g(float x) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast_g(float x) { return fmaf(tanh_fast_g(0.5f * x), 0.5f, 0.5f); }
+
+template <typename OutT, int TN, bool CELL = false>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K) {
+               OutT *__restrict__ D, long long ldd, const float *__restrict__ bias, int M, int N, int K, const CellEpi ce) {
+    static_assert(!CELL || TN == 32, "the cell epilogue works on 32-column tiles");
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using C = PCfg<TN>;
@@ -299,7 +330,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + c0), r);
                 tmem_ld_wait();
                 const int col0 = tile_n * TN + c0;
-                if (row < M && col0 < N) {
+                if (CELL) {
+                    if (row < M) {                                          // (N = 4H is a multiple of 32)
+                        long long tok = ce.y[row];
+                        tok = tok < 0 ? 0 : (tok >= ce.V ? ce.V - 1 : tok);
+                        const float4 *em4 = reinterpret_cast<const float4 *>(ce.embT + (size_t)tok * 4 * ce.H + col0);
+                        const int unit0 = col0 >> 2;
+                        float4 *c4 = reinterpret_cast<float4 *>(ce.c + (size_t)row * ce.H + unit0);
+                        const float4 cA = c4[0], cB = c4[1];
+                        const float cp[8] = {cA.x, cA.y, cA.z, cA.w, cB.x, cB.y, cB.z, cB.w};
+                        float cn[8], hn[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 em = __ldg(em4 + u);
+                            const float ig = sigmoid_fast_g(__uint_as_float(r[4 * u]) + bias_s[acc * TN + 4 * u] + em.x);
+                            const float fg = sigmoid_fast_g(__uint_as_float(r[4 * u + 1]) + bias_s[acc * TN + 4 * u + 1] + em.y);
+                            const float gg = tanh_fast_g(__uint_as_float(r[4 * u + 2]) + bias_s[acc * TN + 4 * u + 2] + em.z);
+                            const float og = sigmoid_fast_g(__uint_as_float(r[4 * u + 3]) + bias_s[acc * TN + 4 * u + 3] + em.w);
+                            cn[u] = fmaf(fg, cp[u], ig * gg);
+                            hn[u] = og * tanh_fast_g(cn[u]);
+                        }
+                        c4[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        c4[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                        uint4 hb;
+                        hb.x = pack2<__nv_bfloat16>(hn[0], hn[1]); hb.y = pack2<__nv_bfloat16>(hn[2], hn[3]);
+                        hb.z = pack2<__nv_bfloat16>(hn[4], hn[5]); hb.w = pack2<__nv_bfloat16>(hn[6], hn[7]);
+                        *reinterpret_cast<uint4 *>(ce.h_out + (size_t)row * ce.h_ld + unit0) = hb;
+                        if (ce.hid_out) {
+                            float4 *o4 = reinterpret_cast<float4 *>(ce.hid_out + (size_t)row * ce.hid_ld + unit0);
+                            o4[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                            o4[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                        }
+                    }
+                } else if (row < M && col0 < N) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[acc * TN + c0 + j];
@@ -318,16 +381,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
-template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
-template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
-template <> __device__ __forceinline__ uint32_t pack2<float>(float a, float) { return __float_as_uint(a); }
 
 // ---- CTA-pair variant: tcgen05.mma.cta_group::2, 256 x 256 output tile per pair ----------------------------
 // The two CTAs of a cluster compute one 256 x 256 tile: CTA r holds A rows [128r, 128r+128) and HALF of the B
@@ -821,8 +874,20 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long
     const int tiles = ((N + TN - 1) / TN) * ((M + BM - 1) / BM);
     const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_tn_kernel<OutT, TN><<<grid, kPThreads, smem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K);
+    gemm_tn_kernel<OutT, TN><<<grid, kPThreads, smem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K, CellEpi{});
     RCNN_LAUNCH_CHECK("gemm_tn_kernel");
+    return RCNN_OK;
+}
+
+int launch_gemm_cell(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, int M, int N, int K, const CellEpi &ce,
+                     cudaStream_t s) {
+    constexpr size_t smem = PCfg<32>::kSmem;
+    RCNN_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<float, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (N / 32) * ((M + BM - 1) / BM);
+    const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
+    ProfScope prof(RCNN_K_GEMM, s);
+    gemm_tn_kernel<float, 32, true><<<grid, kPThreads, smem, s>>>(ta, tb, nullptr, 0, bias, M, N, K, ce);
+    RCNN_LAUNCH_CHECK("gemm_tn_kernel<cell>");
     return RCNN_OK;
 }
 
@@ -941,6 +1006,33 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     if (out_dtype == RCNN_F32) return launch_gemm<float, 128>(ta, tb, D, ldd, bias, M, N, K, s);
     if (out_dtype == RCNN_F16) return launch_gemm<__half, 128>(ta, tb, D, ldd, bias, M, N, K, s);
     return launch_gemm<__nv_bfloat16, 128>(ta, tb, D, ldd, bias, M, N, K, s);
+}
+
+extern "C" int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
+                                    const float *embT_il, const int64_t *y, int B, int H, int K, int V, float *c, void *h_out,
+                                    int64_t h_ld, float *hid_out, int64_t hid_ld, rcnn_stream_t stream) {
+    using namespace rcnn;
+    RCNN_CHECK_ARG(B >= 0 && H >= 8 && H % 8 == 0 && K > 0 && V >= 1, "attn_gates_cell: bad shape B=%d H=%d K=%d V=%d (H %% 8 == 0)",
+                   B, H, K, V);
+    if (B == 0) return RCNN_OK;
+    RCNN_CHECK_ARG(xcat && wcat_il && bias_il && embT_il && y && c && h_out, "attn_gates_cell: null pointer");
+    RCNN_CHECK_ARG(h_out != xcat, "attn_gates_cell: h_out must not alias the A operand (other CTAs still read it)");
+    RCNN_CHECK_ARG(ldx >= K && ldw >= K && (ldx % 8) == 0 && (ldw % 8) == 0 && ((uintptr_t)xcat % 16) == 0 &&
+                       ((uintptr_t)wcat_il % 16) == 0,
+                   "attn_gates_cell: operand rows must be 16-byte aligned");
+    RCNN_CHECK_ARG(h_ld >= H && (h_ld % 8) == 0 && ((uintptr_t)h_out % 16) == 0 && ((uintptr_t)c % 16) == 0 &&
+                       ((uintptr_t)embT_il % 16) == 0 && (hid_out == nullptr || (hid_ld >= H && (hid_ld % 4) == 0 &&
+                                                                                 ((uintptr_t)hid_out % 16) == 0)),
+                   "attn_gates_cell: h_out / c / embT / hid_out must allow 16-byte accesses");
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, xcat, 2, (uint64_t)B, (uint64_t)K, (uint64_t)ldx * 2, BM, BK, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, wcat_il, 2, (uint64_t)4 * H, (uint64_t)K, (uint64_t)ldw * 2, 32, BK, 1);
+    if (rc) return rc;
+    CellEpi ce;
+    ce.embT = embT_il; ce.y = (const long long *)y; ce.c = c; ce.h_out = (__nv_bfloat16 *)h_out; ce.hid_out = hid_out;
+    ce.h_ld = h_ld; ce.hid_ld = hid_ld; ce.V = V; ce.H = H;
+    return launch_gemm_cell(ta, tb, bias_il, B, 4 * H, K, ce, (cudaStream_t)stream);
 }
 
 extern "C" int rcnn_gemm_bf16_atb_grouped(const void *A, int64_t lda, int a_gcols, const void *B, int64_t ldb, int b_gcols,

@@ -105,7 +105,8 @@ def test_argmax_kernel_is_bit_exact():
         assert torch.equal(y, want.argmax(1))
 
 
-@pytest.mark.parametrize("B,T,H,C", [(5, 13, 64, 72), (3, 70, 264, 520), (256, 64, 256, 256), (2, 1, 8, 8)])
+@pytest.mark.parametrize("B,T,H,C", [(5, 13, 64, 72), (3, 70, 264, 520), (256, 64, 256, 256), (2, 1, 8, 8),
+                                     (2, 150, 64, 512)])        # the last: too large to stage in shared memory
 def test_score_context_kernels_match_the_formula(B, T, H, C):
     """K6a (both operand widths) against model/model.py:35-41 in float64 on the same (already rounded) inputs:
     alpha to 2e-3 (tanh.approx / __expf), context to bf16 rounding of the float64 value."""
@@ -155,6 +156,41 @@ def test_score_context_kernels_match_the_formula(B, T, H, C):
     bad = L.rcnn_attn_score_context_bf16(projH.data_ptr(), projh.data_ptr(), projh.stride(0), v.data_ptr(), enc.data_ptr(),
                                          enc.stride(0), enc.stride(1), B, T, H - 1, C, None, xcat.data_ptr(), xcat.stride(0), s)
     assert bad != 0
+
+
+@pytest.mark.parametrize("B,H,C,V", [(256, 512, 512, 194), (5, 8, 16, 3), (130, 72, 40, 50)])
+def test_gate_product_with_cell_epilogue_equals_the_two_launches(B, H, C, V):
+    """rcnn_attn_gates_cell (tcgen05 GEMM over gate-interleaved weights, LSTMCell step in its epilogue) against
+    rcnn_gemm_bf16 + rcnn_attn_cell on the same inputs: c, h (bf16) and the f32 copy of h bit for bit."""
+    from rcnn_ocr_b200 import ops
+    L = R.lib()
+    g = torch.Generator(device="cuda").manual_seed(B + H)
+    K = C + H
+    xcat = torch.randn(B, K, device="cuda", generator=g).bfloat16()
+    wcat = (torch.randn(4 * H, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bcat = torch.randn(4 * H, device="cuda", generator=g)
+    embT = torch.randn(V, 4 * H, device="cuda", generator=g)
+    y = torch.randint(-1, V + 1, (B,), device="cuda", generator=g)               # out-of-range tokens are clamped
+    c0 = torch.randn(B, H, device="cuda", generator=g)
+    s = torch.cuda.current_stream().cuda_stream
+    # two launches
+    gates = ops.gemm_bf16(xcat, wcat, bcat, torch.float32)
+    c_a, x_a, hid_a = c0.clone(), xcat.clone(), torch.zeros(B, 3, H, device="cuda")
+    assert L.rcnn_attn_cell(gates.data_ptr(), embT.data_ptr(), y.data_ptr(), B, H, V, c_a.data_ptr(), x_a.data_ptr(), x_a.stride(0),
+                            C, hid_a[:, 1].data_ptr(), hid_a.stride(0), s) == 0
+    # one launch
+    w_il = wcat.view(4, H, K).permute(1, 0, 2).reshape(4 * H, K).contiguous()
+    b_il = bcat.view(4, H).t().reshape(-1).contiguous()
+    e_il = embT.view(V, 4, H).permute(0, 2, 1).reshape(V, 4 * H).contiguous()
+    c_b, x_b, hid_b = c0.clone(), torch.zeros_like(xcat), torch.zeros(B, 3, H, device="cuda")
+    assert L.rcnn_attn_gates_cell(xcat.data_ptr(), xcat.stride(0), w_il.data_ptr(), w_il.stride(0), b_il.data_ptr(), e_il.data_ptr(),
+                                  y.data_ptr(), B, H, K, V, c_b.data_ptr(), x_b[:, C:].data_ptr(), x_b.stride(0),
+                                  hid_b[:, 1].data_ptr(), hid_b.stride(0), s) == 0
+    assert torch.equal(c_a, c_b) and torch.equal(x_a[:, C:], x_b[:, C:]) and torch.equal(hid_a, hid_b)
+    assert (x_b[:, :C] == 0).all()
+    # writing h into the operand it is computed from is refused
+    assert L.rcnn_attn_gates_cell(xcat.data_ptr(), xcat.stride(0), w_il.data_ptr(), w_il.stride(0), b_il.data_ptr(), e_il.data_ptr(),
+                                  y.data_ptr(), B, H, K, V, c_b.data_ptr(), xcat.data_ptr(), xcat.stride(0), None, 0, s) != 0
 
 
 def test_state_dict_contract_and_errors():
