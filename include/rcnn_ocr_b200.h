@@ -318,6 +318,11 @@ int rcnn_debug_refetch_counter(void *counter);
  * reducer reserves 16: NCCL's all-reduce kernels then run beside a weight-gradient or input-gradient GEMM instead of waiting
  * for the one CTA per SM it would hold until its last tile (rcnn-ocr_b200/dist.py). */
 int rcnn_reserve_sms(int n);
+/* on != 0: the GEMM (rcnn_gemm_bf16, rcnn_attn_gates_cell) and attention step (rcnn_attn_step_bf16 / _score_context_bf16)
+ * kernels launched from now on carry cudaLaunchAttributeProgrammaticStreamSerialization: each may start its CTAs while its
+ * predecessor in the stream drains and waits (griddepcontrol.wait) before touching anything that predecessor produced.  Meant
+ * for a chain of short dependent kernels -- the decoder's step loop sets it around the loop.  Process-wide; default off. */
+int rcnn_chain_launches(int on);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long rcnn_launch_count(void);
 int rcnn_prof_enable(int on);

@@ -138,6 +138,9 @@ class Attention(nn.Module):
             # [context | h] rows, h_0 = 0.  Two of them: the fused gate GEMM + cell writes h_t into the other one, because
             # CTAs that are still in their K loop read h_{t-1} from this one
             fused = half and os.environ.get("RCNN_ATTN_FUSED_CELL", "1") != "0"
+            # the step loop is a chain of short dependent kernels: launched with programmatic stream serialization (the
+            # bf16 step kernel and the tcgen05 GEMMs wait on the device for their predecessor; the fp32 kernels do not take part)
+            chain = fused and os.environ.get("RCNN_ATTN_CHAIN", "1") != "0"
             xc = [torch.zeros((B, C + H), dtype=torch.bfloat16, device=dev) for _ in range(2 if fused else 1)]
             c = torch.zeros((B, H), dtype=torch.float32, device=dev)
             gates = None if fused else torch.empty((B, 4 * H), dtype=torch.float32, device=dev)
@@ -173,21 +176,29 @@ class Attention(nn.Module):
                 hg = torch.empty((B, Np), dtype=torch.float32, device=dev)
                 hg[:, :H] = w["h2h_b"]                                             # h2h(h_0 = 0) = its bias
                 lg = hg[:, H:].data_ptr()
-                for t in range(steps):
-                    score_context(xc[t % len(xc)], hg, hg.stride(0),
-                                  None if t == 0 else (lg, hg.stride(0), probs[:, t - 1].data_ptr(), y.data_ptr()))
-                    hbuf = gates_cell(t, y, None)
-                    ops.gemm_bf16(hbuf[:, C:], w["comb"], w["comb_b"], torch.float32, out=hg)
+                L.rcnn_chain_launches(int(chain))
+                try:
+                    for t in range(steps):
+                        score_context(xc[t % len(xc)], hg, hg.stride(0),
+                                      None if t == 0 else (lg, hg.stride(0), probs[:, t - 1].data_ptr(), y.data_ptr()))
+                        hbuf = gates_cell(t, y, None)
+                        ops.gemm_bf16(hbuf[:, C:], w["comb"], w["comb_b"], torch.float32, out=hg)
+                finally:
+                    L.rcnn_chain_launches(0)
                 _lib.check(L.rcnn_attn_argmax_ld(lg, hg.stride(0), B, V, blank, probs[:, steps - 1].data_ptr(), probs.stride(0),
                                                  y.data_ptr(), s), "rcnn_attn_argmax")
                 return probs
             projh = torch.empty((B, H), dtype=torch.float32, device=dev)
-            for t in range(steps):
-                yt = text[:, t].contiguous()
-                cur = xc[t % len(xc)]
-                ops.gemm_bf16(cur[:, C:], w["h2h"], w["h2h_b"], torch.float32, out=projh)
-                score_context(cur, projh, projh.stride(0))
-                gates_cell(t, yt, out_hid[:, t])
+            tokens = text[:, :steps].t().contiguous()                               # [steps, B]: row t = the step's input tokens
+            L.rcnn_chain_launches(int(chain))
+            try:
+                for t in range(steps):
+                    cur = xc[t % len(xc)]
+                    ops.gemm_bf16(cur[:, C:], w["h2h"], w["h2h_b"], torch.float32, out=projh)
+                    score_context(cur, projh, projh.stride(0))
+                    gates_cell(t, tokens[t], out_hid[:, t])
+            finally:
+                L.rcnn_chain_launches(0)
             # teacher forcing: logits = generator(out_hid) in one GEMM, then the blank mask (model/model.py:146-148)
             out = ops.gemm_bf16(ops.cast_bf16_2d(out_hid.view(B * steps, H)), w["gen"], w["gen_b"], torch.float32)
             out = out.view(B, steps, V)

@@ -28,6 +28,11 @@ int gemm_sms() {
     return n < 2 ? 2 : n;
 }
 
+// rcnn_chain_launches: kernels of a dependent chain (the attention decoder's step loop) are launched with programmatic stream
+// serialization, so that a kernel's CTAs are dispatched -- and run their prologue -- while its predecessor drains
+static int g_chain = 0;
+bool chain_launches() { return g_chain != 0; }
+
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;   // keyed by the device id: re-read when the thread switches device
     int dev = 0;
@@ -129,6 +134,11 @@ int rcnn_reserve_sms(int n) {
         return RCNN_ERR_ARG;
     }
     rcnn::g_reserved_sms = n;
+    return RCNN_OK;
+}
+
+int rcnn_chain_launches(int on) {
+    rcnn::g_chain = on ? 1 : 0;
     return RCNN_OK;
 }
 

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
     const __nv_bfloat16 *pb = projH + (size_t)b * T * H;
     const __nv_bfloat16 *eb = enc + (size_t)b * enc_sb;
 
+    griddep_launch();
     // score pass, work items (frame block, unit block) double-buffered: item i+1 is requested before item i is used
     const int nJ = (H + 255) / 256, nTb = warp < T ? (T - warp + 63) / 64 : 0, nI = nTb * nJ;
     uint4 qa[8], qb[8];
@@ -238,7 +239,10 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              dst0 + (uint32_t)t * bytes), "l"(eb + (size_t)t * enc_st), "r"(bytes), "r"(bar) : "memory");
     }
-    for (int j = threadIdx.x; j < H; j += 256) { ph[j] = projh[(size_t)b * projh_ld + j]; vs[j] = v[j]; }
+    // chained launches: proj_H, enc and v above are the loop's constants; proj_h and the logits come from the predecessor
+    for (int j = threadIdx.x; j < H; j += 256) vs[j] = v[j];
+    griddep_wait();
+    for (int j = threadIdx.x; j < H; j += 256) ph[j] = projh[(size_t)b * projh_ld + j];
     if (prev_logits != nullptr && warp == 7) {                // K6c of the previous step for this sequence (saves a launch)
         const int arg = warp_argmax_row(prev_logits + (size_t)b * prev_ld, V, blank,
                                         prev_probs ? prev_probs + (size_t)b * probs_ld : nullptr, lane);
@@ -408,9 +412,13 @@ extern "C" int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_
     RCNN_CHECK_ARG(smem <= 200 * 1024, "attn_score_context_bf16: T=%d, H=%d, C=%d exceed shared memory", T, H, C);
     auto kern = stage ? attn_score_context_bf16_kernel<true> : attn_score_context_bf16_kernel<false>;
     if (smem > 48 * 1024) RCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, 256, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)projH, projh, v, (const __nv_bfloat16 *)enc, enc_stride_b, enc_stride_t, T, H, C, alpha_out,
-        (__nv_bfloat16 *)xcat, ldx, projh_ld, prev_logits, prev_ld, V, blank, prev_probs, probs_ld, (long long *)y);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    chain_config(cfg, attr, (unsigned)B, 256, smem, (cudaStream_t)stream);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16 *)projH, projh, v, (const __nv_bfloat16 *)enc,
+                                 (long long)enc_stride_b, (long long)enc_stride_t, T, H, C, alpha_out, (__nv_bfloat16 *)xcat,
+                                 (long long)ldx, (long long)projh_ld, prev_logits, (long long)prev_ld, V, blank, prev_probs,
+                                 (long long)probs_ld, (long long *)y));
     RCNN_LAUNCH_CHECK("attn_score_context_bf16_kernel");
     return RCNN_OK;
 }

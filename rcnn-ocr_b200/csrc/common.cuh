@@ -33,6 +33,21 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 int num_sms();
+bool chain_launches();   // rcnn_chain_launches(1): launch with cudaLaunchAttributeProgrammaticStreamSerialization
+inline void chain_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, unsigned grid, unsigned block, size_t smem,
+                         cudaStream_t s) {
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (chain_launches()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 1;
+    }
+}
 int gemm_sms();   // num_sms() minus the SMs reserved for concurrent collectives (rcnn_reserve_sms)
 // optional per-step clock64 timeline of cluster 0 / CTA 0 of the recurrent kernels (debug aid)
 long long *debug_timeline();
@@ -116,5 +131,13 @@ __device__ __forceinline__ float lg2(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+
+// Programmatic dependent launch: griddep_launch() lets the next kernel of the stream start its CTAs (they run up to their own
+// griddep_wait()); griddep_wait() returns once the previous kernel has completed and its writes are visible.  Both are no-ops
+// for a kernel launched without the attribute.  Every kernel of a chain must wait before it reads or overwrites anything a
+// predecessor touches -- a kernel that skipped the wait could finish before its predecessor and release its successor early.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 }  // namespace rcnn

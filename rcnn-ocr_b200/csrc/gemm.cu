@@ -241,6 +241,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_tiles = ntn * ntm;
     const int rounds = (K + PCfg<TN>::kBoxes * BK - 1) / (PCfg<TN>::kBoxes * BK);
 
+    griddep_launch();                                         // (chained launches: the successor may set up meanwhile)
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1) {
         if (lane == 0) {
@@ -255,6 +256,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();                                           // the predecessor's output is complete from here on
 
     if (warp == 0 || warp == 6) {
         // ===== TMA producers: warp 0 streams A, warp 6 streams B (independent issuers) =============
@@ -874,8 +876,11 @@ int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, void *D, long long
     const int tiles = ((N + TN - 1) / TN) * ((M + BM - 1) / BM);
     const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_tn_kernel<OutT, TN><<<grid, kPThreads, smem, s>>>(ta, tb, (OutT *)D, ldd, bias, M, N, K, CellEpi{});
-    RCNN_LAUNCH_CHECK("gemm_tn_kernel");
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    chain_config(cfg, attr, grid, kPThreads, smem, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<OutT, TN>, ta, tb, (OutT *)D, (long long)ldd, bias, M, N, K, CellEpi{}));
+    count_launch();
     return RCNN_OK;
 }
 
@@ -886,8 +891,11 @@ int launch_gemm_cell(const CUtensorMap &ta, const CUtensorMap &tb, const float *
     const int tiles = (N / 32) * ((M + BM - 1) / BM);
     const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
     ProfScope prof(RCNN_K_GEMM, s);
-    gemm_tn_kernel<float, 32, true><<<grid, kPThreads, smem, s>>>(ta, tb, nullptr, 0, bias, M, N, K, ce);
-    RCNN_LAUNCH_CHECK("gemm_tn_kernel<cell>");
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    chain_config(cfg, attr, grid, kPThreads, smem, s);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<float, 32, true>, ta, tb, (float *)nullptr, (long long)0, bias, M, N, K, ce));
+    count_launch();
     return RCNN_OK;
 }
 
