@@ -297,6 +297,38 @@ int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *wcat_il, int
                          int64_t h_ld, float *hid_out, int64_t hid_ld, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Attention decoder, teacher-forced TRAINING pass (model/model.py:110-148 under autograd; the reference's live loss path,
+ * training/train.py:499-505).  Forward step t: rcnn_gemm_bf16 (h2h) -> rcnn_attn_step_train -> rcnn_attn_gates_cell_train;
+ * backward step t: rcnn_attn_cell_bwd -> rcnn_gemm_bf16 (dcontext) -> rcnn_attn_step_bwd -> rcnn_gemm_bf16 (dh_{t-1});
+ * after the loop rcnn_attn_dprojH once and the weight gradients as products over all (step, sequence) rows.
+ *
+ * rcnn_attn_step_train: rcnn_attn_score_context_bf16 that also returns alpha (before dropout; required) and multiplies it by
+ *   alpha_scale [B,T] (F.dropout(alpha), model/model.py:40: 0 or 1/(1-p), drawn by the caller; NULL = no dropout) for the context.
+ * rcnn_attn_gates_cell_train: rcnn_attn_gates_cell with c_{t-1} read from c_in, c_t written to c, and the gate activations
+ *   (sigmoid i, sigmoid f, tanh g, sigmoid o; gate-interleaved [B,4H] f32) kept in gates_act (may be NULL).
+ * rcnn_attn_cell_bwd: dh = dh_a (+ dh_b if not NULL), dc [B,H] holds dc_t on entry and dc_{t-1} on return; writes the gradients
+ *   of the gate pre-activations as bf16, gate-interleaved, to dg (row pitch ldg >= 4H).  c_prev NULL = zeros (t = 0).
+ * rcnn_attn_step_bwd: from dcontext [B, dctx_ld], alpha, alpha_scale, enc / proj_H (bf16), proj_h, v: de [B,T] (gradient of the
+ *   scores), d proj_h as bf16 (row pitch dprojh_ld) and dv_acc[b, :] += sum_t de[t] tanh(.) (one row per sequence; the caller
+ *   sums the rows at the end).
+ * rcnn_attn_dprojH: dprojH[b,t,j] (bf16) = v[j] sum_s de_all[s,b,t] (1 - tanh^2(projH[b,t,j] + projh_all[s,b,j])).
+ * ------------------------------------------------------------------------------------- */
+int rcnn_attn_step_train(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                         int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out,
+                         const float *alpha_scale, void *xcat, int64_t ldx, rcnn_stream_t stream);
+int rcnn_attn_gates_cell_train(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
+                               const float *embT_il, const int64_t *y, int B, int H, int K, int V, const float *c_in, float *c,
+                               void *h_out, int64_t h_ld, float *hid_out, int64_t hid_ld, float *gates_act, rcnn_stream_t stream);
+int rcnn_attn_cell_bwd(const float *gates_act, const float *c_prev, const float *c_t, const float *dh_a, int64_t dh_a_ld,
+                       const float *dh_b, int64_t dh_b_ld, float *dc, int B, int H, void *dg, int64_t ldg, rcnn_stream_t stream);
+int rcnn_attn_step_bwd(const float *dctx, int64_t dctx_ld, const float *alpha, const float *alpha_scale, const void *enc,
+                       int64_t enc_stride_b, int64_t enc_stride_t, const void *projH, const float *projh, int64_t projh_ld,
+                       const float *v, int B, int T, int H, int C, float *de_out, void *dprojh, int64_t dprojh_ld, float *dv_acc,
+                       rcnn_stream_t stream);
+int rcnn_attn_dprojH(const float *de_all, const float *projh_all, const void *projH, const float *v, int S, int B, int T, int H,
+                     void *dprojH, rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

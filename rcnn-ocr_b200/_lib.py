@@ -64,6 +64,16 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_attn_gates_cell.argtypes = [vp, i64, vp, i64, vp, vp, vp, i, i, i, i, vp, vp, i64, vp, i64, vp]
     L.rcnn_chain_launches.restype = i
     L.rcnn_chain_launches.argtypes = [i]
+    L.rcnn_attn_step_train.restype = i
+    L.rcnn_attn_step_train.argtypes = [vp, vp, i64, vp, vp, i64, i64, i, i, i, i, vp, vp, vp, i64, vp]
+    L.rcnn_attn_gates_cell_train.restype = i
+    L.rcnn_attn_gates_cell_train.argtypes = [vp, i64, vp, i64, vp, vp, vp, i, i, i, i, vp, vp, vp, i64, vp, i64, vp, vp]
+    L.rcnn_attn_cell_bwd.restype = i
+    L.rcnn_attn_cell_bwd.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, i, i, vp, i64, vp]
+    L.rcnn_attn_step_bwd.restype = i
+    L.rcnn_attn_step_bwd.argtypes = [vp, i64, vp, vp, vp, i64, i64, vp, vp, i64, vp, i, i, i, i, vp, vp, i64, vp, vp]
+    L.rcnn_attn_dprojH.restype = i
+    L.rcnn_attn_dprojH.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp]
     L.rcnn_attn_argmax_ld.restype = i
     L.rcnn_attn_argmax_ld.argtypes = [vp, i64, i, i, i, vp, i64, vp, vp]
     L.rcnn_lstm_forward_fused.restype = i

@@ -16,6 +16,10 @@ elementwise torch ops.  Dropout (``dropout_p`` on alpha and on the generator inp
 scheduled sampling (``sampling_prob``: one ``torch.rand(1)`` per step on the CPU generator as at :139, the fed-back
 token is the argmax of that step's logits) follow the reference; gradients are pinned to the reference module's own
 (tests/golden/attn_train_*.npz).  With autograd disabled the fused inference kernels (K6) run.
+
+Teacher forcing without scheduled sampling (the reference's default, ``sampling_prob = 0``) takes the fused training
+path ``_TeacherForcedFn``: forward on the inference step kernels (alpha and the gate activations kept), backward on
+``csrc/attn_bwd.cu`` + the tcgen05 GEMMs, alpha dropout as a multiplier drawn once for all steps.
 """
 from __future__ import annotations
 
@@ -40,6 +44,128 @@ class AttentionCell(nn.Module):
         self.dropout_p = dropout_p
 
 
+
+class _TeacherForcedFn(torch.autograd.Function):
+    """out_hid [B, steps, H] of the teacher-forced pass (model/model.py:131-135 for every step), forward and backward on
+    the fused kernels (csrc/attn.cu, attn_bwd.cu, the tcgen05 GEMMs): three launches per forward step, four per backward
+    step, the weight gradients as products over all (step, sequence) rows after the loop.  bf16 operands, fp32 state and
+    accumulation.  ``tokens`` [steps, B] are the step inputs (text[:, t]), ``alpha_scale`` [steps, B, T] the dropout
+    multipliers of alpha (0 or 1 / (1 - p)) or None."""
+
+    @staticmethod
+    def forward(ctx, batch_H, tokens, alpha_scale, i2h_w, h2h_w, h2h_b, score_w, w_ih, w_hh, b_ih, b_hh):
+        L = _lib.lib()
+        B, T, C = batch_H.shape
+        H = h2h_w.shape[0]
+        V = w_ih.shape[1] - C
+        S = tokens.shape[0]
+        K = C + H
+        dev = batch_H.device
+        with torch.cuda.device(dev):
+            enc = batch_H.detach().float()
+            if enc.stride(2) != 1:
+                enc = enc.contiguous()
+            encb = ops.cast_bf16_3d(enc)
+            i2h16 = ops.cast_bf16_2d(i2h_w.detach())
+            h2h16 = ops.cast_bf16_2d(h2h_w.detach())
+            projH = ops.gemm_bf16(encb.view(B * T, C), i2h16, None, torch.bfloat16)                       # [B*T, H]
+            v = score_w.detach().float().reshape(-1).contiguous()
+            wcat = torch.cat([w_ih.detach()[:, :C], w_hh.detach()], 1)                                     # [4H, C+H]
+            wcat_il = ops.cast_bf16_2d(wcat.view(4, H, K).permute(1, 0, 2).reshape(4 * H, K).contiguous())
+            bcat_il = (b_ih.detach() + b_hh.detach()).float().view(4, H).t().reshape(-1).contiguous()
+            embT_il = w_ih.detach()[:, C:].t().float().reshape(V, 4, H).permute(0, 2, 1).reshape(V, 4 * H).contiguous()
+            h2h_bias = h2h_b.detach().float().contiguous()
+            xcat_all = torch.zeros((S + 1, B, K), dtype=torch.bfloat16, device=dev)     # row block t: [context_t | h_{t-1}]
+            c_all = torch.zeros((S + 1, B, H), dtype=torch.float32, device=dev)         # c_all[t] = c_{t-1}
+            gates_all = torch.empty((S, B, 4 * H), dtype=torch.float32, device=dev)
+            alpha_all = torch.empty((S, B, T), dtype=torch.float32, device=dev)
+            projh_all = torch.empty((S, B, H), dtype=torch.float32, device=dev)
+            out_hid = torch.empty((B, S, H), dtype=torch.float32, device=dev)
+            if alpha_scale is not None:
+                alpha_scale = alpha_scale.to(device=dev, dtype=torch.float32).contiguous()
+            tokens = tokens.to(device=dev, dtype=torch.int64).contiguous()
+            s = _lib.stream_ptr()
+            L.rcnn_chain_launches(1)
+            try:
+                for t in range(S):
+                    cur, nxt = xcat_all[t], xcat_all[t + 1]
+                    ops.gemm_bf16(cur[:, C:], h2h16, h2h_bias, torch.float32, out=projh_all[t])
+                    _lib.check(L.rcnn_attn_step_train(projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), encb.data_ptr(),
+                                                      encb.stride(0), encb.stride(1), B, T, H, C, alpha_all[t].data_ptr(),
+                                                      alpha_scale[t].data_ptr() if alpha_scale is not None else None,
+                                                      cur.data_ptr(), K, s), "rcnn_attn_step_train")
+                    _lib.check(L.rcnn_attn_gates_cell_train(cur.data_ptr(), K, wcat_il.data_ptr(), K, bcat_il.data_ptr(),
+                                                            embT_il.data_ptr(), tokens[t].data_ptr(), B, H, K, V,
+                                                            c_all[t].data_ptr(), c_all[t + 1].data_ptr(), nxt[:, C:].data_ptr(), K,
+                                                            out_hid[:, t].data_ptr(), out_hid.stride(0), gates_all[t].data_ptr(),
+                                                            s), "rcnn_attn_gates_cell_train")
+            finally:
+                L.rcnn_chain_launches(0)
+        ctx.save_for_backward(encb, projH, v, wcat_il, h2h16, i2h16, xcat_all, c_all, gates_all, alpha_all, projh_all, tokens,
+                              alpha_scale if alpha_scale is not None else torch.empty(0, device=dev))
+        ctx.dims = (B, T, C, H, V, S)
+        ctx.in_dtype = batch_H.dtype
+        return out_hid
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (encb, projH, v, wcat_il, h2h16, i2h16, xcat_all, c_all, gates_all, alpha_all, projh_all, tokens, alpha_scale) = ctx.saved_tensors
+        B, T, C, H, V, S = ctx.dims
+        K = C + H
+        L = _lib.lib()
+        dev = encb.device
+        scale = alpha_scale if alpha_scale.numel() else None
+        with torch.cuda.device(dev):
+            d_out = d_out.float().contiguous()                                             # [B, S, H]
+            b1 = wcat_il[:, :C].t().contiguous()                                           # [C, 4H]: dcontext = dgates @ W_ih[:, :C]
+            b2 = torch.cat([wcat_il[:, C:].t(), h2h16.t()], 1).contiguous()                # [H, 5H]: dh = [dgates | dproj_h] @ [W_hh; W_h2h]
+            dg_all = torch.zeros((S, B, 5 * H), dtype=torch.bfloat16, device=dev)          # [dgates (interleaved) | dproj_h]
+            dctx_all = torch.empty((S, B, C), dtype=torch.float32, device=dev)
+            de_all = torch.empty((S, B, T), dtype=torch.float32, device=dev)
+            dv_acc = torch.zeros((B, H), dtype=torch.float32, device=dev)
+            dc = torch.zeros((B, H), dtype=torch.float32, device=dev)
+            dh = torch.empty((B, H), dtype=torch.float32, device=dev)
+            s = _lib.stream_ptr()
+            for t in range(S - 1, -1, -1):
+                last = t == S - 1
+                _lib.check(L.rcnn_attn_cell_bwd(gates_all[t].data_ptr(), c_all[t].data_ptr(), c_all[t + 1].data_ptr(),
+                                                d_out[:, t].data_ptr(), d_out.stride(0), None if last else dh.data_ptr(), H,
+                                                dc.data_ptr(), B, H, dg_all[t].data_ptr(), 5 * H, s), "rcnn_attn_cell_bwd")
+                ops.gemm_bf16(dg_all[t][:, :4 * H], b1, None, torch.float32, out=dctx_all[t])
+                _lib.check(L.rcnn_attn_step_bwd(dctx_all[t].data_ptr(), C, alpha_all[t].data_ptr(),
+                                                scale[t].data_ptr() if scale is not None else None, encb.data_ptr(), encb.stride(0),
+                                                encb.stride(1), projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), B, T, H,
+                                                C, de_all[t].data_ptr(), dg_all[t][:, 4 * H:].data_ptr(), 5 * H, dv_acc.data_ptr(),
+                                                s), "rcnn_attn_step_bwd")
+                if t > 0:
+                    ops.gemm_bf16(dg_all[t], b2, None, torch.float32, out=dh)              # dh_{t-1} through the gates and h2h
+            dprojH = torch.empty((B * T, H), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.rcnn_attn_dprojH(de_all.data_ptr(), projh_all.data_ptr(), projH.data_ptr(), v.data_ptr(), S, B, T, H,
+                                          dprojH.data_ptr(), s), "rcnn_attn_dprojH")
+            rows_g = dg_all.view(S * B, 5 * H)
+            dgates, dproj = rows_g[:, :4 * H], rows_g[:, 4 * H:]
+            rows_x = xcat_all[:S].view(S * B, K)
+            # parameter gradients
+            d_i2h = ops.gemm_bf16_atb(dprojH, encb.view(B * T, C))                         # [H, C]
+            d_h2h_w = ops.gemm_bf16_atb(dproj, rows_x[:, C:])                              # [H, H]
+            d_h2h_b = dproj.float().sum(0)
+            d_score = dv_acc.sum(0).view(1, H)
+            dwcat = ops.gemm_bf16_atb(dgates, rows_x).view(H, 4, K).permute(1, 0, 2).reshape(4 * H, K)   # back to torch's gate order
+            dgf = dgates.float()
+            d_emb = torch.zeros((V, 4 * H), dtype=torch.float32, device=dev).index_add_(0, tokens.view(-1).clamp(0, V - 1), dgf)
+            d_w_ih = torch.cat([dwcat[:, :C], d_emb.view(V, H, 4).permute(2, 1, 0).reshape(4 * H, V)], 1)
+            d_w_hh = dwcat[:, C:].contiguous()
+            d_b = dgf.sum(0).view(H, 4).t().reshape(-1)
+            # encoder gradient: through proj_H and through the context
+            d_enc = ops.gemm_bf16(dprojH, i2h16.t().contiguous(), None, torch.float32).view(B, T, C)
+            alpha_d = alpha_all * scale if scale is not None else alpha_all
+            d_enc = d_enc + torch.bmm(alpha_d.permute(1, 2, 0), dctx_all.permute(1, 0, 2))
+        need = ctx.needs_input_grad
+        return (d_enc.to(ctx.in_dtype) if need[0] else None, None, None, d_i2h if need[3] else None, d_h2h_w if need[4] else None,
+                d_h2h_b if need[5] else None, d_score if need[6] else None, d_w_ih if need[7] else None,
+                d_w_hh if need[8] else None, d_b if need[9] else None, d_b.clone() if need[10] else None)
+
+
 class Attention(nn.Module):
     def __init__(self, input_size, hidden_size, num_classes, sos_id: int, eos_id: int, pad_id: int,
                  blank_id=None, dropout_p: float = 0.1, sampling_prob: float = 0.0):
@@ -53,6 +179,7 @@ class Attention(nn.Module):
         self.dropout_p = dropout_p
         self.sampling_prob = sampling_prob
         self._prepared = None
+        self._alpha_scale_override = None      # [steps, B, T] multipliers used instead of drawing the alpha dropout mask
 
     # ---- bf16 / transposed views of the parameters, rebuilt only when a parameter changed ------------
     def _weights(self):
@@ -218,8 +345,23 @@ class Attention(nn.Module):
         H = self.hidden_size
         dev = batch_H.device
         text = text.to(device=dev, dtype=torch.int64)
-        enc = batch_H.float()
         drop = self.dropout_p if self.training else 0.0
+        sampling = self.sampling_prob if self.training else 0.0
+        if sampling <= 0 and os.environ.get("RCNN_ATTN_FUSED_TRAIN", "1") != "0":
+            # teacher forcing only (the reference's default, sampling_prob = 0): the fused forward / backward kernels
+            scale = self._alpha_scale_override
+            if scale is None and drop > 0:
+                scale = (torch.rand((steps, B, T), device=dev) >= drop).to(torch.float32) / (1.0 - drop)
+            out_hid = _TeacherForcedFn.apply(batch_H, text[:, :steps].t().contiguous(), scale, cell.i2h.weight, cell.h2h.weight,
+                                             cell.h2h.bias, cell.score.weight, cell.rnn.weight_ih, cell.rnn.weight_hh,
+                                             cell.rnn.bias_ih, cell.rnn.bias_hh)
+            logits = _LinearFn.apply(out_hid, self.generator.weight, self.generator.bias, True)
+            if self.blank_id is not None:
+                mask = torch.zeros(self.num_classes, dtype=torch.bool, device=dev)
+                mask[int(self.blank_id)] = True
+                logits = logits.masked_fill(mask, -1e4)
+            return logits
+        enc = batch_H.float()
         projH = _LinearFn.apply(enc, cell.i2h.weight, None, True)                       # hoisted i2h(batch_H) [B,T,H]
         wcat = torch.cat([cell.rnn.weight_ih[:, :C], cell.rnn.weight_hh], 1)            # [4H, C+H]
         bcat = cell.rnn.bias_ih + cell.rnn.bias_hh
@@ -232,7 +374,10 @@ class Attention(nn.Module):
         for t in range(steps):
             proj_h = _LinearFn.apply(h, cell.h2h.weight, cell.h2h.bias, True)
             e = (torch.tanh(projH + proj_h.unsqueeze(1)) * v).sum(-1)                   # [B,T]
-            alpha = F.dropout(torch.softmax(e, dim=1), p=drop, training=drop > 0)
+            if self._alpha_scale_override is not None:                                  # (tests: the same mask on both paths)
+                alpha = torch.softmax(e, dim=1) * self._alpha_scale_override[t]
+            else:
+                alpha = F.dropout(torch.softmax(e, dim=1), p=drop, training=drop > 0)
             context = (alpha.unsqueeze(2) * enc).sum(1)                                 # [B,C]
             gates = _LinearFn.apply(torch.cat([context, h], 1), wcat, bcat, True) + embT.index_select(0, targets)
             gi, gf, gg, go = gates.chunk(4, 1)

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
     const __nv_bfloat16 *__restrict__ enc, long long enc_sb, long long enc_st, int T, int H, int C,
     float *__restrict__ alpha_out, __nv_bfloat16 *__restrict__ xcat, long long ldx, long long projh_ld,
     const float *__restrict__ prev_logits, long long prev_ld, int V, int blank, float *__restrict__ prev_probs,
-    long long probs_ld, long long *__restrict__ y) {
+    long long probs_ld, long long *__restrict__ y, const float *__restrict__ alpha_scale) {
     extern __shared__ __align__(16) float sm[];
     float *ph = sm, *vs = sm + H, *e = sm + 2 * H, *part = e + ((T + 3) & ~3);      // [H], [H], [T], [8][C]
     __nv_bfloat16 *enc_s = reinterpret_cast<__nv_bfloat16 *>(part + 8 * (size_t)C);  // [T][C] (STAGE)
@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(256) attn_score_context_bf16_kernel(
     const float m = red[0], iz = red[1];
     for (int t = threadIdx.x; t < T; t += 256) {
         const float a = __expf(e[t] - m) * iz;
-        e[t] = a;
         if (alpha_out) alpha_out[(size_t)b * T + t] = a;
+        // training: F.dropout(alpha) (model/model.py:40) as a per-element multiplier 0 or 1 / (1 - p) drawn by the caller
+        e[t] = alpha_scale ? a * alpha_scale[(size_t)b * T + t] : a;
     }
     __syncthreads();
     for (int c = 8 * lane; c < C; c += 256) {
@@ -392,10 +393,34 @@ extern "C" int rcnn_attn_score_context_ld(const float *projH, const float *projh
     return RCNN_OK;
 }
 
+namespace {
+int attn_step_launch(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                     int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out, void *xcat, int64_t ldx,
+                     const float *prev_logits, int64_t prev_ld, int V, int blank, float *prev_probs, int64_t probs_ld, int64_t *y,
+                     const float *alpha_scale, rcnn_stream_t stream);
+}
 extern "C" int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
                                    int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out,
                                    void *xcat, int64_t ldx, const float *prev_logits, int64_t prev_ld, int V, int blank,
                                    float *prev_probs, int64_t probs_ld, int64_t *y, rcnn_stream_t stream) {
+    return attn_step_launch(projH, projh, projh_ld, v, enc, enc_stride_b, enc_stride_t, B, T, H, C, alpha_out, xcat, ldx,
+                            prev_logits, prev_ld, V, blank, prev_probs, probs_ld, y, nullptr, stream);
+}
+extern "C" int rcnn_attn_step_train(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                                    int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out,
+                                    const float *alpha_scale, void *xcat, int64_t ldx, rcnn_stream_t stream) {
+    if (alpha_out == nullptr) {
+        rcnn::set_error("attn_step_train: alpha_out is required (the backward pass reads it)");
+        return RCNN_ERR_ARG;
+    }
+    return attn_step_launch(projH, projh, projh_ld, v, enc, enc_stride_b, enc_stride_t, B, T, H, C, alpha_out, xcat, ldx, nullptr, 0,
+                            0, -1, nullptr, 0, nullptr, alpha_scale, stream);
+}
+namespace {
+int attn_step_launch(const void *projH, const float *projh, int64_t projh_ld, const float *v, const void *enc,
+                     int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H, int C, float *alpha_out, void *xcat, int64_t ldx,
+                     const float *prev_logits, int64_t prev_ld, int V, int blank, float *prev_probs, int64_t probs_ld, int64_t *y,
+                     const float *alpha_scale, rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && T >= 1 && H >= 1 && C >= 1 && ldx >= C && projh_ld >= H, "attn_score_context_bf16: bad shape");
     RCNN_CHECK_ARG(prev_logits == nullptr || (V >= 1 && prev_ld >= V && (prev_probs == nullptr || probs_ld >= V)),
@@ -418,10 +443,11 @@ extern "C" int rcnn_attn_step_bf16(const void *projH, const float *projh, int64_
     RCNN_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16 *)projH, projh, v, (const __nv_bfloat16 *)enc,
                                  (long long)enc_stride_b, (long long)enc_stride_t, T, H, C, alpha_out, (__nv_bfloat16 *)xcat,
                                  (long long)ldx, (long long)projh_ld, prev_logits, (long long)prev_ld, V, blank, prev_probs,
-                                 (long long)probs_ld, (long long *)y));
+                                 (long long)probs_ld, (long long *)y, alpha_scale));
     RCNN_LAUNCH_CHECK("attn_score_context_bf16_kernel");
     return RCNN_OK;
 }
+}  // namespace
 
 extern "C" int rcnn_attn_score_context_bf16(const void *projH, const float *projh, int64_t projh_ld, const float *v,
                                             const void *enc, int64_t enc_stride_b, int64_t enc_stride_t, int B, int T, int H,

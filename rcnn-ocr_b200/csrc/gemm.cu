@@ -205,7 +205,9 @@ template <> __device__ __forceinline__ uint32_t pack2<float>(float a, float) { r
 struct CellEpi {
     const float *embT;           // [V, 4H] gate-interleaved: the one-hot half of the LSTMCell input, one row per token
     const long long *y;          // [M] previous tokens
-    float *c;                    // [M, H] cell state, in place
+    float *c;                    // [M, H] cell state c_t out (in place when c_in == c)
+    const float *c_in;           // [M, H] c_{t-1}
+    float *gates_act;            // optional [M, 4H] gate-interleaved: sigmoid(i), sigmoid(f), tanh(g), sigmoid(o), kept for backward
     __nv_bfloat16 *h_out;        // h_t as bf16, row pitch h_ld (NOT the A operand's buffer: other CTAs still read that)
     float *hid_out;              // optional f32 copy, row pitch hid_ld
     long long h_ld, hid_ld;
@@ -339,7 +341,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const float4 *em4 = reinterpret_cast<const float4 *>(ce.embT + (size_t)tok * 4 * ce.H + col0);
                         const int unit0 = col0 >> 2;
                         float4 *c4 = reinterpret_cast<float4 *>(ce.c + (size_t)row * ce.H + unit0);
-                        const float4 cA = c4[0], cB = c4[1];
+                        const float4 *ci4 = reinterpret_cast<const float4 *>(ce.c_in + (size_t)row * ce.H + unit0);
+                        float4 *ga4 = ce.gates_act ? reinterpret_cast<float4 *>(ce.gates_act + (size_t)row * 4 * ce.H + col0) : nullptr;
+                        const float4 cA = ci4[0], cB = ci4[1];
                         const float cp[8] = {cA.x, cA.y, cA.z, cA.w, cB.x, cB.y, cB.z, cB.w};
                         float cn[8], hn[8];
 #pragma unroll
@@ -351,6 +355,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float og = sigmoid_fast_g(__uint_as_float(r[4 * u + 3]) + bias_s[acc * TN + 4 * u + 3] + em.w);
                             cn[u] = fmaf(fg, cp[u], ig * gg);
                             hn[u] = og * tanh_fast_g(cn[u]);
+                            if (ga4) ga4[u] = make_float4(ig, fg, gg, og);
                         }
                         c4[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
                         c4[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
@@ -1016,14 +1021,27 @@ extern "C" int rcnn_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t
     return launch_gemm<__nv_bfloat16, 128>(ta, tb, D, ldd, bias, M, N, K, s);
 }
 
+extern "C" int rcnn_attn_gates_cell_train(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
+                                          const float *embT_il, const int64_t *y, int B, int H, int K, int V, const float *c_in,
+                                          float *c, void *h_out, int64_t h_ld, float *hid_out, int64_t hid_ld, float *gates_act,
+                                          rcnn_stream_t stream);
 extern "C" int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
                                     const float *embT_il, const int64_t *y, int B, int H, int K, int V, float *c, void *h_out,
                                     int64_t h_ld, float *hid_out, int64_t hid_ld, rcnn_stream_t stream) {
+    return rcnn_attn_gates_cell_train(xcat, ldx, wcat_il, ldw, bias_il, embT_il, y, B, H, K, V, c, c, h_out, h_ld, hid_out, hid_ld,
+                                      nullptr, stream);
+}
+
+extern "C" int rcnn_attn_gates_cell_train(const void *xcat, int64_t ldx, const void *wcat_il, int64_t ldw, const float *bias_il,
+                                          const float *embT_il, const int64_t *y, int B, int H, int K, int V, const float *c_in,
+                                          float *c, void *h_out, int64_t h_ld, float *hid_out, int64_t hid_ld, float *gates_act,
+                                          rcnn_stream_t stream) {
     using namespace rcnn;
     RCNN_CHECK_ARG(B >= 0 && H >= 8 && H % 8 == 0 && K > 0 && V >= 1, "attn_gates_cell: bad shape B=%d H=%d K=%d V=%d (H %% 8 == 0)",
                    B, H, K, V);
     if (B == 0) return RCNN_OK;
-    RCNN_CHECK_ARG(xcat && wcat_il && bias_il && embT_il && y && c && h_out, "attn_gates_cell: null pointer");
+    RCNN_CHECK_ARG(xcat && wcat_il && bias_il && embT_il && y && c && c_in && h_out, "attn_gates_cell: null pointer");
+    RCNN_CHECK_ARG(((uintptr_t)c_in % 16) == 0 && ((uintptr_t)gates_act % 16) == 0, "attn_gates_cell: c_in / gates_act alignment");
     RCNN_CHECK_ARG(h_out != xcat, "attn_gates_cell: h_out must not alias the A operand (other CTAs still read it)");
     RCNN_CHECK_ARG(ldx >= K && ldw >= K && (ldx % 8) == 0 && (ldw % 8) == 0 && ((uintptr_t)xcat % 16) == 0 &&
                        ((uintptr_t)wcat_il % 16) == 0,
@@ -1038,7 +1056,8 @@ extern "C" int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *w
     rc = make_tmap_2d(&tb, wcat_il, 2, (uint64_t)4 * H, (uint64_t)K, (uint64_t)ldw * 2, 32, BK, 1);
     if (rc) return rc;
     CellEpi ce;
-    ce.embT = embT_il; ce.y = (const long long *)y; ce.c = c; ce.h_out = (__nv_bfloat16 *)h_out; ce.hid_out = hid_out;
+    ce.embT = embT_il; ce.y = (const long long *)y; ce.c = c; ce.c_in = c_in; ce.gates_act = gates_act;
+    ce.h_out = (__nv_bfloat16 *)h_out; ce.hid_out = hid_out;
     ce.h_ld = h_ld; ce.hid_ld = hid_ld; ce.V = V; ce.H = H;
     return launch_gemm_cell(ta, tb, bias_il, B, 4 * H, K, ce, (cudaStream_t)stream);
 }

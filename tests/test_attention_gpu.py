@@ -245,6 +245,31 @@ def test_training_path_matches_the_reference_gradients(name):
     assert worst[k] <= 2e-2, worst
 
 
+@pytest.mark.parametrize("B,T,C,H,V,steps", [(6, 10, 64, 64, 30, 6), (130, 33, 72, 136, 50, 4)])
+def test_fused_training_path_equals_the_autograd_path(B, T, C, H, V, steps, monkeypatch):
+    """_TeacherForcedFn (fused forward / backward kernels) against the op-by-op autograd path on the same weights, inputs
+    and the SAME alpha dropout mask: logits and every gradient to 2e-2 of the tensor's max (bf16 operands on both)."""
+    torch.manual_seed(3)
+    m = R.Attention(C, H, V, 1, 2, 0, 3, dropout_p=0.3).cuda().train()
+    x0 = torch.randn(B, T, C, device="cuda")
+    text = torch.randint(0, V, (B, steps + 1), device="cuda")
+    text[:, 0] = 1
+    w = torch.randn(B, steps, V, device="cuda")
+    m._alpha_scale_override = (torch.rand(steps, B, T, device="cuda") >= 0.3).float() / 0.7
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RCNN_ATTN_FUSED_TRAIN", mode)
+        m.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        logits = m(x, text=text, is_train=True, batch_max_length=steps - 1)
+        (logits * w).sum().backward()
+        res[mode] = {"logits": logits.detach(), "batch_H": x.grad.clone(), **{k: p.grad.clone() for k, p in m.named_parameters()}}
+    worst = {k: ((res["1"][k] - res["0"][k]).abs().max() / res["0"][k].abs().max().clamp_min(1e-30)).item() for k in res["0"]}
+    k = max(worst, key=worst.get)
+    print(f"\nfused vs autograd training path: worst max|diff|/max {worst[k]:.2e} ({k})")
+    assert worst[k] <= 2e-2, worst
+
+
 def test_dropout_and_attention_rcnn_train_step(tmp_path):
     """Dropout is live in train() mode (two passes differ, eval passes agree), and RCNN(decoder="attention") trains the
     way training/train.py:499-505 does: teacher forcing, cross entropy with ignore_index=<PAD>, backward through the
