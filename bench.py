@@ -791,7 +791,66 @@ def run_ours(args, rank, world, local_rank):
         attn_res = {"value": round(B * world / (ms_attn * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms_attn, 4),
                     "config": {"B": B, "T_enc": CFG["T"], "hidden": CFG["H"], "classes": CFG["C"] - 1, "steps": 26},
                     "note": "Attention._greedy_decode (model/model.py:89-108) on the device: hoisted i2h GEMM + 26 x "
-                            "(h2h GEMM, score/softmax/context, gate GEMM, LSTMCell, generator GEMM, mask+argmax)"}
+                            "(score/softmax/context with the previous step's mask+argmax, gate GEMM with the LSTMCell step in "
+                            "its epilogue, one GEMM for h2h | generator), launched as a programmatic-dependent chain"}
+        # the decoder's training step (the reference's live loss path, training/train.py:499-505): teacher forcing with the
+        # default alpha dropout 0.1, cross entropy, backward, Adam -- fused forward / backward kernels, one graph replay
+        import torch.nn.functional as F
+        attn_t = step.R.Attention(CFG["H"], CFG["H"], CFG["C"] - 1, 1, 2, 0, 3, dropout_p=0.1).to(device).train()
+        opt_t = torch.optim.Adam(attn_t.parameters(), lr=5.1e-4, fused=True, capturable=True)
+        Vt, St = CFG["C"] - 1, 26
+        gt = torch.Generator().manual_seed(5 + rank)
+        texts = [torch.randint(4, Vt, (B, St + 1), generator=gt).to(device) for _ in range(RING)]
+        for tx in texts:
+            tx[:, 0] = 1
+
+        def attn_train(e, tx):
+            opt_t.zero_grad(set_to_none=True)
+            logits = attn_t(e.detach().requires_grad_(True), tx[:, :St], is_train=True, batch_max_length=St - 1)
+            loss = F.cross_entropy(logits.reshape(-1, Vt), tx[:, 1:].reshape(-1), ignore_index=0)
+            loss.backward()
+            opt_t.step()
+            return loss
+
+        ms_at_eager = max_over_ranks(timed(lambda i: attn_train(encs[i % RING], texts[i % RING]), min(args.steps, 10), 3, sync, barrier))
+        g_at = step.R.GraphedStep(attn_train, [encs[0], texts[0]]) if use_graph else attn_train
+        ms_at = max_over_ranks(timed(lambda i: g_at(encs[i % RING], texts[i % RING]), args.steps, args.warmup, sync, barrier))
+        attn_res["train"] = {"value": round(B * world / (ms_at * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_at, 4),
+                             "ms_per_step_eager_launches": round(ms_at_eager, 4),
+                             "note": "teacher-forced forward (26 steps, alpha dropout 0.1) + cross entropy + backward + Adam on "
+                                     "the fused kernels (attention._TeacherForcedFn), one CUDA-graph replay per step"}
+        if rank == 0 and world == 1 and not args.no_extras:
+            from oracle.ref_port import RefAttention
+            ref_t = RefAttention(CFG["H"], CFG["H"], Vt).to(device).train()
+            ref_t.load_state_dict(attn_t.state_dict(), strict=True)
+            opt_r = torch.optim.Adam(ref_t.parameters(), lr=5.1e-4, fused=True)
+
+            def vendor_train(e, tx):                      # model/model.py:110-148 op by op on torch's CUDA kernels, bf16 autocast
+                opt_r.zero_grad(set_to_none=True)
+                e = e.detach().requires_grad_(True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    cell = ref_t.attention_cell
+                    h = e.new_zeros(B, CFG["H"]); c = e.new_zeros(B, CFG["H"])
+                    hs = []
+                    for t in range(St):
+                        onehot = F.one_hot(tx[:, t], Vt).float()
+                        ee = cell.score(torch.tanh(cell.i2h(e) + cell.h2h(h).unsqueeze(1)))
+                        alpha = F.dropout(F.softmax(ee, dim=1), p=0.1, training=True)
+                        context = torch.bmm(alpha.transpose(1, 2), e).squeeze(1)
+                        h, c = cell.rnn(torch.cat([context, onehot], 1), (h, c))
+                        hs.append(h)
+                    logits = ref_t.generator(torch.stack(hs, 1)).float()
+                loss = F.cross_entropy(logits.reshape(-1, Vt), tx[:, 1:].reshape(-1), ignore_index=0)
+                loss.backward()
+                opt_r.step()
+                return loss
+
+            ms_vt = timed(lambda i: vendor_train(encs[i % RING], texts[i % RING]), 5, 3, sync, lambda: None)
+            attn_res["train"]["vendor"] = {"value": round(B / (ms_vt * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_vt, 4),
+                                           "note": "the reference's op sequence (nn.Linear / nn.LSTMCell / bmm, proj_H recomputed "
+                                                   "every step) on torch's CUDA kernels under bf16 autocast, eager, same GPU"}
+            attn_res["train"]["vs_vendor"] = round(ms_vt / ms_at, 2)
+            del ref_t, opt_r
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle.ref_port import RefAttention
             torch.set_num_threads(os.cpu_count() or 1)

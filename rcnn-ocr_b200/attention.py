@@ -357,8 +357,7 @@ class Attention(nn.Module):
                                              cell.rnn.bias_ih, cell.rnn.bias_hh)
             logits = _LinearFn.apply(out_hid, self.generator.weight, self.generator.bias, True)
             if self.blank_id is not None:
-                mask = torch.zeros(self.num_classes, dtype=torch.bool, device=dev)
-                mask[int(self.blank_id)] = True
+                mask = torch.arange(self.num_classes, device=dev) == int(self.blank_id)     # (device ops only: capturable)
                 logits = logits.masked_fill(mask, -1e4)
             return logits
         enc = batch_H.float()
@@ -394,8 +393,7 @@ class Attention(nn.Module):
         out_hid = torch.stack(hids, 1)                                                  # [B,steps,H]
         logits = _LinearFn.apply(out_hid, self.generator.weight, self.generator.bias, True)
         if self.blank_id is not None:
-            mask = torch.zeros(self.num_classes, dtype=torch.bool, device=dev)
-            mask[int(self.blank_id)] = True
+            mask = torch.arange(self.num_classes, device=dev) == int(self.blank_id)
             logits = logits.masked_fill(mask, -1e4)
         return logits
 
