@@ -126,19 +126,23 @@ class _TeacherForcedFn(torch.autograd.Function):
             dc = torch.zeros((B, H), dtype=torch.float32, device=dev)
             dh = torch.empty((B, H), dtype=torch.float32, device=dev)
             s = _lib.stream_ptr()
-            for t in range(S - 1, -1, -1):
-                last = t == S - 1
-                _lib.check(L.rcnn_attn_cell_bwd(gates_all[t].data_ptr(), c_all[t].data_ptr(), c_all[t + 1].data_ptr(),
-                                                d_out[:, t].data_ptr(), d_out.stride(0), None if last else dh.data_ptr(), H,
-                                                dc.data_ptr(), B, H, dg_all[t].data_ptr(), 5 * H, s), "rcnn_attn_cell_bwd")
-                ops.gemm_bf16(dg_all[t][:, :4 * H], b1, None, torch.float32, out=dctx_all[t])
-                _lib.check(L.rcnn_attn_step_bwd(dctx_all[t].data_ptr(), C, alpha_all[t].data_ptr(),
-                                                scale[t].data_ptr() if scale is not None else None, encb.data_ptr(), encb.stride(0),
-                                                encb.stride(1), projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), B, T, H,
-                                                C, de_all[t].data_ptr(), dg_all[t][:, 4 * H:].data_ptr(), 5 * H, dv_acc.data_ptr(),
-                                                s), "rcnn_attn_step_bwd")
-                if t > 0:
-                    ops.gemm_bf16(dg_all[t], b2, None, torch.float32, out=dh)              # dh_{t-1} through the gates and h2h
+            L.rcnn_chain_launches(1)
+            try:
+                for t in range(S - 1, -1, -1):
+                    last = t == S - 1
+                    _lib.check(L.rcnn_attn_cell_bwd(gates_all[t].data_ptr(), c_all[t].data_ptr(), c_all[t + 1].data_ptr(),
+                                                    d_out[:, t].data_ptr(), d_out.stride(0), None if last else dh.data_ptr(), H,
+                                                    dc.data_ptr(), B, H, dg_all[t].data_ptr(), 5 * H, s), "rcnn_attn_cell_bwd")
+                    ops.gemm_bf16(dg_all[t][:, :4 * H], b1, None, torch.float32, out=dctx_all[t])
+                    _lib.check(L.rcnn_attn_step_bwd(dctx_all[t].data_ptr(), C, alpha_all[t].data_ptr(),
+                                                    scale[t].data_ptr() if scale is not None else None, encb.data_ptr(), encb.stride(0),
+                                                    encb.stride(1), projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), B, T, H,
+                                                    C, de_all[t].data_ptr(), dg_all[t][:, 4 * H:].data_ptr(), 5 * H, dv_acc.data_ptr(),
+                                                    s), "rcnn_attn_step_bwd")
+                    if t > 0:
+                        ops.gemm_bf16(dg_all[t], b2, None, torch.float32, out=dh)              # dh_{t-1} through the gates and h2h
+            finally:
+                L.rcnn_chain_launches(0)
             dprojH = torch.empty((B * T, H), dtype=torch.bfloat16, device=dev)
             _lib.check(L.rcnn_attn_dprojH(de_all.data_ptr(), projh_all.data_ptr(), projH.data_ptr(), v.data_ptr(), S, B, T, H,
                                           dprojH.data_ptr(), s), "rcnn_attn_dprojH")
@@ -148,14 +152,19 @@ class _TeacherForcedFn(torch.autograd.Function):
             # parameter gradients
             d_i2h = ops.gemm_bf16_atb(dprojH, encb.view(B * T, C))                         # [H, C]
             d_h2h_w = ops.gemm_bf16_atb(dproj, rows_x[:, C:])                              # [H, H]
-            d_h2h_b = dproj.float().sum(0)
             d_score = dv_acc.sum(0).view(1, H)
             dwcat = ops.gemm_bf16_atb(dgates, rows_x).view(H, 4, K).permute(1, 0, 2).reshape(4 * H, K)   # back to torch's gate order
-            dgf = dgates.float()
-            d_emb = torch.zeros((V, 4 * H), dtype=torch.float32, device=dev).index_add_(0, tokens.view(-1).clamp(0, V - 1), dgf)
-            d_w_ih = torch.cat([dwcat[:, :C], d_emb.view(V, H, 4).permute(2, 1, 0).reshape(4 * H, V)], 1)
+            # the one-hot half of W_ih and the three bias gradients in ONE product: [onehot(y) | 1]^T @ [dgates | dproj_h] --
+            # row v < V = the sum of the rows whose input token was v, row V = the column sums
+            Vp = (V + 1 + 7) // 8 * 8
+            oh = torch.zeros((S * B, Vp), dtype=torch.bfloat16, device=dev)
+            oh.scatter_(1, tokens.view(-1, 1).clamp(0, V - 1), 1.0)
+            oh[:, V] = 1.0
+            sums = ops.gemm_bf16_atb(oh, rows_g)                                            # [Vp, 5H]
+            d_emb, d_b_il, d_h2h_b = sums[:V, :4 * H], sums[V, :4 * H], sums[V, 4 * H:].contiguous()
+            d_w_ih = torch.cat([dwcat[:, :C], d_emb.reshape(V, H, 4).permute(2, 1, 0).reshape(4 * H, V)], 1)
             d_w_hh = dwcat[:, C:].contiguous()
-            d_b = dgf.sum(0).view(H, 4).t().reshape(-1)
+            d_b = d_b_il.reshape(H, 4).t().reshape(-1)
             # encoder gradient: through proj_H and through the context
             d_enc = ops.gemm_bf16(dprojH, i2h16.t().contiguous(), None, torch.float32).view(B, T, C)
             alpha_d = alpha_all * scale if scale is not None else alpha_all

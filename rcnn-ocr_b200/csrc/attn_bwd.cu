@@ -36,6 +36,8 @@ __global__ void attn_cell_bwd_kernel(const float *__restrict__ gates_act, const 
                                      const float *__restrict__ c_t, const float *__restrict__ dh_a, long long dh_a_ld,
                                      const float *__restrict__ dh_b, long long dh_b_ld, float *__restrict__ dc, int B, int H,
                                      __nv_bfloat16 *__restrict__ dg, long long ldg) {
+    griddep_launch();
+    griddep_wait();                                           // (chained launches: dh / dc come from the predecessor)
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)B * H) return;
     const int b = (int)(idx / H), u = (int)(idx % H);
@@ -68,7 +70,9 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(
     float *ph = sm, *dcs = sm + H, *de = dcs + C, *part = de + ((T + 3) & ~3);      // [H], [C], [T], [8][2][H]
     __shared__ float red;
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = threadIdx.x; j < H; j += 256) ph[j] = projh[(size_t)b * projh_ld + j];
+    griddep_launch();
+    for (int j = threadIdx.x; j < H; j += 256) ph[j] = projh[(size_t)b * projh_ld + j];     // (kept from the forward pass)
+    griddep_wait();                                           // chained launches: dctx is the predecessor's output
     for (int c = threadIdx.x; c < C; c += 256) dcs[c] = dctx[(size_t)b * dctx_ld + c];
     __syncthreads();
     // pass A: d alpha_dropped[t] = <dctx, enc[t]>; through the dropout multiplier
@@ -179,6 +183,50 @@ __global__ void __launch_bounds__(128) attn_dprojH_kernel(const float *__restric
     }
 }
 
+// K6f, the usual case: a CTA handles eight frames of one sequence and keeps proj_h of all S steps in shared memory
+// ([S][H] f32: 53 KB at S = 26, H = 512), so the steps' rows are read from L2 once per eight frames instead of once per frame
+constexpr int kDpFrames = 8;
+__global__ void __launch_bounds__(256) attn_dprojH_smem_kernel(const float *__restrict__ de_all, const float *__restrict__ projh_all,
+                                                               const __nv_bfloat16 *__restrict__ projH, const float *__restrict__ v,
+                                                               int S, int B, int T, int H, __nv_bfloat16 *__restrict__ dprojH) {
+    extern __shared__ __align__(16) float dsm[];
+    float *phs = dsm, *des = dsm + (size_t)S * H;             // [S][H], [S][kDpFrames]
+    const int t0 = blockIdx.x * kDpFrames, b = blockIdx.y;
+    for (int i = 4 * threadIdx.x; i < S * H; i += 4 * 256) {
+        const int sidx = i / H, j = i - sidx * H;
+        *reinterpret_cast<float4 *>(phs + i) = *reinterpret_cast<const float4 *>(projh_all + ((size_t)sidx * B + b) * H + j);
+    }
+    for (int i = threadIdx.x; i < S * kDpFrames; i += 256) {
+        const int sidx = i / kDpFrames, f = i - sidx * kDpFrames;
+        des[i] = t0 + f < T ? de_all[((size_t)sidx * B + b) * T + t0 + f] : 0.f;
+    }
+    __syncthreads();
+    for (int j = 2 * threadIdx.x; j < H; j += 512) {
+        float x0[kDpFrames], x1[kDpFrames], a0[kDpFrames], a1[kDpFrames];
+#pragma unroll
+        for (int f = 0; f < kDpFrames; ++f) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(projH + ((size_t)b * T + min(t0 + f, T - 1)) * H + j);
+            x0[f] = __uint_as_float(w << 16); x1[f] = __uint_as_float(w & 0xffff0000u);
+            a0[f] = 0.f; a1[f] = 0.f;
+        }
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const float2 p = *reinterpret_cast<const float2 *>(phs + (size_t)sidx * H + j);
+#pragma unroll
+            for (int f = 0; f < kDpFrames; ++f) {
+                const float d = des[sidx * kDpFrames + f];
+                const float u0 = tanh_fast_b(x0[f] + p.x), u1 = tanh_fast_b(x1[f] + p.y);
+                a0[f] = fmaf(d, fmaf(-u0, u0, 1.f), a0[f]);
+                a1[f] = fmaf(d, fmaf(-u1, u1, 1.f), a1[f]);
+            }
+        }
+        const float v0 = v[j], v1 = v[j + 1];
+#pragma unroll
+        for (int f = 0; f < kDpFrames; ++f)
+            if (t0 + f < T)
+                *reinterpret_cast<__nv_bfloat162 *>(dprojH + ((size_t)b * T + t0 + f) * H + j) = __floats2bfloat162_rn(v0 * a0[f], v1 * a1[f]);
+    }
+}
+
 }  // namespace
 }  // namespace rcnn
 
@@ -192,8 +240,11 @@ extern "C" int rcnn_attn_cell_bwd(const float *gates_act, const float *c_prev, c
     RCNN_CHECK_ARG(gates_act && c_t && dh_a && dc && dg, "attn_cell_bwd: null pointer");
     RCNN_CHECK_ARG(((uintptr_t)gates_act & 15) == 0 && ((uintptr_t)dg & 7) == 0 && (ldg & 3) == 0, "attn_cell_bwd: alignment");
     const long long total = (long long)B * H;
-    attn_cell_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        gates_act, c_prev, c_t, dh_a, dh_a_ld, dh_b, dh_b_ld, dc, B, H, (__nv_bfloat16 *)dg, ldg);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    chain_config(cfg, attr, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, attn_cell_bwd_kernel, gates_act, c_prev, c_t, dh_a, (long long)dh_a_ld, dh_b,
+                                 (long long)dh_b_ld, dc, B, H, (__nv_bfloat16 *)dg, (long long)ldg));
     RCNN_LAUNCH_CHECK("attn_cell_bwd_kernel");
     return RCNN_OK;
 }
@@ -213,10 +264,13 @@ extern "C" int rcnn_attn_step_bwd(const float *dctx, int64_t dctx_ld, const floa
     RCNN_CHECK_ARG(smem <= 200 * 1024, "attn_step_bwd: T=%d, H=%d, C=%d exceed shared memory", T, H, C);
     if (smem > 48 * 1024)
         RCNN_CUDA(cudaFuncSetAttribute(attn_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_step_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(dctx, dctx_ld, alpha, alpha_scale, (const __nv_bfloat16 *)enc,
-                                                               enc_stride_b, enc_stride_t, (const __nv_bfloat16 *)projH, projh,
-                                                               projh_ld, v, T, H, C, de_out, (__nv_bfloat16 *)dprojh, dprojh_ld,
-                                                               dv_acc);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    chain_config(cfg, attr, (unsigned)B, 256, smem, (cudaStream_t)stream);
+    RCNN_CUDA(cudaLaunchKernelEx(&cfg, attn_step_bwd_kernel, dctx, (long long)dctx_ld, alpha, alpha_scale,
+                                 (const __nv_bfloat16 *)enc, (long long)enc_stride_b, (long long)enc_stride_t,
+                                 (const __nv_bfloat16 *)projH, projh, (long long)projh_ld, v, T, H, C, de_out,
+                                 (__nv_bfloat16 *)dprojh, (long long)dprojh_ld, dv_acc));
     RCNN_LAUNCH_CHECK("attn_step_bwd_kernel");
     return RCNN_OK;
 }
@@ -228,6 +282,15 @@ extern "C" int rcnn_attn_dprojH(const float *de_all, const float *projh_all, con
     if (B == 0) return RCNN_OK;
     RCNN_CHECK_ARG(de_all && projh_all && projH && v && dprojH, "attn_dprojH: null pointer");
     RCNN_CHECK_ARG(S * sizeof(float) <= 48 * 1024, "attn_dprojH: too many steps");
+    const size_t smem_all = sizeof(float) * ((size_t)S * H + (size_t)S * kDpFrames);
+    if (smem_all <= 100 * 1024 && H % 4 == 0 && ((uintptr_t)projh_all & 15) == 0) {
+        if (smem_all > 48 * 1024)
+            RCNN_CUDA(cudaFuncSetAttribute(attn_dprojH_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all));
+        attn_dprojH_smem_kernel<<<dim3((unsigned)((T + kDpFrames - 1) / kDpFrames), (unsigned)B), 256, smem_all, (cudaStream_t)stream>>>(
+            de_all, projh_all, (const __nv_bfloat16 *)projH, v, S, B, T, H, (__nv_bfloat16 *)dprojH);
+        RCNN_LAUNCH_CHECK("attn_dprojH_smem_kernel");
+        return RCNN_OK;
+    }
     attn_dprojH_kernel<<<dim3((unsigned)T, (unsigned)B), 128, S * sizeof(float), (cudaStream_t)stream>>>(
         de_all, projh_all, (const __nv_bfloat16 *)projH, v, S, B, T, H, (__nv_bfloat16 *)dprojH);
     RCNN_LAUNCH_CHECK("attn_dprojH_kernel");

@@ -27,6 +27,14 @@ def step_ours():
     return loss
 
 
+def step_ours_on(e, tx):
+    ours.zero_grad(set_to_none=True)
+    logits = ours(e.detach().requires_grad_(True), tx[:, :steps], is_train=True, batch_max_length=steps - 1)
+    loss = F.cross_entropy(logits.reshape(-1, V), tgt.reshape(-1))
+    loss.backward()
+    return loss
+
+
 def step_ref():
     cell = ref.attention_cell
     h = enc.new_zeros(B, H); c = enc.new_zeros(B, H)
@@ -57,9 +65,14 @@ def timed(fn, n=10):
     return a.elapsed_time(b) / n, (time.perf_counter() - t0) / n * 1e3
 
 
-for name, fn in (("ours (autograd on K1)", step_ours), ("torch fp32 eager", step_ref)):
+for name, fn in (("ours, eager launches", step_ours),) + ((("torch fp32 eager", step_ref),) if len(sys.argv) < 2 else ()):
     dev, wall = timed(fn)
     print(f"{name:24s} {dev:8.2f} ms per step (wall {wall:.2f})  {B / dev * 1e3:9.0f} lines/s   loss {fn().item():.4f}")
+g = R.GraphedStep(lambda e, tx: step_ours_on(e, tx), [enc.detach(), text])
+dev, wall = timed(lambda: g(enc.detach(), text), 30)
+print(f"{'ours, one graph replay':24s} {dev:8.3f} ms per step (wall {wall:.2f})  {B / dev * 1e3:9.0f} lines/s")
+if len(sys.argv) > 1 and sys.argv[1] == "ours":
+    sys.exit(0)
 for dt in (torch.bfloat16,):
     def ac():
         with torch.autocast("cuda", dtype=dt):
