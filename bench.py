@@ -819,6 +819,8 @@ def run_ours(args, rank, world, local_rank):
                              "ms_per_step_eager_launches": round(ms_at_eager, 4),
                              "note": "teacher-forced forward (26 steps, alpha dropout 0.1) + cross entropy + backward + Adam on "
                                      "the fused kernels (attention._TeacherForcedFn), one CUDA-graph replay per step"}
+        if world > 1:
+            attn_res["train"]["note"] += "; at N > 1: independent per-GPU replicas of the decoder (no gradient all-reduce in this sub-measurement)"
         if rank == 0 and world == 1 and not args.no_extras:
             from oracle.ref_port import RefAttention
             ref_t = RefAttention(CFG["H"], CFG["H"], Vt).to(device).train()
