@@ -423,7 +423,33 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
         torch.cuda.synchronize()
         host_prep_ms = (time.perf_counter() - t0) / 3 * 1e3
     T = int(model._features(dev[0]).shape[1])
+    # the encoder's TRAIN step at this shape (T = 16, H = 256, 32 lines; features given): T does not fill the 64-step K chunks
+    # of rcnn_lstm_weight_grads, so the weight gradients take the h_prev-copy + grouped-product + unpack route (ops.py)
+    from rcnn_ocr_b200 import ops as _ops
+    enc_a = R.make_enc_rnn(512, 256).to(device)
+    head_a = R.CTCHead(256, 195).to(device)
+    opt_a = torch.optim.Adam(list(enc_a.parameters()) + list(head_a.parameters()), lr=5.1e-4, fused=True, capturable=True)
+    ga = torch.Generator().manual_seed(77)
+    fa = [torch.randn(32, T, 512, generator=ga).to(device) for _ in range(4)]
+    tga = torch.randint(1, 195, (32, 8), generator=ga).to(device)
+    ila, tla = torch.full((32,), T, dtype=torch.int64, device=device), torch.randint(1, 7, (32,), generator=ga).to(device)
+
+    def train_a(f):
+        opt_a.zero_grad(set_to_none=True)
+        loss = R.ctc_loss_from_logits(head_a(enc_a(f.detach().requires_grad_(True))).permute(1, 0, 2), tga, ila, tla, 0, "mean", True,
+                                      max_target_length=8)
+        loss.backward()
+        opt_a.step()
+        return loss
+
+    g_a = R.GraphedStep(train_a, [fa[0]]) if args.graph else train_a
+    ms_ta = timed_fn(lambda i: g_a(fa[i % 4]))
+    train_shape = {"value": round(32 / (ms_ta * 1e-3), 1), "unit": "lines/s", "ms_per_step": round(ms_ta, 4),
+                   "weight_grads_fast_path": bool(_ops.weight_grads_supported(512, 256, T)),
+                   "note": "encoder (2 x BiLSTM 256) + CTC head + fused CTC + backward + Adam on [32, %d, 512] features, graph replay" % T}
+    del enc_a, head_a, opt_a, g_a
     out = {"value": round(32 / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms, 4), "launch_mode": mode,
+           "encoder_train_step": train_shape,
            "e2e": {"value": round(32 / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 4),
                    "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 32 * (T + 1) * 4},
            "e2e_from_pixels": {"value": round(32 / (ms_pix * 1e-3), 1), "ms_per_batch": round(ms_pix, 4),
