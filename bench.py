@@ -103,7 +103,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def start(self):
         if self.nv is not None:
