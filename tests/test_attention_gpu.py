@@ -193,6 +193,32 @@ def test_gate_product_with_cell_epilogue_equals_the_two_launches(B, H, C, V):
                                   y.data_ptr(), B, H, K, V, c_b.data_ptr(), xcat.data_ptr(), xcat.stride(0), None, 0, s) != 0
 
 
+def test_chained_launches_reproduce_the_serialised_decode_bit_for_bit(monkeypatch):
+    """The greedy step loop is launched as a programmatic-dependent chain (each kernel may start while its predecessor drains
+    and waits on the device before touching its output).  The kernels hold no atomics, so the chained run must equal the
+    fully serialised one bit for bit, every time: 30 repeats at a shape with more CTAs than SMs, and through a graph."""
+    torch.manual_seed(11)
+    m = R.Attention(512, 512, 194, 1, 2, 0, 3).cuda().eval()
+    x = torch.randn(300, 40, 512, device="cuda")
+    monkeypatch.setenv("RCNN_ATTN_CHAIN", "0")
+    with torch.no_grad():
+        want = m(x, is_train=False, batch_max_length=12).clone()
+        monkeypatch.setenv("RCNN_ATTN_CHAIN", "1")
+        for _ in range(30):
+            assert torch.equal(m(x, is_train=False, batch_max_length=12), want)
+        g = R.GraphedStep(lambda e: m(e, is_train=False, batch_max_length=12), [x])
+        for _ in range(10):
+            assert torch.equal(g(x), want)
+        text = want.argmax(2)
+        text = torch.cat([torch.ones_like(text[:, :1]), text[:, :-1]], 1)
+        tf_want = None
+        for mode in ("0", "1", "1"):
+            monkeypatch.setenv("RCNN_ATTN_CHAIN", mode)
+            got = m(x, text=text, is_train=True, batch_max_length=12)
+            tf_want = got.clone() if tf_want is None else tf_want
+            assert torch.equal(got, tf_want)
+
+
 def test_state_dict_contract_and_errors():
     m = R.Attention(64, 64, 20, 1, 2, 0, 3)
     want = {"attention_cell.i2h.weight": (64, 64), "attention_cell.h2h.weight": (64, 64), "attention_cell.h2h.bias": (64,),
