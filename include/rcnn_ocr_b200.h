@@ -296,6 +296,18 @@ int rcnn_attn_gates_cell(const void *xcat, int64_t ldx, const void *wcat_il, int
                          const float *embT_il, const int64_t *y, int B, int H, int K, int V, float *c, void *h_out,
                          int64_t h_ld, float *hid_out, int64_t hid_ld, rcnn_stream_t stream);
 
+/* Attention._greedy_decode (model/model.py:89-108) as one host call: `steps` times (rcnn_attn_step_bf16, rcnn_attn_gates_cell,
+ * rcnn_gemm_bf16 over comb_w = [W_h2h ; W_generator] padded to comb_rows >= H + V rows) and a final rcnn_attn_argmax_ld.
+ * The caller provides: projH [B,T,H] bf16 (i2h(batch_H), hoisted), enc [B,T,C] bf16, the gate-interleaved weights of
+ * rcnn_attn_gates_cell, y [B] = <SOS>, xcat0 / xcat1 [B, C+H] bf16 and c [B,H] f32 zeroed, hg [B, comb_rows] f32 with columns [0, H)
+ * = the h2h bias (h_0 = 0).  Writes probs [B, steps, V] (blank-masked logits) and leaves the last tokens in y.  chain != 0 launches
+ * the loop as a programmatic-dependent chain (rcnn_chain_launches). */
+int rcnn_attn_greedy_decode(const void *projH, const float *v, const void *enc, int64_t enc_stride_b, int64_t enc_stride_t,
+                            const void *wcat_il, const float *bcat_il, const float *embT_il, const void *comb_w,
+                            const float *comb_b, int comb_rows, int B, int T, int H, int C, int V, int steps, int blank,
+                            int64_t *y, void *xcat0, void *xcat1, float *c, float *hg, float *probs, int chain,
+                            rcnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Attention decoder, teacher-forced TRAINING pass (model/model.py:110-148 under autograd; the reference's live loss path,
  * training/train.py:499-505).  Forward step t: rcnn_gemm_bf16 (h2h) -> rcnn_attn_step_train -> rcnn_attn_gates_cell_train;

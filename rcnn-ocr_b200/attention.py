@@ -311,6 +311,16 @@ class Attention(nn.Module):
                 Np = w["comb"].shape[0]
                 hg = torch.empty((B, Np), dtype=torch.float32, device=dev)
                 hg[:, :H] = w["h2h_b"]                                             # h2h(h_0 = 0) = its bias
+                if fused and os.environ.get("RCNN_ATTN_PYLOOP", "0") != "1":
+                    # the whole loop from C++ (one trip through the binding instead of 3 * steps + 1: an eager decode is then
+                    # bound by the device)
+                    _lib.check(L.rcnn_attn_greedy_decode(projH.data_ptr(), w["v"].data_ptr(), encb.data_ptr(), encb.stride(0),
+                                                         encb.stride(1), w["wcat_il"].data_ptr(), w["bcat_il"].data_ptr(),
+                                                         w["embT_il"].data_ptr(), w["comb"].data_ptr(), w["comb_b"].data_ptr(), Np,
+                                                         B, T, H, C, V, steps, blank, y.data_ptr(), xc[0].data_ptr(),
+                                                         xc[1].data_ptr(), c.data_ptr(), hg.data_ptr(), probs.data_ptr(),
+                                                         int(chain), s), "rcnn_attn_greedy_decode")
+                    return probs
                 lg = hg[:, H:].data_ptr()
                 L.rcnn_chain_launches(int(chain))
                 try:

@@ -209,6 +209,9 @@ def test_chained_launches_reproduce_the_serialised_decode_bit_for_bit(monkeypatc
         g = R.GraphedStep(lambda e: m(e, is_train=False, batch_max_length=12), [x])
         for _ in range(10):
             assert torch.equal(g(x), want)
+        monkeypatch.setenv("RCNN_ATTN_PYLOOP", "1")            # the same launches issued from Python instead of rcnn_attn_greedy_decode
+        assert torch.equal(m(x, is_train=False, batch_max_length=12), want)
+        monkeypatch.delenv("RCNN_ATTN_PYLOOP")
         text = want.argmax(2)
         text = torch.cat([torch.ones_like(text[:, :1]), text[:, :-1]], 1)
         tf_want = None
