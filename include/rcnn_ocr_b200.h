@@ -337,6 +337,21 @@ int rcnn_attn_step_bwd(const float *dctx, int64_t dctx_ld, const float *alpha, c
                        int64_t enc_stride_b, int64_t enc_stride_t, const void *projH, const float *projh, int64_t projh_ld,
                        const float *v, int B, int T, int H, int C, float *de_out, void *dprojh, int64_t dprojh_ld, float *dv_acc,
                        rcnn_stream_t stream);
+/* The two step loops of the training pass as single host calls (the same launches in the same order).  Shapes: tokens [S,B] int64,
+ * alpha_scale [S,B,T] or NULL, xcat_all [S+1, B, C+H] bf16 (zeroed; row block t = [context_t | h_{t-1}]), c_all [S+1, B, H] f32
+ * (zeroed; block t = c_{t-1}), gates_all [S,B,4H], alpha_all [S,B,T], projh_all [S,B,H], out_hid [B,S,H]; backward: d_out [B,S,H],
+ * b1 [C,4H] = (W_ih[:, :C], gate-interleaved)^T, b2 [H,5H] = [W_hh (gate-interleaved)^T | W_h2h^T], dg_all [S,B,5H] bf16 (zeroed),
+ * dctx_all [S,B,C], de_all [S,B,T], dv_acc [B,H] and dc [B,H] zeroed, dh [B,H] scratch. */
+int rcnn_attn_train_forward(const void *projH, const float *v, const void *enc, int64_t enc_stride_b, int64_t enc_stride_t,
+                            const void *h2h_w, const float *h2h_b, const void *wcat_il, const float *bcat_il, const float *embT_il,
+                            const int64_t *tokens, const float *alpha_scale, int B, int T, int H, int C, int V, int S,
+                            void *xcat_all, float *c_all, float *gates_all, float *alpha_all, float *projh_all, float *out_hid,
+                            rcnn_stream_t stream);
+int rcnn_attn_train_backward(const float *d_out, const float *gates_all, const float *c_all, const void *b1, const void *b2,
+                             const float *alpha_all, const float *alpha_scale, const void *enc, int64_t enc_stride_b,
+                             int64_t enc_stride_t, const void *projH, const float *projh_all, const float *v, int B, int T, int H,
+                             int C, int S, void *dg_all, float *dctx_all, float *de_all, float *dv_acc, float *dc, float *dh,
+                             rcnn_stream_t stream);
 int rcnn_attn_dprojH(const float *de_all, const float *projh_all, const void *projH, const float *v, int S, int B, int T, int H,
                      void *dprojH, rcnn_stream_t stream);
 

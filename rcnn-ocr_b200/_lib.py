@@ -76,6 +76,10 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_attn_dprojH.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp]
     L.rcnn_attn_greedy_decode.restype = i
     L.rcnn_attn_greedy_decode.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i, vp]
+    L.rcnn_attn_train_forward.restype = i
+    L.rcnn_attn_train_forward.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.rcnn_attn_train_backward.restype = i
+    L.rcnn_attn_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.rcnn_attn_argmax_ld.restype = i
     L.rcnn_attn_argmax_ld.argtypes = [vp, i64, i, i, i, vp, i64, vp, vp]
     L.rcnn_lstm_forward_fused.restype = i

@@ -84,23 +84,14 @@ class _TeacherForcedFn(torch.autograd.Function):
             if alpha_scale is not None:
                 alpha_scale = alpha_scale.to(device=dev, dtype=torch.float32).contiguous()
             tokens = tokens.to(device=dev, dtype=torch.int64).contiguous()
-            s = _lib.stream_ptr()
-            L.rcnn_chain_launches(1)
-            try:
-                for t in range(S):
-                    cur, nxt = xcat_all[t], xcat_all[t + 1]
-                    ops.gemm_bf16(cur[:, C:], h2h16, h2h_bias, torch.float32, out=projh_all[t])
-                    _lib.check(L.rcnn_attn_step_train(projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), encb.data_ptr(),
-                                                      encb.stride(0), encb.stride(1), B, T, H, C, alpha_all[t].data_ptr(),
-                                                      alpha_scale[t].data_ptr() if alpha_scale is not None else None,
-                                                      cur.data_ptr(), K, s), "rcnn_attn_step_train")
-                    _lib.check(L.rcnn_attn_gates_cell_train(cur.data_ptr(), K, wcat_il.data_ptr(), K, bcat_il.data_ptr(),
-                                                            embT_il.data_ptr(), tokens[t].data_ptr(), B, H, K, V,
-                                                            c_all[t].data_ptr(), c_all[t + 1].data_ptr(), nxt[:, C:].data_ptr(), K,
-                                                            out_hid[:, t].data_ptr(), out_hid.stride(0), gates_all[t].data_ptr(),
-                                                            s), "rcnn_attn_gates_cell_train")
-            finally:
-                L.rcnn_chain_launches(0)
+            # the step loop (h2h GEMM -> step kernel -> gate GEMM + cell, S times) as one host call
+            _lib.check(L.rcnn_attn_train_forward(projH.data_ptr(), v.data_ptr(), encb.data_ptr(), encb.stride(0), encb.stride(1),
+                                                 h2h16.data_ptr(), h2h_bias.data_ptr(), wcat_il.data_ptr(), bcat_il.data_ptr(),
+                                                 embT_il.data_ptr(), tokens.data_ptr(),
+                                                 alpha_scale.data_ptr() if alpha_scale is not None else None, B, T, H, C, V, S,
+                                                 xcat_all.data_ptr(), c_all.data_ptr(), gates_all.data_ptr(), alpha_all.data_ptr(),
+                                                 projh_all.data_ptr(), out_hid.data_ptr(), _lib.stream_ptr()),
+                       "rcnn_attn_train_forward")
         ctx.save_for_backward(encb, projH, v, wcat_il, h2h16, i2h16, xcat_all, c_all, gates_all, alpha_all, projh_all, tokens,
                               alpha_scale if alpha_scale is not None else torch.empty(0, device=dev))
         ctx.dims = (B, T, C, H, V, S)
@@ -126,23 +117,13 @@ class _TeacherForcedFn(torch.autograd.Function):
             dc = torch.zeros((B, H), dtype=torch.float32, device=dev)
             dh = torch.empty((B, H), dtype=torch.float32, device=dev)
             s = _lib.stream_ptr()
-            L.rcnn_chain_launches(1)
-            try:
-                for t in range(S - 1, -1, -1):
-                    last = t == S - 1
-                    _lib.check(L.rcnn_attn_cell_bwd(gates_all[t].data_ptr(), c_all[t].data_ptr(), c_all[t + 1].data_ptr(),
-                                                    d_out[:, t].data_ptr(), d_out.stride(0), None if last else dh.data_ptr(), H,
-                                                    dc.data_ptr(), B, H, dg_all[t].data_ptr(), 5 * H, s), "rcnn_attn_cell_bwd")
-                    ops.gemm_bf16(dg_all[t][:, :4 * H], b1, None, torch.float32, out=dctx_all[t])
-                    _lib.check(L.rcnn_attn_step_bwd(dctx_all[t].data_ptr(), C, alpha_all[t].data_ptr(),
-                                                    scale[t].data_ptr() if scale is not None else None, encb.data_ptr(), encb.stride(0),
-                                                    encb.stride(1), projH.data_ptr(), projh_all[t].data_ptr(), H, v.data_ptr(), B, T, H,
-                                                    C, de_all[t].data_ptr(), dg_all[t][:, 4 * H:].data_ptr(), 5 * H, dv_acc.data_ptr(),
-                                                    s), "rcnn_attn_step_bwd")
-                    if t > 0:
-                        ops.gemm_bf16(dg_all[t], b2, None, torch.float32, out=dh)              # dh_{t-1} through the gates and h2h
-            finally:
-                L.rcnn_chain_launches(0)
+            # the step loop (cell backward -> dcontext GEMM -> attention-step backward -> dh GEMM, S times) as one host call
+            _lib.check(L.rcnn_attn_train_backward(d_out.data_ptr(), gates_all.data_ptr(), c_all.data_ptr(), b1.data_ptr(),
+                                                  b2.data_ptr(), alpha_all.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                                  encb.data_ptr(), encb.stride(0), encb.stride(1), projH.data_ptr(),
+                                                  projh_all.data_ptr(), v.data_ptr(), B, T, H, C, S, dg_all.data_ptr(),
+                                                  dctx_all.data_ptr(), de_all.data_ptr(), dv_acc.data_ptr(), dc.data_ptr(),
+                                                  dh.data_ptr(), s), "rcnn_attn_train_backward")
             dprojH = torch.empty((B * T, H), dtype=torch.bfloat16, device=dev)
             _lib.check(L.rcnn_attn_dprojH(de_all.data_ptr(), projh_all.data_ptr(), projH.data_ptr(), v.data_ptr(), S, B, T, H,
                                           dprojH.data_ptr(), s), "rcnn_attn_dprojH")
