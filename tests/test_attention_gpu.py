@@ -222,6 +222,50 @@ def test_chained_launches_reproduce_the_serialised_decode_bit_for_bit(monkeypatc
             assert torch.equal(got, tf_want)
 
 
+@pytest.mark.parametrize("B,T,H,C,S", [(3, 7, 16, 24, 2), (130, 33, 136, 72, 3)])
+def test_attention_backward_kernels_match_autograd_of_the_formula(B, T, H, C, S):
+    """K6e (rcnn_attn_step_bwd) and K6f (rcnn_attn_dprojH) against torch autograd of model/model.py:35-41 in float64 on the same
+    (bf16-rounded) inputs: de, d proj_h, dv and d proj_H for S independent steps that share proj_H, with a dropout multiplier."""
+    L = R.lib()
+    g = torch.Generator(device="cuda").manual_seed(B + T)
+    projH = torch.randn(B, T, H, device="cuda", generator=g).bfloat16()
+    enc = torch.randn(B, T, C, device="cuda", generator=g).bfloat16()
+    ph_all = torch.randn(S, B, H, device="cuda", generator=g)
+    v = torch.randn(H, device="cuda", generator=g) / H ** 0.5
+    scale = (torch.rand(S, B, T, device="cuda", generator=g) >= 0.25).float() / 0.75
+    dctx = torch.randn(S, B, C, device="cuda", generator=g)
+    # reference: autograd in float64
+    pH = projH.double().requires_grad_(True)
+    ph = ph_all.double().requires_grad_(True)
+    vv = v.double().requires_grad_(True)
+    e = (torch.tanh(pH.unsqueeze(0) + ph.unsqueeze(2)) * vv).sum(-1)                   # [S,B,T]
+    e.retain_grad()
+    alpha = torch.softmax(e, 2)
+    ctx = ((alpha * scale.double()).unsqueeze(3) * enc.double().unsqueeze(0)).sum(2)    # [S,B,C]
+    (ctx * dctx.double()).sum().backward()
+    # kernels
+    s = torch.cuda.current_stream().cuda_stream
+    de_all = torch.empty(S, B, T, device="cuda")
+    dproj = torch.zeros(S, B, H, dtype=torch.bfloat16, device="cuda")
+    dv_acc = torch.zeros(B, H, device="cuda")
+    a32 = alpha.detach().float().contiguous()
+    for t in range(S):
+        assert L.rcnn_attn_step_bwd(dctx[t].data_ptr(), C, a32[t].data_ptr(), scale[t].data_ptr(), enc.data_ptr(), enc.stride(0),
+                                    enc.stride(1), projH.data_ptr(), ph_all[t].data_ptr(), H, v.data_ptr(), B, T, H, C,
+                                    de_all[t].data_ptr(), dproj[t].data_ptr(), H, dv_acc.data_ptr(), s) == 0
+    dprojH = torch.empty(B, T, H, dtype=torch.bfloat16, device="cuda")
+    assert L.rcnn_attn_dprojH(de_all.data_ptr(), ph_all.data_ptr(), projH.data_ptr(), v.data_ptr(), S, B, T, H, dprojH.data_ptr(), s) == 0
+
+    def close(got, want, what, rel):
+        err = (got.double() - want).abs().max().item()
+        assert err <= rel * want.abs().max().item() + 1e-6, (what, err, want.abs().max().item())
+
+    close(de_all, e.grad, "de", 4e-3)
+    close(dproj, ph.grad, "d proj_h", 1e-2)              # bf16 output
+    close(dv_acc.sum(0), vv.grad, "dv", 4e-3)
+    close(dprojH, pH.grad, "d proj_H", 1e-2)             # bf16 output
+
+
 def test_state_dict_contract_and_errors():
     m = R.Attention(64, 64, 20, 1, 2, 0, 3)
     want = {"attention_cell.i2h.weight": (64, 64), "attention_cell.h2h.weight": (64, 64), "attention_cell.h2h.bias": (64,),
