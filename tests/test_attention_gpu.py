@@ -266,6 +266,33 @@ def test_attention_backward_kernels_match_autograd_of_the_formula(B, T, H, C, S)
     close(dprojH, pH.grad, "d proj_H", 1e-2)             # bf16 output
 
 
+def test_cell_backward_kernel_matches_autograd():
+    """K6d (rcnn_attn_cell_bwd) against autograd of the LSTMCell pointwise step in float64: gate-interleaved pre-activation
+    gradients (bf16) and dc_{t-1}, with both dh addends and an incoming dc."""
+    L = R.lib()
+    B, H = 37, 24
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pre = torch.randn(B, H, 4, device="cuda", generator=g).double().requires_grad_(True)      # [.., (i, f, g, o)] interleaved
+    c_prev = torch.randn(B, H, device="cuda", generator=g).double().requires_grad_(True)
+    i, f, gg, o = torch.sigmoid(pre[..., 0]), torch.sigmoid(pre[..., 1]), torch.tanh(pre[..., 2]), torch.sigmoid(pre[..., 3])
+    c_t = f * c_prev + i * gg
+    h = o * torch.tanh(c_t)
+    dh_a = torch.randn(B, 3, H, device="cuda", generator=g)
+    dh_b = torch.randn(B, H, device="cuda", generator=g)
+    dc_in = torch.randn(B, H, device="cuda", generator=g)
+    (h * (dh_a[:, 1] + dh_b).double() + c_t * dc_in.double()).sum().backward()
+    acts = torch.stack([i, f, gg, o], -1).detach().float().reshape(B, 4 * H).contiguous()
+    dc = dc_in.clone()
+    dg = torch.zeros(B, 5 * H, dtype=torch.bfloat16, device="cuda")
+    assert L.rcnn_attn_cell_bwd(acts.data_ptr(), c_prev.detach().float().contiguous().data_ptr(), c_t.detach().float().contiguous().data_ptr(),
+                                dh_a[:, 1].data_ptr(), dh_a.stride(0), dh_b.data_ptr(), H, dc.data_ptr(), B, H, dg.data_ptr(), 5 * H,
+                                torch.cuda.current_stream().cuda_stream) == 0
+    want = pre.grad.reshape(B, 4 * H)
+    assert (dg[:, :4 * H].double() - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+    assert (dc.double() - c_prev.grad).abs().max().item() <= 2e-3 * c_prev.grad.abs().max().item()
+    assert (dg[:, 4 * H:] == 0).all()
+
+
 def test_state_dict_contract_and_errors():
     m = R.Attention(64, 64, 20, 1, 2, 0, 3)
     want = {"attention_cell.i2h.weight": (64, 64), "attention_cell.h2h.weight": (64, 64), "attention_cell.h2h.bias": (64,),
