@@ -367,6 +367,9 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
     host = [(torch.rand(32, 3, 32, 128, generator=g) * 2 - 1).pin_memory() for _ in range(4)]
     dev = [h.to(device).contiguous(memory_format=torch.channels_last) for h in host]
 
+    if os.environ.get("RCNN_FOLD_BACKBONE", "1") == "1":
+        model.fold_backbone(torch.bfloat16)                 # BatchNorm folded, conv + bias + ReLU fused (model.FoldedBackbone)
+
     @torch.no_grad()
     def fwd(x):
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -462,7 +465,8 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
                                         "note": "same RCNN, backbone in fp32 / NCHW / eager launches (the reference's GPU settings), "
                                                 "device-resident; `value` above uses channels_last + bf16 autocast + graph replay"},
            "config": {"workload": "cfg1 minimal_inference: RCNN(194, hidden 256) eval, x[32,3,32,128] in [-1,1], greedy "
-                                  "CTC decode -> strings", "T": T, "backbone": "torch/cuDNN, channels_last + bf16 autocast"}}
+                                  "CTC decode -> strings", "T": T, "backbone": "torch/cuDNN, channels_last + bf16, BatchNorm folded into the convolutions, conv + bias + ReLU "
+                                  "as one cuDNN call (model.FoldedBackbone), graph replay"}}
     if cpu:
         from oracle import ref_port
         torch.set_num_threads(os.cpu_count() or 1)

@@ -18,7 +18,7 @@ from ._lib import lib, library_path, LibraryMissing  # noqa: F401
 from .charset import load_charset, decode_tokens, ctc_alphabet  # noqa: F401
 from .decode import ctc_greedy_decoder, decode, ctc_greedy_ids, ids_to_text, ids_to_text_async, PendingTexts  # noqa: F401
 from .ctc import CTCLoss, ctc_loss, ctc_loss_from_logits  # noqa: F401
-from .model import BidirectionalLSTM, CTCHead, RCNN, SEResNet31, make_enc_rnn  # noqa: F401
+from .model import BidirectionalLSTM, CTCHead, FoldedBackbone, RCNN, SEResNet31, make_enc_rnn  # noqa: F401
 from .inference import OCRInference  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from .attention import Attention, AttentionCell  # noqa: F401

@@ -22,7 +22,7 @@ from .preprocess import LinePreprocessor
 class OCRInference:
     def __init__(self, model_path=None, charset_path=None, device: str = "auto", img_h: int = 64,
                  img_w: int = 256, model: RCNN | None = None, hidden_size: int = 256,
-                 decoder: str | None = None):
+                 decoder: str | None = None, backbone_dtype: torch.dtype | None = torch.float32):
         if device == "auto":
             device = "cuda"
         self.device = torch.device(device)
@@ -65,6 +65,10 @@ class OCRInference:
                         warnings.warn(f"{len(self.unused_checkpoint_keys)} checkpoint keys were not used: "
                                       f"{self.unused_checkpoint_keys[:5]}")
         self.model = model.to(self.device).eval()
+        # inference-only copy of the backbone with BatchNorm folded into the convolutions and conv + bias + ReLU as one
+        # cuDNN call (model.FoldedBackbone).  float32 (default) reproduces the module to rounding; torch.bfloat16 is the fast
+        # setting bench.py's cfg 1 measures; None keeps the module as it is
+        self.model.fold_backbone(backbone_dtype)
         self.transform = LinePreprocessor(img_h, img_w, self.device)      # get_val_transform(img_h, img_w), on the device
 
     @torch.no_grad()

@@ -376,6 +376,75 @@ class SEResNet31(nn.Module):
         return self.conv_out(x)
 
 
+class FoldedBackbone(nn.Module):
+    """Inference-only copy of an ``SEResNet31`` (the cheap wins): every BatchNorm folded into the
+    convolution before it (eval statistics), conv + bias + ReLU as ONE cuDNN call where a ReLU follows directly
+    (``torch.cudnn_convolution_relu``), weights held in ``dtype`` (bf16) and channels_last.  43 fewer launches per image
+    batch than the module it copies; the module itself (and its state dict) is left untouched.  Built from a snapshot
+    of the weights: rebuild after loading a checkpoint."""
+
+    def __init__(self, cnn: "SEResNet31", dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        import copy
+        from torch.nn.utils.fusion import fuse_conv_bn_weights
+        self.dtype = dtype
+        self._n = 0
+
+        def fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+            w, b = fuse_conv_bn_weights(conv.weight.detach().float(), None if conv.bias is None else conv.bias.detach().float(),
+                                        bn.running_mean.float(), bn.running_var.float(), bn.eps,
+                                        bn.weight.detach().float(), bn.bias.detach().float())
+            i = self._n
+            self._n += 1
+            self.register_buffer(f"w{i}", w.detach().to(dtype).contiguous(memory_format=torch.channels_last), persistent=False)
+            self.register_buffer(f"b{i}", b.detach().to(dtype).contiguous(), persistent=False)
+            return (i, tuple(conv.stride), tuple(conv.padding))
+
+        def seq(mods):                                       # [conv, bn, relu, conv, bn, relu(, pool)] -> folded conv + relu pairs
+            mods = list(mods)
+            out, k = [], 0
+            while k < len(mods):
+                if isinstance(mods[k], nn.Conv2d):
+                    out.append(("cr", fold(mods[k], mods[k + 1])))
+                    k += 3
+                else:
+                    out.append(("pool", mods[k]))
+                    k += 1
+            return out
+
+        self.stem = seq(cnn.conv0)
+        self.tail = seq(cnn.conv_out)
+        self.blocks = []
+        self.se = nn.ModuleList()
+        for idx in range(1, 5):
+            for blk in getattr(cnn, f"layer{idx}"):
+                ds = None if blk.downsample is None else fold(blk.downsample[0], blk.downsample[1])
+                self.blocks.append((fold(blk.conv1, blk.bn1), fold(blk.conv2, blk.bn2), ds))
+                self.se.append(copy.deepcopy(blk.se.fc).to(dtype))
+        self.pools = nn.ModuleList([m for kind, m in self.stem if kind == "pool"])
+
+    def _conv(self, x, spec, relu: bool):
+        i, stride, padding = spec
+        w, b = getattr(self, f"w{i}"), getattr(self, f"b{i}")
+        if relu and x.is_cuda:
+            return torch.cudnn_convolution_relu(x, w, b, stride, padding, (1, 1), 1)
+        y = torch.nn.functional.conv2d(x, w, b, stride, padding)
+        return torch.relu_(y) if relu else y
+
+    @torch.no_grad()
+    def forward(self, x):
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        for kind, spec in self.stem:
+            x = self._conv(x, spec, True) if kind == "cr" else spec(x)
+        for (c1, c2, ds), fc in zip(self.blocks, self.se):
+            y = self._conv(self._conv(x, c1, True), c2, False)
+            y = y * fc(y.mean(dim=(2, 3)))[:, :, None, None]
+            x = torch.relu_(y + (x if ds is None else self._conv(x, ds, False)))
+        for kind, spec in self.tail:
+            x = self._conv(x, spec, True)
+        return x
+
+
 class RCNN(nn.Module):
     """Drop-in for model.model.RCNN (model/model.py:166-227) with a CTC head.
 
@@ -421,7 +490,20 @@ class RCNN(nn.Module):
         # bf16 when the CTC head follows (its GEMM operand format), fp32 for the attention decoder
         return self.enc_dropout(self.enc_rnn(feats))
 
+    def fold_backbone(self, dtype: torch.dtype = torch.bfloat16):
+        """Inference: build the folded copy of the backbone (``FoldedBackbone``) from the current weights, on their device;
+        ``forward`` / ``encode`` use it whenever the model is in eval() mode.  Call again after loading other weights;
+        ``fold_backbone(None)`` drops it.  The copy lives outside the module tree: the state dict keeps the reference's keys."""
+        folded = None
+        if dtype is not None:
+            folded = FoldedBackbone(self.cnn, dtype).to(next(self.cnn.parameters()).device).eval()
+        object.__setattr__(self, "_folded", folded)
+        return self
+
     def _features(self, x: torch.Tensor) -> torch.Tensor:
+        folded = getattr(self, "_folded", None)
+        if folded is not None and not self.training:
+            return folded(x).float().mean(dim=2).permute(0, 2, 1)
         return self.cnn(x).mean(dim=2).permute(0, 2, 1)   # AdaptiveAvgPool2d((1, None)) + squeeze(2): [B, W', C]
 
     def encode(self, x: torch.Tensor) -> torch.Tensor:

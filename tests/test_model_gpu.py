@@ -154,3 +154,49 @@ def test_graphed_step_replays_the_eager_train_step():
         assert abs(le - lg) <= 2e-3 * max(1.0, abs(le)), (le, lg)
     for a, b in zip(p_e, p_g):
         assert (a - b).abs().max().item() <= 5e-3 * (a.abs().max().item() + 1e-3)
+
+
+def test_folded_backbone_matches_the_module():
+    """model.FoldedBackbone (BatchNorm folded, conv + bias + ReLU fused) against the SEResNet31 it copies, eval mode,
+    non-trivial BatchNorm statistics: float32 to 1e-4 of the output's max, bf16 to 3e-2; RCNN uses it in eval() only and its
+    state dict keeps the reference's keys."""
+    import rcnn_ocr_b200 as R
+    torch.manual_seed(0)
+    model = R.RCNN(30, hidden_size=64).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for m in model.cnn.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, device="cuda", generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, device="cuda", generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, device="cuda", generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, device="cuda", generator=g) * 0.1)
+    keys = set(model.state_dict().keys())
+    model.eval()
+    x = torch.rand(5, 3, 32, 128, device="cuda", generator=g) * 2 - 1
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                  # (so that float32 means float32 on both sides)
+    try:
+        with torch.no_grad():
+            want = model.cnn(x)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                want_bf16 = model.cnn(x).float()             # the module under bf16 autocast: the same precision class
+            errs = {}
+            for dtype in (torch.float32, torch.bfloat16):
+                got = R.FoldedBackbone(model.cnn, dtype).cuda()(x).float()
+                assert got.shape == want.shape
+                errs[dtype] = (got - want).abs().max().item() / want.abs().max().item()
+            errs["autocast"] = (want_bf16 - want).abs().max().item() / want.abs().max().item()
+            print(f"\nfolded backbone vs module: max|diff|/max fp32 {errs[torch.float32]:.2e}, bf16 {errs[torch.bfloat16]:.2e} "
+                  f"(module under bf16 autocast: {errs['autocast']:.2e})")
+            assert errs[torch.float32] <= 1e-4, errs
+            assert errs[torch.bfloat16] <= max(2.0 * errs["autocast"], 3e-2), errs
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    with torch.no_grad():
+        ref_logits = model(x, is_train=False)
+        model.fold_backbone(torch.float32)
+        assert set(model.state_dict().keys()) == keys
+        folded_logits = model(x, is_train=False)
+        assert (folded_logits - ref_logits).abs().max().item() <= 2e-2 * ref_logits.abs().max().item()
+        model.fold_backbone(None)
+        assert getattr(model, "_folded", None) is None
