@@ -356,6 +356,18 @@ int rcnn_attn_dprojH(const float *de_all, const float *projh_all, const void *pr
                      void *dprojH, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Backbone, inference: the squeeze-and-excitation tail of an SE-ResNet block (model/seresnet31.py:
+ * SELayer, then the block's residual add and ReLU) in two launches.  Tensors channels_last: y / skip / out [B, HW, C] with C
+ * contiguous, dtype RCNN_F32 or RCNN_BF16; w1 [Cr, C], w2 [C, Cr] f32 (no biases); gate [B, C] f32.
+ *   rcnn_se_gate:  gate = sigmoid(w2 relu(w1 mean_over_HW(y)))
+ *   rcnn_se_apply: out = relu(y * gate + skip)      (C a multiple of 8 (bf16) / 4 (f32); out may alias y or skip)
+ * ------------------------------------------------------------------------------------- */
+int rcnn_se_gate(const void *y, int dtype, int B, int HW, int C, const float *w1, const float *w2, int Cr, float *gate,
+                 rcnn_stream_t stream);
+int rcnn_se_apply(const void *y, const void *skip, const float *gate, int dtype, int B, int HW, int C, void *out,
+                  rcnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch
  * of a dominant kernel is bracketed by cudaEventRecord on the launching stream.
  * rcnn_prof_read synchronises the recorded events and returns the summed duration.

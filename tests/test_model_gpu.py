@@ -200,3 +200,30 @@ def test_folded_backbone_matches_the_module():
         assert (folded_logits - ref_logits).abs().max().item() <= 2e-2 * ref_logits.abs().max().item()
         model.fold_backbone(None)
         assert getattr(model, "_folded", None) is None
+
+
+@pytest.mark.parametrize("B,C,H,W,Cr", [(32, 256, 8, 32, 16), (3, 512, 4, 16, 32), (2, 64, 5, 7, 4), (1, 8, 1, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_se_tail_kernels_match_the_formula(B, C, H, W, Cr, dtype):
+    """rcnn_se_gate / rcnn_se_apply (csrc/se_gate.cu) against relu(y * sigmoid(W2 relu(W1 mean(y))) + skip) in float64 on the same
+    (rounded) channels_last inputs: gate to 1e-5 (f32 sums), output to the rounding of its dtype."""
+    import rcnn_ocr_b200 as R
+    L = R.lib()
+    g = torch.Generator(device="cuda").manual_seed(B * C + H)
+    y = torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    skip = torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    w1 = torch.randn(Cr, C, device="cuda", generator=g) / C ** 0.5
+    w2 = torch.randn(C, Cr, device="cuda", generator=g)
+    gate = torch.empty(B, C, device="cuda")
+    out = torch.empty_like(y)
+    s = torch.cuda.current_stream().cuda_stream
+    dt = 1 if dtype == torch.bfloat16 else 0
+    assert L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2.data_ptr(), Cr, gate.data_ptr(), s) == 0
+    assert L.rcnn_se_apply(y.data_ptr(), skip.data_ptr(), gate.data_ptr(), dt, B, H * W, C, out.data_ptr(), s) == 0
+    yd = y.double()
+    gw = torch.sigmoid(torch.relu(yd.mean(dim=(2, 3)) @ w1.double().t()) @ w2.double().t())
+    want = torch.relu(yd * gw[:, :, None, None] + skip.double())
+    assert (gate.double() - gw).abs().max().item() <= 1e-5
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 1e-5
+    assert ((out.double() - want).abs() <= tol * want.abs() + 1e-5).all()
+    assert out.is_contiguous(memory_format=torch.channels_last)
