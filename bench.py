@@ -451,8 +451,32 @@ def run_cfg1(args, device, timed_fn, cpu: bool):
                    "weight_grads_fast_path": bool(_ops.weight_grads_supported(512, 256, T)),
                    "note": "encoder (2 x BiLSTM 256) + CTC head + fused CTC + backward + Adam on [32, %d, 512] features, graph replay" % T}
     del enc_a, head_a, opt_a, g_a
+    # the reference's LIVE model at this configuration: the same backbone and encoder with its attention decoder
+    # (RCNN(decoder="attention"): model/model.py:223-227 -> Attention._greedy_decode, 26 steps) -> token ids
+    model_at = R.RCNN(194, hidden_size=256, decoder="attention").to(device).eval().to(memory_format=torch.channels_last)
+    if os.environ.get("RCNN_FOLD_BACKBONE", "1") == "1":
+        model_at.fold_backbone(torch.bfloat16)
+
+    @torch.no_grad()
+    def fwd_at(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feats = model_at._features(x)
+        enc = model_at._encode_features(feats)
+        return model_at.attn(enc.float(), is_train=False, batch_max_length=25).argmax(dim=-1)
+
+    g_at = fwd_at
+    if args.graph:
+        try:
+            g_at = R.GraphedStep(fwd_at, [dev[0]])
+        except Exception:  # noqa: BLE001
+            torch.cuda.synchronize()
+    ms_at = timed_fn(lambda i: g_at(dev[i % 4]))
+    attn_shape = {"value": round(32 / (ms_at * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms_at, 4),
+                  "note": "RCNN(194, hidden 256, decoder='attention') eval: backbone -> encoder -> the reference's attention decoder "
+                          "(greedy, 26 steps) -> token ids, device-resident, " + ("graph replay" if g_at is not fwd_at else "eager")}
+    del model_at, g_at
     out = {"value": round(32 / (ms * 1e-3), 1), "unit": "lines/s", "ms_per_batch": round(ms, 4), "launch_mode": mode,
-           "encoder_train_step": train_shape,
+           "encoder_train_step": train_shape, "attention_decoder": attn_shape,
            "e2e": {"value": round(32 / (ms_e2e * 1e-3), 1), "ms_per_batch": round(ms_e2e, 4),
                    "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 32 * (T + 1) * 4},
            "e2e_from_pixels": {"value": round(32 / (ms_pix * 1e-3), 1), "ms_per_batch": round(ms_pix, 4),
