@@ -357,15 +357,21 @@ int rcnn_attn_dprojH(const float *de_all, const float *projh_all, const void *pr
 
 /* ---------------------------------------------------------------------------------------
  * Backbone, inference: the squeeze-and-excitation tail of an SE-ResNet block (model/seresnet31.py:
- * SELayer, then the block's residual add and ReLU) in two launches.  Tensors channels_last: y / skip / out [B, HW, C] with C
- * contiguous, dtype RCNN_F32 or RCNN_BF16; w1 [Cr, C], w2 [C, Cr] f32 (no biases); gate [B, C] f32.
- *   rcnn_se_gate:  gate = sigmoid(w2 relu(w1 mean_over_HW(y)))
- *   rcnn_se_apply: out = relu(y * gate + skip)      (C a multiple of 8 (bf16) / 4 (f32); out may alias y or skip)
+ * SELayer, then the block's residual add and ReLU) in two launches, and the stem's max pooling.  Tensors channels_last: y / skip /
+ * out [B, HW, C] with C contiguous, dtype RCNN_F32 or RCNN_BF16; w1 [Cr, C] f32, w2t [Cr, C] f32 = the second product's weight [C, Cr] TRANSPOSED; gate [B, C] f32; ybias / sbias [C]
+ * f32 or NULL: the biases of the convolutions that produced y / skip (folded BatchNorm shifts), added here instead of in a pass
+ * of their own.
+ *   rcnn_se_gate:  gate = sigmoid(w2t^T relu(w1 (mean_over_HW(y) + ybias))).  workspace: rcnn_se_gate_workspace_bytes(B, C) bytes,
+ *                  ZEROED by the caller before the first use and left zeroed (partial sums + one counter per image).
+ *   rcnn_se_apply: out = relu((y + ybias) * gate + skip + sbias)      (C a multiple of 8 (bf16) / 4 (f32); out may alias y or skip)
+ *   rcnn_maxpool2x2_nhwc: 2 x 2 max pooling, stride 2 (nn.MaxPool2d(2, 2)); H, W even; NaN propagates as in torch.
  * ------------------------------------------------------------------------------------- */
-int rcnn_se_gate(const void *y, int dtype, int B, int HW, int C, const float *w1, const float *w2, int Cr, float *gate,
-                 rcnn_stream_t stream);
-int rcnn_se_apply(const void *y, const void *skip, const float *gate, int dtype, int B, int HW, int C, void *out,
-                  rcnn_stream_t stream);
+size_t rcnn_se_gate_workspace_bytes(int B, int C);
+int rcnn_se_gate(const void *y, int dtype, int B, int HW, int C, const float *w1, const float *w2t, int Cr, const float *ybias,
+                 float *gate, void *workspace, rcnn_stream_t stream);
+int rcnn_se_apply(const void *y, const void *skip, const float *gate, const float *ybias, const float *sbias, int dtype, int B,
+                  int HW, int C, void *out, rcnn_stream_t stream);
+int rcnn_maxpool2x2_nhwc(const void *x, int dtype, int B, int H, int W, int C, void *out, rcnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-kernel device timing for the roofline report (bench.py): when enabled, every launch

