@@ -384,7 +384,8 @@ class FoldedBackbone(nn.Module):
     (csrc/se_gate.cu) instead of ten; the stem's max pooling on this library's kernel; the 3-channel input padded to 8
     channels so that the first convolution takes cuDNN's tensor-core path; weights held in ``dtype`` (bf16) and
     channels_last.  About 130 fewer launches per image batch than the module it copies; the module itself (and its state
-    dict) is left untouched.  Built from a snapshot of the weights: rebuild after loading a checkpoint."""
+    dict) is left untouched.  Built from a snapshot of the weights: rebuild after loading a checkpoint.  One stream at a time:
+    the blocks share the SE kernels' workspace (as the reference's single Python thread / default stream does)."""
 
     def __init__(self, cnn: "SEResNet31", dtype: torch.dtype = torch.bfloat16):
         super().__init__()
