@@ -6,7 +6,11 @@ decoder="attention": the reference's own path -- greedy attention decoding on th
 ``predict`` takes what the reference's takes (inference.py:93-124): file paths, PIL images, uint8 numpy arrays
 ([H,W], [H,W,3] RGB, [H,W,4] RGBA) or a list of them -- resized, padded, normalised and batched on the device by ONE
 launch per batch (preprocess.LinePreprocessor, kernel K7, instead of cv2 + albumentations + a copy per image) -- and,
-in addition, preprocessed tensors [3, img_h, img_w] in [-1, 1] (or an already batched [B, 3, H, W] tensor)."""
+in addition, preprocessed tensors [3, img_h, img_w] in [-1, 1] (or an already batched [B, 3, H, W] tensor).
+
+The backbone runs as ``model.FoldedBackbone`` (BatchNorm folded into the convolutions, fused conv + bias + ReLU, the SE
+tails on this library's kernels): ``backbone_dtype=torch.float32`` (default) equals the module to rounding,
+``torch.bfloat16`` is the fast setting, ``None`` keeps the module's own eager path."""
 from __future__ import annotations
 
 from typing import List, Union
