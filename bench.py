@@ -554,6 +554,9 @@ def run_cfg4(args, device, world, rank, timed_fn, hidden=256):
         tg = torch.randint(4, 195, (Bl, lmax), generator=g).to(device)      # itos[3:] -> CTC classes 4..194
         batches.append([x, tg, torch.full((Bl,), T, dtype=torch.long, device=device), tl])
     fn, mode = step, "eager"
+    # cuDNN picks the backbone's forward / dgrad / wgrad algorithms by measurement during the warm-up steps (before the capture)
+    bench_prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = os.environ.get("RCNN_CUDNN_BENCHMARK", "1") == "1"
     if args.graph and (world == 1 or args.graph_dp):
         try:
             fn = R.GraphedStep(step, batches[0])
@@ -562,6 +565,7 @@ def run_cfg4(args, device, world, rank, timed_fn, hidden=256):
             torch.cuda.synchronize()
             fn, mode = step, f"eager (capture failed: {type(e).__name__})"
     ms = timed_fn(lambda i: fn(*batches[i % 4]))
+    torch.backends.cudnn.benchmark = bench_prev
     # share of the step that is this repo's kernels: the same step without the backbone (features as inputs)
     return {"ms": ms, "mode": mode, "T": T, "lmax": lmax, "per_gpu_batch": Bl, "hidden": hidden, "keep": (step, fn)}
 
